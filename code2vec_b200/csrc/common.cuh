@@ -1,0 +1,87 @@
+// Shared device helpers for the path-attention engine (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <math.h>
+
+namespace c2v {
+
+constexpr int kWarp = 32;
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Philox4x32-10 (Salmon et al., SC'11).  Counter-based, so the dropout mask of the forward pass
+// is regenerated -- not stored -- in the backward pass, and oracle/path_attention_oracle.py
+// (dropout_keep_mask) reproduces it bit for bit.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
+  constexpr uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(M0, c.x), lo0 = M0 * c.x;
+    const uint32_t hi1 = __umulhi(M1, c.z), lo1 = M1 * c.z;
+    c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
+    k.x += W0;
+    k.y += W1;
+  }
+  return c;
+}
+
+// Dropout description shared by the forward and backward kernels.
+//   ext   : caller-supplied 0/1 mask [rows, ctx_dim] (tests) or nullptr
+//   thr   : keep iff u32 < thr   (thr = floor(keep * 2^32)); enabled == 0 -> identity
+//   scale : 1/keep, applied to survivors   (tensorflow_model.py:245-246: x * scale * mask)
+struct Dropout {
+  const float* ext;
+  uint32_t thr;
+  float scale;
+  uint2 key;      // (seed_lo, seed_hi)
+  uint2 step;     // (step_lo, step_hi)
+  int ctx_dim;    // 3d
+  int enabled;
+};
+
+// Multipliers (0 or scale) for the 4 consecutive columns [col4*4, col4*4+4) of context row `row`.
+__device__ __forceinline__ float4 dropout_mult4(const Dropout& dp, int row, int col4) {
+  if (!dp.enabled) return make_float4(1.f, 1.f, 1.f, 1.f);
+  if (dp.ext) {
+    const float4 m = *reinterpret_cast<const float4*>(dp.ext + (size_t)row * dp.ctx_dim + col4 * 4);
+    return make_float4(m.x * dp.scale, m.y * dp.scale, m.z * dp.scale, m.w * dp.scale);
+  }
+  const uint4 r = philox4x32_10(make_uint4((uint32_t)row, (uint32_t)col4, dp.step.x, dp.step.y), dp.key);
+  return make_float4(r.x < dp.thr ? dp.scale : 0.f, r.y < dp.thr ? dp.scale : 0.f,
+                     r.z < dp.thr ? dp.scale : 0.f, r.w < dp.thr ? dp.scale : 0.f);
+}
+
+// The three index arrays + two tables that define the gathered context matrix
+// X[n, 0:3d] = [ tok[src[n]] | path[pth[n]] | tok[tgt[n]] ]      (tensorflow_model.py:238-243)
+struct ContextSource {
+  const int32_t* src;
+  const int32_t* pth;
+  const int32_t* tgt;
+  const float* tok;     // [T, d]
+  const float* path;    // [P, d]
+  int d;
+  int rows;             // B*C
+};
+
+// pointer to X[n, j] for j in segment-aligned groups of 4 (d % 4 == 0 so a float4 never straddles)
+__device__ __forceinline__ const float* ctx_ptr(const ContextSource& cs, int n, int j) {
+  const int seg = j / cs.d;
+  const int off = j - seg * cs.d;
+  if (seg == 0) return cs.tok + (size_t)__ldg(cs.src + n) * cs.d + off;
+  if (seg == 1) return cs.path + (size_t)__ldg(cs.pth + n) * cs.d + off;
+  return cs.tok + (size_t)__ldg(cs.tgt + n) * cs.d + off;
+}
+
+}  // namespace c2v

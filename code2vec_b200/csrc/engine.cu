@@ -1,0 +1,567 @@
+// C ABI of the path-attention engine (see include/c2v_b200.h) and the orchestration of one
+// forward / train / predict pass.  Host code only launches kernels: all arithmetic of the path
+// (tensorflow_model.py:197-309) runs in the kernels of sgemm.cuh / kernels.cuh / umma_gemm.cuh.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <string>
+
+#include "../../include/c2v_b200.h"
+#include "common.cuh"
+#include "kernels.cuh"
+#include "sgemm.cuh"
+
+using namespace c2v;
+
+namespace {
+
+thread_local std::string g_create_error = "";
+
+constexpr size_t kAlign = 256;
+inline size_t align_up(size_t x, size_t a = kAlign) { return (x + a - 1) / a * a; }
+
+constexpr int kSplitDv = 16;   // split-K slices for dv = P . Y      (K = |Y|)
+constexpr int kSplitDw = 32;   // split-K slices for dW = X'^T . dU  (K = B*C)
+
+// Carve-up of the caller-provided workspace (offsets in bytes).
+struct Workspace {
+  size_t H, alpha, v, dv, S, loss_b, lse, loss, part, da_part;
+  size_t st_src, st_pth, st_tgt, st_mask, st_target, st_topk_idx, st_topk_val, st_code, st_attn;
+  size_t total;
+  size_t ldS;
+};
+
+bool dims_ok(const c2v_dims* d, std::string* why) {
+  auto bad = [&](const char* m) { if (why) *why = m; return false; };
+  if (!d) return bad("dims is NULL");
+  if (d->token_vocab < 1 || d->path_vocab < 1 || d->target_vocab < 1) return bad("vocab sizes must be >= 1");
+  if (d->embed_dim < 4 || d->embed_dim % 4) return bad("embed_dim must be a positive multiple of 4");
+  if (d->code_dim < 4 || d->code_dim % 4 || d->code_dim > 1024) return bad("code_dim must be a multiple of 4 in [4, 1024]");
+  if (d->max_contexts < 1) return bad("max_contexts must be >= 1");
+  if (d->max_batch < 1) return bad("max_batch must be >= 1");
+  if (d->top_k < 1 || d->top_k > 64) return bad("top_k must be in [1, 64]");
+  if ((double)d->max_batch * d->max_contexts > 2.0e9) return bad("max_batch * max_contexts overflows int32");
+  return true;
+}
+
+Workspace carve(const c2v_dims& d) {
+  Workspace w{};
+  const size_t N = (size_t)d.max_batch * d.max_contexts, D = d.code_dim, B = d.max_batch, X = 3 * (size_t)d.embed_dim;
+  w.ldS = align_up((size_t)d.target_vocab, 64);
+  size_t off = 0;
+  auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes); return o; };
+  w.H = take(N * D * 4);
+  w.alpha = take(N * 4);
+  w.v = take(B * D * 4);
+  w.dv = take(B * D * 4);
+  w.S = take(B * w.ldS * 4);
+  w.loss_b = take(B * 4);
+  w.lse = take(B * 4);
+  w.loss = take(64);
+  size_t part = (size_t)kSplitDv * B * D;
+  if ((size_t)kSplitDw * X * D > part) part = (size_t)kSplitDw * X * D;
+  w.part = take(part * 4);
+  w.da_part = take(B * D * 4);
+  w.st_src = take(N * 4);
+  w.st_pth = take(N * 4);
+  w.st_tgt = take(N * 4);
+  w.st_mask = take(N * 4);
+  w.st_target = take(B * 4);
+  w.st_topk_idx = take(B * (size_t)d.top_k * 4);
+  w.st_topk_val = take(B * (size_t)d.top_k * 4);
+  w.st_code = take(B * D * 4);
+  w.st_attn = take(N * 4);
+  w.total = off;
+  return w;
+}
+
+}  // namespace
+
+struct c2v_engine {
+  c2v_dims dims;
+  int device;
+  Workspace ws;
+  char* wbase;
+  size_t wbytes;
+  c2v_tensors theta, grad, am, av;
+  bool has_theta, has_grad, has_adam;
+  bool emb_grads_clean;      // token/path gradient tables are known to be all-zero
+  int math_mode;
+  int deterministic;
+  int64_t launches;
+  std::string err;
+};
+
+namespace {
+
+int fail(c2v_engine* e, int code, const std::string& msg) {
+  if (e) e->err = msg; else g_create_error = msg;
+  return code;
+}
+
+#define C2V_CUDA(e, expr)                                                                         \
+  do {                                                                                            \
+    cudaError_t _c = (expr);                                                                      \
+    if (_c != cudaSuccess)                                                                        \
+      return fail((e), C2V_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_c));         \
+  } while (0)
+
+// every kernel launch goes through this so the launch counter is truthful
+#define C2V_LAUNCH(e, ...)                                                                        \
+  do {                                                                                            \
+    __VA_ARGS__;                                                                                  \
+    cudaError_t _c = cudaGetLastError();                                                          \
+    if (_c != cudaSuccess)                                                                        \
+      return fail((e), C2V_ERR_CUDA, std::string("kernel launch failed: ") + cudaGetErrorString(_c)); \
+    (e)->launches++;                                                                              \
+  } while (0)
+
+template <class T> T* wsp(c2v_engine* e, size_t off) { return reinterpret_cast<T*>(e->wbase + off); }
+
+inline bool has_all(const c2v_tensors* t) { return t && t->tok && t->path && t->tgt && t->W && t->a; }
+
+Dropout make_dropout(const c2v_dims& d, float keep, uint64_t seed, uint64_t step, const float* ext) {
+  Dropout dp{};
+  dp.ctx_dim = 3 * d.embed_dim;
+  dp.enabled = (keep < 1.0f) ? 1 : 0;
+  dp.ext = ext;
+  dp.scale = 1.0f / keep;
+  double thr = (double)keep * 4294967296.0;
+  dp.thr = thr >= 4294967295.0 ? 0xFFFFFFFFu : (uint32_t)thr;
+  dp.key = make_uint2((uint32_t)(seed & 0xFFFFFFFFull), (uint32_t)(seed >> 32));
+  dp.step = make_uint2((uint32_t)(step & 0xFFFFFFFFull), (uint32_t)(step >> 32));
+  return dp;
+}
+
+int check_batch(c2v_engine* e, int32_t B) {
+  if (!e) return C2V_ERR_INVALID;
+  if (B < 1 || B > e->dims.max_batch) return fail(e, C2V_ERR_INVALID, "batch size out of range [1, max_batch]");
+  if (!e->wbase) return fail(e, C2V_ERR_STATE, "workspace not bound (c2v_bind_workspace)");
+  if (!e->has_theta) return fail(e, C2V_ERR_STATE, "parameters not bound (c2v_bind_params)");
+  return C2V_OK;
+}
+
+// ---- attention kernels: dispatch on ceil(D / 128) ------------------------------------------------
+int launch_attn_fwd(c2v_engine* e, cudaStream_t st, const float* H, const float* mask, int B, float* alpha, float* v) {
+  const int C = e->dims.max_contexts, D = e->dims.code_dim;
+  const size_t smem = ((size_t)((C + 3) & ~3) + 32 + kAttnWarps + (size_t)kAttnWarps * D) * sizeof(float);
+  const float* a = e->theta.a;
+#define C2V_AF(NV)                                                                                        \
+  do {                                                                                                    \
+    if (smem > 48 * 1024)                                                                                 \
+      C2V_CUDA(e, cudaFuncSetAttribute(attn_fwd_kernel<NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    C2V_LAUNCH(e, (attn_fwd_kernel<NV><<<B, kAttnThreads, smem, st>>>(H, a, mask, C, D, alpha, v)));      \
+  } while (0)
+  switch ((D + 127) / 128) {
+    case 1: C2V_AF(1); break;
+    case 2: C2V_AF(2); break;
+    case 3: C2V_AF(3); break;
+    case 4: C2V_AF(4); break;
+    case 5: case 6: C2V_AF(6); break;
+    default: C2V_AF(8); break;
+  }
+#undef C2V_AF
+  return C2V_OK;
+}
+
+int launch_attn_bwd(c2v_engine* e, cudaStream_t st, float* H, const float* alpha, const float* dv, int B, float* da_part) {
+  const int C = e->dims.max_contexts, D = e->dims.code_dim;
+  const size_t smem = ((size_t)((C + 3) & ~3) + 32 + (size_t)kAttnWarps * D) * sizeof(float);
+  const float* a = e->theta.a;
+#define C2V_AB(NV)                                                                                        \
+  do {                                                                                                    \
+    if (smem > 48 * 1024)                                                                                 \
+      C2V_CUDA(e, cudaFuncSetAttribute(attn_bwd_kernel<NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    C2V_LAUNCH(e, (attn_bwd_kernel<NV><<<B, kAttnThreads, smem, st>>>(H, alpha, dv, a, C, D, da_part)));  \
+  } while (0)
+  switch ((D + 127) / 128) {
+    case 1: C2V_AB(1); break;
+    case 2: C2V_AB(2); break;
+    case 3: C2V_AB(3); break;
+    case 4: C2V_AB(4); break;
+    case 5: case 6: C2V_AB(6); break;
+    default: C2V_AB(8); break;
+  }
+#undef C2V_AB
+  return C2V_OK;
+}
+
+int launch_colsum(c2v_engine* e, cudaStream_t st, const float* in, size_t stride, int R, int n, float* out) {
+  C2V_LAUNCH(e, (colsum_kernel<<<(n + 31) / 32, dim3(32, 32), 0, st>>>(in, stride, R, n, out)));
+  return C2V_OK;
+}
+
+ContextSource make_source(c2v_engine* e, const int32_t* src, const int32_t* pth, const int32_t* tgt, int B) {
+  ContextSource cs{};
+  cs.src = src; cs.pth = pth; cs.tgt = tgt;
+  cs.tok = e->theta.tok; cs.path = e->theta.path;
+  cs.d = e->dims.embed_dim;
+  cs.rows = B * e->dims.max_contexts;
+  return cs;
+}
+
+// H = tanh(X' . W)   (tensorflow_model.py:238-252)
+int run_ctx_fwd(c2v_engine* e, cudaStream_t st, const ContextSource& cs, const Dropout& dp, float* H) {
+  const int D = e->dims.code_dim, K = 3 * e->dims.embed_dim;
+  simt::GatherRowsK al{cs, dp};
+  simt::ColsX bl{e->theta.W, (size_t)D};
+  simt::TanhStore ep{H, (size_t)D};
+  C2V_LAUNCH(e, C2V_CUDA(e, simt::launch(st, cs.rows, D, K, 1, al, bl, ep)));
+  return C2V_OK;
+}
+
+// S[B, Y] = v . Ytab^T   (tensorflow_model.py:226,297)
+int run_logits(c2v_engine* e, cudaStream_t st, const float* v, int B, float* S) {
+  const int D = e->dims.code_dim, Y = e->dims.target_vocab;
+  simt::RowsK al{v, (size_t)D};
+  simt::RowsK bl{e->theta.tgt, (size_t)D};
+  simt::StoreC ep{S, e->ws.ldS, 0};
+  C2V_LAUNCH(e, C2V_CUDA(e, simt::launch(st, B, Y, D, 1, al, bl, ep)));
+  return C2V_OK;
+}
+
+int forward_impl(c2v_engine* e, cudaStream_t st, const int32_t* src, const int32_t* pth, const int32_t* tgt,
+                 const float* mask, int B, const Dropout& dp, float* code_vec, float* attn) {
+  ContextSource cs = make_source(e, src, pth, tgt, B);
+  float* H = wsp<float>(e, e->ws.H);
+  int rc = run_ctx_fwd(e, st, cs, dp, H);
+  if (rc) return rc;
+  return launch_attn_fwd(e, st, H, mask, B, attn, code_vec);
+}
+
+int topk_impl(c2v_engine* e, cudaStream_t st, const float* code_vec, int B, int32_t* idx, float* val, int normalize) {
+  float* S = wsp<float>(e, e->ws.S);
+  int rc = run_logits(e, st, code_vec, B, S);
+  if (rc) return rc;
+  const int Y = e->dims.target_vocab;
+  const int k = e->dims.top_k < Y ? e->dims.top_k : Y;
+  if (k <= 16)
+    C2V_LAUNCH(e, (topk_kernel<16><<<B, kTopkThreads, 0, st>>>(S, e->ws.ldS, Y, k, normalize, idx, val)));
+  else
+    C2V_LAUNCH(e, (topk_iter_kernel<<<B, kTopkThreads, 0, st>>>(S, e->ws.ldS, Y, k, normalize, idx, val)));
+  return C2V_OK;
+}
+
+// Backward of everything below the code vector, given dv: gradients of a, W and the two
+// embedding tables.
+int context_backward(c2v_engine* e, cudaStream_t st, const ContextSource& cs, const float* mask, int B,
+                     const Dropout& dp, const float* dv) {
+  const int D = e->dims.code_dim, d = e->dims.embed_dim, K3 = 3 * d, N = cs.rows;
+  float* H = wsp<float>(e, e->ws.H);
+  float* alpha = wsp<float>(e, e->ws.alpha);
+  float* da_part = wsp<float>(e, e->ws.da_part);
+  float* part = wsp<float>(e, e->ws.part);
+  int rc = launch_attn_bwd(e, st, H, alpha, dv, B, da_part);          // H now holds dU
+  if (rc) return rc;
+  rc = launch_colsum(e, st, da_part, (size_t)D, B, D, e->grad.a);
+  if (rc) return rc;
+  {  // dW = X'^T . dU   (split-K over the B*C contexts, fixed-order reduction)
+    simt::GatherColsX al{cs, dp};
+    simt::ColsX bl{H, (size_t)D};
+    const int ks = simt::effective_ksplit(N, kSplitDw);
+    simt::StoreC ep{part, (size_t)D, (size_t)K3 * D};
+    C2V_LAUNCH(e, C2V_CUDA(e, simt::launch(st, K3, D, N, kSplitDw, al, bl, ep)));
+    rc = launch_colsum(e, st, part, (size_t)K3 * D, ks, K3 * D, e->grad.W);
+    if (rc) return rc;
+  }
+  {  // dX' = dU . W^T -> dropout backward -> scatter-add into the embedding gradient tables
+    if (!e->emb_grads_clean) {
+      C2V_CUDA(e, cudaMemsetAsync(e->grad.tok, 0, (size_t)e->dims.token_vocab * d * 4, st));
+      C2V_CUDA(e, cudaMemsetAsync(e->grad.path, 0, (size_t)e->dims.path_vocab * d * 4, st));
+    }
+    simt::RowsK al{H, (size_t)D};
+    simt::RowsK bl{e->theta.W, (size_t)D};
+    simt::ScatterDx ep{cs, e->grad.tok, e->grad.path, mask, dp};
+    C2V_LAUNCH(e, C2V_CUDA(e, simt::launch(st, N, K3, D, 1, al, bl, ep)));
+    e->emb_grads_clean = false;
+  }
+  return C2V_OK;
+}
+
+int train_step_impl(c2v_engine* e, cudaStream_t st, const int32_t* src, const int32_t* pth, const int32_t* tgt,
+                    const float* mask, const int32_t* target, int B, float keep, uint64_t seed, uint64_t step,
+                    const float* ext_mask, float* loss_out) {
+  if (!e->has_grad) return fail(e, C2V_ERR_STATE, "gradients not bound (c2v_bind_grads)");
+  if (!(keep > 0.f) || keep > 1.f) return fail(e, C2V_ERR_INVALID, "keep_prob must be in (0, 1]");
+  const int D = e->dims.code_dim, Y = e->dims.target_vocab;
+  const Dropout dp = make_dropout(e->dims, keep, seed, step, ext_mask);
+  ContextSource cs = make_source(e, src, pth, tgt, B);
+  float* H = wsp<float>(e, e->ws.H);
+  float* alpha = wsp<float>(e, e->ws.alpha);
+  float* v = wsp<float>(e, e->ws.v);
+  float* dv = wsp<float>(e, e->ws.dv);
+  float* S = wsp<float>(e, e->ws.S);
+  float* loss_b = wsp<float>(e, e->ws.loss_b);
+  float* lse = wsp<float>(e, e->ws.lse);
+  float* part = wsp<float>(e, e->ws.part);
+  int rc;
+  if ((rc = run_ctx_fwd(e, st, cs, dp, H))) return rc;
+  if ((rc = launch_attn_fwd(e, st, H, mask, B, alpha, v))) return rc;
+  if ((rc = run_logits(e, st, v, B, S))) return rc;
+  const float invB = 1.0f / (float)B;
+  C2V_LAUNCH(e, (xent_kernel<<<B, kXentThreads, 0, st>>>(S, e->ws.ldS, target, Y, invB, loss_b, lse, 1)));
+  C2V_LAUNCH(e, (loss_reduce_kernel<<<1, 256, 0, st>>>(loss_b, B, invB, loss_out)));
+  {  // dv = P . Ytab   (K = |Y| split, fixed-order reduction)
+    simt::RowsK al{S, e->ws.ldS};
+    simt::ColsX bl{e->theta.tgt, (size_t)D};
+    const int ks = simt::effective_ksplit(Y, kSplitDv);
+    simt::StoreC ep{part, (size_t)D, (size_t)B * D};
+    C2V_LAUNCH(e, C2V_CUDA(e, simt::launch(st, B, D, Y, kSplitDv, al, bl, ep)));
+    if ((rc = launch_colsum(e, st, part, (size_t)B * D, ks, B * D, dv))) return rc;
+  }
+  {  // dYtab = P^T . v
+    simt::ColsX al{S, e->ws.ldS};
+    simt::ColsX bl{v, (size_t)D};
+    simt::StoreC ep{e->grad.tgt, (size_t)D, 0};
+    C2V_LAUNCH(e, C2V_CUDA(e, simt::launch(st, Y, D, B, 1, al, bl, ep)));
+  }
+  return context_backward(e, st, cs, mask, B, dp, dv);
+}
+
+int adam_impl(c2v_engine* e, cudaStream_t st, float lr, float b1, float b2, float eps, int64_t t) {
+  if (!e->has_grad || !e->has_adam) return fail(e, C2V_ERR_STATE, "gradients / Adam state not bound");
+  if (t < 1) return fail(e, C2V_ERR_INVALID, "Adam step count t must be >= 1");
+  const double lr_t_d = (double)lr * sqrt(1.0 - pow((double)b2, (double)t)) / (1.0 - pow((double)b1, (double)t));
+  const float lr_t = (float)lr_t_d;
+  const c2v_dims& d = e->dims;
+  const size_t n[5] = {(size_t)d.token_vocab * d.embed_dim, (size_t)d.path_vocab * d.embed_dim,
+                       (size_t)d.target_vocab * d.code_dim, (size_t)3 * d.embed_dim * d.code_dim, (size_t)d.code_dim};
+  float* P[5] = {e->theta.tok, e->theta.path, e->theta.tgt, e->theta.W, e->theta.a};
+  float* G[5] = {e->grad.tok, e->grad.path, e->grad.tgt, e->grad.W, e->grad.a};
+  float* M[5] = {e->am.tok, e->am.path, e->am.tgt, e->am.W, e->am.a};
+  float* V[5] = {e->av.tok, e->av.path, e->av.tgt, e->av.W, e->av.a};
+  for (int i = 0; i < 5; ++i) {
+    const size_t n4 = n[i] / 4;
+    size_t blocks = (n4 + 255) / 256;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    if (blocks < 1) blocks = 1;
+    const int zero = (i < 2) ? 1 : 0;   // embedding gradient tables are cleared for the next scatter-add
+    C2V_LAUNCH(e, (adam_kernel<<<(unsigned)blocks, 256, 0, st>>>(P[i], G[i], M[i], V[i], n4, lr_t, b1, b2, eps, zero)));
+  }
+  e->emb_grads_clean = true;
+  return C2V_OK;
+}
+
+}  // namespace
+
+// ================================== C ABI =======================================================
+extern "C" {
+
+int c2v_abi_version(void) { return C2V_ABI_VERSION; }
+
+const char* c2v_last_error(const c2v_engine* e) { return e ? e->err.c_str() : g_create_error.c_str(); }
+
+size_t c2v_workspace_bytes(const c2v_dims* dims) {
+  std::string why;
+  if (!dims_ok(dims, &why)) { g_create_error = why; return 0; }
+  return carve(*dims).total;
+}
+
+int c2v_create(const c2v_dims* dims, int device, c2v_engine** out) {
+  if (!out) return fail(nullptr, C2V_ERR_INVALID, "out is NULL");
+  *out = nullptr;
+  std::string why;
+  if (!dims_ok(dims, &why)) return fail(nullptr, C2V_ERR_INVALID, why);
+  int ndev = 0;
+  cudaError_t c = cudaGetDeviceCount(&ndev);
+  if (c != cudaSuccess || ndev < 1)
+    return fail(nullptr, C2V_ERR_CUDA, std::string("no CUDA device: ") + cudaGetErrorString(c));
+  if (device < 0 || device >= ndev) return fail(nullptr, C2V_ERR_INVALID, "device ordinal out of range");
+  cudaDeviceProp prop;
+  c = cudaGetDeviceProperties(&prop, device);
+  if (c != cudaSuccess) return fail(nullptr, C2V_ERR_CUDA, cudaGetErrorString(c));
+  if (prop.major != 10)
+    return fail(nullptr, C2V_ERR_UNSUPPORTED, "this library is built for sm_100a (B200) only");
+  c2v_engine* e = new c2v_engine();
+  e->dims = *dims;
+  e->device = device;
+  e->ws = carve(*dims);
+  e->wbase = nullptr;
+  e->wbytes = 0;
+  e->has_theta = e->has_grad = e->has_adam = false;
+  e->emb_grads_clean = false;
+  e->math_mode = C2V_MATH_FP32;
+  e->deterministic = 0;
+  e->launches = 0;
+  *out = e;
+  return C2V_OK;
+}
+
+void c2v_destroy(c2v_engine* e) { delete e; }
+
+int c2v_bind_workspace(c2v_engine* e, void* dev_ptr, size_t bytes) {
+  if (!e) return C2V_ERR_INVALID;
+  if (!dev_ptr) return fail(e, C2V_ERR_INVALID, "workspace pointer is NULL");
+  if (((uintptr_t)dev_ptr) % kAlign) return fail(e, C2V_ERR_INVALID, "workspace must be 256-byte aligned");
+  if (bytes < e->ws.total) return fail(e, C2V_ERR_INVALID, "workspace smaller than c2v_workspace_bytes()");
+  e->wbase = (char*)dev_ptr;
+  e->wbytes = bytes;
+  return C2V_OK;
+}
+
+int c2v_bind_params(c2v_engine* e, const c2v_tensors* t) {
+  if (!e) return C2V_ERR_INVALID;
+  if (!has_all(t)) return fail(e, C2V_ERR_INVALID, "all five parameter pointers must be non-NULL");
+  e->theta = *t; e->has_theta = true;
+  return C2V_OK;
+}
+
+int c2v_bind_grads(c2v_engine* e, const c2v_tensors* t) {
+  if (!e) return C2V_ERR_INVALID;
+  if (!has_all(t)) return fail(e, C2V_ERR_INVALID, "all five gradient pointers must be non-NULL");
+  e->grad = *t; e->has_grad = true; e->emb_grads_clean = false;
+  return C2V_OK;
+}
+
+int c2v_bind_adam_state(c2v_engine* e, const c2v_tensors* m, const c2v_tensors* v) {
+  if (!e) return C2V_ERR_INVALID;
+  if (!has_all(m) || !has_all(v)) return fail(e, C2V_ERR_INVALID, "all ten Adam slot pointers must be non-NULL");
+  e->am = *m; e->av = *v; e->has_adam = true;
+  return C2V_OK;
+}
+
+int c2v_set_option(c2v_engine* e, const char* key, int64_t value) {
+  if (!e || !key) return C2V_ERR_INVALID;
+  if (!strcmp(key, "math_mode")) {
+    if (value != C2V_MATH_FP32 && value != C2V_MATH_TF32) return fail(e, C2V_ERR_INVALID, "unknown math_mode");
+    if (value == C2V_MATH_TF32) return fail(e, C2V_ERR_UNSUPPORTED, "tf32 path not built");
+    e->math_mode = (int)value;
+    return C2V_OK;
+  }
+  if (!strcmp(key, "deterministic")) { e->deterministic = value ? 1 : 0; return C2V_OK; }
+  return fail(e, C2V_ERR_INVALID, std::string("unknown option: ") + key);
+}
+
+int c2v_get_option(const c2v_engine* e, const char* key, int64_t* value) {
+  if (!e || !key || !value) return C2V_ERR_INVALID;
+  if (!strcmp(key, "math_mode")) { *value = e->math_mode; return C2V_OK; }
+  if (!strcmp(key, "deterministic")) { *value = e->deterministic; return C2V_OK; }
+  return C2V_ERR_INVALID;
+}
+
+int c2v_forward(c2v_engine* e, const int32_t* src, const int32_t* path, const int32_t* tgt, const float* mask,
+                int32_t B, float* code_vec, float* attn, void* stream) {
+  int rc = check_batch(e, B);
+  if (rc) return rc;
+  if (!src || !path || !tgt || !mask || !code_vec) return fail(e, C2V_ERR_INVALID, "NULL argument");
+  C2V_CUDA(e, cudaSetDevice(e->device));
+  const Dropout dp = make_dropout(e->dims, 1.0f, 0, 0, nullptr);
+  return forward_impl(e, (cudaStream_t)stream, src, path, tgt, mask, B, dp, code_vec, attn);
+}
+
+int c2v_topk(c2v_engine* e, const float* code_vec, int32_t B, int32_t* idx, float* val, int32_t normalize,
+             void* stream) {
+  int rc = check_batch(e, B);
+  if (rc) return rc;
+  if (!code_vec || !idx || !val) return fail(e, C2V_ERR_INVALID, "NULL argument");
+  C2V_CUDA(e, cudaSetDevice(e->device));
+  return topk_impl(e, (cudaStream_t)stream, code_vec, B, idx, val, normalize);
+}
+
+int c2v_loss(c2v_engine* e, const float* code_vec, const int32_t* target, int32_t B, float* loss_out, void* stream) {
+  int rc = check_batch(e, B);
+  if (rc) return rc;
+  if (!code_vec || !target || !loss_out) return fail(e, C2V_ERR_INVALID, "NULL argument");
+  C2V_CUDA(e, cudaSetDevice(e->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  float* S = wsp<float>(e, e->ws.S);
+  if ((rc = run_logits(e, st, code_vec, B, S))) return rc;
+  const float invB = 1.0f / (float)B;
+  C2V_LAUNCH(e, (xent_kernel<<<B, kXentThreads, 0, st>>>(S, e->ws.ldS, target, e->dims.target_vocab, invB,
+                                                          wsp<float>(e, e->ws.loss_b), wsp<float>(e, e->ws.lse), 0)));
+  C2V_LAUNCH(e, (loss_reduce_kernel<<<1, 256, 0, st>>>(wsp<float>(e, e->ws.loss_b), B, invB, loss_out)));
+  return C2V_OK;
+}
+
+int c2v_train_step(c2v_engine* e, const int32_t* src, const int32_t* path, const int32_t* tgt, const float* mask,
+                   const int32_t* target, int32_t B, float keep_prob, uint64_t seed, uint64_t step,
+                   const float* dropout_mask, float* loss_out, void* stream) {
+  int rc = check_batch(e, B);
+  if (rc) return rc;
+  if (!src || !path || !tgt || !mask || !target || !loss_out) return fail(e, C2V_ERR_INVALID, "NULL argument");
+  C2V_CUDA(e, cudaSetDevice(e->device));
+  return train_step_impl(e, (cudaStream_t)stream, src, path, tgt, mask, target, B, keep_prob, seed, step,
+                         dropout_mask, loss_out);
+}
+
+int c2v_sampled_train_step(c2v_engine* e, const int32_t*, const int32_t*, const int32_t*, const float*,
+                           const int32_t*, int32_t, const int32_t*, int32_t, const float*, const float*, float,
+                           uint64_t, uint64_t, const float*, float*, void*) {
+  return fail(e, C2V_ERR_UNSUPPORTED, "sampled softmax not built yet");
+}
+
+int c2v_adam_step(c2v_engine* e, float lr, float beta1, float beta2, float eps, int64_t t, void* stream) {
+  if (!e) return C2V_ERR_INVALID;
+  if (!e->has_theta) return fail(e, C2V_ERR_STATE, "parameters not bound");
+  C2V_CUDA(e, cudaSetDevice(e->device));
+  return adam_impl(e, (cudaStream_t)stream, lr, beta1, beta2, eps, t);
+}
+
+int c2v_train_batch_host(c2v_engine* e, const int32_t* h_src, const int32_t* h_path, const int32_t* h_tgt,
+                         const float* h_mask, const int32_t* h_target, int32_t B, float keep_prob, uint64_t seed,
+                         int64_t t, float lr, float beta1, float beta2, float eps, float* h_loss, void* stream) {
+  int rc = check_batch(e, B);
+  if (rc) return rc;
+  if (!h_src || !h_path || !h_tgt || !h_mask || !h_target || !h_loss) return fail(e, C2V_ERR_INVALID, "NULL argument");
+  C2V_CUDA(e, cudaSetDevice(e->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t nb = (size_t)B * e->dims.max_contexts * 4;
+  int32_t* src = wsp<int32_t>(e, e->ws.st_src);
+  int32_t* pth = wsp<int32_t>(e, e->ws.st_pth);
+  int32_t* tgt = wsp<int32_t>(e, e->ws.st_tgt);
+  float* mask = wsp<float>(e, e->ws.st_mask);
+  int32_t* target = wsp<int32_t>(e, e->ws.st_target);
+  float* loss = wsp<float>(e, e->ws.loss);
+  C2V_CUDA(e, cudaMemcpyAsync(src, h_src, nb, cudaMemcpyHostToDevice, st));
+  C2V_CUDA(e, cudaMemcpyAsync(pth, h_path, nb, cudaMemcpyHostToDevice, st));
+  C2V_CUDA(e, cudaMemcpyAsync(tgt, h_tgt, nb, cudaMemcpyHostToDevice, st));
+  C2V_CUDA(e, cudaMemcpyAsync(mask, h_mask, nb, cudaMemcpyHostToDevice, st));
+  C2V_CUDA(e, cudaMemcpyAsync(target, h_target, (size_t)B * 4, cudaMemcpyHostToDevice, st));
+  // the Adam step count doubles as the dropout stream position
+  if ((rc = train_step_impl(e, st, src, pth, tgt, mask, target, B, keep_prob, seed, (uint64_t)t, nullptr, loss))) return rc;
+  if ((rc = adam_impl(e, st, lr, beta1, beta2, eps, t))) return rc;
+  C2V_CUDA(e, cudaMemcpyAsync(h_loss, loss, 4, cudaMemcpyDeviceToHost, st));
+  C2V_CUDA(e, cudaStreamSynchronize(st));
+  return C2V_OK;
+}
+
+int c2v_predict_batch_host(c2v_engine* e, const int32_t* h_src, const int32_t* h_path, const int32_t* h_tgt,
+                           const float* h_mask, int32_t B, int32_t normalize, int32_t* h_topk_idx, float* h_topk_val,
+                           float* h_code_vec, float* h_attn, void* stream) {
+  int rc = check_batch(e, B);
+  if (rc) return rc;
+  if (!h_src || !h_path || !h_tgt || !h_mask || !h_topk_idx || !h_topk_val) return fail(e, C2V_ERR_INVALID, "NULL argument");
+  C2V_CUDA(e, cudaSetDevice(e->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t nb = (size_t)B * e->dims.max_contexts * 4;
+  int32_t* src = wsp<int32_t>(e, e->ws.st_src);
+  int32_t* pth = wsp<int32_t>(e, e->ws.st_pth);
+  int32_t* tgt = wsp<int32_t>(e, e->ws.st_tgt);
+  float* mask = wsp<float>(e, e->ws.st_mask);
+  float* code = wsp<float>(e, e->ws.st_code);
+  float* attn = wsp<float>(e, e->ws.st_attn);
+  int32_t* tki = wsp<int32_t>(e, e->ws.st_topk_idx);
+  float* tkv = wsp<float>(e, e->ws.st_topk_val);
+  C2V_CUDA(e, cudaMemcpyAsync(src, h_src, nb, cudaMemcpyHostToDevice, st));
+  C2V_CUDA(e, cudaMemcpyAsync(pth, h_path, nb, cudaMemcpyHostToDevice, st));
+  C2V_CUDA(e, cudaMemcpyAsync(tgt, h_tgt, nb, cudaMemcpyHostToDevice, st));
+  C2V_CUDA(e, cudaMemcpyAsync(mask, h_mask, nb, cudaMemcpyHostToDevice, st));
+  const Dropout dp = make_dropout(e->dims, 1.0f, 0, 0, nullptr);
+  if ((rc = forward_impl(e, st, src, pth, tgt, mask, B, dp, code, attn))) return rc;
+  if ((rc = topk_impl(e, st, code, B, tki, tkv, normalize))) return rc;
+  const int Y = e->dims.target_vocab;
+  const int k = e->dims.top_k < Y ? e->dims.top_k : Y;
+  C2V_CUDA(e, cudaMemcpyAsync(h_topk_idx, tki, (size_t)B * k * 4, cudaMemcpyDeviceToHost, st));
+  C2V_CUDA(e, cudaMemcpyAsync(h_topk_val, tkv, (size_t)B * k * 4, cudaMemcpyDeviceToHost, st));
+  if (h_code_vec) C2V_CUDA(e, cudaMemcpyAsync(h_code_vec, code, (size_t)B * e->dims.code_dim * 4, cudaMemcpyDeviceToHost, st));
+  if (h_attn) C2V_CUDA(e, cudaMemcpyAsync(h_attn, attn, nb, cudaMemcpyDeviceToHost, st));
+  C2V_CUDA(e, cudaStreamSynchronize(st));
+  return C2V_OK;
+}
+
+int64_t c2v_launch_count(const c2v_engine* e) { return e ? e->launches : 0; }
+
+}  // extern "C"

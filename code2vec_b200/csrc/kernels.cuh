@@ -1,0 +1,449 @@
+// Non-GEMM kernels of the path-attention engine: attention softmax / weighted sum and its
+// backward, fused cross-entropy, top-k, TF1 Adam, small deterministic reductions.
+#pragma once
+#include <float.h>
+#include <limits.h>
+#include "common.cuh"
+
+namespace c2v {
+
+constexpr int kAttnThreads = 256;
+constexpr int kAttnWarps = kAttnThreads / 32;
+
+// Deterministic block-wide sum (fixed tree); `red` is shared scratch of >= 32 floats.
+__device__ __forceinline__ float block_sum(float v, float* red) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  v = warp_sum(v);
+  __syncthreads();
+  if (lane == 0) red[warp] = v;
+  __syncthreads();
+  float r = (threadIdx.x < nw) ? red[threadIdx.x] : 0.f;
+  if (warp == 0) {
+    r = warp_sum(r);
+    if (lane == 0) red[0] = r;
+  }
+  __syncthreads();
+  r = red[0];
+  __syncthreads();
+  return r;
+}
+__device__ __forceinline__ float block_max(float v, float* red) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  v = warp_max(v);
+  __syncthreads();
+  if (lane == 0) red[warp] = v;
+  __syncthreads();
+  float r = (threadIdx.x < nw) ? red[threadIdx.x] : -INFINITY;
+  if (warp == 0) {
+    r = warp_max(r);
+    if (lane == 0) red[0] = r;
+  }
+  __syncthreads();
+  r = red[0];
+  __syncthreads();
+  return r;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Attention forward: z_c = h_c . a + log(mask_c); alpha = softmax_c(z); v = sum_c alpha_c h_c
+// (tensorflow_model.py:254-263).  One CTA per example (bag); a warp per context; online softmax
+// so H is read once.  A bag with no valid context gives NaN (tf.nn.softmax of all -inf).
+// ---------------------------------------------------------------------------------------------
+template <int NV>
+__global__ void __launch_bounds__(kAttnThreads)
+attn_fwd_kernel(const float* __restrict__ H, const float* __restrict__ a, const float* __restrict__ mask,
+                int C, int D, float* __restrict__ alpha, float* __restrict__ v) {
+  extern __shared__ float sm[];
+  float* zs = sm;                       // [C]
+  float* red = zs + ((C + 3) & ~3);     // [32]
+  float* wm = red + 32;                 // [kAttnWarps]
+  float* vbuf = wm + kAttnWarps;        // [kAttnWarps][D]
+  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+  float4 av[NV];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int j = i * 128 + lane * 4;
+    av[i] = (j < D) ? *reinterpret_cast<const float4*>(a + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  float m_w = -INFINITY;
+  float4 acc[NV];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+
+  for (int c = warp; c < C; c += kAttnWarps) {
+    const float* h = H + ((size_t)b * C + c) * D;
+    float4 hv[NV];
+    float part = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int j = i * 128 + lane * 4;
+      hv[i] = (j < D) ? *reinterpret_cast<const float4*>(h + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+      part += hv[i].x * av[i].x + hv[i].y * av[i].y + hv[i].z * av[i].z + hv[i].w * av[i].w;
+    }
+    const float z = warp_sum(part) + logf(mask[(size_t)b * C + c]);     // log(0) = -inf
+    if (lane == 0) zs[c] = z;
+    const float nm = fmaxf(m_w, z);
+    if (nm > -INFINITY) {                        // NaN z falls through: poisons acc like TF would
+      const float sc = expf(m_w - nm), e = expf(z - nm);
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        acc[i].x = acc[i].x * sc + e * hv[i].x;
+        acc[i].y = acc[i].y * sc + e * hv[i].y;
+        acc[i].z = acc[i].z * sc + e * hv[i].z;
+        acc[i].w = acc[i].w * sc + e * hv[i].w;
+      }
+      m_w = nm;
+    } else if (z != z) {
+      m_w = z;
+    }
+  }
+  if (lane == 0) wm[warp] = m_w;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int j = i * 128 + lane * 4;
+    if (j < D) *reinterpret_cast<float4*>(vbuf + (size_t)warp * D + j) = acc[i];
+  }
+  __syncthreads();
+  float zmax = -INFINITY;
+  for (int c = tid; c < C; c += kAttnThreads) zmax = fmaxf(zmax, zs[c]);
+  zmax = block_max(zmax, red);
+  float s = 0.f;
+  for (int c = tid; c < C; c += kAttnThreads) s += expf(zs[c] - zmax);    // -inf - -inf = NaN: all-masked bag
+  s = block_sum(s, red);
+  const float inv = 1.f / s;
+  if (alpha)
+    for (int c = tid; c < C; c += kAttnThreads) alpha[(size_t)b * C + c] = expf(zs[c] - zmax) * inv;
+  for (int j = tid; j < D; j += kAttnThreads) {
+    float r = 0.f;
+#pragma unroll
+    for (int w = 0; w < kAttnWarps; ++w) {
+      const float mw = wm[w];
+      if (mw > -INFINITY || mw != mw) r += vbuf[(size_t)w * D + j] * expf(mw - zmax);
+    }
+    v[(size_t)b * D + j] = (zmax > -INFINITY) ? r * inv : NAN;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Attention backward:  dalpha_c = h_c.dv ; dz = alpha (dalpha - sum alpha dalpha) ;
+// dh = alpha dv + dz a ; du = dh (1 - h^2) written over H ; da partial per example.
+// ---------------------------------------------------------------------------------------------
+template <int NV>
+__global__ void __launch_bounds__(kAttnThreads)
+attn_bwd_kernel(float* __restrict__ H, const float* __restrict__ alpha, const float* __restrict__ dv,
+                const float* __restrict__ a, int C, int D, float* __restrict__ da_part) {
+  extern __shared__ float sm[];
+  float* dal = sm;                      // [C]
+  float* red = dal + ((C + 3) & ~3);    // [32]
+  float* dabuf = red + 32;              // [kAttnWarps][D]
+  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  float4 av[NV], gv[NV], dacc[NV];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int j = i * 128 + lane * 4;
+    const bool ok = j < D;
+    av[i] = ok ? *reinterpret_cast<const float4*>(a + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+    gv[i] = ok ? *reinterpret_cast<const float4*>(dv + (size_t)b * D + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+    dacc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  for (int c = warp; c < C; c += kAttnWarps) {
+    const float al = alpha[(size_t)b * C + c];
+    float part = 0.f;
+    if (al != 0.f) {
+      const float* h = H + ((size_t)b * C + c) * D;
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        const int j = i * 128 + lane * 4;
+        if (j < D) {
+          const float4 hv = *reinterpret_cast<const float4*>(h + j);
+          part += hv.x * gv[i].x + hv.y * gv[i].y + hv.z * gv[i].z + hv.w * gv[i].w;
+        }
+      }
+      part = warp_sum(part);
+    }
+    if (lane == 0) dal[c] = part;
+  }
+  __syncthreads();
+  float t = 0.f;
+  for (int c = tid; c < C; c += kAttnThreads) {
+    const float al = alpha[(size_t)b * C + c];
+    if (al != 0.f) t += al * dal[c];
+  }
+  t = block_sum(t, red);
+  for (int c = warp; c < C; c += kAttnWarps) {
+    const float al = alpha[(size_t)b * C + c];
+    float* h = H + ((size_t)b * C + c) * D;
+    if (al == 0.f) {                    // masked context: exact zeros (alpha == 0)
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        const int j = i * 128 + lane * 4;
+        if (j < D) *reinterpret_cast<float4*>(h + j) = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+      continue;
+    }
+    const float dz = al * (dal[c] - t);
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int j = i * 128 + lane * 4;
+      if (j < D) {
+        const float4 hv = *reinterpret_cast<const float4*>(h + j);
+        float4 du;
+        du.x = (al * gv[i].x + dz * av[i].x) * (1.f - hv.x * hv.x);
+        du.y = (al * gv[i].y + dz * av[i].y) * (1.f - hv.y * hv.y);
+        du.z = (al * gv[i].z + dz * av[i].z) * (1.f - hv.z * hv.z);
+        du.w = (al * gv[i].w + dz * av[i].w) * (1.f - hv.w * hv.w);
+        *reinterpret_cast<float4*>(h + j) = du;
+        dacc[i].x += dz * hv.x; dacc[i].y += dz * hv.y; dacc[i].z += dz * hv.z; dacc[i].w += dz * hv.w;
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int j = i * 128 + lane * 4;
+    if (j < D) *reinterpret_cast<float4*>(dabuf + (size_t)warp * D + j) = dacc[i];
+  }
+  __syncthreads();
+  for (int j = tid; j < D; j += kAttnThreads) {
+    float r = 0.f;
+#pragma unroll
+    for (int w = 0; w < kAttnWarps; ++w) r += dabuf[(size_t)w * D + j];
+    da_part[(size_t)b * D + j] = r;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Fused sparse-softmax cross entropy over one row of the logits slab S[b, 0:Y]
+// (tensorflow_model.py:227-230).  Pass 1: online (max, sum-exp) -> lse, loss_b = lse - S[y_b].
+// Pass 2 (write_probs): S <- (softmax - onehot) / B in place  = dL/dlogits.
+// ---------------------------------------------------------------------------------------------
+constexpr int kXentThreads = 512;
+
+__global__ void __launch_bounds__(kXentThreads)
+xent_kernel(float* __restrict__ S, size_t ldS, const int32_t* __restrict__ target, int Y, float inv_batch,
+            float* __restrict__ loss_b, float* __restrict__ lse_out, int write_probs) {
+  __shared__ float red[32];
+  float* row = S + (size_t)blockIdx.x * ldS;
+  const int tid = threadIdx.x;
+  const int Y4 = Y >> 2;
+  const int y = target[blockIdx.x];
+  const float logit_y = row[y];          // read before pass 2 overwrites the row
+  float m = -INFINITY, s = 0.f;
+  for (int q = tid; q < Y4; q += kXentThreads) {
+    const float4 x = *reinterpret_cast<const float4*>(row + 4 * q);
+    const float m4 = fmaxf(fmaxf(x.x, x.y), fmaxf(x.z, x.w));
+    if (m4 > m) { s *= expf(m - m4); m = m4; }
+    s += expf(x.x - m) + expf(x.y - m) + expf(x.z - m) + expf(x.w - m);
+  }
+  for (int j = 4 * Y4 + tid; j < Y; j += kXentThreads) {
+    const float x = row[j];
+    if (x > m) { s *= expf(m - x); m = x; }
+    s += expf(x - m);
+  }
+  const float M = block_max(m, red);
+  s = (m > -INFINITY) ? s * expf(m - M) : 0.f;
+  s = block_sum(s, red);
+  const float lse = M + logf(s);
+  if (tid == 0) {
+    loss_b[blockIdx.x] = lse - logit_y;
+    if (lse_out) lse_out[blockIdx.x] = lse;
+  }
+  if (!write_probs) return;
+  for (int q = tid; q < Y4; q += kXentThreads) {
+    float4 x = *reinterpret_cast<const float4*>(row + 4 * q);
+    x.x = expf(x.x - lse) * inv_batch; x.y = expf(x.y - lse) * inv_batch;
+    x.z = expf(x.z - lse) * inv_batch; x.w = expf(x.w - lse) * inv_batch;
+    const int j = 4 * q;
+    if (y >= j && y < j + 4) {
+      if (y == j) x.x -= inv_batch; else if (y == j + 1) x.y -= inv_batch;
+      else if (y == j + 2) x.z -= inv_batch; else x.w -= inv_batch;
+    }
+    *reinterpret_cast<float4*>(row + 4 * q) = x;
+  }
+  for (int j = 4 * Y4 + tid; j < (int)ldS; j += kXentThreads) {
+    float p = 0.f;
+    if (j < Y) { p = expf(row[j] - lse) * inv_batch; if (j == y) p -= inv_batch; }
+    row[j] = p;                          // padding columns [Y, ldS) are zeroed
+  }
+}
+
+// loss = (sum_b loss_b) * inv_batch, fixed summation order.
+__global__ void __launch_bounds__(256) loss_reduce_kernel(const float* __restrict__ loss_b, int B, float inv_batch,
+                                                          float* __restrict__ out) {
+  __shared__ float red[32];
+  float s = 0.f;
+  for (int i = threadIdx.x; i < B; i += 256) s += loss_b[i];
+  s = block_sum(s, red);
+  if (threadIdx.x == 0) out[0] = s * inv_batch;
+}
+
+// out[j] = sum_{r<R} in[r*stride + j] for j < n   (split-K partials, per-example da partials).
+// block (32, 32): thread (x, y) sums rows y, y+32, ...; fixed-order tree over y.
+__global__ void __launch_bounds__(1024) colsum_kernel(const float* __restrict__ in, size_t stride, int R, int n,
+                                                      float* __restrict__ out) {
+  __shared__ float t[32][33];
+  const int x = threadIdx.x, y = threadIdx.y;
+  const int j = blockIdx.x * 32 + x;
+  float s = 0.f;
+  if (j < n)
+    for (int r = y; r < R; r += 32) s += in[(size_t)r * stride + j];
+  t[y][x] = s;
+  __syncthreads();
+  for (int o = 16; o > 0; o >>= 1) {
+    if (y < o) t[y][x] += t[y + o][x];
+    __syncthreads();
+  }
+  if (y == 0 && j < n) out[j] = t[0][x];
+}
+
+// ---------------------------------------------------------------------------------------------
+// tf.nn.top_k over a row of scores: sorted descending, ties -> lower index   [TF-lib]
+// (tensorflow_model.py:299-304); normalize: softmax over the k values (:305-306).
+// ---------------------------------------------------------------------------------------------
+constexpr int kTopkThreads = 256;
+
+struct ValIdx { float v; int i; };
+__device__ __forceinline__ bool better(float va, int ia, float vb, int ib) {   // a strictly before b
+  return va > vb || (va == vb && ia < ib);
+}
+__device__ __forceinline__ ValIdx block_argbest(float v, int i, ValIdx* red) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ov = __shfl_xor_sync(0xffffffffu, v, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, i, o);
+    if (better(ov, oi, v, i)) { v = ov; i = oi; }
+  }
+  __syncthreads();
+  if (lane == 0) { red[warp].v = v; red[warp].i = i; }
+  __syncthreads();
+  if (warp == 0) {
+    v = (lane < kTopkThreads / 32) ? red[lane].v : -INFINITY;
+    i = (lane < kTopkThreads / 32) ? red[lane].i : INT_MAX;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ov = __shfl_xor_sync(0xffffffffu, v, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, i, o);
+      if (better(ov, oi, v, i)) { v = ov; i = oi; }
+    }
+    if (lane == 0) { red[0].v = v; red[0].i = i; }
+  }
+  __syncthreads();
+  ValIdx r = red[0];
+  __syncthreads();
+  return r;
+}
+
+__device__ __forceinline__ void topk_finish(float* vals, int k, int normalize, float* val_out) {
+  // thread 0 only
+  if (normalize) {
+    float mx = vals[0], s = 0.f;
+    for (int q = 0; q < k; ++q) s += expf(vals[q] - mx);
+    for (int q = 0; q < k; ++q) val_out[q] = expf(vals[q] - mx) / s;
+  } else {
+    for (int q = 0; q < k; ++q) val_out[q] = vals[q];
+  }
+}
+
+// Fast path, k <= K: per-thread sorted register list, then k rounds of block arg-best over the heads.
+template <int K>
+__global__ void __launch_bounds__(kTopkThreads)
+topk_kernel(const float* __restrict__ S, size_t ldS, int Y, int k, int normalize, int32_t* __restrict__ idx_out,
+            float* __restrict__ val_out) {
+  __shared__ ValIdx red[32];
+  __shared__ float cv[kTopkThreads * K];
+  __shared__ int ci[kTopkThreads * K];
+  __shared__ float outv[K];
+  const float* row = S + (size_t)blockIdx.x * ldS;
+  const int tid = threadIdx.x;
+  float tv[K];
+  int ti[K];
+#pragma unroll
+  for (int q = 0; q < K; ++q) { tv[q] = -INFINITY; ti[q] = INT_MAX; }
+  auto consider = [&](float x, int j) {
+    if (x > tv[K - 1]) {
+      tv[K - 1] = x; ti[K - 1] = j;
+#pragma unroll
+      for (int q = K - 1; q > 0; --q) {
+        if (tv[q] > tv[q - 1]) {
+          const float fv = tv[q]; tv[q] = tv[q - 1]; tv[q - 1] = fv;
+          const int fi = ti[q]; ti[q] = ti[q - 1]; ti[q - 1] = fi;
+        }
+      }
+    }
+  };
+  const int Y4 = Y >> 2;
+  for (int q = tid; q < Y4; q += kTopkThreads) {
+    const float4 x = *reinterpret_cast<const float4*>(row + 4 * q);
+    consider(x.x, 4 * q); consider(x.y, 4 * q + 1); consider(x.z, 4 * q + 2); consider(x.w, 4 * q + 3);
+  }
+  for (int j = 4 * Y4 + tid; j < Y; j += kTopkThreads) consider(row[j], j);
+#pragma unroll
+  for (int q = 0; q < K; ++q) { cv[tid * K + q] = tv[q]; ci[tid * K + q] = ti[q]; }
+  int head = 0;
+  for (int r = 0; r < k; ++r) {
+    const float hv = (head < K) ? cv[tid * K + head] : -INFINITY;
+    const int hi = (head < K) ? ci[tid * K + head] : INT_MAX;
+    const ValIdx w = block_argbest(hv, hi, red);
+    if (w.i == hi && hi != INT_MAX) ++head;
+    if (tid == 0) { idx_out[(size_t)blockIdx.x * k + r] = w.i; outv[r] = w.v; }
+  }
+  if (tid == 0) topk_finish(outv, k, normalize, val_out + (size_t)blockIdx.x * k);
+}
+
+// General path (any k <= 64): k rounds, each a block arg-best over the entries ordered after
+// the previous pick.
+__global__ void __launch_bounds__(kTopkThreads)
+topk_iter_kernel(const float* __restrict__ S, size_t ldS, int Y, int k, int normalize, int32_t* __restrict__ idx_out,
+                 float* __restrict__ val_out) {
+  __shared__ ValIdx red[32];
+  __shared__ float outv[64];
+  const float* row = S + (size_t)blockIdx.x * ldS;
+  const int tid = threadIdx.x;
+  float pv = INFINITY;
+  int pi = -1;
+  for (int r = 0; r < k; ++r) {
+    float bv = -INFINITY;
+    int bi = INT_MAX;
+    for (int j = tid; j < Y; j += kTopkThreads) {
+      const float x = row[j];
+      const bool after = (x < pv) || (x == pv && j > pi);
+      if (after && better(x, j, bv, bi)) { bv = x; bi = j; }
+    }
+    const ValIdx w = block_argbest(bv, bi, red);
+    pv = w.v; pi = w.i;
+    if (tid == 0) { idx_out[(size_t)blockIdx.x * k + r] = w.i; outv[r] = w.v; }
+  }
+  if (tid == 0) topk_finish(outv, k, normalize, val_out + (size_t)blockIdx.x * k);
+}
+
+// ---------------------------------------------------------------------------------------------
+// tf.compat.v1.train.AdamOptimizer dense apply (tensorflow_model.py:232).  Every
+// element is visited (TF1's sparse apply decays m, v and moves theta on all rows).  Rounding
+// order matches oracle.adam_step.  zero_grad: clear g after use, so the next step's scatter-add
+// starts from zero without a separate memset pass.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+adam_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, size_t n4,
+            float lr_t, float b1, float b2, float eps, int zero_grad) {
+  const float omb1 = __fsub_rn(1.f, b1), omb2 = __fsub_rn(1.f, b2);
+  auto upd = [&](float& pp, float gg, float& mm, float& vv) {
+    mm = __fadd_rn(__fmul_rn(mm, b1), __fmul_rn(omb1, gg));
+    vv = __fadd_rn(__fmul_rn(vv, b2), __fmul_rn(omb2, __fmul_rn(gg, gg)));
+    pp = __fsub_rn(pp, __fdiv_rn(__fmul_rn(lr_t, mm), __fadd_rn(__fsqrt_rn(vv), eps)));
+  };
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    float4 P = reinterpret_cast<float4*>(p)[i];
+    const float4 G = reinterpret_cast<const float4*>(g)[i];
+    float4 Mm = reinterpret_cast<float4*>(m)[i];
+    float4 V = reinterpret_cast<float4*>(v)[i];
+    upd(P.x, G.x, Mm.x, V.x); upd(P.y, G.y, Mm.y, V.y); upd(P.z, G.z, Mm.z, V.z); upd(P.w, G.w, Mm.w, V.w);
+    reinterpret_cast<float4*>(p)[i] = P;
+    reinterpret_cast<float4*>(m)[i] = Mm;
+    reinterpret_cast<float4*>(v)[i] = V;
+    if (zero_grad) reinterpret_cast<float4*>(g)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+}
+
+}  // namespace c2v

@@ -1,0 +1,333 @@
+"""ctypes binding of libc2v_b200.so (include/c2v_b200.h) and the storage that goes with it.
+
+PyTorch is used for device/pinned memory, streams and (elsewhere) torch.distributed only; every
+arithmetic step of the hot path runs inside the C-ABI library's CUDA kernels.  There is no CPU
+fallback: if the library cannot be loaded this module raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from dataclasses import dataclass
+from typing import Dict, Optional, Tuple
+
+import numpy as np
+
+from . import build as _build
+
+PARAM_NAMES = ("tok", "path", "tgt", "W", "a")
+
+MATH_FP32 = 0
+MATH_TF32 = 1
+
+
+class c2v_dims(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("token_vocab", "path_vocab", "target_vocab", "embed_dim",
+                                         "code_dim", "max_contexts", "max_batch", "top_k")]
+
+
+class c2v_tensors(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in PARAM_NAMES]
+
+
+# every symbol include/c2v_b200.h declares: (restype, argtypes)
+_P = C.c_void_p
+_I32 = C.c_int32
+_SIGNATURES = {
+    "c2v_abi_version": (C.c_int, []),
+    "c2v_last_error": (C.c_char_p, [_P]),
+    "c2v_workspace_bytes": (C.c_size_t, [C.POINTER(c2v_dims)]),
+    "c2v_create": (C.c_int, [C.POINTER(c2v_dims), C.c_int, C.POINTER(_P)]),
+    "c2v_destroy": (None, [_P]),
+    "c2v_bind_workspace": (C.c_int, [_P, _P, C.c_size_t]),
+    "c2v_bind_params": (C.c_int, [_P, C.POINTER(c2v_tensors)]),
+    "c2v_bind_grads": (C.c_int, [_P, C.POINTER(c2v_tensors)]),
+    "c2v_bind_adam_state": (C.c_int, [_P, C.POINTER(c2v_tensors), C.POINTER(c2v_tensors)]),
+    "c2v_set_option": (C.c_int, [_P, C.c_char_p, C.c_int64]),
+    "c2v_get_option": (C.c_int, [_P, C.c_char_p, C.POINTER(C.c_int64)]),
+    "c2v_forward": (C.c_int, [_P, _P, _P, _P, _P, _I32, _P, _P, _P]),
+    "c2v_topk": (C.c_int, [_P, _P, _I32, _P, _P, _I32, _P]),
+    "c2v_loss": (C.c_int, [_P, _P, _P, _I32, _P, _P]),
+    "c2v_train_step": (C.c_int, [_P, _P, _P, _P, _P, _P, _I32, C.c_float, C.c_uint64, C.c_uint64, _P, _P, _P]),
+    "c2v_sampled_train_step": (C.c_int, [_P, _P, _P, _P, _P, _P, _I32, _P, _I32, _P, _P, C.c_float,
+                                         C.c_uint64, C.c_uint64, _P, _P, _P]),
+    "c2v_adam_step": (C.c_int, [_P, C.c_float, C.c_float, C.c_float, C.c_float, C.c_int64, _P]),
+    "c2v_train_batch_host": (C.c_int, [_P, _P, _P, _P, _P, _P, _I32, C.c_float, C.c_uint64, C.c_int64,
+                                       C.c_float, C.c_float, C.c_float, C.c_float, _P, _P]),
+    "c2v_predict_batch_host": (C.c_int, [_P, _P, _P, _P, _P, _I32, _I32, _P, _P, _P, _P, _P]),
+    "c2v_launch_count": (C.c_int64, [_P]),
+}
+
+_lib = None
+
+
+def library_path() -> str:
+    return _build.LIB_PATH
+
+
+def load_library():
+    """Loads (building first if the in-tree .so is missing or stale) and types the C ABI."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if _build.needs_build():
+        _build.build()
+    if not os.path.exists(_build.LIB_PATH):
+        raise RuntimeError("libc2v_b200.so is missing; run `python -m code2vec_b200.build`")
+    lib = C.CDLL(_build.LIB_PATH)
+    for name, (res, args) in _SIGNATURES.items():
+        fn = getattr(lib, name)          # AttributeError if the header and the library disagree
+        fn.restype = res
+        fn.argtypes = args
+    if lib.c2v_abi_version() != 1:
+        raise RuntimeError("libc2v_b200.so ABI version mismatch")
+    _lib = lib
+    return lib
+
+
+class EngineError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__("c2v error %d: %s" % (code, msg))
+        self.code = code
+
+
+@dataclass
+class EngineDims:
+    token_vocab: int
+    path_vocab: int
+    target_vocab: int
+    embed_dim: int
+    code_dim: int
+    max_contexts: int
+    max_batch: int
+    top_k: int = 10
+
+    def shapes(self) -> Dict[str, Tuple[int, ...]]:
+        d, D = self.embed_dim, self.code_dim
+        return {"tok": (self.token_vocab, d), "path": (self.path_vocab, d), "tgt": (self.target_vocab, D),
+                "W": (3 * d, D), "a": (D,)}
+
+    def to_c(self) -> c2v_dims:
+        return c2v_dims(self.token_vocab, self.path_vocab, self.target_vocab, self.embed_dim, self.code_dim,
+                        self.max_contexts, self.max_batch, self.top_k)
+
+
+def _ptr(t) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+class PathAttentionEngine:
+    """Owns the storage (torch tensors) and one c2v_engine handle on one GPU."""
+
+    def __init__(self, dims: EngineDims, device: int = 0, training: bool = True):
+        import torch
+        if not torch.cuda.is_available():
+            raise RuntimeError("PathAttentionEngine needs a CUDA device (B200); no CPU fallback exists")
+        self.torch = torch
+        self.lib = load_library()
+        self.dims = dims
+        self.device = int(device)
+        self.dev = torch.device("cuda", self.device)
+        self.training = training
+        cd = dims.to_c()
+        h = _P()
+        rc = self.lib.c2v_create(C.byref(cd), self.device, C.byref(h))
+        if rc != 0:
+            raise EngineError(rc, self.lib.c2v_last_error(None).decode())
+        self.h = h
+        f32 = torch.float32
+        with torch.cuda.device(self.dev):
+            wbytes = self.lib.c2v_workspace_bytes(C.byref(cd))
+            self.workspace = torch.empty(wbytes, dtype=torch.uint8, device=self.dev)
+            self._check(self.lib.c2v_bind_workspace(self.h, self.workspace.data_ptr(), wbytes))
+            shp = dims.shapes()
+            self.params = {k: torch.zeros(shp[k], dtype=f32, device=self.dev) for k in PARAM_NAMES}
+            self._check(self.lib.c2v_bind_params(self.h, C.byref(self._tensors(self.params))))
+            self.grads = self.adam_m = self.adam_v = None
+            if training:
+                self.grads = {k: torch.zeros(shp[k], dtype=f32, device=self.dev) for k in PARAM_NAMES}
+                self.adam_m = {k: torch.zeros(shp[k], dtype=f32, device=self.dev) for k in PARAM_NAMES}
+                self.adam_v = {k: torch.zeros(shp[k], dtype=f32, device=self.dev) for k in PARAM_NAMES}
+                self._check(self.lib.c2v_bind_grads(self.h, C.byref(self._tensors(self.grads))))
+                self._check(self.lib.c2v_bind_adam_state(self.h, C.byref(self._tensors(self.adam_m)),
+                                                         C.byref(self._tensors(self.adam_v))))
+            self._loss = torch.zeros(1, dtype=f32, device=self.dev)
+        self.adam_t = 0
+
+    # ---- plumbing -------------------------------------------------------------------------
+    @staticmethod
+    def _tensors(d) -> c2v_tensors:
+        return c2v_tensors(*[d[k].data_ptr() for k in PARAM_NAMES])
+
+    def _check(self, rc: int):
+        if rc != 0:
+            raise EngineError(rc, self.lib.c2v_last_error(self.h).decode())
+
+    def _stream(self) -> int:
+        return self.torch.cuda.current_stream(self.dev).cuda_stream
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.c2v_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_option(self, key: str, value: int):
+        self._check(self.lib.c2v_set_option(self.h, key.encode(), int(value)))
+
+    def get_option(self, key: str) -> int:
+        v = C.c_int64()
+        self._check(self.lib.c2v_get_option(self.h, key.encode(), C.byref(v)))
+        return v.value
+
+    @property
+    def launch_count(self) -> int:
+        return int(self.lib.c2v_launch_count(self.h))
+
+    # ---- parameters -----------------------------------------------------------------------
+    def init_params(self, seed: int = 4321):
+        """The reference's initialisers (tensorflow_model.py:205-220,249-250): tables
+        U(+-sqrt(3/cols)) (variance_scaling fan_out uniform), TRANSFORM / ATTENTION glorot-uniform.
+        Drawn on the device with torch's generator (initialisation is not the hot path)."""
+        torch = self.torch
+        g = torch.Generator(device=self.dev)
+        g.manual_seed(seed)
+        d, D = self.dims.embed_dim, self.dims.code_dim
+        lim = {"tok": (3.0 / d) ** 0.5, "path": (3.0 / d) ** 0.5, "tgt": (3.0 / D) ** 0.5,
+               "W": (6.0 / (3 * d + D)) ** 0.5, "a": (6.0 / (D + 1)) ** 0.5}
+        for k in PARAM_NAMES:
+            self.params[k].uniform_(-lim[k], lim[k], generator=g)
+
+    def load_params(self, arrays: Dict[str, np.ndarray]):
+        torch = self.torch
+        for k in PARAM_NAMES:
+            src = torch.from_numpy(np.ascontiguousarray(arrays[k], dtype=np.float32))
+            if tuple(src.shape) != tuple(self.params[k].shape):
+                raise ValueError("parameter %s has shape %s, expected %s" % (k, tuple(src.shape), tuple(self.params[k].shape)))
+            self.params[k].copy_(src)
+
+    def export_params(self) -> Dict[str, np.ndarray]:
+        return {k: self.params[k].detach().cpu().numpy() for k in PARAM_NAMES}
+
+    def export_grads(self) -> Dict[str, np.ndarray]:
+        return {k: self.grads[k].detach().cpu().numpy() for k in PARAM_NAMES}
+
+    def reset_optimizer(self):
+        for d in (self.adam_m, self.adam_v):
+            for t in d.values():
+                t.zero_()
+        self.adam_t = 0
+
+    def to_device(self, arr, dtype):
+        torch = self.torch
+        if isinstance(arr, torch.Tensor):
+            return arr.to(device=self.dev, dtype=dtype).contiguous()
+        return torch.from_numpy(np.ascontiguousarray(arr)).to(device=self.dev, dtype=dtype)
+
+    # ---- device-pointer entry points ---------------------------------------------------------
+    def forward(self, src, path, tgt, mask, want_attention: bool = True):
+        """c2v_forward: (code_vectors [B, D], attention [B, C] or None) as device tensors."""
+        torch = self.torch
+        B, Cn = src.shape
+        code = torch.empty((B, self.dims.code_dim), dtype=torch.float32, device=self.dev)
+        attn = torch.empty((B, Cn), dtype=torch.float32, device=self.dev) if want_attention else None
+        self._check(self.lib.c2v_forward(self.h, src.data_ptr(), path.data_ptr(), tgt.data_ptr(), mask.data_ptr(),
+                                         B, code.data_ptr(), _ptr(attn), self._stream()))
+        return code, attn
+
+    def topk(self, code_vec, normalize: bool = False):
+        torch = self.torch
+        B = code_vec.shape[0]
+        k = min(self.dims.top_k, self.dims.target_vocab)
+        idx = torch.empty((B, k), dtype=torch.int32, device=self.dev)
+        val = torch.empty((B, k), dtype=torch.float32, device=self.dev)
+        self._check(self.lib.c2v_topk(self.h, code_vec.data_ptr(), B, idx.data_ptr(), val.data_ptr(),
+                                      1 if normalize else 0, self._stream()))
+        return idx, val
+
+    def loss(self, code_vec, target):
+        out = self.torch.empty(1, dtype=self.torch.float32, device=self.dev)
+        self._check(self.lib.c2v_loss(self.h, code_vec.data_ptr(), target.data_ptr(), code_vec.shape[0],
+                                      out.data_ptr(), self._stream()))
+        return out
+
+    def train_step(self, src, path, tgt, mask, target, keep: float = 1.0, seed: int = 0, step: int = 0,
+                   dropout_mask=None, loss_out=None):
+        out = self._loss if loss_out is None else loss_out
+        self._check(self.lib.c2v_train_step(self.h, src.data_ptr(), path.data_ptr(), tgt.data_ptr(), mask.data_ptr(),
+                                            target.data_ptr(), src.shape[0], float(keep), int(seed), int(step),
+                                            _ptr(dropout_mask), out.data_ptr(), self._stream()))
+        return out
+
+    def sampled_train_step(self, src, path, tgt, mask, target, sampled, logq_true, logq_sampled, keep: float = 1.0,
+                           seed: int = 0, step: int = 0, dropout_mask=None, loss_out=None):
+        out = self._loss if loss_out is None else loss_out
+        self._check(self.lib.c2v_sampled_train_step(
+            self.h, src.data_ptr(), path.data_ptr(), tgt.data_ptr(), mask.data_ptr(), target.data_ptr(),
+            src.shape[0], sampled.data_ptr(), sampled.shape[0], logq_true.data_ptr(), logq_sampled.data_ptr(),
+            float(keep), int(seed), int(step), _ptr(dropout_mask), out.data_ptr(), self._stream()))
+        return out
+
+    def adam_step(self, lr=1e-3, beta1=0.9, beta2=0.999, eps=1e-8, t: Optional[int] = None):
+        if t is None:
+            self.adam_t += 1
+            t = self.adam_t
+        else:
+            self.adam_t = t
+        self._check(self.lib.c2v_adam_step(self.h, lr, beta1, beta2, eps, int(t), self._stream()))
+
+    # ---- host-buffer entry points ------------------------------------------------------------
+    def train_batch_host(self, src, path, tgt, mask, target, keep: float = 1.0, seed: int = 0,
+                         lr=1e-3, beta1=0.9, beta2=0.999, eps=1e-8) -> float:
+        """One reference `sess.run([optimizer, train_loss])` on HOST arrays (numpy or pinned torch
+        tensors): H2D copies, train step, Adam, loss read-back -- all inside the C-ABI call."""
+        self.adam_t += 1
+        loss = np.zeros(1, dtype=np.float32)
+        B = int(src.shape[0])
+        src, path, tgt, target = (_as_host(x, np.int32) for x in (src, path, tgt, target))
+        mask = _as_host(mask, np.float32)
+        self._check(self.lib.c2v_train_batch_host(
+            self.h, _host_ptr(src), _host_ptr(path), _host_ptr(tgt), _host_ptr(mask), _host_ptr(target), B,
+            float(keep), int(seed), int(self.adam_t), lr, beta1, beta2, eps, loss.ctypes.data, self._stream()))
+        return float(loss[0])
+
+    def predict_batch_host(self, src, path, tgt, mask, normalize: bool = False, want_code: bool = True,
+                           want_attention: bool = True):
+        B, Cn = int(src.shape[0]), int(src.shape[1])
+        src, path, tgt = (_as_host(x, np.int32) for x in (src, path, tgt))
+        mask = _as_host(mask, np.float32)
+        k = min(self.dims.top_k, self.dims.target_vocab)
+        idx = np.empty((B, k), dtype=np.int32)
+        val = np.empty((B, k), dtype=np.float32)
+        code = np.empty((B, self.dims.code_dim), dtype=np.float32) if want_code else None
+        attn = np.empty((B, Cn), dtype=np.float32) if want_attention else None
+        self._check(self.lib.c2v_predict_batch_host(
+            self.h, _host_ptr(src), _host_ptr(path), _host_ptr(tgt), _host_ptr(mask), B, 1 if normalize else 0,
+            idx.ctypes.data, val.ctypes.data, None if code is None else code.ctypes.data,
+            None if attn is None else attn.ctypes.data, self._stream()))
+        return idx, val, code, attn
+
+
+def _as_host(a, dtype):
+    """numpy arrays are made contiguous/typed (no copy when already so); torch CPU tensors pass through."""
+    if isinstance(a, np.ndarray):
+        return np.ascontiguousarray(a, dtype=dtype)
+    return a
+
+
+def _host_ptr(a) -> int:
+    """Address of a contiguous host buffer: numpy array or (pinned) CPU torch tensor."""
+    if isinstance(a, np.ndarray):
+        if not a.flags["C_CONTIGUOUS"]:
+            raise ValueError("host buffer must be C-contiguous")
+        return a.ctypes.data
+    if hasattr(a, "data_ptr"):
+        if a.device.type != "cpu" or not a.is_contiguous():
+            raise ValueError("host buffer must be a contiguous CPU tensor")
+        return a.data_ptr()
+    raise TypeError("unsupported host buffer type %r" % type(a))

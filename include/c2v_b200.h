@@ -1,0 +1,177 @@
+/*
+ * c2v_b200.h -- C ABI of the B200-native path-attention engine (libc2v_b200.so).
+ *
+ * This is the drop-in boundary for code2vec's ONE hot path.  The reference (tech-srl/code2vec)
+ * has no FFI of its own: its seam is the Python ABC Code2VecModelBase (model_base.py:37-182)
+ * whose TensorFlow backend runs the whole path inside sess.run() calls.  Each entry point below
+ * names the reference statement(s) it replaces (file:line relative to the reference root), so a
+ * maintainer can bind it from a third backend (`--framework b200`).
+ *
+ * Conventions
+ *   - plain C, no CUDA / torch types: device pointers are `void*`/`float*`/`int32_t*` holding
+ *     device addresses, a stream is the `cudaStream_t` value passed as `void*` (NULL = default).
+ *   - every function returns 0 (C2V_OK) or a negative c2v_status; the message of the last
+ *     failure is kept per engine (c2v_last_error).  Nothing throws across the boundary.
+ *   - the caller owns all big buffers (parameters, gradients, Adam slots, workspace) -- in the
+ *     Python backend they are torch tensors used purely as storage.  The engine allocates
+ *     nothing on the device after c2v_create.
+ *   - all calls are asynchronous w.r.t. the host on `stream`, except the *_host entry points,
+ *     which synchronise the stream before returning because they hand results back to the host.
+ *   - one host thread per engine at a time; engines are independent.
+ *   - layouts: row-major, float32 parameters, int32 indices, float32 0/1 mask -- the dtypes the
+ *     reference reader emits (path_context_reader.py:32-44,214; vocabularies.py:112).
+ */
+#ifndef C2V_B200_H_
+#define C2V_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define C2V_ABI_VERSION 1
+
+typedef struct c2v_engine c2v_engine;
+
+typedef enum c2v_status {
+  C2V_OK = 0,
+  C2V_ERR_INVALID = -1,      /* bad argument (NULL, size out of range, unsupported dims)   */
+  C2V_ERR_CUDA = -2,         /* a CUDA runtime call or kernel launch failed                */
+  C2V_ERR_STATE = -3,        /* call order violated (e.g. train step before binding grads) */
+  C2V_ERR_UNSUPPORTED = -4   /* valid request this build cannot serve                      */
+} c2v_status;
+
+/* Shapes of the model (config.py:60-68; vocab sizes include the special words,
+ * vocabularies.py:51-55).  code_dim is CODE_VECTOR_SIZE (= 3*embed_dim by default). */
+typedef struct c2v_dims {
+  int32_t token_vocab;   /* T: rows of WORDS_VOCAB          (tensorflow_model.py:206-209) */
+  int32_t path_vocab;    /* P: rows of PATHS_VOCAB          (tensorflow_model.py:217-220) */
+  int32_t target_vocab;  /* Y: rows of TARGET_WORDS_VOCAB   (tensorflow_model.py:210-213) */
+  int32_t embed_dim;     /* d: TOKEN/PATH_EMBEDDINGS_SIZE, multiple of 4                  */
+  int32_t code_dim;      /* D: CODE_VECTOR_SIZE, multiple of 4, <= 1024                   */
+  int32_t max_contexts;  /* C: MAX_CONTEXTS                                               */
+  int32_t max_batch;     /* largest batch any call will pass                              */
+  int32_t top_k;         /* TOP_K_WORDS_CONSIDERED_DURING_PREDICTION (<= 64)              */
+} c2v_dims;
+
+/* The five variables of the model, in the order the reference creates them
+ * (tensorflow_model.py:32-36,205-220,249-250).  Used for parameters, gradients and Adam slots.
+ *   tok  [T, d]   WORDS_VOCAB            path [P, d]   PATHS_VOCAB
+ *   tgt  [Y, D]   TARGET_WORDS_VOCAB     W    [3d, D]  TRANSFORM          a [D] ATTENTION */
+typedef struct c2v_tensors {
+  float* tok;
+  float* path;
+  float* tgt;
+  float* W;
+  float* a;
+} c2v_tensors;
+
+/* Arithmetic of the three big matrix products (projection, logits, their gradients).
+ *   C2V_MATH_FP32  : fp32 FFMA on the SIMT pipe -- the reference's own arithmetic class
+ *                    (cuBLAS/Eigen SGEMM); used for bit-level top-k parity.
+ *   C2V_MATH_TF32  : tcgen05.mma kind::tf32 (fp32 storage, 10-bit mantissa operands, fp32
+ *                    accumulate in TMEM) -- what TensorFlow itself runs on Ampere+ GPUs. */
+typedef enum c2v_math_mode { C2V_MATH_FP32 = 0, C2V_MATH_TF32 = 1 } c2v_math_mode;
+
+int c2v_abi_version(void);
+
+/* Message of the last failed call on `e`; with e == NULL, of the last failed c2v_create /
+ * c2v_workspace_bytes on this thread.  Never NULL. */
+const char* c2v_last_error(const c2v_engine* e);
+
+/* Bytes of device scratch the engine needs for `dims` (activations kept for the backward pass,
+ * the [B, Y] logits slab, split-K partials, host-API staging).  0 on invalid dims. */
+size_t c2v_workspace_bytes(const c2v_dims* dims);
+
+/* Create an engine for CUDA device `device`.  Replaces Code2VecModel.__init__'s
+ * tf.compat.v1.Session() (tensorflow_model.py:19-38). */
+int c2v_create(const c2v_dims* dims, int device, c2v_engine** out);
+
+/* Replaces close_session() (tensorflow_model.py:439-440).  NULL is a no-op. */
+void c2v_destroy(c2v_engine* e);
+
+int c2v_bind_workspace(c2v_engine* e, void* dev_ptr, size_t bytes);   /* >= c2v_workspace_bytes, 256-B aligned */
+int c2v_bind_params(c2v_engine* e, const c2v_tensors* theta);         /* tf.get_variable x5, :205-220,249-250   */
+int c2v_bind_grads(c2v_engine* e, const c2v_tensors* grads);          /* autodiff outputs of minimize(), :232   */
+int c2v_bind_adam_state(c2v_engine* e, const c2v_tensors* m, const c2v_tensors* v);  /* Adam slots, :232       */
+
+/* Options: "math_mode" (c2v_math_mode), "deterministic" (0/1: 1 = fixed-order reductions for
+ * the scatter-add of embedding gradients instead of float atomics). */
+int c2v_set_option(c2v_engine* e, const char* key, int64_t value);
+int c2v_get_option(const c2v_engine* e, const char* key, int64_t* value);
+
+/* _calculate_weighted_contexts(..., is_evaluating=True)  (tensorflow_model.py:236-265):
+ * three gathers, concat, tanh(x.W), attention score, log-mask, softmax over the bag, weighted
+ * sum.  src/path/tgt/mask: device [B, C].  code_vec: device [B, D].  attn: device [B, C] or
+ * NULL.  A bag with no valid context yields NaN (as tf.nn.softmax of all -inf does). */
+int c2v_forward(c2v_engine* e, const int32_t* src, const int32_t* path, const int32_t* tgt,
+                const float* mask, int32_t B, float* code_vec, float* attn, void* stream);
+
+/* scores = code_vec . TARGET_WORDS_VOCAB^T ; tf.nn.top_k(scores, k) sorted descending, ties to
+ * the lower index; normalize != 0 applies softmax over the k values (predict)
+ * (tensorflow_model.py:297-306).  idx: device int32 [B, k]; val: device float [B, k]. */
+int c2v_topk(c2v_engine* e, const float* code_vec, int32_t B, int32_t* idx, float* val,
+             int32_t normalize, void* stream);
+
+/* Mean sparse-softmax cross entropy of code_vec against `target` without gradients
+ * (tensorflow_model.py:226-230).  loss_out: device float[1]. */
+int c2v_loss(c2v_engine* e, const float* code_vec, const int32_t* target, int32_t B,
+             float* loss_out, void* stream);
+
+/* Forward + backward of the training graph (tensorflow_model.py:197-234 without the Adam
+ * update): dropout with keep probability `keep_prob` (config.py:69; 1.0 disables it), full
+ * softmax loss, gradients of all five variables written to the bound gradient tensors
+ * (overwriting them; embedding rows that received no contribution are exactly 0).
+ *   dropout_mask : NULL -> counter-based Philox4x32-10 mask from (seed, step), regenerated in
+ *                  the backward pass; or device float [B*C, 3d] of 0/1 supplied by the caller.
+ *   loss_out     : device float[1], mean loss over the B examples (dynamic batch, :227).
+ * target: device int32 [B]. */
+int c2v_train_step(c2v_engine* e, const int32_t* src, const int32_t* path, const int32_t* tgt,
+                   const float* mask, const int32_t* target, int32_t B, float keep_prob,
+                   uint64_t seed, uint64_t step, const float* dropout_mask, float* loss_out,
+                   void* stream);
+
+/* Same with a sampled softmax over {target_b} U sampled[0..S) instead of the full softmax.
+ * NOT IN THE REFERENCE (BASELINE config 3; semantics defined in DESIGN.md after
+ * tf.nn.sampled_softmax_loss): logq_* are the log expected counts subtracted from the logits,
+ * a sampled class equal to a row's target is masked out for that row. */
+int c2v_sampled_train_step(c2v_engine* e, const int32_t* src, const int32_t* path,
+                           const int32_t* tgt, const float* mask, const int32_t* target,
+                           int32_t B, const int32_t* sampled, int32_t S, const float* logq_true,
+                           const float* logq_sampled, float keep_prob, uint64_t seed,
+                           uint64_t step, const float* dropout_mask, float* loss_out,
+                           void* stream);
+
+/* tf.compat.v1.train.AdamOptimizer() update of all five variables from the bound gradients
+ * (tensorflow_model.py:232): lr_t = lr*sqrt(1-b2^t)/(1-b1^t); m,v decay on EVERY row (TF1's
+ * sparse apply is not lazy); theta -= lr_t*m/(sqrt(v)+eps).  t is the 1-based step count. */
+int c2v_adam_step(c2v_engine* e, float lr, float beta1, float beta2, float eps, int64_t t,
+                  void* stream);
+
+/* --- host-buffer entry points: what the backend's train()/evaluate()/predict() call -------- */
+
+/* One `sess.run([optimizer, train_loss])` (tensorflow_model.py:80): copies the batch from host
+ * memory (pinned memory makes the copies asynchronous), runs c2v_train_step + c2v_adam_step
+ * with the TF defaults given, copies the loss back and synchronises.  h_* are HOST pointers. */
+int c2v_train_batch_host(c2v_engine* e, const int32_t* h_src, const int32_t* h_path,
+                         const int32_t* h_tgt, const float* h_mask, const int32_t* h_target,
+                         int32_t B, float keep_prob, uint64_t seed, int64_t t, float lr,
+                         float beta1, float beta2, float eps, float* h_loss, void* stream);
+
+/* One `sess.run([top_words, top_values, ..., code_vectors])` of the test graph
+ * (tensorflow_model.py:157-161,331-335).  Outputs are HOST pointers; h_code_vec [B, D] and
+ * h_attn [B, C] may be NULL. */
+int c2v_predict_batch_host(c2v_engine* e, const int32_t* h_src, const int32_t* h_path,
+                           const int32_t* h_tgt, const float* h_mask, int32_t B,
+                           int32_t normalize, int32_t* h_topk_idx, float* h_topk_val,
+                           float* h_code_vec, float* h_attn, void* stream);
+
+/* Introspection for tests and bench: number of kernels the engine has launched so far. */
+int64_t c2v_launch_count(const c2v_engine* e);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* C2V_B200_H_ */
