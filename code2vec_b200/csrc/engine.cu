@@ -8,6 +8,8 @@
 #include <string.h>
 
 #include <string>
+#include <utility>
+#include <vector>
 
 #include "../../include/c2v_b200.h"
 #include "common.cuh"
@@ -80,7 +82,22 @@ Workspace carve(const c2v_dims& d) {
 
 }  // namespace
 
+// Phases of a pass, for per-kernel timing (option "profile"): CUDA events bracket each phase on
+// the launching stream; c2v_phase_stats() resolves them.
+enum Phase { PH_CTX_FWD = 0, PH_ATTN_FWD, PH_LOGITS, PH_XENT, PH_DV, PH_DY, PH_ATTN_BWD, PH_DW, PH_DX_SCATTER,
+             PH_ADAM, PH_TOPK, PH_SAMPLED, PH_COUNT };
+const char* const kPhaseNames[PH_COUNT] = {"ctx_fwd", "attn_fwd", "logits", "xent", "dv", "dY", "attn_bwd", "dW",
+                                           "dx_scatter", "adam", "topk", "sampled_softmax"};
+struct PhaseLog {
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pending;
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> free_list;
+  double total_ms = 0.0;
+  int64_t count = 0;
+};
+
 struct c2v_engine {
+  PhaseLog phase[PH_COUNT];
+  int profile = 0;
   c2v_dims dims;
   int device;
   Workspace ws;
@@ -101,6 +118,21 @@ int fail(c2v_engine* e, int code, const std::string& msg) {
   if (e) e->err = msg; else g_create_error = msg;
   return code;
 }
+
+struct PhaseTimer {
+  c2v_engine* e; int ph; cudaStream_t st; cudaEvent_t stop = nullptr;
+  PhaseTimer(c2v_engine* e_, int ph_, cudaStream_t st_) : e(e_), ph(ph_), st(st_) {
+    if (!e->profile) return;
+    PhaseLog& L = e->phase[ph];
+    std::pair<cudaEvent_t, cudaEvent_t> ev;
+    if (!L.free_list.empty()) { ev = L.free_list.back(); L.free_list.pop_back(); }
+    else { cudaEventCreate(&ev.first); cudaEventCreate(&ev.second); }
+    cudaEventRecord(ev.first, st);
+    stop = ev.second;
+    L.pending.push_back(ev);
+  }
+  ~PhaseTimer() { if (stop) cudaEventRecord(stop, st); }
+};
 
 #define C2V_CUDA(e, expr)                                                                         \
   do {                                                                                            \
@@ -149,6 +181,7 @@ int launch_attn_fwd(c2v_engine* e, cudaStream_t st, const float* H, const float*
   const int C = e->dims.max_contexts, D = e->dims.code_dim;
   const size_t smem = ((size_t)((C + 3) & ~3) + 32 + kAttnWarps + (size_t)kAttnWarps * D) * sizeof(float);
   const float* a = e->theta.a;
+  PhaseTimer pt(e, PH_ATTN_FWD, st);
 #define C2V_AF(NV)                                                                                        \
   do {                                                                                                    \
     if (smem > 48 * 1024)                                                                                 \
@@ -171,6 +204,7 @@ int launch_attn_bwd(c2v_engine* e, cudaStream_t st, float* H, const float* alpha
   const int C = e->dims.max_contexts, D = e->dims.code_dim;
   const size_t smem = ((size_t)((C + 3) & ~3) + 32 + (size_t)kAttnWarps * D) * sizeof(float);
   const float* a = e->theta.a;
+  PhaseTimer pt(e, PH_ATTN_BWD, st);
 #define C2V_AB(NV)                                                                                        \
   do {                                                                                                    \
     if (smem > 48 * 1024)                                                                                 \
@@ -206,6 +240,7 @@ ContextSource make_source(c2v_engine* e, const int32_t* src, const int32_t* pth,
 // H = tanh(X' . W)   (tensorflow_model.py:238-252)
 int run_ctx_fwd(c2v_engine* e, cudaStream_t st, const ContextSource& cs, const Dropout& dp, float* H) {
   const int D = e->dims.code_dim, K = 3 * e->dims.embed_dim;
+  PhaseTimer pt(e, PH_CTX_FWD, st);
   simt::GatherRowsK al{cs, dp};
   simt::ColsX bl{e->theta.W, (size_t)D};
   simt::TanhStore ep{H, (size_t)D};
@@ -216,6 +251,7 @@ int run_ctx_fwd(c2v_engine* e, cudaStream_t st, const ContextSource& cs, const D
 // S[B, Y] = v . Ytab^T   (tensorflow_model.py:226,297)
 int run_logits(c2v_engine* e, cudaStream_t st, const float* v, int B, float* S) {
   const int D = e->dims.code_dim, Y = e->dims.target_vocab;
+  PhaseTimer pt(e, PH_LOGITS, st);
   simt::RowsK al{v, (size_t)D};
   simt::RowsK bl{e->theta.tgt, (size_t)D};
   simt::StoreC ep{S, e->ws.ldS, 0};
@@ -238,6 +274,7 @@ int topk_impl(c2v_engine* e, cudaStream_t st, const float* code_vec, int B, int3
   if (rc) return rc;
   const int Y = e->dims.target_vocab;
   const int k = e->dims.top_k < Y ? e->dims.top_k : Y;
+  PhaseTimer pt(e, PH_TOPK, st);
   if (k <= 16)
     C2V_LAUNCH(e, (topk_kernel<16><<<B, kTopkThreads, 0, st>>>(S, e->ws.ldS, Y, k, normalize, idx, val)));
   else
@@ -259,6 +296,7 @@ int context_backward(c2v_engine* e, cudaStream_t st, const ContextSource& cs, co
   rc = launch_colsum(e, st, da_part, (size_t)D, B, D, e->grad.a);
   if (rc) return rc;
   {  // dW = X'^T . dU   (split-K over the B*C contexts, fixed-order reduction)
+    PhaseTimer pt(e, PH_DW, st);
     simt::GatherColsX al{cs, dp};
     simt::ColsX bl{H, (size_t)D};
     const int ks = simt::effective_ksplit(N, kSplitDw);
@@ -272,6 +310,7 @@ int context_backward(c2v_engine* e, cudaStream_t st, const ContextSource& cs, co
       C2V_CUDA(e, cudaMemsetAsync(e->grad.tok, 0, (size_t)e->dims.token_vocab * d * 4, st));
       C2V_CUDA(e, cudaMemsetAsync(e->grad.path, 0, (size_t)e->dims.path_vocab * d * 4, st));
     }
+    PhaseTimer pt(e, PH_DX_SCATTER, st);
     simt::RowsK al{H, (size_t)D};
     simt::RowsK bl{e->theta.W, (size_t)D};
     simt::ScatterDx ep{cs, e->grad.tok, e->grad.path, mask, dp};
@@ -302,9 +341,13 @@ int train_step_impl(c2v_engine* e, cudaStream_t st, const int32_t* src, const in
   if ((rc = launch_attn_fwd(e, st, H, mask, B, alpha, v))) return rc;
   if ((rc = run_logits(e, st, v, B, S))) return rc;
   const float invB = 1.0f / (float)B;
-  C2V_LAUNCH(e, (xent_kernel<<<B, kXentThreads, 0, st>>>(S, e->ws.ldS, target, Y, invB, loss_b, lse, 1)));
-  C2V_LAUNCH(e, (loss_reduce_kernel<<<1, 256, 0, st>>>(loss_b, B, invB, loss_out)));
+  {
+    PhaseTimer pt(e, PH_XENT, st);
+    C2V_LAUNCH(e, (xent_kernel<<<B, kXentThreads, 0, st>>>(S, e->ws.ldS, target, Y, invB, loss_b, lse, 1)));
+    C2V_LAUNCH(e, (loss_reduce_kernel<<<1, 256, 0, st>>>(loss_b, B, invB, loss_out)));
+  }
   {  // dv = P . Ytab   (K = |Y| split, fixed-order reduction)
+    PhaseTimer pt(e, PH_DV, st);
     simt::RowsK al{S, e->ws.ldS};
     simt::ColsX bl{e->theta.tgt, (size_t)D};
     const int ks = simt::effective_ksplit(Y, kSplitDv);
@@ -313,6 +356,7 @@ int train_step_impl(c2v_engine* e, cudaStream_t st, const int32_t* src, const in
     if ((rc = launch_colsum(e, st, part, (size_t)B * D, ks, B * D, dv))) return rc;
   }
   {  // dYtab = P^T . v
+    PhaseTimer pt(e, PH_DY, st);
     simt::ColsX al{S, e->ws.ldS};
     simt::ColsX bl{v, (size_t)D};
     simt::StoreC ep{e->grad.tgt, (size_t)D, 0};
@@ -333,6 +377,7 @@ int adam_impl(c2v_engine* e, cudaStream_t st, float lr, float b1, float b2, floa
   float* G[5] = {e->grad.tok, e->grad.path, e->grad.tgt, e->grad.W, e->grad.a};
   float* M[5] = {e->am.tok, e->am.path, e->am.tgt, e->am.W, e->am.a};
   float* V[5] = {e->av.tok, e->av.path, e->av.tgt, e->av.W, e->av.a};
+  PhaseTimer pt(e, PH_ADAM, st);
   for (int i = 0; i < 5; ++i) {
     const size_t n4 = n[i] / 4;
     size_t blocks = (n4 + 255) / 256;
@@ -390,7 +435,14 @@ int c2v_create(const c2v_dims* dims, int device, c2v_engine** out) {
   return C2V_OK;
 }
 
-void c2v_destroy(c2v_engine* e) { delete e; }
+void c2v_destroy(c2v_engine* e) {
+  if (!e) return;
+  for (auto& L : e->phase) {
+    for (auto& ev : L.pending) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
+    for (auto& ev : L.free_list) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
+  }
+  delete e;
+}
 
 int c2v_bind_workspace(c2v_engine* e, void* dev_ptr, size_t bytes) {
   if (!e) return C2V_ERR_INVALID;
@@ -432,6 +484,7 @@ int c2v_set_option(c2v_engine* e, const char* key, int64_t value) {
     return C2V_OK;
   }
   if (!strcmp(key, "deterministic")) { e->deterministic = value ? 1 : 0; return C2V_OK; }
+  if (!strcmp(key, "profile")) { e->profile = value ? 1 : 0; return C2V_OK; }
   return fail(e, C2V_ERR_INVALID, std::string("unknown option: ") + key);
 }
 
@@ -439,6 +492,7 @@ int c2v_get_option(const c2v_engine* e, const char* key, int64_t* value) {
   if (!e || !key || !value) return C2V_ERR_INVALID;
   if (!strcmp(key, "math_mode")) { *value = e->math_mode; return C2V_OK; }
   if (!strcmp(key, "deterministic")) { *value = e->deterministic; return C2V_OK; }
+  if (!strcmp(key, "profile")) { *value = e->profile; return C2V_OK; }
   return C2V_ERR_INVALID;
 }
 
@@ -563,5 +617,26 @@ int c2v_predict_batch_host(c2v_engine* e, const int32_t* h_src, const int32_t* h
 }
 
 int64_t c2v_launch_count(const c2v_engine* e) { return e ? e->launches : 0; }
+
+int c2v_phase_count(void) { return PH_COUNT; }
+
+const char* c2v_phase_name(int phase) { return (phase >= 0 && phase < PH_COUNT) ? kPhaseNames[phase] : ""; }
+
+int c2v_phase_stats(c2v_engine* e, int phase, double* total_ms, int64_t* count, int reset) {
+  if (!e || phase < 0 || phase >= PH_COUNT) return C2V_ERR_INVALID;
+  C2V_CUDA(e, cudaSetDevice(e->device));
+  PhaseLog& L = e->phase[phase];
+  if (!L.pending.empty()) C2V_CUDA(e, cudaDeviceSynchronize());
+  for (auto& ev : L.pending) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, ev.first, ev.second) == cudaSuccess) { L.total_ms += ms; L.count++; }
+    L.free_list.push_back(ev);
+  }
+  L.pending.clear();
+  if (total_ms) *total_ms = L.total_ms;
+  if (count) *count = L.count;
+  if (reset) { L.total_ms = 0.0; L.count = 0; }
+  return C2V_OK;
+}
 
 }  // extern "C"

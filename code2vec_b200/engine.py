@@ -56,6 +56,9 @@ _SIGNATURES = {
                                        C.c_float, C.c_float, C.c_float, C.c_float, _P, _P]),
     "c2v_predict_batch_host": (C.c_int, [_P, _P, _P, _P, _P, _I32, _I32, _P, _P, _P, _P, _P]),
     "c2v_launch_count": (C.c_int64, [_P]),
+    "c2v_phase_count": (C.c_int, []),
+    "c2v_phase_name": (C.c_char_p, [C.c_int]),
+    "c2v_phase_stats": (C.c_int, [_P, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_int64), C.c_int]),
 }
 
 _lib = None
@@ -188,6 +191,17 @@ class PathAttentionEngine:
     @property
     def launch_count(self) -> int:
         return int(self.lib.c2v_launch_count(self.h))
+
+    def phase_stats(self, reset: bool = False) -> Dict[str, Tuple[float, int]]:
+        """{phase name: (total device ms, number of timed occurrences)} since the last reset
+        (needs set_option("profile", 1)).  Synchronises the device."""
+        out = {}
+        for i in range(self.lib.c2v_phase_count()):
+            ms, n = C.c_double(), C.c_int64()
+            self._check(self.lib.c2v_phase_stats(self.h, i, C.byref(ms), C.byref(n), 1 if reset else 0))
+            if n.value:
+                out[self.lib.c2v_phase_name(i).decode()] = (ms.value, n.value)
+        return out
 
     # ---- parameters -----------------------------------------------------------------------
     def init_params(self, seed: int = 4321):

@@ -98,7 +98,8 @@ int c2v_bind_grads(c2v_engine* e, const c2v_tensors* grads);          /* autodif
 int c2v_bind_adam_state(c2v_engine* e, const c2v_tensors* m, const c2v_tensors* v);  /* Adam slots, :232       */
 
 /* Options: "math_mode" (c2v_math_mode), "deterministic" (0/1: 1 = fixed-order reductions for
- * the scatter-add of embedding gradients instead of float atomics). */
+ * the scatter-add of embedding gradients instead of float atomics), "profile" (0/1: per-phase
+ * CUDA-event timing, read with c2v_phase_stats). */
 int c2v_set_option(c2v_engine* e, const char* key, int64_t value);
 int c2v_get_option(const c2v_engine* e, const char* key, int64_t* value);
 
@@ -170,6 +171,13 @@ int c2v_predict_batch_host(c2v_engine* e, const int32_t* h_src, const int32_t* h
 
 /* Introspection for tests and bench: number of kernels the engine has launched so far. */
 int64_t c2v_launch_count(const c2v_engine* e);
+
+/* Per-phase device timing (option "profile" = 1): CUDA events bracket every phase of a pass on
+ * the launching stream.  c2v_phase_stats synchronises, folds the pending events into the
+ * running totals and returns them (reset != 0 clears the totals afterwards). */
+int c2v_phase_count(void);
+const char* c2v_phase_name(int phase);
+int c2v_phase_stats(c2v_engine* e, int phase, double* total_ms, int64_t* count, int reset);
 
 #ifdef __cplusplus
 }
