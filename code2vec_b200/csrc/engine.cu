@@ -15,6 +15,7 @@
 #include "common.cuh"
 #include "kernels.cuh"
 #include "sgemm.cuh"
+#include "umma_gemm.cuh"
 
 using namespace c2v;
 
@@ -25,12 +26,12 @@ thread_local std::string g_create_error = "";
 constexpr size_t kAlign = 256;
 inline size_t align_up(size_t x, size_t a = kAlign) { return (x + a - 1) / a * a; }
 
-constexpr int kSplitDv = 16;   // split-K slices for dv = P . Y      (K = |Y|)
-constexpr int kSplitDw = 32;   // split-K slices for dW = X'^T . dU  (K = B*C)
+constexpr int kSplitDv = 18;   // split-K slices for dv = P . Y      (K = |Y|)
+constexpr int kSplitDw = 48;   // split-K slices for dW = X'^T . dU  (K = B*C)
 
 // Carve-up of the caller-provided workspace (offsets in bytes).
 struct Workspace {
-  size_t H, alpha, v, dv, S, loss_b, lse, loss, part, da_part;
+  size_t H, Xg, alpha, v, dv, S, loss_b, lse, loss, part, da_part;
   size_t st_src, st_pth, st_tgt, st_mask, st_target, st_topk_idx, st_topk_val, st_code, st_attn;
   size_t total;
   size_t ldS;
@@ -56,6 +57,7 @@ Workspace carve(const c2v_dims& d) {
   size_t off = 0;
   auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes); return o; };
   w.H = take(N * D * 4);
+  w.Xg = take(N * X * 4);      // gathered context matrix X' (tf32 path), reused for dX'
   w.alpha = take(N * 4);
   w.v = take(B * D * 4);
   w.dv = take(B * D * 4);
@@ -85,9 +87,9 @@ Workspace carve(const c2v_dims& d) {
 // Phases of a pass, for per-kernel timing (option "profile"): CUDA events bracket each phase on
 // the launching stream; c2v_phase_stats() resolves them.
 enum Phase { PH_CTX_FWD = 0, PH_ATTN_FWD, PH_LOGITS, PH_XENT, PH_DV, PH_DY, PH_ATTN_BWD, PH_DW, PH_DX_SCATTER,
-             PH_ADAM, PH_TOPK, PH_SAMPLED, PH_COUNT };
+             PH_ADAM, PH_TOPK, PH_SAMPLED, PH_GATHER, PH_DX_GEMM, PH_COUNT };
 const char* const kPhaseNames[PH_COUNT] = {"ctx_fwd", "attn_fwd", "logits", "xent", "dv", "dY", "attn_bwd", "dW",
-                                           "dx_scatter", "adam", "topk", "sampled_softmax"};
+                                           "dx_scatter", "adam", "topk", "sampled_softmax", "gather", "dx_gemm"};
 struct PhaseLog {
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pending;
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> free_list;
@@ -107,6 +109,7 @@ struct c2v_engine {
   bool has_theta, has_grad, has_adam;
   bool emb_grads_clean;      // token/path gradient tables are known to be all-zero
   int math_mode;
+  int num_sms;
   int deterministic;
   int64_t launches;
   std::string err;
@@ -240,6 +243,19 @@ ContextSource make_source(c2v_engine* e, const int32_t* src, const int32_t* pth,
 // H = tanh(X' . W)   (tensorflow_model.py:238-252)
 int run_ctx_fwd(c2v_engine* e, cudaStream_t st, const ContextSource& cs, const Dropout& dp, float* H) {
   const int D = e->dims.code_dim, K = 3 * e->dims.embed_dim;
+  if (e->math_mode == C2V_MATH_TF32) {
+    float* Xg = wsp<float>(e, e->ws.Xg);
+    {
+      PhaseTimer pt(e, PH_GATHER, st);
+      C2V_LAUNCH(e, (gather_ctx_kernel<<<(cs.rows + 7) / 8, 256, 0, st>>>(cs, dp, Xg)));
+    }
+    PhaseTimer pt(e, PH_CTX_FWD, st);
+    umma::Operand opA{Xg, (size_t)K, false};
+    umma::Operand opB{e->theta.W, (size_t)D, true};
+    umma::EpiTanhStore ep{H, (size_t)D};
+    C2V_LAUNCH(e, C2V_CUDA(e, (umma::launch<192, 5>(st, cs.rows, D, K, 1, opA, opB, ep, e->num_sms))));
+    return C2V_OK;
+  }
   PhaseTimer pt(e, PH_CTX_FWD, st);
   simt::GatherRowsK al{cs, dp};
   simt::ColsX bl{e->theta.W, (size_t)D};
@@ -252,6 +268,13 @@ int run_ctx_fwd(c2v_engine* e, cudaStream_t st, const ContextSource& cs, const D
 int run_logits(c2v_engine* e, cudaStream_t st, const float* v, int B, float* S) {
   const int D = e->dims.code_dim, Y = e->dims.target_vocab;
   PhaseTimer pt(e, PH_LOGITS, st);
+  if (e->math_mode == C2V_MATH_TF32 && (reinterpret_cast<uintptr_t>(v) % 16 == 0)) {
+    umma::Operand opA{v, (size_t)D, false};
+    umma::Operand opB{e->theta.tgt, (size_t)D, false};
+    umma::EpiStore ep{S, e->ws.ldS, 0};
+    C2V_LAUNCH(e, C2V_CUDA(e, (umma::launch<256, 4>(st, B, Y, D, 1, opA, opB, ep, e->num_sms))));
+    return C2V_OK;
+  }
   simt::RowsK al{v, (size_t)D};
   simt::RowsK bl{e->theta.tgt, (size_t)D};
   simt::StoreC ep{S, e->ws.ldS, 0};
@@ -295,6 +318,36 @@ int context_backward(c2v_engine* e, cudaStream_t st, const ContextSource& cs, co
   if (rc) return rc;
   rc = launch_colsum(e, st, da_part, (size_t)D, B, D, e->grad.a);
   if (rc) return rc;
+  if (e->math_mode == C2V_MATH_TF32) {
+    float* Xg = wsp<float>(e, e->ws.Xg);
+    {  // dW = X'^T . dU on the gathered X' kept from the forward pass
+      PhaseTimer pt(e, PH_DW, st);
+      umma::Operand opA{Xg, (size_t)K3, true};
+      umma::Operand opB{H, (size_t)D, true};
+      const int ks = umma::effective_splits(N, kSplitDw);
+      umma::EpiStore ep{part, (size_t)D, (size_t)K3 * D};
+      C2V_LAUNCH(e, C2V_CUDA(e, (umma::launch<192, 5>(st, K3, D, N, kSplitDw, opA, opB, ep, e->num_sms))));
+      rc = launch_colsum(e, st, part, (size_t)K3 * D, ks, K3 * D, e->grad.W);
+      if (rc) return rc;
+    }
+    {  // dX' = dU . W^T, written over X' (no longer needed)
+      PhaseTimer pt(e, PH_DX_GEMM, st);
+      umma::Operand opA{H, (size_t)D, false};
+      umma::Operand opB{e->theta.W, (size_t)D, false};
+      umma::EpiStore ep{Xg, (size_t)K3, 0};
+      C2V_LAUNCH(e, C2V_CUDA(e, (umma::launch<192, 5>(st, N, K3, D, 1, opA, opB, ep, e->num_sms))));
+    }
+    if (!e->emb_grads_clean) {
+      C2V_CUDA(e, cudaMemsetAsync(e->grad.tok, 0, (size_t)e->dims.token_vocab * d * 4, st));
+      C2V_CUDA(e, cudaMemsetAsync(e->grad.path, 0, (size_t)e->dims.path_vocab * d * 4, st));
+    }
+    {
+      PhaseTimer pt(e, PH_DX_SCATTER, st);
+      C2V_LAUNCH(e, (scatter_dx_kernel<<<(N + 7) / 8, 256, 0, st>>>(cs, dp, mask, Xg, e->grad.tok, e->grad.path)));
+    }
+    e->emb_grads_clean = false;
+    return C2V_OK;
+  }
   {  // dW = X'^T . dU   (split-K over the B*C contexts, fixed-order reduction)
     PhaseTimer pt(e, PH_DW, st);
     simt::GatherColsX al{cs, dp};
@@ -345,6 +398,25 @@ int train_step_impl(c2v_engine* e, cudaStream_t st, const int32_t* src, const in
     PhaseTimer pt(e, PH_XENT, st);
     C2V_LAUNCH(e, (xent_kernel<<<B, kXentThreads, 0, st>>>(S, e->ws.ldS, target, Y, invB, loss_b, lse, 1)));
     C2V_LAUNCH(e, (loss_reduce_kernel<<<1, 256, 0, st>>>(loss_b, B, invB, loss_out)));
+  }
+  if (e->math_mode == C2V_MATH_TF32) {
+    {  // dv = P . Ytab   (split-K over |Y|, fixed-order reduction of the slices)
+      PhaseTimer pt(e, PH_DV, st);
+      umma::Operand opA{S, e->ws.ldS, false};
+      umma::Operand opB{e->theta.tgt, (size_t)D, true};
+      const int ks = umma::effective_splits(Y, kSplitDv);
+      umma::EpiStore ep{part, (size_t)D, (size_t)B * D};
+      C2V_LAUNCH(e, C2V_CUDA(e, (umma::launch<192, 5>(st, B, D, Y, kSplitDv, opA, opB, ep, e->num_sms))));
+      if ((rc = launch_colsum(e, st, part, (size_t)B * D, ks, B * D, dv))) return rc;
+    }
+    {  // dYtab = P^T . v
+      PhaseTimer pt(e, PH_DY, st);
+      umma::Operand opA{S, e->ws.ldS, true};
+      umma::Operand opB{v, (size_t)D, true};
+      umma::EpiStore ep{e->grad.tgt, (size_t)D, 0};
+      C2V_LAUNCH(e, C2V_CUDA(e, (umma::launch<192, 5>(st, Y, D, B, 1, opA, opB, ep, e->num_sms))));
+    }
+    return context_backward(e, st, cs, mask, B, dp, dv);
   }
   {  // dv = P . Ytab   (K = |Y| split, fixed-order reduction)
     PhaseTimer pt(e, PH_DV, st);
@@ -429,6 +501,7 @@ int c2v_create(const c2v_dims* dims, int device, c2v_engine** out) {
   e->has_theta = e->has_grad = e->has_adam = false;
   e->emb_grads_clean = false;
   e->math_mode = C2V_MATH_FP32;
+  e->num_sms = prop.multiProcessorCount;
   e->deterministic = 0;
   e->launches = 0;
   *out = e;
@@ -479,7 +552,8 @@ int c2v_set_option(c2v_engine* e, const char* key, int64_t value) {
   if (!e || !key) return C2V_ERR_INVALID;
   if (!strcmp(key, "math_mode")) {
     if (value != C2V_MATH_FP32 && value != C2V_MATH_TF32) return fail(e, C2V_ERR_INVALID, "unknown math_mode");
-    if (value == C2V_MATH_TF32) return fail(e, C2V_ERR_UNSUPPORTED, "tf32 path not built");
+    if (value == C2V_MATH_TF32 && !umma::get_encode_fn())
+      return fail(e, C2V_ERR_UNSUPPORTED, "cuTensorMapEncodeTiled not available from the driver");
     e->math_mode = (int)value;
     return C2V_OK;
   }
@@ -614,6 +688,22 @@ int c2v_predict_batch_host(c2v_engine* e, const int32_t* h_src, const int32_t* h
   if (h_attn) C2V_CUDA(e, cudaMemcpyAsync(h_attn, attn, nb, cudaMemcpyDeviceToHost, st));
   C2V_CUDA(e, cudaStreamSynchronize(st));
   return C2V_OK;
+}
+
+int c2v_selftest_gemm(c2v_engine* e, int32_t a_mn, int32_t b_mn, int32_t bn, int32_t M, int32_t N, int32_t K,
+                      int32_t splits, const float* A, size_t lda, const float* Bm, size_t ldb, float* C, size_t ldc,
+                      void* stream) {
+  if (!e || !A || !Bm || !C) return C2V_ERR_INVALID;
+  C2V_CUDA(e, cudaSetDevice(e->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  umma::Operand opA{A, lda, a_mn != 0};
+  umma::Operand opB{Bm, ldb, b_mn != 0};
+  if (!umma::operand_ok(opA) || !umma::operand_ok(opB)) return fail(e, C2V_ERR_INVALID, "operand not TMA-compatible");
+  umma::EpiStore ep{C, ldc, (size_t)M * ldc};
+  if (bn == 256) C2V_LAUNCH(e, C2V_CUDA(e, (umma::launch<256, 4>(st, M, N, K, splits, opA, opB, ep, e->num_sms))));
+  else if (bn == 192) C2V_LAUNCH(e, C2V_CUDA(e, (umma::launch<192, 5>(st, M, N, K, splits, opA, opB, ep, e->num_sms))));
+  else return fail(e, C2V_ERR_INVALID, "bn must be 192 or 256");
+  return umma::effective_splits(K, splits);
 }
 
 int64_t c2v_launch_count(const c2v_engine* e) { return e ? e->launches : 0; }

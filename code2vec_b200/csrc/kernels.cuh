@@ -446,4 +446,44 @@ adam_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m,
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// tf32 path only: materialise the gathered, dropped-out context matrix once per step
+//   X'[n, :] = dropout([ tok[src[n]] | path[pth[n]] | tok[tgt[n]] ])   (tensorflow_model.py:238-246)
+// so the three projection GEMMs can be fed by TMA; and its inverse, the scatter-add of dX' rows
+// into the embedding gradient tables.  One warp per context row, 128-bit accesses.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) gather_ctx_kernel(ContextSource cs, Dropout dp, float* __restrict__ Xg) {
+  const int n = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (n >= cs.rows) return;
+  const int K3 = 3 * cs.d;
+  float* dst = Xg + (size_t)n * K3;
+  for (int j = lane * 4; j < K3; j += 128) {
+    float4 x = __ldg(reinterpret_cast<const float4*>(ctx_ptr(cs, n, j)));
+    const float4 m = dropout_mult4(dp, n, j >> 2);
+    x.x *= m.x; x.y *= m.y; x.z *= m.z; x.w *= m.w;
+    *reinterpret_cast<float4*>(dst + j) = x;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+scatter_dx_kernel(ContextSource cs, Dropout dp, const float* __restrict__ mask, const float* __restrict__ dXg,
+                  float* __restrict__ g_tok, float* __restrict__ g_path) {
+  const int n = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (n >= cs.rows) return;
+  if (mask[n] == 0.f) return;                 // masked contexts carry exact zeros
+  const int K3 = 3 * cs.d;
+  const float* src = dXg + (size_t)n * K3;
+  for (int j = lane * 4; j < K3; j += 128) {
+    float4 g = *reinterpret_cast<const float4*>(src + j);
+    const float4 m = dropout_mult4(dp, n, j >> 2);
+    g.x *= m.x; g.y *= m.y; g.z *= m.z; g.w *= m.w;
+    const int seg = j / cs.d, off = j - seg * cs.d;
+    float* dst;
+    if (seg == 0) dst = g_tok + (size_t)cs.src[n] * cs.d + off;
+    else if (seg == 1) dst = g_path + (size_t)cs.pth[n] * cs.d + off;
+    else dst = g_tok + (size_t)cs.tgt[n] * cs.d + off;
+    atomicAdd(reinterpret_cast<float4*>(dst), g);
+  }
+}
+
 }  // namespace c2v

@@ -1,0 +1,404 @@
+// tcgen05 (5th-gen tensor core) GEMM for sm_100a:  C[M,N] = A[M,K] . B[K,N],  fp32 storage,
+// kind::tf32 operands (10-bit mantissa), fp32 accumulation in TMEM  (C2V_MATH_TF32).
+//
+// Persistent, warp-specialised, one CTA per SM:
+//   warp 0      : TMA producer   -- cp.async.bulk.tensor (SWIZZLE_128B) into a 4..5-stage smem ring
+//   warp 1      : MMA issuer     -- one elected lane issues tcgen05.mma.cta_group::1.kind::tf32
+//                                   (UMMA 128 x BN x 8), tcgen05.commit frees smem stages / publishes
+//                                   the accumulator; also owns the TMEM allocation
+//   warps 2..5  : epilogue       -- tcgen05.ld (32x32b) of their TMEM lane quadrant, fused epilogue
+//                                   functor (store / tanh / split-K slice), vectorised global stores
+// The accumulator is double-buffered in TMEM (2 x BN columns) so the epilogue of tile i overlaps
+// the MMAs of tile i+1.  Operands may be K-major (K contiguous) or MN-major (M resp. N
+// contiguous) in global memory; both are staged as 128-byte swizzled rows and described to the
+// tensor core through shared-memory matrix descriptors.  Out-of-range rows / K-tail are
+// zero-filled by TMA, so any M, N, K work; split-K over blockIdx-independent work items.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "common.cuh"
+
+namespace c2v {
+namespace umma {
+
+constexpr int BM = 128;          // UMMA_M (cta_group::1)
+constexpr int BK = 32;           // fp32 elements per stage along K = one 128-byte swizzle row
+constexpr int UMMA_K = 8;        // K per tcgen05.mma for 32-bit operands (32 bytes)
+constexpr int kThreads = 192;    // 6 warps
+constexpr int kEpiWarp0 = 2;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// ---- mbarrier ---------------------------------------------------------------------------------
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+  return ok != 0;
+}
+// Bounded wait: a pipeline bug traps (reported as a CUDA error) instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > 20000000000LL) __trap();     // ~10 s at 2 GHz
+  }
+}
+
+// ---- TMA ----------------------------------------------------------------------------------------
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
+}
+
+// ---- tcgen05 ------------------------------------------------------------------------------------
+__device__ __forceinline__ void tmem_alloc(uint32_t* smem_result, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_result)), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// 32 lanes x 32 consecutive 32-bit columns: thread i gets row (lane_base + i), columns [c, c+32)
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// ---- descriptors ----------------------------------------------------------------------------------
+// Shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout): start address >> 4 in
+// [0,14), leading byte offset >> 4 in [16,30), stride byte offset >> 4 in [32,46), version = 1 in
+// [46,48), layout type SWIZZLE_128B = 2 in [61,64).
+__host__ __device__ constexpr uint64_t make_smem_desc_hi(uint32_t sbo_bytes) {
+  return (uint64_t)((sbo_bytes >> 4) & 0x3FFF) | (1ull << 14) | (2ull << 29);     // upper 32 bits
+}
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  const uint32_t lo = ((smem_addr >> 4) & 0x3FFF) | (((lbo_bytes >> 4) & 0x3FFF) << 16);
+  return ((uint64_t)make_smem_desc_hi(sbo_bytes) << 32) | lo;
+}
+// Instruction descriptor (cute::UMMA::InstrDescriptor): D = F32, A = B = TF32, majors, N >> 3, M >> 4.
+__host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N, bool a_mn, bool b_mn) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((a_mn ? 1u : 0u) << 15) | ((b_mn ? 1u : 0u) << 16) |
+         ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+// ---- epilogues: (row m, column n0, 32 accumulators for columns n0..n0+31, nvalid columns) -------------
+struct EpiStore {
+  float* C;
+  size_t ldc;
+  size_t split_stride;
+  __device__ __forceinline__ void operator()(int m, int n, const uint32_t (&r)[32], int nvalid, int split) const {
+    float* p = C + (size_t)split * split_stride + (size_t)m * ldc + n;
+    if (nvalid >= 32) {
+#pragma unroll
+      for (int j = 0; j < 32; j += 4)
+        *reinterpret_cast<float4*>(p + j) = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]),
+                                                        __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (j < nvalid) p[j] = __uint_as_float(r[j]);
+    }
+  }
+};
+struct EpiTanhStore {
+  float* C;
+  size_t ldc;
+  __device__ __forceinline__ void operator()(int m, int n, const uint32_t (&r)[32], int nvalid, int) const {
+    float* p = C + (size_t)m * ldc + n;
+    if (nvalid >= 32) {
+#pragma unroll
+      for (int j = 0; j < 32; j += 4)
+        *reinterpret_cast<float4*>(p + j) = make_float4(tanhf(__uint_as_float(r[j])), tanhf(__uint_as_float(r[j + 1])),
+                                                        tanhf(__uint_as_float(r[j + 2])), tanhf(__uint_as_float(r[j + 3])));
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (j < nvalid) p[j] = tanhf(__uint_as_float(r[j]));
+    }
+  }
+};
+
+// ---- kernel -------------------------------------------------------------------------------------------
+struct GemmShape {
+  int M, N, K;
+  int m_tiles, n_tiles, splits;
+  int kblocks_per_split;      // K blocks (of BK) per split-K slice
+};
+
+template <int BN, int STAGES>
+struct SmemLayout {
+  static constexpr int kABytes = BM * BK * 4;          // 16 KB
+  static constexpr int kBBytes = BN * BK * 4;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kBarOffset = STAGES * kStageBytes;
+  static constexpr int kTotal = kBarOffset + 256 + 1024;   // barriers + tmem ptr, + slack for 1024-B alignment
+};
+
+template <int BN, int STAGES, bool A_MN, bool B_MN, class Epi>
+__global__ void __launch_bounds__(kThreads, 1)
+umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, GemmShape gs, Epi epi) {
+  using L = SmemLayout<BN, STAGES>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::kBarOffset);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tfull_bar = empty_bar + STAGES;      // [2]
+  uint64_t* tempty_bar = tfull_bar + 2;          // [2]
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  constexpr uint32_t kTmemCols = (2 * BN <= 256) ? 256 : 512;
+  const int total_items = gs.m_tiles * gs.n_tiles * gs.splits;
+  const int total_kblocks = (gs.K + BK - 1) / BK;
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], 4); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) tmem_alloc(tmem_ptr, kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  // work item -> (m tile, n tile, split): m fastest so CTAs running together share B tiles in L2
+  auto decode = [&](int item, int& mt, int& nt, int& sp) {
+    mt = item % gs.m_tiles;
+    const int r = item / gs.m_tiles;
+    nt = r % gs.n_tiles;
+    sp = r / gs.n_tiles;
+  };
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
+        int mt, nt, sp;
+        decode(item, mt, nt, sp);
+        const int kb0 = sp * gs.kblocks_per_split;
+        const int kb1 = min(total_kblocks, kb0 + gs.kblocks_per_split);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * L::kStageBytes;
+          uint8_t* sb = sa + L::kABytes;
+          mbar_expect_tx(&full_bar[stage], L::kStageBytes);
+          if (A_MN) {
+            // global A^T is [K rows, M contiguous]: boxes of {32 m, BK k-rows} (4 KB each)
+#pragma unroll
+            for (int c = 0; c < BM / 32; ++c) tma_load_2d(sa + c * (BK * 128), &tmA, &full_bar[stage], mt * BM + c * 32, kb * BK);
+          } else {
+            // global A is [M rows, K contiguous]: one box {BK k, BM rows}
+            tma_load_2d(sa, &tmA, &full_bar[stage], kb * BK, mt * BM);
+          }
+          if (B_MN) {
+#pragma unroll
+            for (int c = 0; c < BN / 32; ++c) tma_load_2d(sb + c * (BK * 128), &tmB, &full_bar[stage], nt * BN + c * 32, kb * BK);
+          } else {
+            tma_load_2d(sb, &tmB, &full_bar[stage], kb * BK, nt * BN);
+          }
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_tf32(BM, BN, A_MN, B_MN);
+      // K-major: rows of 128 B, 8-row groups 1024 B apart (SBO); K step = 32 B inside the swizzle row.
+      // MN-major: 32-element MN chunks of BK k-rows (LBO = BK*128 B apart), 8-k-row groups 1024 B
+      //           apart (SBO); K step = 8 k-rows = 1024 B.
+      constexpr uint32_t a_lbo = A_MN ? BK * 128 : 0, b_lbo = B_MN ? BK * 128 : 0;
+      constexpr uint32_t a_kstep = A_MN ? 1024 : UMMA_K * 4, b_kstep = B_MN ? 1024 : UMMA_K * 4;
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
+        int mt, nt, sp;
+        decode(item, mt, nt, sp);
+        const int kb0 = sp * gs.kblocks_per_split;
+        const int kb1 = min(total_kblocks, kb0 + gs.kblocks_per_split);
+        mbar_wait(&tempty_bar[acc], acc_phase ^ 1);          // epilogue has drained this accumulator
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + acc * BN;
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * L::kStageBytes);
+          const uint32_t sb = sa + L::kABytes;
+          const uint64_t adesc = make_smem_desc(sa, a_lbo, 1024);
+          const uint64_t bdesc = make_smem_desc(sb, b_lbo, 1024);
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k) {
+            mma_tf32(tmem_d, adesc + (uint64_t)((k * a_kstep) >> 4), bdesc + (uint64_t)((k * b_kstep) >> 4), idesc,
+                     (kb > kb0 || k > 0) ? 1u : 0u);
+          }
+          tc_commit(&empty_bar[stage]);                       // frees the smem stage when the MMAs retire
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        tc_commit(&tfull_bar[acc]);                           // accumulator complete -> epilogue
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else {
+    // ===================== epilogue warps (TMEM lane quadrant = warp % 4) =====================
+    const int q = warp & 3;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
+      int mt, nt, sp;
+      decode(item, mt, nt, sp);
+      mbar_wait(&tfull_bar[acc], acc_phase);
+      tc_fence_after();
+      const int m = mt * BM + q * 32 + lane;
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN;
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        uint32_t r[32];
+        tmem_ld32(taddr + c * 32, r);
+        tmem_ld_wait();
+        const int n = nt * BN + c * 32;
+        if (m < gs.M && n < gs.N) epi(m, n, r, gs.N - n, sp);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, kTmemCols);
+}
+
+// ---- host side ------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+inline EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess && p)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+// 2-D fp32 tensor map over a row-major [rows, cols] matrix with row pitch ld (floats); box = {32 cols, box_rows}.
+inline bool make_tensor_map(CUtensorMap* map, const float* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return false;
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {ld * sizeof(float)};
+  cuuint32_t box[2] = {32, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS;
+}
+
+// Operand description: `major_mn == false`: element (x, k) at base[x*ld + k] (K contiguous);
+//                      `major_mn == true` : element (x, k) at base[k*ld + x] (M / N contiguous).
+struct Operand {
+  const float* base;
+  size_t ld;
+  bool major_mn;
+};
+
+template <int BN, int STAGES, bool A_MN, bool B_MN, class Epi>
+inline cudaError_t launch_cfg(cudaStream_t st, int M, int N, int K, int splits, const Operand& A, const Operand& B, const Epi& epi,
+                              int num_sms) {
+  using L = SmemLayout<BN, STAGES>;
+  CUtensorMap tmA, tmB;
+  const bool okA = A_MN ? make_tensor_map(&tmA, A.base, (uint64_t)K, (uint64_t)M, A.ld, BK)
+                        : make_tensor_map(&tmA, A.base, (uint64_t)M, (uint64_t)K, A.ld, BM);
+  const bool okB = B_MN ? make_tensor_map(&tmB, B.base, (uint64_t)K, (uint64_t)N, B.ld, BK)
+                        : make_tensor_map(&tmB, B.base, (uint64_t)N, (uint64_t)K, B.ld, BN);
+  if (!okA || !okB) return cudaErrorInvalidValue;
+  GemmShape gs;
+  gs.M = M; gs.N = N; gs.K = K;
+  gs.m_tiles = (M + BM - 1) / BM;
+  gs.n_tiles = (N + BN - 1) / BN;
+  const int total_kblocks = (K + BK - 1) / BK;
+  if (splits < 1) splits = 1;
+  if (splits > total_kblocks) splits = total_kblocks;
+  gs.kblocks_per_split = (total_kblocks + splits - 1) / splits;
+  gs.splits = (total_kblocks + gs.kblocks_per_split - 1) / gs.kblocks_per_split;
+  auto kern = umma_gemm_kernel<BN, STAGES, A_MN, B_MN, Epi>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal);
+  if (e != cudaSuccess) return e;
+  int grid = gs.m_tiles * gs.n_tiles * gs.splits;
+  if (grid > num_sms) grid = num_sms;
+  kern<<<grid, kThreads, L::kTotal, st>>>(tmA, tmB, gs, epi);
+  return cudaGetLastError();
+}
+
+// number of split-K slices launch_cfg will actually produce
+inline int effective_splits(int K, int splits) {
+  const int total_kblocks = (K + BK - 1) / BK;
+  if (splits < 1) splits = 1;
+  if (splits > total_kblocks) splits = total_kblocks;
+  const int per = (total_kblocks + splits - 1) / splits;
+  return (total_kblocks + per - 1) / per;
+}
+
+// Runtime dispatch over operand majors.  BN = 256 uses 4 stages (192 KB), BN = 192 uses 5 (200 KB).
+template <int BN, int STAGES, class Epi>
+inline cudaError_t launch(cudaStream_t st, int M, int N, int K, int splits, const Operand& A, const Operand& B, const Epi& epi,
+                          int num_sms) {
+  if (!A.major_mn && !B.major_mn) return launch_cfg<BN, STAGES, false, false, Epi>(st, M, N, K, splits, A, B, epi, num_sms);
+  if (!A.major_mn && B.major_mn) return launch_cfg<BN, STAGES, false, true, Epi>(st, M, N, K, splits, A, B, epi, num_sms);
+  if (A.major_mn && !B.major_mn) return launch_cfg<BN, STAGES, true, false, Epi>(st, M, N, K, splits, A, B, epi, num_sms);
+  return launch_cfg<BN, STAGES, true, true, Epi>(st, M, N, K, splits, A, B, epi, num_sms);
+}
+
+// TMA constraints on an operand: 16-byte aligned base, row pitch a multiple of 16 bytes.
+inline bool operand_ok(const Operand& o) {
+  return (reinterpret_cast<uintptr_t>(o.base) % 16 == 0) && (o.ld % 4 == 0);
+}
+
+}  // namespace umma
+}  // namespace c2v

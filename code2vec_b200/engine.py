@@ -55,6 +55,8 @@ _SIGNATURES = {
     "c2v_train_batch_host": (C.c_int, [_P, _P, _P, _P, _P, _P, _I32, C.c_float, C.c_uint64, C.c_int64,
                                        C.c_float, C.c_float, C.c_float, C.c_float, _P, _P]),
     "c2v_predict_batch_host": (C.c_int, [_P, _P, _P, _P, _P, _I32, _I32, _P, _P, _P, _P, _P]),
+    "c2v_selftest_gemm": (C.c_int, [_P, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _P, C.c_size_t, _P, C.c_size_t,
+                                    _P, C.c_size_t, _P]),
     "c2v_launch_count": (C.c_int64, [_P]),
     "c2v_phase_count": (C.c_int, []),
     "c2v_phase_name": (C.c_char_p, [C.c_int]),
@@ -191,6 +193,17 @@ class PathAttentionEngine:
     @property
     def launch_count(self) -> int:
         return int(self.lib.c2v_launch_count(self.h))
+
+    def selftest_gemm(self, A, B, a_mn: bool, b_mn: bool, M: int, N: int, K: int, bn: int = 192, splits: int = 1):
+        """Test hook: C[M,N] = A.B on the tcgen05 path.  A is [M,K] (a_mn False) or [K,M] (True) row-major,
+        B is [N,K] (b_mn False) or [K,N] (True); returns C (slices summed on the host side of the test)."""
+        torch = self.torch
+        out = torch.zeros((max(splits, 1), M, N), dtype=torch.float32, device=self.dev)
+        rc = self.lib.c2v_selftest_gemm(self.h, int(a_mn), int(b_mn), bn, M, N, K, splits, A.data_ptr(), A.stride(0),
+                                        B.data_ptr(), B.stride(0), out.data_ptr(), N, self._stream())
+        if rc < 0:
+            self._check(rc)
+        return out[:rc].sum(dim=0)
 
     def phase_stats(self, reset: bool = False) -> Dict[str, Tuple[float, int]]:
         """{phase name: (total device ms, number of timed occurrences)} since the last reset

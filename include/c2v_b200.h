@@ -169,6 +169,15 @@ int c2v_predict_batch_host(c2v_engine* e, const int32_t* h_src, const int32_t* h
                            int32_t normalize, int32_t* h_topk_idx, float* h_topk_val,
                            float* h_code_vec, float* h_attn, void* stream);
 
+/* Test hook for the tcgen05 GEMM building block: C = A . B with tf32 operands.  a_mn / b_mn
+ * select the operand layout (0: K contiguous, element (x,k) at p[x*ld+k]; 1: M resp. N
+ * contiguous, element (x,k) at p[k*ld+x]); bn is the N tile (192 or 256); with splits > 1,
+ * slice s of the K range is written to C + s*M*ldc.  Returns the number of slices (> 0) or an
+ * error (< 0).  All pointers are device pointers. */
+int c2v_selftest_gemm(c2v_engine* e, int32_t a_mn, int32_t b_mn, int32_t bn, int32_t M, int32_t N,
+                      int32_t K, int32_t splits, const float* A, size_t lda, const float* B,
+                      size_t ldb, float* C, size_t ldc, void* stream);
+
 /* Introspection for tests and bench: number of kernels the engine has launched so far. */
 int64_t c2v_launch_count(const c2v_engine* e);
 

@@ -1,0 +1,63 @@
+"""The tensor-core path (math_mode = tf32: tcgen05.mma kind::tf32, fp32 accumulate) against the fp32
+oracle.  tf32 operands keep 10 mantissa bits, so outputs are compared at tf32-level tolerances
+(stated per assertion); the loss bound of BASELINE.json (1e-4) still holds."""
+import numpy as np
+import pytest
+
+from oracle import path_attention_oracle as O
+from tests.util import dev_batch, make_engine, rel_err
+
+pytestmark = pytest.mark.gpu
+
+TINY = O.Dims(token_vocab=1001, path_vocab=501, target_vocab=1001, embed_dim=32, code_dim=96, max_contexts=20)
+ODD = O.Dims(token_vocab=777, path_vocab=333, target_vocab=1537, embed_dim=20, code_dim=52, max_contexts=13)
+MID = O.Dims(token_vocab=5003, path_vocab=3001, target_vocab=4099, embed_dim=128, code_dim=384, max_contexts=200)
+
+
+@pytest.mark.parametrize("dims,B", [(TINY, 64), (ODD, 37), (MID, 48)])
+def test_tf32_forward_and_topk(dims, B):
+    eng, params = make_engine(dims, max_batch=B)
+    eng.set_option("math_mode", 1)
+    assert eng.get_option("math_mode") == 1
+    src, pth, tgt, mask, _ = O.synthetic_batch(dims, B, seed=11)
+    idx_ref, val_ref, v_ref, alpha_ref, scores = O.evaluate_topk(params, src, pth, tgt, mask, k=10)
+    code, attn = eng.forward(*dev_batch(eng, src, pth, tgt, mask))
+    assert rel_err(code.cpu().numpy(), v_ref) < 3e-3
+    assert np.abs(attn.cpu().numpy() - alpha_ref).max() < 2e-3
+    idx, val = eng.topk(code)
+    assert np.abs(val.cpu().numpy() - val_ref).max() < 3e-3 * max(1.0, np.abs(val_ref).max())
+    # top-1 agrees wherever the fp32 margin exceeds the tf32 error bound
+    srt = -np.sort(-scores, axis=1)
+    clear = (srt[:, 0] - srt[:, 1]) > 2e-3
+    assert np.array_equal(idx.cpu().numpy()[clear, 0], idx_ref[clear, 0])
+
+
+@pytest.mark.parametrize("dims,B", [(TINY, 64), (ODD, 37), (MID, 48)])
+def test_tf32_train_step(dims, B):
+    eng, params = make_engine(dims, max_batch=B)
+    eng.set_option("math_mode", 1)
+    src, pth, tgt, mask, target = O.synthetic_batch(dims, B, seed=21)
+    src[0, 0] = tgt[0, 0] = src[1, 0] = 3
+    dm = O.dropout_keep_mask(seed=5, step=2, n_rows=B * dims.max_contexts, ctx_dim=dims.ctx_dim, keep=0.75)
+    loss_ref, g_ref, _ = O.train_loss_and_grads(params, src, pth, tgt, mask, target, keep=0.75, dropout_mask=dm)
+    d = dev_batch(eng, src, pth, tgt, mask, target)
+    loss = float(eng.train_step(*d, keep=0.75, seed=5, step=2).cpu()[0])
+    assert abs(loss - loss_ref) < 1e-4                      # BASELINE.json's loss bound
+    g = eng.export_grads()
+    for k in O.PARAM_NAMES:
+        assert rel_err(g[k], g_ref[k]) < 1e-2, k            # tf32 operands: ~1e-3 relative per product
+    touched = np.zeros(dims.token_vocab, bool)
+    touched[src[mask > 0]] = True
+    touched[tgt[mask > 0]] = True
+    assert np.all(g["tok"][~touched] == 0.0)
+    # three optimizer steps stay close to the fp32 oracle trajectory
+    params = {k: v.copy() for k, v in params.items()}
+    eng.load_params(params)
+    m = {k: np.zeros_like(p) for k, p in params.items()}
+    v = {k: np.zeros_like(p) for k, p in params.items()}
+    for t in (1, 2, 3):
+        lr, gr, _ = O.train_loss_and_grads(params, src, pth, tgt, mask, target)
+        O.adam_step(params, gr, m, v, t)
+        l = float(eng.train_step(*d).cpu()[0])
+        eng.adam_step()
+        assert abs(l - lr) < 1e-4
