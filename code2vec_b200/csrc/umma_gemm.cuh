@@ -103,13 +103,18 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 // ---- descriptors ----------------------------------------------------------------------------------
 // Shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout): start address >> 4 in
 // [0,14), leading byte offset >> 4 in [16,30), stride byte offset >> 4 in [32,46), version = 1 in
-// [46,48), layout type SWIZZLE_128B = 2 in [61,64).
-__host__ __device__ constexpr uint64_t make_smem_desc_hi(uint32_t sbo_bytes) {
-  return (uint64_t)((sbo_bytes >> 4) & 0x3FFF) | (1ull << 14) | (2ull << 29);     // upper 32 bits
+// [46,48), layout type in [61,64): SWIZZLE_128B = 2 (16-byte chunks swizzled over 8 rows; K-major
+// operands) or SWIZZLE_128B_BASE32B = 1 (32-byte chunks swizzled over 4 rows) -- the only layout the
+// tensor core accepts for MN-major 32-bit (tf32) operands; TMA writes it with
+// CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B.
+constexpr uint32_t kLayoutSw128 = 2, kLayoutSw128Base32 = 1;
+__host__ __device__ constexpr uint64_t make_smem_desc_hi(uint32_t sbo_bytes, uint32_t layout_type) {
+  return (uint64_t)((sbo_bytes >> 4) & 0x3FFF) | (1ull << 14) | ((uint64_t)layout_type << 29);     // upper 32 bits
 }
-__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes,
+                                                   uint32_t layout_type) {
   const uint32_t lo = ((smem_addr >> 4) & 0x3FFF) | (((lbo_bytes >> 4) & 0x3FFF) << 16);
-  return ((uint64_t)make_smem_desc_hi(sbo_bytes) << 32) | lo;
+  return ((uint64_t)make_smem_desc_hi(sbo_bytes, layout_type) << 32) | lo;
 }
 // Instruction descriptor (cute::UMMA::InstrDescriptor): D = F32, A = B = TF32, majors, N >> 3, M >> 4.
 __host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N, bool a_mn, bool b_mn) {
@@ -243,10 +248,14 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     // ===================== MMA issuer =====================
     if (lane == 0) {
       constexpr uint32_t idesc = make_idesc_tf32(BM, BN, A_MN, B_MN);
-      // K-major: rows of 128 B, 8-row groups 1024 B apart (SBO); K step = 32 B inside the swizzle row.
-      // MN-major: 32-element MN chunks of BK k-rows (LBO = BK*128 B apart), 8-k-row groups 1024 B
-      //           apart (SBO); K step = 8 k-rows = 1024 B.
+      // K-major (SWIZZLE_128B): rows of 128 B, 8-row groups 1024 B apart (SBO); one MMA consumes
+      //   32 B of each row, so the K step is +32 B inside the swizzle row.
+      // MN-major (SWIZZLE_128B_BASE32B): chunks of 32 M/N-elements x BK k-rows (128 B per k-row);
+      //   chunks are BK*128 B apart (LBO), 4-k-row swizzle atoms 512 B apart (SBO); one MMA consumes
+      //   8 k-rows, so the K step is +1024 B.
       constexpr uint32_t a_lbo = A_MN ? BK * 128 : 0, b_lbo = B_MN ? BK * 128 : 0;
+      constexpr uint32_t a_sbo = A_MN ? 512 : 1024, b_sbo = B_MN ? 512 : 1024;
+      constexpr uint32_t a_lt = A_MN ? kLayoutSw128Base32 : kLayoutSw128, b_lt = B_MN ? kLayoutSw128Base32 : kLayoutSw128;
       constexpr uint32_t a_kstep = A_MN ? 1024 : UMMA_K * 4, b_kstep = B_MN ? 1024 : UMMA_K * 4;
       int stage = 0;
       uint32_t phase = 0;
@@ -265,8 +274,8 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + stage * L::kStageBytes);
           const uint32_t sb = sa + L::kABytes;
-          const uint64_t adesc = make_smem_desc(sa, a_lbo, 1024);
-          const uint64_t bdesc = make_smem_desc(sb, b_lbo, 1024);
+          const uint64_t adesc = make_smem_desc(sa, a_lbo, a_sbo, a_lt);
+          const uint64_t bdesc = make_smem_desc(sb, b_lbo, b_sbo, b_lt);
 #pragma unroll
           for (int k = 0; k < BK / UMMA_K; ++k) {
             mma_tf32(tmem_d, adesc + (uint64_t)((k * a_kstep) >> 4), bdesc + (uint64_t)((k * b_kstep) >> 4), idesc,
@@ -327,7 +336,8 @@ inline EncodeTiledFn get_encode_fn() {
 }
 
 // 2-D fp32 tensor map over a row-major [rows, cols] matrix with row pitch ld (floats); box = {32 cols, box_rows}.
-inline bool make_tensor_map(CUtensorMap* map, const float* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows) {
+inline bool make_tensor_map(CUtensorMap* map, const float* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows,
+                            bool atom32) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) return false;
   cuuint64_t dims[2] = {cols, rows};
@@ -335,7 +345,8 @@ inline bool make_tensor_map(CUtensorMap* map, const float* base, uint64_t rows, 
   cuuint32_t box[2] = {32, box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, atom32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS;
 }
@@ -353,10 +364,10 @@ inline cudaError_t launch_cfg(cudaStream_t st, int M, int N, int K, int splits, 
                               int num_sms) {
   using L = SmemLayout<BN, STAGES>;
   CUtensorMap tmA, tmB;
-  const bool okA = A_MN ? make_tensor_map(&tmA, A.base, (uint64_t)K, (uint64_t)M, A.ld, BK)
-                        : make_tensor_map(&tmA, A.base, (uint64_t)M, (uint64_t)K, A.ld, BM);
-  const bool okB = B_MN ? make_tensor_map(&tmB, B.base, (uint64_t)K, (uint64_t)N, B.ld, BK)
-                        : make_tensor_map(&tmB, B.base, (uint64_t)N, (uint64_t)K, B.ld, BN);
+  const bool okA = A_MN ? make_tensor_map(&tmA, A.base, (uint64_t)K, (uint64_t)M, A.ld, BK, true)
+                        : make_tensor_map(&tmA, A.base, (uint64_t)M, (uint64_t)K, A.ld, BM, false);
+  const bool okB = B_MN ? make_tensor_map(&tmB, B.base, (uint64_t)K, (uint64_t)N, B.ld, BK, true)
+                        : make_tensor_map(&tmB, B.base, (uint64_t)N, (uint64_t)K, B.ld, BN, false);
   if (!okA || !okB) return cudaErrorInvalidValue;
   GemmShape gs;
   gs.M = M; gs.N = N; gs.K = K;
