@@ -174,7 +174,7 @@ def run_ours(args):
     sync_all()
     eng.set_option("profile", 1)
     eng.phase_stats(reset=True)
-    clocks = ClockSampler(local_rank)
+    clocks = ClockSampler(local_rank, period_ms=20)
     if rank == 0:
         clocks.start()
         time.sleep(0.3)
@@ -361,7 +361,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="java14m", choices=sorted(WORKLOADS))
     ap.add_argument("--batch", type=int, default=0)
-    ap.add_argument("--math", default=os.environ.get("C2V_MATH", "fp32"), choices=["fp32", "tf32"])
+    ap.add_argument("--math", default=os.environ.get("C2V_MATH", "tf32"), choices=["fp32", "tf32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
