@@ -110,6 +110,7 @@ struct c2v_engine {
   bool emb_grads_clean;      // token/path gradient tables are known to be all-zero
   int math_mode;
   int num_sms;
+  cudaEvent_t ev_tgt_ready = nullptr;   // recorded after dY (caller-owned)
   int deterministic;
   int64_t launches;
   std::string err;
@@ -416,6 +417,7 @@ int train_step_impl(c2v_engine* e, cudaStream_t st, const int32_t* src, const in
       umma::EpiStore ep{e->grad.tgt, (size_t)D, 0};
       C2V_LAUNCH(e, C2V_CUDA(e, (umma::launch<192, 5>(st, Y, D, B, 1, opA, opB, ep, e->num_sms))));
     }
+    if (e->ev_tgt_ready) C2V_CUDA(e, cudaEventRecord(e->ev_tgt_ready, st));
     return context_backward(e, st, cs, mask, B, dp, dv);
   }
   {  // dv = P . Ytab   (K = |Y| split, fixed-order reduction)
@@ -434,6 +436,7 @@ int train_step_impl(c2v_engine* e, cudaStream_t st, const int32_t* src, const in
     simt::StoreC ep{e->grad.tgt, (size_t)D, 0};
     C2V_LAUNCH(e, C2V_CUDA(e, simt::launch(st, Y, D, B, 1, al, bl, ep)));
   }
+  if (e->ev_tgt_ready) C2V_CUDA(e, cudaEventRecord(e->ev_tgt_ready, st));
   return context_backward(e, st, cs, mask, B, dp, dv);
 }
 
@@ -626,6 +629,32 @@ int c2v_adam_step(c2v_engine* e, float lr, float beta1, float beta2, float eps, 
   if (!e->has_theta) return fail(e, C2V_ERR_STATE, "parameters not bound");
   C2V_CUDA(e, cudaSetDevice(e->device));
   return adam_impl(e, (cudaStream_t)stream, lr, beta1, beta2, eps, t);
+}
+
+int c2v_set_event(c2v_engine* e, const char* name, void* cuda_event) {
+  if (!e || !name) return C2V_ERR_INVALID;
+  if (!strcmp(name, "target_grads_ready")) { e->ev_tgt_ready = (cudaEvent_t)cuda_event; return C2V_OK; }
+  return fail(e, C2V_ERR_INVALID, std::string("unknown event: ") + name);
+}
+
+int c2v_adam_step_range(c2v_engine* e, float* theta, const float* grad, float* m, float* v, size_t count, float lr,
+                        float beta1, float beta2, float eps, int64_t t, void* stream) {
+  if (!e) return C2V_ERR_INVALID;
+  if (!theta || !grad || !m || !v) return fail(e, C2V_ERR_INVALID, "NULL argument");
+  if (count % 4 || ((uintptr_t)theta | (uintptr_t)grad | (uintptr_t)m | (uintptr_t)v) % 16)
+    return fail(e, C2V_ERR_INVALID, "slice must be a multiple of 4 floats and 16-byte aligned");
+  if (t < 1) return fail(e, C2V_ERR_INVALID, "Adam step count t must be >= 1");
+  C2V_CUDA(e, cudaSetDevice(e->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  const float lr_t = (float)((double)lr * sqrt(1.0 - pow((double)beta2, (double)t)) / (1.0 - pow((double)beta1, (double)t)));
+  const size_t n4 = count / 4;
+  if (n4 == 0) return C2V_OK;
+  size_t blocks = (n4 + 255) / 256;
+  if (blocks > (size_t)e->num_sms * 16) blocks = (size_t)e->num_sms * 16;
+  PhaseTimer pt(e, PH_ADAM, st);
+  C2V_LAUNCH(e, (adam_kernel<<<(unsigned)blocks, 256, 0, st>>>(theta, const_cast<float*>(grad), m, v, n4, lr_t, beta1, beta2,
+                                                               eps, 0)));
+  return C2V_OK;
 }
 
 int c2v_train_batch_host(c2v_engine* e, const int32_t* h_src, const int32_t* h_path, const int32_t* h_tgt,

@@ -52,11 +52,14 @@ _SIGNATURES = {
     "c2v_sampled_train_step": (C.c_int, [_P, _P, _P, _P, _P, _P, _I32, _P, _I32, _P, _P, C.c_float,
                                          C.c_uint64, C.c_uint64, _P, _P, _P]),
     "c2v_adam_step": (C.c_int, [_P, C.c_float, C.c_float, C.c_float, C.c_float, C.c_int64, _P]),
+    "c2v_adam_step_range": (C.c_int, [_P, _P, _P, _P, _P, C.c_size_t, C.c_float, C.c_float, C.c_float, C.c_float,
+                                      C.c_int64, _P]),
     "c2v_train_batch_host": (C.c_int, [_P, _P, _P, _P, _P, _P, _I32, C.c_float, C.c_uint64, C.c_int64,
                                        C.c_float, C.c_float, C.c_float, C.c_float, _P, _P]),
     "c2v_predict_batch_host": (C.c_int, [_P, _P, _P, _P, _P, _I32, _I32, _P, _P, _P, _P, _P]),
     "c2v_selftest_gemm": (C.c_int, [_P, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _P, C.c_size_t, _P, C.c_size_t,
                                     _P, C.c_size_t, _P]),
+    "c2v_set_event": (C.c_int, [_P, C.c_char_p, _P]),
     "c2v_launch_count": (C.c_int64, [_P]),
     "c2v_phase_count": (C.c_int, []),
     "c2v_phase_name": (C.c_char_p, [C.c_int]),
@@ -145,14 +148,17 @@ class PathAttentionEngine:
             wbytes = self.lib.c2v_workspace_bytes(C.byref(cd))
             self.workspace = torch.empty(wbytes, dtype=torch.uint8, device=self.dev)
             self._check(self.lib.c2v_bind_workspace(self.h, self.workspace.data_ptr(), wbytes))
-            shp = dims.shapes()
-            self.params = {k: torch.zeros(shp[k], dtype=f32, device=self.dev) for k in PARAM_NAMES}
+            # One flat fp32 buffer per role (parameters, gradients, Adam m, Adam v) with the five
+            # tensors as views at 256-byte-aligned offsets: a data-parallel run can then
+            # reduce-scatter / all-gather the whole model in one collective and run Adam on a slice.
+            self.flat_params, self.params = self._alloc_flat()
             self._check(self.lib.c2v_bind_params(self.h, C.byref(self._tensors(self.params))))
             self.grads = self.adam_m = self.adam_v = None
+            self.flat_grads = self.flat_m = self.flat_v = None
             if training:
-                self.grads = {k: torch.zeros(shp[k], dtype=f32, device=self.dev) for k in PARAM_NAMES}
-                self.adam_m = {k: torch.zeros(shp[k], dtype=f32, device=self.dev) for k in PARAM_NAMES}
-                self.adam_v = {k: torch.zeros(shp[k], dtype=f32, device=self.dev) for k in PARAM_NAMES}
+                self.flat_grads, self.grads = self._alloc_flat()
+                self.flat_m, self.adam_m = self._alloc_flat()
+                self.flat_v, self.adam_v = self._alloc_flat()
                 self._check(self.lib.c2v_bind_grads(self.h, C.byref(self._tensors(self.grads))))
                 self._check(self.lib.c2v_bind_adam_state(self.h, C.byref(self._tensors(self.adam_m)),
                                                          C.byref(self._tensors(self.adam_v))))
@@ -160,6 +166,43 @@ class PathAttentionEngine:
         self.adam_t = 0
 
     # ---- plumbing -------------------------------------------------------------------------
+    FLAT_ALIGN = 1024          # floats: keeps every view 256-byte aligned and any world size <= 256 dividing the total
+
+    FLAT_ORDER = ("tgt", "tok", "path", "W", "a")   # target table first: its gradient is complete first (bucket A)
+
+    def flat_layout(self):
+        """[(name, offset, numel)] of the five tensors inside a flat buffer, and its padded length."""
+        out, off = [], 0
+        shapes = self.dims.shapes()
+        for k in self.FLAT_ORDER:
+            n = int(np.prod(shapes[k]))
+            out.append((k, off, n))
+            off = (off + n + self.FLAT_ALIGN - 1) // self.FLAT_ALIGN * self.FLAT_ALIGN
+        return out, off
+
+    def bucket_bounds(self):
+        """Two gradient buckets of the flat buffer: A = target table (ready right after the dY GEMM),
+        B = token/path tables, TRANSFORM, ATTENTION (ready at the end of the backward pass)."""
+        layout, total = self.flat_layout()
+        split = layout[1][1]            # offset of the first tensor after `tgt`
+        return (0, split), (split, total)
+
+    def set_event(self, name: str, event) -> None:
+        """Ask the engine to record `event` (torch.cuda.Event) on the launching stream at a named point
+        of c2v_train_step ("target_grads_ready": right after dY is complete)."""
+        event.record(self.torch.cuda.current_stream(self.dev))          # forces creation of the cudaEvent_t
+        self._events = getattr(self, "_events", {})
+        self._events[name] = event
+        self._check(self.lib.c2v_set_event(self.h, name.encode(), event.cuda_event))
+
+    def _alloc_flat(self):
+        torch = self.torch
+        layout, total = self.flat_layout()
+        flat = torch.zeros(total, dtype=torch.float32, device=self.dev)
+        shp = self.dims.shapes()
+        views = {k: flat[off:off + n].view(shp[k]) for k, off, n in layout}
+        return flat, views
+
     @staticmethod
     def _tensors(d) -> c2v_tensors:
         return c2v_tensors(*[d[k].data_ptr() for k in PARAM_NAMES])
@@ -307,6 +350,14 @@ class PathAttentionEngine:
         else:
             self.adam_t = t
         self._check(self.lib.c2v_adam_step(self.h, lr, beta1, beta2, eps, int(t), self._stream()))
+
+    def adam_step_range(self, theta, grad, m, v, t: int, lr=1e-3, beta1=0.9, beta2=0.999, eps=1e-8):
+        """TF1 Adam on one contiguous slice (the sharded-optimizer path): flat 1-D tensors of equal length."""
+        n = int(theta.numel())
+        assert grad.numel() == n and m.numel() == n and v.numel() == n
+        self.adam_t = int(t)
+        self._check(self.lib.c2v_adam_step_range(self.h, theta.data_ptr(), grad.data_ptr(), m.data_ptr(), v.data_ptr(),
+                                                 n, lr, beta1, beta2, eps, int(t), self._stream()))
 
     # ---- host-buffer entry points ------------------------------------------------------------
     def train_batch_host(self, src, path, tgt, mask, target, keep: float = 1.0, seed: int = 0,

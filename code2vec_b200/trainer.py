@@ -4,10 +4,20 @@ Single GPU: one C-ABI call per batch (c2v_train_batch_host == the reference's
 ``sess.run([optimizer, train_loss])``, tensorflow_model.py:80).
 
 Data parallel (BASELINE config 4; the reference has no multi-GPU path): the
-batch is sharded across ranks, tables are replicated, and the only collective is one all-reduce
-(mean) of the five gradient tensors between c2v_train_step and c2v_adam_step, so every replica
-applies the identical Adam update.  torch.distributed (NCCL over NVLink/NVSwitch, gloo in the CPU
-tests of the host logic) is plumbing; all arithmetic stays in the engine's kernels.
+batch is sharded across ranks and the tables are replicated.  Two interchangeable schedules, both
+leaving every replica with bit-identical parameters:
+
+  "allreduce" : all-reduce(mean) of the five gradient tensors, then the full Adam on every rank.
+  "sharded"   : (default) the model lives in one flat buffer split into two buckets -- A = the
+                target table, whose gradient is complete right after the dY GEMM, B = the rest.
+                Each bucket is reduce-scattered (mean) so that rank r owns 1/world of it, Adam runs
+                on the owned slices only (c2v_adam_step_range: 1/world of the 9.2 GB optimizer
+                traffic), and the updated slices are all-gathered back.  Bucket A's
+                reduce-scatter is issued on a side stream as soon as the engine's
+                "target_grads_ready" event fires, so it overlaps the context backward pass.
+
+torch.distributed (NCCL over NVLink/NVSwitch; gloo in the CPU tests of the host logic) is plumbing;
+all arithmetic stays in the engine's kernels.
 """
 from __future__ import annotations
 
@@ -20,22 +30,23 @@ from .engine import PARAM_NAMES, PathAttentionEngine
 ADAM_DEFAULTS = dict(lr=1e-3, beta1=0.9, beta2=0.999, eps=1e-8)   # tf.compat.v1.train.AdamOptimizer()
 
 
+def _dist():
+    import torch.distributed as dist
+    return dist
+
+
 def allreduce_mean_(tensors, group=None):
     """In-place mean over ranks of each tensor in `tensors` (list).  NCCL averages in the
     collective itself; gloo (CPU tests) sums and scales."""
-    import torch.distributed as dist
+    dist = _dist()
     if not (dist.is_available() and dist.is_initialized()):
         return
     world = dist.get_world_size(group)
     if world == 1:
         return
     backend = dist.get_backend(group)
-    handles = []
-    for t in tensors:
-        if backend == "nccl":
-            handles.append(dist.all_reduce(t, op=dist.ReduceOp.AVG, group=group, async_op=True))
-        else:
-            handles.append(dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group, async_op=True))
+    op = dist.ReduceOp.AVG if backend == "nccl" else dist.ReduceOp.SUM
+    handles = [dist.all_reduce(t, op=op, group=group, async_op=True) for t in tensors]
     for h in handles:
         h.wait()
     if backend != "nccl":
@@ -43,8 +54,34 @@ def allreduce_mean_(tensors, group=None):
             t.mul_(1.0 / world)
 
 
+def reduce_scatter_mean(out_shard, flat, group=None, async_op=False):
+    """out_shard <- mean over ranks of this rank's 1/world slice of `flat` (len(flat) % world == 0)."""
+    dist = _dist()
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    if dist.get_backend(group) == "nccl":
+        return dist.reduce_scatter_tensor(out_shard, flat, op=dist.ReduceOp.AVG, group=group, async_op=async_op)
+    # gloo has no reduce-scatter: all-reduce a copy and keep the owned slice (CPU tests only)
+    tmp = flat.clone()
+    dist.all_reduce(tmp, op=dist.ReduceOp.SUM, group=group)
+    n = flat.numel() // world
+    out_shard.copy_(tmp[rank * n:(rank + 1) * n] / world)
+    return None
+
+
+def all_gather_flat(flat, shard, group=None, async_op=False):
+    """flat <- concatenation over ranks of `shard` (len(flat) == world * len(shard))."""
+    dist = _dist()
+    if dist.get_backend(group) == "nccl":
+        return dist.all_gather_into_tensor(flat, shard, group=group, async_op=async_op)
+    world = dist.get_world_size(group)
+    n = shard.numel()
+    parts = [flat[i * n:(i + 1) * n] for i in range(world)]
+    dist.all_gather(parts, shard.clone(), group=group)
+    return None
+
+
 def shard_bounds(n: int, rank: int, world: int):
-    """Contiguous slice [lo, hi) of n examples owned by `rank` (sizes differ by at most 1)."""
+    """Contiguous slice [lo, hi) of n items owned by `rank` (sizes differ by at most 1)."""
     base, rem = divmod(n, world)
     lo = rank * base + min(rank, rem)
     return lo, lo + base + (1 if rank < rem else 0)
@@ -52,18 +89,18 @@ def shard_bounds(n: int, rank: int, world: int):
 
 class Trainer:
     def __init__(self, engine: PathAttentionEngine, keep_prob: float = 0.75, seed: int = 0, group=None,
-                 adam: Optional[dict] = None):
+                 adam: Optional[dict] = None, schedule: str = "sharded"):
         self.e = engine
         self.keep = float(keep_prob)
         self.seed = int(seed)
         self.group = group
         self.adam = dict(ADAM_DEFAULTS, **(adam or {}))
         torch = engine.torch
-        import torch.distributed as dist
+        dist = _dist()
         self.world = dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
         self.rank = dist.get_rank(group) if self.world > 1 else 0
+        self.schedule = schedule if self.world > 1 else "single"
         B, C = engine.dims.max_batch, engine.dims.max_contexts
-        # device staging for the multi-GPU host path (single GPU stages inside the C ABI)
         self._dev = None
         if self.world > 1:
             i32, f32 = torch.int32, torch.float32
@@ -72,19 +109,56 @@ class Trainer:
                              tgt=torch.empty((B, C), dtype=i32, device=engine.dev),
                              mask=torch.empty((B, C), dtype=f32, device=engine.dev),
                              target=torch.empty((B,), dtype=i32, device=engine.dev))
+        if self.schedule == "sharded":
+            (a0, a1), (b0, b1) = engine.bucket_bounds()
+            w, r = self.world, self.rank
+            assert (a1 - a0) % w == 0 and (b1 - b0) % w == 0
+            na, nb = (a1 - a0) // w, (b1 - b0) // w
+            self._bucket = [(a0, a1, a0 + r * na, a0 + (r + 1) * na), (b0, b1, b0 + r * nb, b0 + (r + 1) * nb)]
+            self._gshard = [torch.empty(na, dtype=torch.float32, device=engine.dev),
+                            torch.empty(nb, dtype=torch.float32, device=engine.dev)]
+            self._side = torch.cuda.Stream(device=engine.dev)
+            self._ev_tgt = torch.cuda.Event()
+            with torch.cuda.device(engine.dev):
+                engine.set_event("target_grads_ready", self._ev_tgt)
         self._loss_host = torch.zeros(1, dtype=torch.float32).pin_memory()
 
     # ---- inputs already resident on the device ----------------------------------------------
     def step_device(self, src, path, tgt, mask, target):
-        """Forward+backward, (all-reduce), Adam.  Returns the device loss tensor (no sync)."""
+        """Forward+backward, gradient exchange, Adam.  Returns the device loss tensor (no sync)."""
         e = self.e
         t = e.adam_t + 1
-        # dropout stream position: (seed, t) on every rank, offset by rank so replicas differ
+        # dropout stream position (seed, t); replicas use different seeds so their masks differ
         loss = e.train_step(src, path, tgt, mask, target, keep=self.keep, seed=self.seed + self.rank, step=t)
-        if self.world > 1:
+        if self.schedule == "single":
+            e.adam_step(t=t, **self.adam)
+        elif self.schedule == "allreduce":
             allreduce_mean_([e.grads[k] for k in PARAM_NAMES], self.group)
-        e.adam_step(t=t, **self.adam)
+            e.adam_step(t=t, **self.adam)
+        else:
+            self._sharded_update(t)
         return loss
+
+    def _sharded_update(self, t: int):
+        e, torch = self.e, self.e.torch
+        main = torch.cuda.current_stream(e.dev)
+        (a0, a1, alo, ahi), (b0, b1, blo, bhi) = self._bucket
+        # bucket A: may start as soon as dY is done (event recorded inside c2v_train_step)
+        self._side.wait_event(self._ev_tgt)
+        with torch.cuda.stream(self._side):
+            wa = reduce_scatter_mean(self._gshard[0], e.flat_grads[a0:a1], self.group, async_op=True)
+        wb = reduce_scatter_mean(self._gshard[1], e.flat_grads[b0:b1], self.group, async_op=True)
+        for wk in (wa, wb):
+            if wk is not None:
+                wk.wait()                       # current (main) stream waits for the collective
+        main.wait_stream(self._side)
+        e.adam_step_range(e.flat_params[alo:ahi], self._gshard[0], e.flat_m[alo:ahi], e.flat_v[alo:ahi], t, **self.adam)
+        e.adam_step_range(e.flat_params[blo:bhi], self._gshard[1], e.flat_m[blo:bhi], e.flat_v[blo:bhi], t, **self.adam)
+        ga = all_gather_flat(e.flat_params[a0:a1], e.flat_params[alo:ahi], self.group, async_op=True)
+        gb = all_gather_flat(e.flat_params[b0:b1], e.flat_params[blo:bhi], self.group, async_op=True)
+        for wk in (ga, gb):
+            if wk is not None:
+                wk.wait()
 
     # ---- inputs in host memory (what train() does per batch) ---------------------------------
     def step_host(self, src, path, tgt, mask, target) -> float:

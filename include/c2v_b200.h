@@ -151,6 +151,19 @@ int c2v_sampled_train_step(c2v_engine* e, const int32_t* src, const int32_t* pat
 int c2v_adam_step(c2v_engine* e, float lr, float beta1, float beta2, float eps, int64_t t,
                   void* stream);
 
+/* The same update on one contiguous slice of caller-provided device arrays (count % 4 == 0,
+ * 16-byte aligned): the sharded-optimizer path of a data-parallel run, where each rank owns
+ * 1/world of the flat parameter buffer (reduce-scatter grads -> this -> all-gather params). */
+int c2v_adam_step_range(c2v_engine* e, float* theta, const float* grad, float* m, float* v,
+                        size_t count, float lr, float beta1, float beta2, float eps, int64_t t,
+                        void* stream);
+
+/* Register a cudaEvent_t (passed as void*; NULL unregisters) that c2v_train_step records on its
+ * stream at a named point, so the caller can start communication early on another stream:
+ *   "target_grads_ready" : the TARGET_WORDS_VOCAB gradient is complete (right after dY), while
+ *                          the context backward pass is still to run. */
+int c2v_set_event(c2v_engine* e, const char* name, void* cuda_event);
+
 /* --- host-buffer entry points: what the backend's train()/evaluate()/predict() call -------- */
 
 /* One `sess.run([optimizer, train_loss])` (tensorflow_model.py:80): copies the batch from host

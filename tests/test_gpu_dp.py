@@ -1,0 +1,61 @@
+"""Data-parallel schedules on real GPUs (needs >= 2; skipped otherwise): two ranks, each with half of
+a global batch, must end every step with bit-identical parameters on both ranks, equal (to fp32
+rounding) to one engine training on the whole batch -- for both the all-reduce and the sharded
+(reduce-scatter / sliced Adam / all-gather, overlapped) schedules."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import path_attention_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+DIMS = O.Dims(token_vocab=2003, path_vocab=1009, target_vocab=3001, embed_dim=32, code_dim=96, max_contexts=20)
+B_LOCAL = 32
+
+
+def _worker(rank, world, port, schedule, math_mode, out_dir):
+    import torch
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    from code2vec_b200.engine import EngineDims, PathAttentionEngine
+    from code2vec_b200.trainer import Trainer
+    eng = PathAttentionEngine(EngineDims(DIMS.token_vocab, DIMS.path_vocab, DIMS.target_vocab, DIMS.embed_dim,
+                                         DIMS.code_dim, DIMS.max_contexts, B_LOCAL, 10), device=rank, training=True)
+    eng.load_params(O.init_params(DIMS, seed=4321))
+    eng.set_option("math_mode", math_mode)
+    tr = Trainer(eng, keep_prob=1.0, seed=0, schedule=schedule)
+    src, pth, tgt, mask, target = O.synthetic_batch(DIMS, B_LOCAL * world, seed=77)
+    lo, hi = rank * B_LOCAL, (rank + 1) * B_LOCAL
+    losses = []
+    for _ in range(3):
+        losses.append(tr.step_host(src[lo:hi], pth[lo:hi], tgt[lo:hi], mask[lo:hi], target[lo:hi]))
+    np.savez(os.path.join(out_dir, "rank%d.npz" % rank), losses=np.array(losses), **eng.export_params())
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("schedule", ["allreduce", "sharded"])
+def test_two_rank_data_parallel_matches_single_engine(tmp_path, schedule):
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import torch.multiprocessing as mp
+    world, port = 2, 29500 + (os.getpid() % 1000)
+    mp.spawn(_worker, args=(world, port, schedule, 0, str(tmp_path)), nprocs=world, join=True)
+    r0 = np.load(str(tmp_path / "rank0.npz"))
+    r1 = np.load(str(tmp_path / "rank1.npz"))
+    for k in O.PARAM_NAMES:
+        assert np.array_equal(r0[k], r1[k]), "replicas diverged on %s" % k
+    # single engine on the global batch (mean loss over 2*B_LOCAL == average of the two local means)
+    from tests.util import make_engine
+    eng, _ = make_engine(DIMS, max_batch=B_LOCAL * world)
+    src, pth, tgt, mask, target = O.synthetic_batch(DIMS, B_LOCAL * world, seed=77)
+    for _ in range(3):
+        eng.train_batch_host(src, pth, tgt, mask, target, keep=1.0)
+    ref = eng.export_params()
+    for k in O.PARAM_NAMES:
+        assert np.abs(r0[k] - ref[k]).max() < 5e-5, k
