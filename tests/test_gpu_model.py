@@ -22,13 +22,13 @@ def _make_dataset(tmp_path, n_train=96, n_test=24, seed=0):
     prefix = str(tmp_path / "ds")
 
     def example():
-        # the target is (mostly) determined by the first context's source token -> learnable
+        # the target is determined by the group (4 tokens per target) the source tokens come from -> learnable
         t = int(rng.integers(0, len(TARGETS)))
         n = int(rng.integers(2, C + 1))
         ctxs = []
         for i in range(n):
-            s = TOKENS[t * 4 + int(rng.integers(0, 2))] if i == 0 else TOKENS[int(rng.integers(0, 40))]
-            ctxs.append("%s,%s,%s" % (s, PATHS[int(rng.integers(0, 25))], TOKENS[int(rng.integers(0, 40))]))
+            s = TOKENS[t * 4 + int(rng.integers(0, 4))]
+            ctxs.append("%s,%s,%s" % (s, PATHS[int(rng.integers(0, 25))], TOKENS[32 + int(rng.integers(0, 8))]))
         return " ".join([TARGETS[t]] + ctxs + [""] * (C - n))
 
     train = [example() for _ in range(n_train)]
@@ -62,7 +62,7 @@ def _config(prefix, tmp_path, **kw):
     cfg.DEFAULT_EMBEDDINGS_SIZE = cfg.TOKEN_EMBEDDINGS_SIZE = cfg.PATH_EMBEDDINGS_SIZE = 16
     cfg.CODE_VECTOR_SIZE = cfg.TARGET_EMBEDDINGS_SIZE = 48
     cfg.TRAIN_BATCH_SIZE = cfg.TEST_BATCH_SIZE = 32
-    cfg.NUM_TRAIN_EPOCHS = 40
+    cfg.NUM_TRAIN_EPOCHS = 150
     cfg.SAVE_EVERY_EPOCHS = 1000
     cfg.NUM_BATCHES_TO_LOG_PROGRESS = 50
     cfg.SHUFFLE_BUFFER_SIZE = 64
