@@ -31,7 +31,7 @@ constexpr int kSplitDw = 48;   // split-K slices for dW = X'^T . dU  (K = B*C)
 
 // Carve-up of the caller-provided workspace (offsets in bytes).
 struct Workspace {
-  size_t H, Xg, alpha, v, dv, S, loss_b, lse, loss, part, da_part;
+  size_t H, Xg, alpha, v, dv, S, loss_b, lse, loss, part, da_part, lse_part;
   size_t st_src, st_pth, st_tgt, st_mask, st_target, st_topk_idx, st_topk_val, st_code, st_attn;
   size_t total;
   size_t ldS;
@@ -69,6 +69,7 @@ Workspace carve(const c2v_dims& d) {
   if ((size_t)kSplitDw * X * D > part) part = (size_t)kSplitDw * X * D;
   w.part = take(part * 4);
   w.da_part = take(B * D * 4);
+  w.lse_part = take(B * (((size_t)d.target_vocab + 255) / 256) * 8);   // (max, sum exp) per (row, 256-col logits tile)
   w.st_src = take(N * 4);
   w.st_pth = take(N * 4);
   w.st_tgt = take(N * 4);
@@ -266,14 +267,20 @@ int run_ctx_fwd(c2v_engine* e, cudaStream_t st, const ContextSource& cs, const D
 }
 
 // S[B, Y] = v . Ytab^T   (tensorflow_model.py:226,297)
-int run_logits(c2v_engine* e, cudaStream_t st, const float* v, int B, float* S) {
+// with_lse (tf32 path only): also emit per-(row, 256-column tile) log-sum-exp partials into ws.lse_part.
+int run_logits(c2v_engine* e, cudaStream_t st, const float* v, int B, float* S, bool with_lse = false) {
   const int D = e->dims.code_dim, Y = e->dims.target_vocab;
   PhaseTimer pt(e, PH_LOGITS, st);
   if (e->math_mode == C2V_MATH_TF32 && (reinterpret_cast<uintptr_t>(v) % 16 == 0)) {
     umma::Operand opA{v, (size_t)D, false};
     umma::Operand opB{e->theta.tgt, (size_t)D, false};
-    umma::EpiStore ep{S, e->ws.ldS, 0};
-    C2V_LAUNCH(e, C2V_CUDA(e, (umma::launch<256, 4>(st, B, Y, D, 1, opA, opB, ep, e->num_sms))));
+    if (with_lse) {
+      umma::EpiStoreLse ep{S, e->ws.ldS, wsp<float2>(e, e->ws.lse_part), (Y + 255) / 256};
+      C2V_LAUNCH(e, C2V_CUDA(e, (umma::launch<256, 4>(st, B, Y, D, 1, opA, opB, ep, e->num_sms))));
+    } else {
+      umma::EpiStore ep{S, e->ws.ldS, 0};
+      C2V_LAUNCH(e, C2V_CUDA(e, (umma::launch<256, 4>(st, B, Y, D, 1, opA, opB, ep, e->num_sms))));
+    }
     return C2V_OK;
   }
   simt::RowsK al{v, (size_t)D};
@@ -393,11 +400,20 @@ int train_step_impl(c2v_engine* e, cudaStream_t st, const int32_t* src, const in
   int rc;
   if ((rc = run_ctx_fwd(e, st, cs, dp, H))) return rc;
   if ((rc = launch_attn_fwd(e, st, H, mask, B, alpha, v))) return rc;
-  if ((rc = run_logits(e, st, v, B, S))) return rc;
+  const bool fused_lse = (e->math_mode == C2V_MATH_TF32);
+  if ((rc = run_logits(e, st, v, B, S, fused_lse))) return rc;
   const float invB = 1.0f / (float)B;
   {
     PhaseTimer pt(e, PH_XENT, st);
-    C2V_LAUNCH(e, (xent_kernel<<<B, kXentThreads, 0, st>>>(S, e->ws.ldS, target, Y, invB, loss_b, lse, 1)));
+    if (fused_lse) {
+      const int n_tiles = (Y + 255) / 256;
+      C2V_LAUNCH(e, (xent_combine_kernel<<<B, 256, 0, st>>>(wsp<float2>(e, e->ws.lse_part), n_tiles, S, e->ws.ldS, target,
+                                                            loss_b, lse)));
+      const int chunks = (int)((e->ws.ldS / 4 + 256 * 8 - 1) / (256 * 8));
+      C2V_LAUNCH(e, (softmax_grad_kernel<<<dim3(chunks, B), 256, 0, st>>>(S, e->ws.ldS, Y, lse, target, invB)));
+    } else {
+      C2V_LAUNCH(e, (xent_kernel<<<B, kXentThreads, 0, st>>>(S, e->ws.ldS, target, Y, invB, loss_b, lse, 1)));
+    }
     C2V_LAUNCH(e, (loss_reduce_kernel<<<1, 256, 0, st>>>(loss_b, B, invB, loss_out)));
   }
   if (e->math_mode == C2V_MATH_TF32) {

@@ -267,6 +267,54 @@ xent_kernel(float* __restrict__ S, size_t ldS, const int32_t* __restrict__ targe
   }
 }
 
+// tf32 path: the logits GEMM epilogue already produced per-(row, n-tile) (max, sum exp) partials.
+// xent_combine_kernel: lse_b from the partials, loss_b = lse_b - S[b, y_b].   One CTA per row.
+__global__ void __launch_bounds__(256)
+xent_combine_kernel(const float2* __restrict__ partial, int n_tiles, const float* __restrict__ S, size_t ldS,
+                    const int32_t* __restrict__ target, float* __restrict__ loss_b, float* __restrict__ lse_out) {
+  __shared__ float red[32];
+  const int b = blockIdx.x;
+  const float2* p = partial + (size_t)b * n_tiles;
+  float m = -INFINITY;
+  for (int i = threadIdx.x; i < n_tiles; i += 256) m = fmaxf(m, p[i].x);
+  const float M = block_max(m, red);
+  float s = 0.f;
+  for (int i = threadIdx.x; i < n_tiles; i += 256) {
+    const float2 v = p[i];
+    if (v.x > -INFINITY) s += v.y * expf(v.x - M);
+  }
+  s = block_sum(s, red);
+  if (threadIdx.x == 0) {
+    const float lse = M + logf(s);
+    lse_out[b] = lse;
+    loss_b[b] = lse - S[(size_t)b * ldS + target[b]];
+  }
+}
+
+// S <- (softmax(S) - onehot(target)) * inv_batch in place, padding columns zeroed.  grid (chunks, B).
+__global__ void __launch_bounds__(256)
+softmax_grad_kernel(float* __restrict__ S, size_t ldS, int Y, const float* __restrict__ lse, const int32_t* __restrict__ target,
+                    float inv_batch) {
+  const int b = blockIdx.y;
+  float* row = S + (size_t)b * ldS;
+  const float l = lse[b];
+  const int y = target[b];
+  const int n4 = (int)(ldS >> 2);
+  for (int q = blockIdx.x * 256 + threadIdx.x; q < n4; q += gridDim.x * 256) {
+    const int j = 4 * q;
+    float4 x = *reinterpret_cast<const float4*>(row + j);
+    x.x = (j + 0 < Y) ? expf(x.x - l) * inv_batch : 0.f;
+    x.y = (j + 1 < Y) ? expf(x.y - l) * inv_batch : 0.f;
+    x.z = (j + 2 < Y) ? expf(x.z - l) * inv_batch : 0.f;
+    x.w = (j + 3 < Y) ? expf(x.w - l) * inv_batch : 0.f;
+    if (y >= j && y < j + 4) {
+      if (y == j) x.x -= inv_batch; else if (y == j + 1) x.y -= inv_batch;
+      else if (y == j + 2) x.z -= inv_batch; else x.w -= inv_batch;
+    }
+    *reinterpret_cast<float4*>(row + j) = x;
+  }
+}
+
 // loss = (sum_b loss_b) * inv_batch, fixed summation order.
 __global__ void __launch_bounds__(256) loss_reduce_kernel(const float* __restrict__ loss_b, int B, float inv_batch,
                                                           float* __restrict__ out) {

@@ -122,12 +122,19 @@ __host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N, bool a_mn, 
          ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
-// ---- epilogues: (row m, column n0, 32 accumulators for columns n0..n0+31, nvalid columns) -------------
+// ---- epilogues ---------------------------------------------------------------------------------------
+// Per output tile each epilogue thread owns one row m: begin(state); then for every 32-column
+// chunk operator()(m, n0, 32 accumulators, nvalid columns, split, state); then end(...).
+struct EpiNoState {};
+
 struct EpiStore {
+  using State = EpiNoState;
   float* C;
   size_t ldc;
   size_t split_stride;
-  __device__ __forceinline__ void operator()(int m, int n, const uint32_t (&r)[32], int nvalid, int split) const {
+  __device__ __forceinline__ void begin(State&) const {}
+  __device__ __forceinline__ void end(int, int, int, bool, State&) const {}
+  __device__ __forceinline__ void operator()(int m, int n, const uint32_t (&r)[32], int nvalid, int split, State&) const {
     float* p = C + (size_t)split * split_stride + (size_t)m * ldc + n;
     if (nvalid >= 32) {
 #pragma unroll
@@ -142,9 +149,12 @@ struct EpiStore {
   }
 };
 struct EpiTanhStore {
+  using State = EpiNoState;
   float* C;
   size_t ldc;
-  __device__ __forceinline__ void operator()(int m, int n, const uint32_t (&r)[32], int nvalid, int) const {
+  __device__ __forceinline__ void begin(State&) const {}
+  __device__ __forceinline__ void end(int, int, int, bool, State&) const {}
+  __device__ __forceinline__ void operator()(int m, int n, const uint32_t (&r)[32], int nvalid, int, State&) const {
     float* p = C + (size_t)m * ldc + n;
     if (nvalid >= 32) {
 #pragma unroll
@@ -159,11 +169,50 @@ struct EpiTanhStore {
   }
 };
 
+// Logits epilogue: stores the tile of S and folds the row-wise (max, sum exp) of this tile's columns
+// into a per-(row, n-tile) partial, so the cross entropy needs no extra pass over S for its
+// log-sum-exp (tensorflow_model.py:227-230).
+struct LsePartial { float mx, sum; };
+struct EpiStoreLse {
+  struct State { float mx, sum; };
+  float* C;
+  size_t ldc;
+  float2* partial;       // [M, n_tiles]
+  int n_tiles;
+  __device__ __forceinline__ void begin(State& st) const { st.mx = -INFINITY; st.sum = 0.f; }
+  __device__ __forceinline__ void end(int m, int nt, int, bool row_ok, State& st) const {
+    if (row_ok) partial[(size_t)m * n_tiles + nt] = make_float2(st.mx, st.sum);
+  }
+  __device__ __forceinline__ void operator()(int m, int n, const uint32_t (&r)[32], int nvalid, int, State& st) const {
+    float* p = C + (size_t)m * ldc + n;
+    float cm = -INFINITY;
+    if (nvalid >= 32) {
+#pragma unroll
+      for (int j = 0; j < 32; j += 4)
+        *reinterpret_cast<float4*>(p + j) = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]),
+                                                        __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
+#pragma unroll
+      for (int j = 0; j < 32; ++j) cm = fmaxf(cm, __uint_as_float(r[j]));
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (j < nvalid) { p[j] = __uint_as_float(r[j]); cm = fmaxf(cm, __uint_as_float(r[j])); }
+    }
+    if (cm > st.mx) { st.sum *= expf(st.mx - cm); st.mx = cm; }
+    float acc = 0.f;
+#pragma unroll
+    for (int j = 0; j < 32; ++j)
+      if (j < nvalid) acc += expf(__uint_as_float(r[j]) - st.mx);
+    st.sum += acc;
+  }
+};
+
 // ---- kernel -------------------------------------------------------------------------------------------
 struct GemmShape {
   int M, N, K;
   int m_tiles, n_tiles, splits;
   int kblocks_per_split;      // K blocks (of BK) per split-K slice
+  int n_fastest;              // raster order of work items: 1 = consecutive items share the A tile
 };
 
 template <int BN, int STAGES>
@@ -205,10 +254,17 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
   // work item -> (m tile, n tile, split): m fastest so CTAs running together share B tiles in L2
   auto decode = [&](int item, int& mt, int& nt, int& sp) {
-    mt = item % gs.m_tiles;
-    const int r = item / gs.m_tiles;
-    nt = r % gs.n_tiles;
-    sp = r / gs.n_tiles;
+    if (gs.n_fastest) {
+      nt = item % gs.n_tiles;
+      const int r = item / gs.n_tiles;
+      mt = r % gs.m_tiles;
+      sp = r / gs.m_tiles;
+    } else {
+      mt = item % gs.m_tiles;
+      const int r = item / gs.m_tiles;
+      nt = r % gs.n_tiles;
+      sp = r / gs.n_tiles;
+    }
   };
 
   if (warp == 0) {
@@ -300,14 +356,17 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       tc_fence_after();
       const int m = mt * BM + q * 32 + lane;
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN;
+      typename Epi::State est;
+      epi.begin(est);
 #pragma unroll 1
       for (int c = 0; c < BN / 32; ++c) {
         uint32_t r[32];
         tmem_ld32(taddr + c * 32, r);
         tmem_ld_wait();
         const int n = nt * BN + c * 32;
-        if (m < gs.M && n < gs.N) epi(m, n, r, gs.N - n, sp);
+        if (m < gs.M && n < gs.N) epi(m, n, r, gs.N - n, sp, est);
       }
+      epi.end(m, nt, sp, m < gs.M, est);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty_bar[acc]);
@@ -378,6 +437,8 @@ inline cudaError_t launch_cfg(cudaStream_t st, int M, int N, int K, int splits, 
   if (splits > total_kblocks) splits = total_kblocks;
   gs.kblocks_per_split = (total_kblocks + splits - 1) / splits;
   gs.splits = (total_kblocks + gs.kblocks_per_split - 1) / gs.kblocks_per_split;
+  // few, wide n-tiles under many m-tiles: walk n fastest so the (large) A tile is fetched from HBM once
+  gs.n_fastest = (gs.n_tiles < gs.m_tiles) ? 1 : 0;
   auto kern = umma_gemm_kernel<BN, STAGES, A_MN, B_MN, Epi>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal);
   if (e != cudaSuccess) return e;
