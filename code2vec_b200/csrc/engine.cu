@@ -31,7 +31,7 @@ constexpr int kSplitDw = 48;   // split-K slices for dW = X'^T . dU  (K = B*C)
 
 // Carve-up of the caller-provided workspace (offsets in bytes).
 struct Workspace {
-  size_t H, Xg, alpha, v, dv, S, loss_b, lse, loss, part, da_part, lse_part;
+  size_t H, Xg, alpha, v, dv, S, loss_b, lse, loss, part, da_part, lse_part, dl;
   size_t st_src, st_pth, st_tgt, st_mask, st_target, st_topk_idx, st_topk_val, st_code, st_attn;
   size_t total;
   size_t ldS;
@@ -69,7 +69,8 @@ Workspace carve(const c2v_dims& d) {
   if ((size_t)kSplitDw * X * D > part) part = (size_t)kSplitDw * X * D;
   w.part = take(part * 4);
   w.da_part = take(B * D * 4);
-  w.lse_part = take(B * (((size_t)d.target_vocab + 255) / 256) * 8);   // (max, sum exp) per (row, 256-col logits tile)
+  w.lse_part = take(B * 2 * (((size_t)d.target_vocab + 255) / 256) * 8);   // (max, sum exp) per (row, 128-col half tile)
+  w.dl = take(B * (size_t)(kMaxSampled + 1) * 4);     // sampled softmax: dL/dlogits [B, 1+S]
   w.st_src = take(N * 4);
   w.st_pth = take(N * 4);
   w.st_tgt = take(N * 4);
@@ -275,7 +276,7 @@ int run_logits(c2v_engine* e, cudaStream_t st, const float* v, int B, float* S, 
     umma::Operand opA{v, (size_t)D, false};
     umma::Operand opB{e->theta.tgt, (size_t)D, false};
     if (with_lse) {
-      umma::EpiStoreLse ep{S, e->ws.ldS, wsp<float2>(e, e->ws.lse_part), (Y + 255) / 256};
+      umma::EpiStoreLse ep{S, e->ws.ldS, wsp<float2>(e, e->ws.lse_part), 2 * ((Y + 255) / 256)};
       C2V_LAUNCH(e, C2V_CUDA(e, (umma::launch<256, 4>(st, B, Y, D, 1, opA, opB, ep, e->num_sms))));
     } else {
       umma::EpiStore ep{S, e->ws.ldS, 0};
@@ -406,7 +407,7 @@ int train_step_impl(c2v_engine* e, cudaStream_t st, const int32_t* src, const in
   {
     PhaseTimer pt(e, PH_XENT, st);
     if (fused_lse) {
-      const int n_tiles = (Y + 255) / 256;
+      const int n_tiles = 2 * ((Y + 255) / 256);       // partial slots per row
       C2V_LAUNCH(e, (xent_combine_kernel<<<B, 256, 0, st>>>(wsp<float2>(e, e->ws.lse_part), n_tiles, S, e->ws.ldS, target,
                                                             loss_b, lse)));
       const int chunks = (int)((e->ws.ldS / 4 + 256 * 8 - 1) / (256 * 8));
@@ -451,6 +452,40 @@ int train_step_impl(c2v_engine* e, cudaStream_t st, const int32_t* src, const in
     simt::ColsX bl{v, (size_t)D};
     simt::StoreC ep{e->grad.tgt, (size_t)D, 0};
     C2V_LAUNCH(e, C2V_CUDA(e, simt::launch(st, Y, D, B, 1, al, bl, ep)));
+  }
+  if (e->ev_tgt_ready) C2V_CUDA(e, cudaEventRecord(e->ev_tgt_ready, st));
+  return context_backward(e, st, cs, mask, B, dp, dv);
+}
+
+int sampled_train_step_impl(c2v_engine* e, cudaStream_t st, const int32_t* src, const int32_t* pth, const int32_t* tgt,
+                             const float* mask, const int32_t* target, int B, const int32_t* sampled, int S,
+                             const float* logq_true, const float* logq_samp, float keep, uint64_t seed, uint64_t step,
+                             const float* ext_mask, float* loss_out) {
+  if (!e->has_grad) return fail(e, C2V_ERR_STATE, "gradients not bound (c2v_bind_grads)");
+  if (!(keep > 0.f) || keep > 1.f) return fail(e, C2V_ERR_INVALID, "keep_prob must be in (0, 1]");
+  if (S < 1 || S > kMaxSampled) return fail(e, C2V_ERR_INVALID, "number of sampled classes must be in [1, 1024]");
+  const int D = e->dims.code_dim;
+  const Dropout dp = make_dropout(e->dims, keep, seed, step, ext_mask);
+  ContextSource cs = make_source(e, src, pth, tgt, B);
+  float* H = wsp<float>(e, e->ws.H);
+  float* alpha = wsp<float>(e, e->ws.alpha);
+  float* v = wsp<float>(e, e->ws.v);
+  float* dv = wsp<float>(e, e->ws.dv);
+  float* loss_b = wsp<float>(e, e->ws.loss_b);
+  float* dl = wsp<float>(e, e->ws.dl);
+  int rc;
+  if ((rc = run_ctx_fwd(e, st, cs, dp, H))) return rc;
+  if ((rc = launch_attn_fwd(e, st, H, mask, B, alpha, v))) return rc;
+  const float invB = 1.0f / (float)B;
+  {
+    PhaseTimer pt(e, PH_SAMPLED, st);
+    const size_t smem = ((size_t)D + S + 1) * sizeof(float);
+    C2V_LAUNCH(e, (sampled_softmax_fwd_kernel<<<B, kSampledThreads, smem, st>>>(v, e->theta.tgt, target, sampled, S, logq_true,
+                                                                                 logq_samp, D, invB, loss_b, dl, dv)));
+    C2V_LAUNCH(e, (loss_reduce_kernel<<<1, 256, 0, st>>>(loss_b, B, invB, loss_out)));
+    // the target-table gradient is sparse here (B + S rows); the bound buffer is dense, so clear it first
+    C2V_CUDA(e, cudaMemsetAsync(e->grad.tgt, 0, (size_t)e->dims.target_vocab * D * 4, st));
+    C2V_LAUNCH(e, (sampled_softmax_bwd_kernel<<<B + S, kSampledThreads, 0, st>>>(v, dl, target, sampled, B, S, D, e->grad.tgt)));
   }
   if (e->ev_tgt_ready) C2V_CUDA(e, cudaEventRecord(e->ev_tgt_ready, st));
   return context_backward(e, st, cs, mask, B, dp, dv);
@@ -634,10 +669,17 @@ int c2v_train_step(c2v_engine* e, const int32_t* src, const int32_t* path, const
                          dropout_mask, loss_out);
 }
 
-int c2v_sampled_train_step(c2v_engine* e, const int32_t*, const int32_t*, const int32_t*, const float*,
-                           const int32_t*, int32_t, const int32_t*, int32_t, const float*, const float*, float,
-                           uint64_t, uint64_t, const float*, float*, void*) {
-  return fail(e, C2V_ERR_UNSUPPORTED, "sampled softmax not built yet");
+int c2v_sampled_train_step(c2v_engine* e, const int32_t* src, const int32_t* path, const int32_t* tgt, const float* mask,
+                           const int32_t* target, int32_t B, const int32_t* sampled, int32_t S, const float* logq_true,
+                           const float* logq_sampled, float keep_prob, uint64_t seed, uint64_t step,
+                           const float* dropout_mask, float* loss_out, void* stream) {
+  int rc = check_batch(e, B);
+  if (rc) return rc;
+  if (!src || !path || !tgt || !mask || !target || !sampled || !logq_true || !logq_sampled || !loss_out)
+    return fail(e, C2V_ERR_INVALID, "NULL argument");
+  C2V_CUDA(e, cudaSetDevice(e->device));
+  return sampled_train_step_impl(e, (cudaStream_t)stream, src, path, tgt, mask, target, B, sampled, S, logq_true,
+                                 logq_sampled, keep_prob, seed, step, dropout_mask, loss_out);
 }
 
 int c2v_adam_step(c2v_engine* e, float lr, float beta1, float beta2, float eps, int64_t t, void* stream) {

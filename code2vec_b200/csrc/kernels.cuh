@@ -315,6 +315,90 @@ softmax_grad_kernel(float* __restrict__ S, size_t ldS, int Y, const float* __res
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Sampled softmax (BASELINE config 3; NOT in the reference, definition in DESIGN.md section 5 after
+// tf.nn.sampled_softmax_loss): logits over {target_b} U sampled[0..S) minus log expected counts,
+// accidental hits masked, cross entropy with the true class in column 0.  One CTA per example:
+// logits, softmax, dl = (p - onehot)/B, loss_b and dv_b = sum_j dl_j * Ytab[row_j].
+// ---------------------------------------------------------------------------------------------
+constexpr int kSampledThreads = 128;
+constexpr int kMaxSampled = 1024;
+
+__global__ void __launch_bounds__(kSampledThreads)
+sampled_softmax_fwd_kernel(const float* __restrict__ v, const float* __restrict__ Ytab, const int32_t* __restrict__ target,
+                           const int32_t* __restrict__ sampled, int S, const float* __restrict__ logq_true,
+                           const float* __restrict__ logq_samp, int D, float inv_batch, float* __restrict__ loss_b,
+                           float* __restrict__ dl, float* __restrict__ dv) {
+  extern __shared__ float sm[];
+  float* vs = sm;                 // [D]
+  float* lg = vs + D;             // [1 + S]
+  __shared__ float red[32];
+  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int y = target[b];
+  for (int i = tid; i < D; i += kSampledThreads) vs[i] = v[(size_t)b * D + i];
+  __syncthreads();
+  for (int j = warp; j <= S; j += kSampledThreads / 32) {
+    const int row = (j == 0) ? y : sampled[j - 1];
+    const float* r = Ytab + (size_t)row * D;
+    float part = 0.f;
+    for (int i = lane * 4; i < D; i += 128) {
+      const float4 a = *reinterpret_cast<const float4*>(r + i);
+      part += a.x * vs[i] + a.y * vs[i + 1] + a.z * vs[i + 2] + a.w * vs[i + 3];
+    }
+    part = warp_sum(part);
+    if (lane == 0) {
+      float l = part - ((j == 0) ? logq_true[b] : logq_samp[j - 1]);
+      if (j > 0 && row == y) l = -1e9f;                     // accidental hit
+      lg[j] = l;
+    }
+  }
+  __syncthreads();
+  float m = -INFINITY;
+  for (int j = tid; j <= S; j += kSampledThreads) m = fmaxf(m, lg[j]);
+  m = block_max(m, red);
+  float s = 0.f;
+  for (int j = tid; j <= S; j += kSampledThreads) s += expf(lg[j] - m);
+  s = block_sum(s, red);
+  const float lse = m + logf(s);
+  if (tid == 0) loss_b[b] = lse - lg[0];
+  __syncthreads();
+  for (int j = tid; j <= S; j += kSampledThreads) {
+    float g = expf(lg[j] - lse);
+    if (j == 0) g -= 1.f;
+    g *= inv_batch;
+    if (j > 0 && sampled[j - 1] == y) g = 0.f;
+    lg[j] = g;
+    dl[(size_t)b * (S + 1) + j] = g;
+  }
+  __syncthreads();
+  for (int i = tid; i < D; i += kSampledThreads) {
+    float acc = lg[0] * Ytab[(size_t)y * D + i];
+    for (int j = 1; j <= S; ++j) acc += lg[j] * Ytab[(size_t)sampled[j - 1] * D + i];
+    dv[(size_t)b * D + i] = acc;
+  }
+}
+
+// target-table gradient of the sampled softmax into a zeroed dense [Y, D] buffer:
+// blocks [0, B): true rows  g[y_b] += dl[b,0] v_b ;  blocks [B, B+S): g[sampled_s] += sum_b dl[b,1+s] v_b.
+__global__ void __launch_bounds__(kSampledThreads)
+sampled_softmax_bwd_kernel(const float* __restrict__ v, const float* __restrict__ dl, const int32_t* __restrict__ target,
+                           const int32_t* __restrict__ sampled, int B, int S, int D, float* __restrict__ g_tgt) {
+  const int blk = blockIdx.x;
+  if (blk < B) {
+    const float g = dl[(size_t)blk * (S + 1)];
+    float* dst = g_tgt + (size_t)target[blk] * D;
+    for (int i = threadIdx.x; i < D; i += kSampledThreads) atomicAdd(dst + i, g * v[(size_t)blk * D + i]);
+  } else {
+    const int s = blk - B;
+    float* dst = g_tgt + (size_t)sampled[s] * D;
+    for (int i = threadIdx.x; i < D; i += kSampledThreads) {
+      float acc = 0.f;
+      for (int b = 0; b < B; ++b) acc += dl[(size_t)b * (S + 1) + 1 + s] * v[(size_t)b * D + i];
+      atomicAdd(dst + i, acc);
+    }
+  }
+}
+
 // loss = (sum_b loss_b) * inv_batch, fixed summation order.
 __global__ void __launch_bounds__(256) loss_reduce_kernel(const float* __restrict__ loss_b, int B, float inv_batch,
                                                           float* __restrict__ out) {

@@ -6,8 +6,9 @@
 //   warp 1      : MMA issuer     -- one elected lane issues tcgen05.mma.cta_group::1.kind::tf32
 //                                   (UMMA 128 x BN x 8), tcgen05.commit frees smem stages / publishes
 //                                   the accumulator; also owns the TMEM allocation
-//   warps 2..5  : epilogue       -- tcgen05.ld (32x32b) of their TMEM lane quadrant, fused epilogue
-//                                   functor (store / tanh / split-K slice), vectorised global stores
+//   warps 2..9  : epilogue       -- tcgen05.ld (32x32b) of their TMEM lane quadrant (two warps per
+//                                   quadrant, half of the columns each), fused epilogue functor
+//                                   (store / tanh / log-sum-exp partials / split-K slice)
 // The accumulator is double-buffered in TMEM (2 x BN columns) so the epilogue of tile i overlaps
 // the MMAs of tile i+1.  Operands may be K-major (K contiguous) or MN-major (M resp. N
 // contiguous) in global memory; both are staged as 128-byte swizzled rows and described to the
@@ -26,8 +27,13 @@ namespace umma {
 constexpr int BM = 128;          // UMMA_M (cta_group::1)
 constexpr int BK = 32;           // fp32 elements per stage along K = one 128-byte swizzle row
 constexpr int UMMA_K = 8;        // K per tcgen05.mma for 32-bit operands (32 bytes)
-constexpr int kThreads = 192;    // 6 warps
+constexpr int kEpiWarps = 8;     // two warps per TMEM lane quadrant, each draining half of the tile's columns
+constexpr int kThreads = 32 * (2 + kEpiWarps);
 constexpr int kEpiWarp0 = 2;
+
+// fast transcendental forms for the tensor-core path (operands are already tf32-rounded):
+// exp via ex2.approx (rel. error 2^-22), tanh(x) = 1 - 2 / (exp(2x) + 1) (abs. error ~1e-7).
+__device__ __forceinline__ float fast_tanh(float x) { return 1.f - __fdividef(2.f, __expf(2.f * x) + 1.f); }
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -159,12 +165,12 @@ struct EpiTanhStore {
     if (nvalid >= 32) {
 #pragma unroll
       for (int j = 0; j < 32; j += 4)
-        *reinterpret_cast<float4*>(p + j) = make_float4(tanhf(__uint_as_float(r[j])), tanhf(__uint_as_float(r[j + 1])),
-                                                        tanhf(__uint_as_float(r[j + 2])), tanhf(__uint_as_float(r[j + 3])));
+        *reinterpret_cast<float4*>(p + j) = make_float4(fast_tanh(__uint_as_float(r[j])), fast_tanh(__uint_as_float(r[j + 1])),
+                                                        fast_tanh(__uint_as_float(r[j + 2])), fast_tanh(__uint_as_float(r[j + 3])));
     } else {
 #pragma unroll
       for (int j = 0; j < 32; ++j)
-        if (j < nvalid) p[j] = tanhf(__uint_as_float(r[j]));
+        if (j < nvalid) p[j] = fast_tanh(__uint_as_float(r[j]));
     }
   }
 };
@@ -177,11 +183,11 @@ struct EpiStoreLse {
   struct State { float mx, sum; };
   float* C;
   size_t ldc;
-  float2* partial;       // [M, n_tiles]
-  int n_tiles;
+  float2* partial;       // [M, slots]; slot = 2 * n_tile + column half
+  int slots;
   __device__ __forceinline__ void begin(State& st) const { st.mx = -INFINITY; st.sum = 0.f; }
-  __device__ __forceinline__ void end(int m, int nt, int, bool row_ok, State& st) const {
-    if (row_ok) partial[(size_t)m * n_tiles + nt] = make_float2(st.mx, st.sum);
+  __device__ __forceinline__ void end(int m, int slot, int, bool row_ok, State& st) const {
+    if (row_ok) partial[(size_t)m * slots + slot] = make_float2(st.mx, st.sum);
   }
   __device__ __forceinline__ void operator()(int m, int n, const uint32_t (&r)[32], int nvalid, int, State& st) const {
     float* p = C + (size_t)m * ldc + n;
@@ -198,12 +204,16 @@ struct EpiStoreLse {
       for (int j = 0; j < 32; ++j)
         if (j < nvalid) { p[j] = __uint_as_float(r[j]); cm = fmaxf(cm, __uint_as_float(r[j])); }
     }
-    if (cm > st.mx) { st.sum *= expf(st.mx - cm); st.mx = cm; }
-    float acc = 0.f;
+    if (cm > st.mx) { st.sum *= __expf(st.mx - cm); st.mx = cm; }
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
 #pragma unroll
-    for (int j = 0; j < 32; ++j)
-      if (j < nvalid) acc += expf(__uint_as_float(r[j]) - st.mx);
-    st.sum += acc;
+    for (int j = 0; j < 32; j += 4) {
+      if (j + 0 < nvalid) a0 += __expf(__uint_as_float(r[j + 0]) - st.mx);
+      if (j + 1 < nvalid) a1 += __expf(__uint_as_float(r[j + 1]) - st.mx);
+      if (j + 2 < nvalid) a2 += __expf(__uint_as_float(r[j + 2]) - st.mx);
+      if (j + 3 < nvalid) a3 += __expf(__uint_as_float(r[j + 3]) - st.mx);
+    }
+    st.sum += (a0 + a1) + (a2 + a3);
   }
 };
 
@@ -243,7 +253,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], 4); }
+    for (int a = 0; a < 2; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], kEpiWarps); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) tmem_alloc(tmem_ptr, kTmemCols);
@@ -346,7 +356,9 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
   } else {
     // ===================== epilogue warps (TMEM lane quadrant = warp % 4) =====================
-    const int q = warp & 3;
+    const int q = warp & 3;                       // TMEM lane quadrant this warp may access
+    const int half = (warp - kEpiWarp0) >> 2;     // which half of the tile's columns it drains
+    constexpr int kChunksPerHalf = BN / 64;
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
@@ -359,14 +371,15 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       typename Epi::State est;
       epi.begin(est);
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
+      for (int cc = 0; cc < kChunksPerHalf; ++cc) {
+        const int c = half * kChunksPerHalf + cc;
         uint32_t r[32];
         tmem_ld32(taddr + c * 32, r);
         tmem_ld_wait();
         const int n = nt * BN + c * 32;
         if (m < gs.M && n < gs.N) epi(m, n, r, gs.N - n, sp, est);
       }
-      epi.end(m, nt, sp, m < gs.M, est);
+      epi.end(m, 2 * nt + half, sp, m < gs.M, est);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty_bar[acc]);

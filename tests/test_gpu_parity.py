@@ -182,3 +182,44 @@ def test_error_behaviour():
     src, pth, tgt, mask, target = O.synthetic_batch(TINY, 8, seed=1)
     with pytest.raises(EngineError):
         eng.forward(*dev_batch(eng, src, pth, tgt, mask))                # B > max_batch
+
+
+@pytest.mark.parametrize("dims,B,S", [(TINY, 64, 25), (ODD, 37, 7), (MID, 48, 25)])
+def test_sampled_softmax_train_step(dims, B, S):
+    """BASELINE config 3.  Not in the reference (tensorflow_model.py:226-230 trains with the full
+    softmax), so this pins the CUDA path to the oracle's stated definition only."""
+    import torch
+    eng, params = make_engine(dims, max_batch=B)
+    src, pth, tgt, mask, target = O.synthetic_batch(dims, B, seed=31)
+    rng = np.random.default_rng(4)
+    sampled = O.log_uniform_sample(rng, S, dims.target_vocab)
+    sampled[0] = target[3]                           # an accidental hit
+    sampled[1] = sampled[2]                          # a duplicate sampled class
+    lq_t = O.log_uniform_logq(target, S, dims.target_vocab)
+    lq_s = O.log_uniform_logq(sampled, S, dims.target_vocab)
+    v_ref, alpha_ref, cache = O.forward(params, src, pth, tgt, mask)
+    loss_ref, dv_ref, g_tgt_ref, _ = O.sampled_softmax_loss_and_grads(params, v_ref, target, sampled, lq_t, lq_s)
+    # context gradients of the oracle given dv (reuse the full-softmax backward with dl replaced): recompute by hand
+    d = dev_batch(eng, src, pth, tgt, mask, target)
+    loss = float(eng.sampled_train_step(*d, eng.to_device(sampled, torch.int32), eng.to_device(lq_t, torch.float32),
+                                        eng.to_device(lq_s, torch.float32)).cpu()[0])
+    assert abs(loss - loss_ref) < LOSS_TOL
+    g = eng.export_grads()
+    assert rel_err(g["tgt"], g_tgt_ref) < 5e-5
+    # chain dv through the oracle's context backward (same code path as the full softmax)
+    hB, C_ = src.shape
+    h = cache.h.reshape(hB, C_, -1)
+    a = params["a"]
+    dalpha = np.einsum("bcd,bd->bc", h, dv_ref)
+    t = (alpha_ref * dalpha).sum(axis=1, keepdims=True)
+    dz = alpha_ref * (dalpha - t)
+    dh = alpha_ref[:, :, None] * dv_ref[:, None, :] + dz[:, :, None] * a[None, None, :]
+    du = (dh * (1.0 - h * h)).reshape(hB * C_, -1).astype(np.float32)
+    assert rel_err(g["a"], np.einsum("bc,bcd->d", dz, h)) < 5e-5
+    assert rel_err(g["W"], cache.x.T @ du) < 5e-5
+    dx = du @ params["W"].T
+    g_tok = np.zeros_like(params["tok"]); g_path = np.zeros_like(params["path"])
+    dd = dims.embed_dim
+    np.add.at(g_tok, src.reshape(-1), dx[:, :dd]); np.add.at(g_path, pth.reshape(-1), dx[:, dd:2 * dd])
+    np.add.at(g_tok, tgt.reshape(-1), dx[:, 2 * dd:])
+    assert rel_err(g["tok"], g_tok) < 5e-5 and rel_err(g["path"], g_path) < 5e-5
