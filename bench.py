@@ -153,7 +153,7 @@ def run_ours(args):
     eng.init_params(seed=4321)                       # replicated: same seed on every rank
     if args.math == "tf32":
         eng.set_option("math_mode", 1)
-    trainer = Trainer(eng, keep_prob=KEEP_PROB, seed=99)
+    trainer = Trainer(eng, keep_prob=KEEP_PROB, seed=99, schedule=args.dp_schedule)
 
     n_batches = 4
     host = make_batches(w, n_batches, seed=1234 + 100003 * rank)
@@ -265,7 +265,7 @@ def run_ours(args):
         "config": {"workload": "java14m-shape train step: T=1301137 P=911418 Y=261246 d=128 D=384 C=200, "
                                "full softmax, dropout keep 0.75, TF1 dense Adam" if args.workload == "java14m" else args.workload,
                    "batch_per_gpu": B, "global_batch": B * world, "contexts_per_example": C,
-                   "parallelism": "dp%d (replicated tables, NCCL grad all-reduce)" % world if world > 1 else "single",
+                   "parallelism": "dp%d (%s)" % (world, trainer.schedule) if world > 1 else "single",
                    "l2": "no flush: >9 GB of parameter/optimizer traffic per step and 4 rotating input batches exceed the 126 MB L2",
                    "math_mode": args.math, "last_loss": round(last_loss, 5)},
         "e2e": {"value": round(e2e_value, 1), "unit": "path-contexts/s", "h2d_bytes_per_step": h2d,
@@ -363,6 +363,8 @@ def main():
     ap.add_argument("--batch", type=int, default=0)
     ap.add_argument("--math", default=os.environ.get("C2V_MATH", "tf32"), choices=["fp32", "tf32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--dp-schedule", default=os.environ.get("C2V_DP_SCHEDULE", "table_sharded"),
+                    choices=["table_sharded", "sharded", "allreduce"])
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -63,14 +63,28 @@ __device__ __forceinline__ float4 dropout_mult4(const Dropout& dp, int row, int 
                      r.z < dp.thr ? dp.scale : 0.f, r.w < dp.thr ? dp.scale : 0.f);
 }
 
+// An embedding table that may be row-sharded over up to 8 GPUs of one NVSwitch domain: global row
+// r lives on shard (r & mask) at local row (r >> shift); base[] holds the local shard and the
+// peers' shards mapped through CUDA IPC, so gathers are plain loads and gradient scatter-adds are
+// plain red.global.add over NVLink.  A replicated / single-GPU table is the 1-shard case.
+constexpr int kMaxShards = 8;
+struct ShardedTable {
+  float* base[kMaxShards];
+  int shift;
+  int mask;
+};
+__device__ __forceinline__ float* table_row(const ShardedTable& t, int idx, int d) {
+  return t.base[idx & t.mask] + (size_t)(idx >> t.shift) * d;
+}
+
 // The three index arrays + two tables that define the gathered context matrix
 // X[n, 0:3d] = [ tok[src[n]] | path[pth[n]] | tok[tgt[n]] ]      (tensorflow_model.py:238-243)
 struct ContextSource {
   const int32_t* src;
   const int32_t* pth;
   const int32_t* tgt;
-  const float* tok;     // [T, d]
-  const float* path;    // [P, d]
+  ShardedTable tok;     // [T, d]
+  ShardedTable path;    // [P, d]
   int d;
   int rows;             // B*C
 };
@@ -79,9 +93,9 @@ struct ContextSource {
 __device__ __forceinline__ const float* ctx_ptr(const ContextSource& cs, int n, int j) {
   const int seg = j / cs.d;
   const int off = j - seg * cs.d;
-  if (seg == 0) return cs.tok + (size_t)__ldg(cs.src + n) * cs.d + off;
-  if (seg == 1) return cs.path + (size_t)__ldg(cs.pth + n) * cs.d + off;
-  return cs.tok + (size_t)__ldg(cs.tgt + n) * cs.d + off;
+  if (seg == 0) return table_row(cs.tok, __ldg(cs.src + n), cs.d) + off;
+  if (seg == 1) return table_row(cs.path, __ldg(cs.pth + n), cs.d) + off;
+  return table_row(cs.tok, __ldg(cs.tgt + n), cs.d) + off;
 }
 
 }  // namespace c2v

@@ -108,6 +108,9 @@ struct c2v_engine {
   char* wbase;
   size_t wbytes;
   c2v_tensors theta, grad, am, av;
+  ShardedTable th_tok{}, th_path{}, gr_tok{}, gr_path{};   // how kernels reach the two embedding tables
+  int table_world = 1;       // > 1: tables are row-sharded over peers (c2v_bind_table_shards)
+  float grad_scale = 1.f;
   bool has_theta, has_grad, has_adam;
   bool emb_grads_clean;      // token/path gradient tables are known to be all-zero
   int math_mode;
@@ -237,7 +240,7 @@ int launch_colsum(c2v_engine* e, cudaStream_t st, const float* in, size_t stride
 ContextSource make_source(c2v_engine* e, const int32_t* src, const int32_t* pth, const int32_t* tgt, int B) {
   ContextSource cs{};
   cs.src = src; cs.pth = pth; cs.tgt = tgt;
-  cs.tok = e->theta.tok; cs.path = e->theta.path;
+  cs.tok = e->th_tok; cs.path = e->th_path;
   cs.d = e->dims.embed_dim;
   cs.rows = B * e->dims.max_contexts;
   return cs;
@@ -346,13 +349,13 @@ int context_backward(c2v_engine* e, cudaStream_t st, const ContextSource& cs, co
       umma::EpiStore ep{Xg, (size_t)K3, 0};
       C2V_LAUNCH(e, C2V_CUDA(e, (umma::launch<192, 5>(st, N, K3, D, 1, opA, opB, ep, e->num_sms))));
     }
-    if (!e->emb_grads_clean) {
+    if (!e->emb_grads_clean && e->table_world == 1) {
       C2V_CUDA(e, cudaMemsetAsync(e->grad.tok, 0, (size_t)e->dims.token_vocab * d * 4, st));
       C2V_CUDA(e, cudaMemsetAsync(e->grad.path, 0, (size_t)e->dims.path_vocab * d * 4, st));
     }
     {
       PhaseTimer pt(e, PH_DX_SCATTER, st);
-      C2V_LAUNCH(e, (scatter_dx_kernel<<<(N + 7) / 8, 256, 0, st>>>(cs, dp, mask, Xg, e->grad.tok, e->grad.path)));
+      C2V_LAUNCH(e, (scatter_dx_kernel<<<(N + 7) / 8, 256, 0, st>>>(cs, dp, mask, Xg, e->gr_tok, e->gr_path, e->grad_scale)));
     }
     e->emb_grads_clean = false;
     return C2V_OK;
@@ -368,14 +371,14 @@ int context_backward(c2v_engine* e, cudaStream_t st, const ContextSource& cs, co
     if (rc) return rc;
   }
   {  // dX' = dU . W^T -> dropout backward -> scatter-add into the embedding gradient tables
-    if (!e->emb_grads_clean) {
+    if (!e->emb_grads_clean && e->table_world == 1) {
       C2V_CUDA(e, cudaMemsetAsync(e->grad.tok, 0, (size_t)e->dims.token_vocab * d * 4, st));
       C2V_CUDA(e, cudaMemsetAsync(e->grad.path, 0, (size_t)e->dims.path_vocab * d * 4, st));
     }
     PhaseTimer pt(e, PH_DX_SCATTER, st);
     simt::RowsK al{H, (size_t)D};
     simt::RowsK bl{e->theta.W, (size_t)D};
-    simt::ScatterDx ep{cs, e->grad.tok, e->grad.path, mask, dp};
+    simt::ScatterDx ep{cs, e->gr_tok, e->gr_path, mask, dp, e->grad_scale};
     C2V_LAUNCH(e, C2V_CUDA(e, simt::launch(st, N, K3, D, 1, al, bl, ep)));
     e->emb_grads_clean = false;
   }
@@ -493,6 +496,8 @@ int sampled_train_step_impl(c2v_engine* e, cudaStream_t st, const int32_t* src, 
 
 int adam_impl(c2v_engine* e, cudaStream_t st, float lr, float b1, float b2, float eps, int64_t t) {
   if (!e->has_grad || !e->has_adam) return fail(e, C2V_ERR_STATE, "gradients / Adam state not bound");
+  if (e->table_world > 1)
+    return fail(e, C2V_ERR_STATE, "embedding tables are sharded: update each slice with c2v_adam_step_range");
   if (t < 1) return fail(e, C2V_ERR_INVALID, "Adam step count t must be >= 1");
   const double lr_t_d = (double)lr * sqrt(1.0 - pow((double)b2, (double)t)) / (1.0 - pow((double)b1, (double)t));
   const float lr_t = (float)lr_t_d;
@@ -585,6 +590,9 @@ int c2v_bind_params(c2v_engine* e, const c2v_tensors* t) {
   if (!e) return C2V_ERR_INVALID;
   if (!has_all(t)) return fail(e, C2V_ERR_INVALID, "all five parameter pointers must be non-NULL");
   e->theta = *t; e->has_theta = true;
+  e->th_tok = ShardedTable{}; e->th_path = ShardedTable{};
+  e->th_tok.base[0] = t->tok; e->th_path.base[0] = t->path;
+  e->table_world = 1; e->grad_scale = 1.f;
   return C2V_OK;
 }
 
@@ -592,6 +600,8 @@ int c2v_bind_grads(c2v_engine* e, const c2v_tensors* t) {
   if (!e) return C2V_ERR_INVALID;
   if (!has_all(t)) return fail(e, C2V_ERR_INVALID, "all five gradient pointers must be non-NULL");
   e->grad = *t; e->has_grad = true; e->emb_grads_clean = false;
+  e->gr_tok = ShardedTable{}; e->gr_path = ShardedTable{};
+  e->gr_tok.base[0] = t->tok; e->gr_path.base[0] = t->path;
   return C2V_OK;
 }
 
@@ -689,14 +699,71 @@ int c2v_adam_step(c2v_engine* e, float lr, float beta1, float beta2, float eps, 
   return adam_impl(e, (cudaStream_t)stream, lr, beta1, beta2, eps, t);
 }
 
+int c2v_bind_table_shards(c2v_engine* e, const c2v_table_shards* params, const c2v_table_shards* grads, float grad_scale) {
+  if (!e) return C2V_ERR_INVALID;
+  if (!params) return fail(e, C2V_ERR_INVALID, "params shards are NULL");
+  if (!e->has_theta) return fail(e, C2V_ERR_STATE, "bind the replicated tensors first (c2v_bind_params)");
+  const int w = params->world;
+  if (!(w == 1 || w == 2 || w == 4 || w == 8)) return fail(e, C2V_ERR_INVALID, "world must be 1, 2, 4 or 8");
+  if (grads && grads->world != w) return fail(e, C2V_ERR_INVALID, "params / grads world mismatch");
+  int shift = 0;
+  while ((1 << shift) < w) ++shift;
+  auto fill = [&](ShardedTable& t, float* const* ptrs) -> bool {
+    t = ShardedTable{};
+    t.shift = shift; t.mask = w - 1;
+    for (int i = 0; i < w; ++i) { if (!ptrs[i]) return false; t.base[i] = ptrs[i]; }
+    return true;
+  };
+  if (!fill(e->th_tok, params->tok) || !fill(e->th_path, params->path)) return fail(e, C2V_ERR_INVALID, "NULL shard pointer");
+  if (grads) {
+    if (!fill(e->gr_tok, grads->tok) || !fill(e->gr_path, grads->path)) return fail(e, C2V_ERR_INVALID, "NULL shard pointer");
+  }
+  e->table_world = w;
+  e->grad_scale = grad_scale;
+  return C2V_OK;
+}
+
+int c2v_ipc_alloc(int device, size_t bytes, void** dev_ptr, unsigned char* handle64) {
+  if (!dev_ptr || !handle64 || bytes == 0) return fail(nullptr, C2V_ERR_INVALID, "bad argument");
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  C2V_CUDA((c2v_engine*)nullptr, cudaSetDevice(device));
+  C2V_CUDA((c2v_engine*)nullptr, cudaMalloc(dev_ptr, bytes));
+  C2V_CUDA((c2v_engine*)nullptr, cudaMemset(*dev_ptr, 0, bytes));
+  cudaIpcMemHandle_t h;
+  C2V_CUDA((c2v_engine*)nullptr, cudaIpcGetMemHandle(&h, *dev_ptr));
+  memcpy(handle64, &h, 64);
+  return C2V_OK;
+}
+
+int c2v_ipc_open(int device, const unsigned char* handle64, void** dev_ptr) {
+  if (!dev_ptr || !handle64) return fail(nullptr, C2V_ERR_INVALID, "bad argument");
+  C2V_CUDA((c2v_engine*)nullptr, cudaSetDevice(device));
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle64, 64);
+  C2V_CUDA((c2v_engine*)nullptr, cudaIpcOpenMemHandle(dev_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+  return C2V_OK;
+}
+
+int c2v_ipc_close(int device, void* dev_ptr) {
+  C2V_CUDA((c2v_engine*)nullptr, cudaSetDevice(device));
+  C2V_CUDA((c2v_engine*)nullptr, cudaIpcCloseMemHandle(dev_ptr));
+  return C2V_OK;
+}
+
+int c2v_ipc_free(int device, void* dev_ptr) {
+  C2V_CUDA((c2v_engine*)nullptr, cudaSetDevice(device));
+  C2V_CUDA((c2v_engine*)nullptr, cudaFree(dev_ptr));
+  return C2V_OK;
+}
+
 int c2v_set_event(c2v_engine* e, const char* name, void* cuda_event) {
   if (!e || !name) return C2V_ERR_INVALID;
   if (!strcmp(name, "target_grads_ready")) { e->ev_tgt_ready = (cudaEvent_t)cuda_event; return C2V_OK; }
   return fail(e, C2V_ERR_INVALID, std::string("unknown event: ") + name);
 }
 
-int c2v_adam_step_range(c2v_engine* e, float* theta, const float* grad, float* m, float* v, size_t count, float lr,
-                        float beta1, float beta2, float eps, int64_t t, void* stream) {
+int c2v_adam_step_range(c2v_engine* e, float* theta, float* grad, float* m, float* v, size_t count, float lr,
+                        float beta1, float beta2, float eps, int64_t t, int32_t zero_grad, void* stream) {
   if (!e) return C2V_ERR_INVALID;
   if (!theta || !grad || !m || !v) return fail(e, C2V_ERR_INVALID, "NULL argument");
   if (count % 4 || ((uintptr_t)theta | (uintptr_t)grad | (uintptr_t)m | (uintptr_t)v) % 16)
@@ -710,8 +777,8 @@ int c2v_adam_step_range(c2v_engine* e, float* theta, const float* grad, float* m
   size_t blocks = (n4 + 255) / 256;
   if (blocks > (size_t)e->num_sms * 16) blocks = (size_t)e->num_sms * 16;
   PhaseTimer pt(e, PH_ADAM, st);
-  C2V_LAUNCH(e, (adam_kernel<<<(unsigned)blocks, 256, 0, st>>>(theta, const_cast<float*>(grad), m, v, n4, lr_t, beta1, beta2,
-                                                               eps, 0)));
+  C2V_LAUNCH(e, (adam_kernel<<<(unsigned)blocks, 256, 0, st>>>(theta, grad, m, v, n4, lr_t, beta1, beta2, eps,
+                                                               zero_grad ? 1 : 0)));
   return C2V_OK;
 }
 

@@ -599,7 +599,7 @@ __global__ void __launch_bounds__(256) gather_ctx_kernel(ContextSource cs, Dropo
 
 __global__ void __launch_bounds__(256)
 scatter_dx_kernel(ContextSource cs, Dropout dp, const float* __restrict__ mask, const float* __restrict__ dXg,
-                  float* __restrict__ g_tok, float* __restrict__ g_path) {
+                  ShardedTable g_tok, ShardedTable g_path, float grad_scale) {
   const int n = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (n >= cs.rows) return;
   if (mask[n] == 0.f) return;                 // masked contexts carry exact zeros
@@ -608,12 +608,12 @@ scatter_dx_kernel(ContextSource cs, Dropout dp, const float* __restrict__ mask, 
   for (int j = lane * 4; j < K3; j += 128) {
     float4 g = *reinterpret_cast<const float4*>(src + j);
     const float4 m = dropout_mult4(dp, n, j >> 2);
-    g.x *= m.x; g.y *= m.y; g.z *= m.z; g.w *= m.w;
+    g.x *= m.x * grad_scale; g.y *= m.y * grad_scale; g.z *= m.z * grad_scale; g.w *= m.w * grad_scale;
     const int seg = j / cs.d, off = j - seg * cs.d;
     float* dst;
-    if (seg == 0) dst = g_tok + (size_t)cs.src[n] * cs.d + off;
-    else if (seg == 1) dst = g_path + (size_t)cs.pth[n] * cs.d + off;
-    else dst = g_tok + (size_t)cs.tgt[n] * cs.d + off;
+    if (seg == 0) dst = table_row(g_tok, cs.src[n], cs.d) + off;
+    else if (seg == 1) dst = table_row(g_path, cs.pth[n], cs.d) + off;
+    else dst = table_row(g_tok, cs.tgt[n], cs.d) + off;
     atomicAdd(reinterpret_cast<float4*>(dst), g);
   }
 }

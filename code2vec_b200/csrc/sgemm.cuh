@@ -123,21 +123,23 @@ struct TanhStore {
 // (autodiff of the three tf.nn.embedding_lookup calls: IndexedSlices summed densely.)
 // Masked contexts carry exact zeros (alpha == 0) and are skipped.
 struct ScatterDx {
-  ContextSource cs;      // tok/path here are the GRADIENT tables
-  float* g_tok;
-  float* g_path;
+  ContextSource cs;      // indices (the parameter tables in it are not used here)
+  ShardedTable g_tok;    // gradient tables (possibly peer shards)
+  ShardedTable g_path;
   const float* mask;     // [rows]
   Dropout dp;
+  float grad_scale;      // 1/world under data parallelism with sharded tables, else 1
   __device__ __forceinline__ void operator()(int m, int n, const float4& v, int nvalid) const {
     if (nvalid < 4) return;                 // 3d % 4 == 0: never partial
     if (mask[m] == 0.f) return;
     const float4 mu = dropout_mult4(dp, m, n >> 2);
-    const float4 g = make_float4(v.x * mu.x, v.y * mu.y, v.z * mu.z, v.w * mu.w);
+    const float4 g = make_float4(v.x * mu.x * grad_scale, v.y * mu.y * grad_scale, v.z * mu.z * grad_scale,
+                                 v.w * mu.w * grad_scale);
     const int seg = n / cs.d, off = n - seg * cs.d;
     float* dst;
-    if (seg == 0) dst = g_tok + (size_t)cs.src[m] * cs.d + off;
-    else if (seg == 1) dst = g_path + (size_t)cs.pth[m] * cs.d + off;
-    else dst = g_tok + (size_t)cs.tgt[m] * cs.d + off;
+    if (seg == 0) dst = table_row(g_tok, cs.src[m], cs.d) + off;
+    else if (seg == 1) dst = table_row(g_path, cs.pth[m], cs.d) + off;
+    else dst = table_row(g_tok, cs.tgt[m], cs.d) + off;
     atomicAdd(reinterpret_cast<float4*>(dst), g);     // red.global.add.v4.f32 (sm_90+)
   }
 };

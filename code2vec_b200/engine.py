@@ -30,6 +30,18 @@ class c2v_tensors(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in PARAM_NAMES]
 
 
+class c2v_table_shards(C.Structure):
+    _fields_ = [("world", C.c_int32), ("rank", C.c_int32), ("tok", C.c_void_p * 8), ("path", C.c_void_p * 8)]
+
+
+class _DeviceArray:
+    """A raw device allocation presented through __cuda_array_interface__ so torch can view it."""
+
+    def __init__(self, ptr: int, shape):
+        self.__cuda_array_interface__ = {"shape": tuple(int(x) for x in shape), "typestr": "<f4", "data": (int(ptr), False),
+                                         "version": 2, "strides": None}
+
+
 # every symbol include/c2v_b200.h declares: (restype, argtypes)
 _P = C.c_void_p
 _I32 = C.c_int32
@@ -53,7 +65,12 @@ _SIGNATURES = {
                                          C.c_uint64, C.c_uint64, _P, _P, _P]),
     "c2v_adam_step": (C.c_int, [_P, C.c_float, C.c_float, C.c_float, C.c_float, C.c_int64, _P]),
     "c2v_adam_step_range": (C.c_int, [_P, _P, _P, _P, _P, C.c_size_t, C.c_float, C.c_float, C.c_float, C.c_float,
-                                      C.c_int64, _P]),
+                                      C.c_int64, _I32, _P]),
+    "c2v_bind_table_shards": (C.c_int, [_P, C.POINTER(c2v_table_shards), C.POINTER(c2v_table_shards), C.c_float]),
+    "c2v_ipc_alloc": (C.c_int, [C.c_int, C.c_size_t, C.POINTER(_P), C.c_char_p]),
+    "c2v_ipc_open": (C.c_int, [C.c_int, C.c_char_p, C.POINTER(_P)]),
+    "c2v_ipc_close": (C.c_int, [C.c_int, _P]),
+    "c2v_ipc_free": (C.c_int, [C.c_int, _P]),
     "c2v_train_batch_host": (C.c_int, [_P, _P, _P, _P, _P, _P, _I32, C.c_float, C.c_uint64, C.c_int64,
                                        C.c_float, C.c_float, C.c_float, C.c_float, _P, _P]),
     "c2v_predict_batch_host": (C.c_int, [_P, _P, _P, _P, _P, _I32, _I32, _P, _P, _P, _P, _P]),
@@ -218,6 +235,9 @@ class PathAttentionEngine:
         if getattr(self, "h", None):
             self.lib.c2v_destroy(self.h)
             self.h = None
+            for p in getattr(self, "_ipc_opened", []):
+                self.lib.c2v_ipc_close(self.device, p)
+            self._ipc_opened = []
 
     def __del__(self):
         try:
@@ -351,13 +371,85 @@ class PathAttentionEngine:
             self.adam_t = t
         self._check(self.lib.c2v_adam_step(self.h, lr, beta1, beta2, eps, int(t), self._stream()))
 
-    def adam_step_range(self, theta, grad, m, v, t: int, lr=1e-3, beta1=0.9, beta2=0.999, eps=1e-8):
-        """TF1 Adam on one contiguous slice (the sharded-optimizer path): flat 1-D tensors of equal length."""
+    def adam_step_range(self, theta, grad, m, v, t: int, lr=1e-3, beta1=0.9, beta2=0.999, eps=1e-8, zero_grad=False):
+        """TF1 Adam on one contiguous slice (the sharded-optimizer path): flat tensors of equal length."""
         n = int(theta.numel())
         assert grad.numel() == n and m.numel() == n and v.numel() == n
         self.adam_t = int(t)
         self._check(self.lib.c2v_adam_step_range(self.h, theta.data_ptr(), grad.data_ptr(), m.data_ptr(), v.data_ptr(),
-                                                 n, lr, beta1, beta2, eps, int(t), self._stream()))
+                                                 n, lr, beta1, beta2, eps, int(t), 1 if zero_grad else 0, self._stream()))
+
+    # ---- row-sharded embedding tables over peer memory (data-parallel runs) ----------------------
+    def enable_table_sharding(self, group=None):
+        """Re-homes WORDS_VOCAB / PATHS_VOCAB (+ gradients, Adam slots) as row-interleaved shards: global
+        row r -> rank r % world, local row r // world.  Parameter and gradient shards live in
+        cudaMalloc'ed memory whose CUDA-IPC handles are exchanged once, so every rank's kernels can
+        load rows from, and red.add gradients into, every other rank's shard over NVLink.  The current
+        contents of the replicated tables are carried over."""
+        import torch.distributed as dist
+        torch = self.torch
+        world, rank = dist.get_world_size(group), dist.get_rank(group)
+        if world not in (1, 2, 4, 8):
+            raise ValueError("table sharding needs a world size of 1, 2, 4 or 8")
+        d = self.dims.embed_dim
+        rows = {"tok": (self.dims.token_vocab + world - 1) // world, "path": (self.dims.path_vocab + world - 1) // world}
+        own, handles = {}, {}
+        for role in ("params", "grads"):
+            for name in ("tok", "path"):
+                ptr, hbuf = _P(), C.create_string_buffer(64)
+                rc = self.lib.c2v_ipc_alloc(self.device, rows[name] * d * 4, C.byref(ptr), hbuf)
+                if rc != 0:
+                    raise EngineError(rc, self.lib.c2v_last_error(None).decode())
+                own[(role, name)] = ptr.value
+                handles[(role, name)] = hbuf.raw
+        gathered = [None] * world
+        dist.all_gather_object(gathered, handles, group=group)
+        ptrs = {}
+        self._ipc_opened = []
+        for r in range(world):
+            for key in handles:
+                if r == rank:
+                    ptrs[(r,) + key] = own[key]
+                else:
+                    p = _P()
+                    rc = self.lib.c2v_ipc_open(self.device, gathered[r][key], C.byref(p))
+                    if rc != 0:
+                        raise EngineError(rc, self.lib.c2v_last_error(None).decode())
+                    ptrs[(r,) + key] = p.value
+                    self._ipc_opened.append(p.value)
+        self._ipc_owned = list(own.values())
+
+        def shards(role):
+            st = c2v_table_shards()
+            st.world, st.rank = world, rank
+            for r in range(world):
+                st.tok[r] = ptrs[(r, role, "tok")]
+                st.path[r] = ptrs[(r, role, "path")]
+            return st
+
+        sp, sg = shards("params"), shards("grads")
+        self._check(self.lib.c2v_bind_table_shards(self.h, C.byref(sp), C.byref(sg) if self.training else None, 1.0 / world))
+        view = lambda key, name: torch.as_tensor(_DeviceArray(own[key], (rows[name], d)), device=self.dev)
+        self.table_world, self.table_rank = world, rank
+        self.shard_params = {n: view(("params", n), n) for n in ("tok", "path")}
+        self.shard_grads = {n: view(("grads", n), n) for n in ("tok", "path")}
+        self.shard_m = {n: torch.zeros((rows[n], d), dtype=torch.float32, device=self.dev) for n in ("tok", "path")}
+        self.shard_v = {n: torch.zeros((rows[n], d), dtype=torch.float32, device=self.dev) for n in ("tok", "path")}
+        for n in ("tok", "path"):
+            mine = self.params[n][rank::world]
+            self.shard_params[n][:mine.shape[0]].copy_(mine)
+        torch.cuda.synchronize(self.dev)
+        dist.barrier(group=group)
+
+    def load_table_shards(self, arrays: Dict[str, np.ndarray]):
+        """Fill this rank's shards from full [T, d] / [P, d] host tables."""
+        torch = self.torch
+        for n in ("tok", "path"):
+            mine = np.ascontiguousarray(arrays[n][self.table_rank::self.table_world], dtype=np.float32)
+            self.shard_params[n][:mine.shape[0]].copy_(torch.from_numpy(mine))
+
+    def export_table_shards(self) -> Dict[str, np.ndarray]:
+        return {n: self.shard_params[n].detach().cpu().numpy() for n in ("tok", "path")}
 
     # ---- host-buffer entry points ------------------------------------------------------------
     def train_batch_host(self, src, path, tgt, mask, target, keep: float = 1.0, seed: int = 0,

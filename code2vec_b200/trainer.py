@@ -16,6 +16,18 @@ leaving every replica with bit-identical parameters:
                 reduce-scatter is issued on a side stream as soon as the engine's
                 "target_grads_ready" event fires, so it overlaps the context backward pass.
 
+  "table_sharded" : (default on 2/4/8 GPUs) as "sharded" for the target table, but the two embedding
+                tables are not replicated at all: they are row-sharded over the ranks and reached
+                through peer memory (PathAttentionEngine.enable_table_sharding).  The forward gather
+                loads rows from the owning GPU over NVLink and the backward scatter-add issues
+                red.global.add to it, so no embedding gradient is ever reduced or gathered (1.13 GB
+                of the 1.53 GB per step disappears from the collectives) and each rank's Adam
+                touches 1/world of every table.  Ordering comes from the collectives that remain:
+                the all-reduce of the TRANSFORM/ATTENTION gradients is issued after the local
+                scatter, so its completion means every rank's scatter has landed (Adam may run);
+                the all-gather of the updated target table is issued after the local Adam, so its
+                completion means every shard is updated (the next gather may run).
+
 torch.distributed (NCCL over NVLink/NVSwitch; gloo in the CPU tests of the host logic) is plumbing;
 all arithmetic stays in the engine's kernels.
 """
@@ -89,7 +101,7 @@ def shard_bounds(n: int, rank: int, world: int):
 
 class Trainer:
     def __init__(self, engine: PathAttentionEngine, keep_prob: float = 0.75, seed: int = 0, group=None,
-                 adam: Optional[dict] = None, schedule: str = "sharded"):
+                 adam: Optional[dict] = None, schedule: str = "table_sharded"):
         self.e = engine
         self.keep = float(keep_prob)
         self.seed = int(seed)
@@ -100,6 +112,8 @@ class Trainer:
         self.world = dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
         self.rank = dist.get_rank(group) if self.world > 1 else 0
         self.schedule = schedule if self.world > 1 else "single"
+        if self.schedule == "table_sharded" and self.world not in (2, 4, 8):
+            self.schedule = "sharded"
         B, C = engine.dims.max_batch, engine.dims.max_contexts
         self._dev = None
         if self.world > 1:
@@ -109,6 +123,21 @@ class Trainer:
                              tgt=torch.empty((B, C), dtype=i32, device=engine.dev),
                              mask=torch.empty((B, C), dtype=f32, device=engine.dev),
                              target=torch.empty((B,), dtype=i32, device=engine.dev))
+        if self.schedule == "table_sharded":
+            with torch.cuda.device(engine.dev):
+                engine.enable_table_sharding(group)
+            (a0, a1), _ = engine.bucket_bounds()
+            layout, total = engine.flat_layout()
+            small0 = [off for k, off, n in layout if k == "W"][0]         # W, a: the tail of the flat buffer
+            w, r = self.world, self.rank
+            na = (a1 - a0) // w
+            self._bucket = [(a0, a1, a0 + r * na, a0 + (r + 1) * na)]
+            self._small = (small0, total)
+            self._gshard = [torch.empty(na, dtype=torch.float32, device=engine.dev)]
+            self._side = torch.cuda.Stream(device=engine.dev)
+            self._ev_tgt = torch.cuda.Event()
+            with torch.cuda.device(engine.dev):
+                engine.set_event("target_grads_ready", self._ev_tgt)
         if self.schedule == "sharded":
             (a0, a1), (b0, b1) = engine.bucket_bounds()
             w, r = self.world, self.rank
@@ -135,9 +164,37 @@ class Trainer:
         elif self.schedule == "allreduce":
             allreduce_mean_([e.grads[k] for k in PARAM_NAMES], self.group)
             e.adam_step(t=t, **self.adam)
+        elif self.schedule == "table_sharded":
+            self._table_sharded_update(t)
         else:
             self._sharded_update(t)
         return loss
+
+    def _table_sharded_update(self, t: int):
+        e, torch = self.e, self.e.torch
+        dist = _dist()
+        main = torch.cuda.current_stream(e.dev)
+        (a0, a1, alo, ahi), = self._bucket
+        s0, s1 = self._small
+        self._side.wait_event(self._ev_tgt)
+        with torch.cuda.stream(self._side):
+            wa = reduce_scatter_mean(self._gshard[0], e.flat_grads[a0:a1], self.group, async_op=True)
+        # TRANSFORM / ATTENTION gradients (0.6 MB): mean over ranks; issued after the local scatter-add, so
+        # its completion also tells this rank that every peer's red.adds into its shards have landed
+        ws = dist.all_reduce(e.flat_grads[s0:s1], op=dist.ReduceOp.AVG, group=self.group, async_op=True)
+        ws.wait()
+        for name in ("tok", "path"):
+            e.adam_step_range(e.shard_params[name], e.shard_grads[name], e.shard_m[name], e.shard_v[name], t,
+                              zero_grad=True, **self.adam)
+        e.adam_step_range(e.flat_params[s0:s1], e.flat_grads[s0:s1], e.flat_m[s0:s1], e.flat_v[s0:s1], t, **self.adam)
+        if wa is not None:
+            wa.wait()
+        main.wait_stream(self._side)
+        e.adam_step_range(e.flat_params[alo:ahi], self._gshard[0], e.flat_m[alo:ahi], e.flat_v[alo:ahi], t, **self.adam)
+        # issued after every local Adam launch: completion == all ranks' shards are updated
+        ga = all_gather_flat(e.flat_params[a0:a1], e.flat_params[alo:ahi], self.group, async_op=True)
+        if ga is not None:
+            ga.wait()
 
     def _sharded_update(self, t: int):
         e, torch = self.e, self.e.torch

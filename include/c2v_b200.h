@@ -154,9 +154,34 @@ int c2v_adam_step(c2v_engine* e, float lr, float beta1, float beta2, float eps, 
 /* The same update on one contiguous slice of caller-provided device arrays (count % 4 == 0,
  * 16-byte aligned): the sharded-optimizer path of a data-parallel run, where each rank owns
  * 1/world of the flat parameter buffer (reduce-scatter grads -> this -> all-gather params). */
-int c2v_adam_step_range(c2v_engine* e, float* theta, const float* grad, float* m, float* v,
+int c2v_adam_step_range(c2v_engine* e, float* theta, float* grad, float* m, float* v,
                         size_t count, float lr, float beta1, float beta2, float eps, int64_t t,
-                        void* stream);
+                        int32_t zero_grad, void* stream);
+
+/* Row-sharded embedding tables over the GPUs of one NVSwitch domain (data-parallel runs).  Global
+ * row r of WORDS_VOCAB / PATHS_VOCAB lives on rank (r % world) at local row (r / world); tok[i] /
+ * path[i] are device pointers to rank i's shard -- the caller's own allocation for i == rank,
+ * CUDA-IPC mappings of the peers' allocations otherwise.  The forward gather then reads peer
+ * memory directly and the backward scatter-add issues red.global.add to the owning rank, scaled
+ * by grad_scale (1/world for a mean over the global batch): no table gradient is ever
+ * all-reduced and each rank updates only its own rows with c2v_adam_step_range.  The caller
+ * provides the cross-rank ordering (all scatters done before Adam; all Adams done before the next
+ * gather).  world must be 1, 2, 4 or 8.  grads may be NULL (inference). */
+typedef struct c2v_table_shards {
+  int32_t world;
+  int32_t rank;
+  float* tok[8];
+  float* path[8];
+} c2v_table_shards;
+int c2v_bind_table_shards(c2v_engine* e, const c2v_table_shards* params, const c2v_table_shards* grads,
+                          float grad_scale);
+
+/* cudaMalloc'ed, zero-filled, IPC-shareable device memory for the shards (not tied to an engine;
+ * errors are reported through c2v_last_error(NULL)).  handle64 is a 64-byte cudaIpcMemHandle_t. */
+int c2v_ipc_alloc(int device, size_t bytes, void** dev_ptr, unsigned char* handle64);
+int c2v_ipc_open(int device, const unsigned char* handle64, void** dev_ptr);
+int c2v_ipc_close(int device, void* dev_ptr);
+int c2v_ipc_free(int device, void* dev_ptr);
 
 /* Register a cudaEvent_t (passed as void*; NULL unregisters) that c2v_train_step records on its
  * stream at a named point, so the caller can start communication early on another stream:

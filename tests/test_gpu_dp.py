@@ -34,11 +34,15 @@ def _worker(rank, world, port, schedule, math_mode, out_dir):
     losses = []
     for _ in range(3):
         losses.append(tr.step_host(src[lo:hi], pth[lo:hi], tgt[lo:hi], mask[lo:hi], target[lo:hi]))
-    np.savez(os.path.join(out_dir, "rank%d.npz" % rank), losses=np.array(losses), **eng.export_params())
+    out = eng.export_params()
+    if schedule == "table_sharded":
+        sh = eng.export_table_shards()
+        out["tok_shard"], out["path_shard"] = sh["tok"], sh["path"]
+    np.savez(os.path.join(out_dir, "rank%d.npz" % rank), losses=np.array(losses), **out)
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("schedule", ["allreduce", "sharded"])
+@pytest.mark.parametrize("schedule", ["allreduce", "sharded", "table_sharded"])
 def test_two_rank_data_parallel_matches_single_engine(tmp_path, schedule):
     import torch
     if torch.cuda.device_count() < 2:
@@ -48,7 +52,8 @@ def test_two_rank_data_parallel_matches_single_engine(tmp_path, schedule):
     mp.spawn(_worker, args=(world, port, schedule, 0, str(tmp_path)), nprocs=world, join=True)
     r0 = np.load(str(tmp_path / "rank0.npz"))
     r1 = np.load(str(tmp_path / "rank1.npz"))
-    for k in O.PARAM_NAMES:
+    replicated = ("tgt", "W", "a") if schedule == "table_sharded" else O.PARAM_NAMES
+    for k in replicated:
         assert np.array_equal(r0[k], r1[k]), "replicas diverged on %s" % k
     # single engine on the global batch (mean loss over 2*B_LOCAL == average of the two local means)
     from tests.util import make_engine
@@ -57,5 +62,11 @@ def test_two_rank_data_parallel_matches_single_engine(tmp_path, schedule):
     for _ in range(3):
         eng.train_batch_host(src, pth, tgt, mask, target, keep=1.0)
     ref = eng.export_params()
-    for k in O.PARAM_NAMES:
+    for k in replicated:
         assert np.abs(r0[k] - ref[k]).max() < 5e-5, k
+    if schedule == "table_sharded":
+        # row r of the global table lives on rank r % 2 at local row r // 2
+        for r, res in ((0, r0), (1, r1)):
+            for name, shard in (("tok", res["tok_shard"]), ("path", res["path_shard"])):
+                want = ref[name][r::2]
+                assert np.abs(shard[:want.shape[0]] - want).max() < 5e-5, (name, r)
