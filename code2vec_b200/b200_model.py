@@ -28,6 +28,33 @@ from .path_context_reader import EstimatorAction, ModelInputTensorsFormer, PathC
 from .trainer import Trainer
 from .vocabularies import VocabType
 
+def _prefetch(iterable, depth: int = 8):
+    """Runs `iterable` (the reader) in a background thread, `depth` batches ahead: the native
+    tensoriser and the C-ABI train call both release the GIL, so parsing the next batches overlaps
+    the GPU step -- the role tf.data's prefetch(40) plays in the reference (path_context_reader.py:150)."""
+    import queue
+    import threading
+    q: "queue.Queue" = queue.Queue(maxsize=depth)
+    done = object()
+
+    def run():
+        try:
+            for item in iterable:
+                q.put(item)
+            q.put(done)
+        except BaseException as exc:          # surface reader errors in the consumer
+            q.put(exc)
+
+    threading.Thread(target=run, daemon=True).start()
+    while True:
+        item = q.get()
+        if item is done:
+            return
+        if isinstance(item, BaseException):
+            raise item
+        yield item
+
+
 _CKPT_MAGIC = b"C2VB200\0"
 _CKPT_SUFFIX = ".c2v_b200"
 
@@ -147,7 +174,7 @@ class Code2VecModel(Code2VecModelBase):
         train_reader = PathContextReader(vocabs=self.vocabs, model_input_tensors_former=_TrainInputFormer(),
                                          config=cfg, estimator_action=EstimatorAction.Train)
         self.log("Started reader...")
-        for batch in train_reader.get_dataset():
+        for batch in _prefetch(train_reader.get_dataset()):
             t = _TrainInputFormer().from_model_input_form(batch)
             batch_num += 1
             batch_loss = self.trainer.step_host(t.path_source_token_indices, t.path_indices, t.path_target_token_indices,
@@ -195,7 +222,7 @@ class Code2VecModel(Code2VecModelBase):
         with open("log.txt", "w") as log_output_file:
             start_time = time.time()
             self.log("Starting evaluation")
-            for batch in self.eval_reader.get_dataset():
+            for batch in _prefetch(self.eval_reader.get_dataset()):
                 t = _EvaluateInputFormer().from_model_input_form(batch)
                 idx, _vals, code_vectors, _attn = self.engine.predict_batch_host(
                     t.path_source_token_indices, t.path_indices, t.path_target_token_indices, t.context_valid_mask,

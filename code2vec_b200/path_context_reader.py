@@ -16,6 +16,11 @@ Semantics restated from the reference (file:line = path_context_reader.py):
     batch (last batch may be short); predict: one unfiltered row, batch axis 1     (:119-151,96-107)
 A "dataset" here is a Python iterable of batches in the model's input form (numpy arrays), which
 replaces the tf.data iterator; end of data is the end of iteration instead of OutOfRangeError.
+
+Two tensorisers implement the same semantics: the pure-Python one below (always used for predict,
+which needs the per-context strings) and the native one (native/batcher.cpp: multi-threaded C++
+parse + hash lookups straight into numpy / pinned buffers) used for train / evaluate files.
+tests/test_reader_native.py checks they agree row for row.
 """
 from __future__ import annotations
 
@@ -25,8 +30,55 @@ from typing import Iterable, Iterator, List, NamedTuple, Optional
 
 import numpy as np
 
+import ctypes as C
+import os
+
 from .config import Config
 from .vocabularies import Code2VecVocabs
+
+_native_lib = None
+
+
+def load_native_tensoriser():
+    """ctypes handle of libc2v_batcher.so (built on first use with g++), or None if it cannot be built."""
+    global _native_lib
+    if _native_lib is None:
+        try:
+            from .native import build_native
+            lib = C.CDLL(build_native.build())
+            P, I32, I64 = C.c_void_p, C.c_int32, C.c_int64
+            lib.c2v_vocab_create.restype = P
+            lib.c2v_vocab_create.argtypes = [P, P, P, I64, I32, I32]
+            lib.c2v_vocab_destroy.restype = None
+            lib.c2v_vocab_destroy.argtypes = [P]
+            lib.c2v_vocab_lookup.restype = I32
+            lib.c2v_vocab_lookup.argtypes = [P, C.c_char_p, I64]
+            lib.c2v_parse_chunk.restype = I64
+            lib.c2v_parse_chunk.argtypes = [P, I64, I32, P, P, P, I32, I32, I64, P, P, P, P, P, P, P, P, C.POINTER(I32)]
+            _native_lib = lib
+        except Exception:
+            _native_lib = False
+    return _native_lib or None
+
+
+class _NativeVocab:
+    def __init__(self, lib, vocab):
+        self.lib = lib
+        words = list(vocab.word_to_index.keys())
+        enc = [w.encode("utf-8") for w in words]
+        offsets = np.zeros(len(enc) + 1, dtype=np.int64)
+        np.cumsum([len(b) for b in enc], out=offsets[1:])
+        blob = b"".join(enc)
+        idx = np.fromiter((vocab.word_to_index[w] for w in words), dtype=np.int32, count=len(words))
+        pad_word = getattr(vocab.special_words, "PAD", vocab.special_words.OOV)
+        self.h = lib.c2v_vocab_create(blob, offsets.ctypes.data, idx.ctypes.data, len(words),
+                                      vocab.word_to_index[vocab.special_words.OOV], vocab.word_to_index[pad_word])
+
+    def __del__(self):
+        try:
+            self.lib.c2v_vocab_destroy(self.h)
+        except Exception:
+            pass
 
 
 class EstimatorAction(Enum):
@@ -79,7 +131,7 @@ class ModelInputTensorsFormer(abc.ABC):
 class PathContextReader:
     def __init__(self, vocabs: Code2VecVocabs, config: Config, model_input_tensors_former: ModelInputTensorsFormer,
                  estimator_action: EstimatorAction, repeat_endlessly: bool = False, shuffle_seed: Optional[int] = None,
-                 keep_context_strings: Optional[bool] = None):
+                 keep_context_strings: Optional[bool] = None, use_native: Optional[bool] = None):
         self.vocabs = vocabs
         self.config = config
         self.model_input_tensors_former = model_input_tensors_former
@@ -101,6 +153,8 @@ class PathContextReader:
         # evaluate() never reads the per-context strings; predict() needs them for the attention dict
         self.keep_context_strings = estimator_action.is_predict if keep_context_strings is None else keep_context_strings
         self._dataset = None
+        self.use_native = use_native
+        self._native = None
 
     @classmethod
     def create_needed_vocabs_lookup_tables(cls, vocabs: Code2VecVocabs):
@@ -221,8 +275,125 @@ class PathContextReader:
         self._rng.shuffle(buf)
         yield from buf
 
+    # ---- native tensoriser path (train / evaluate over files) -----------------------------------------
+    def _native_ready(self) -> bool:
+        if self.use_native is False or self.estimator_action.is_predict or self.keep_context_strings:
+            return False
+        if self._native is None:
+            lib = load_native_tensoriser()
+            if lib is None:
+                if self.use_native:
+                    raise RuntimeError("native tensoriser requested but libc2v_batcher.so could not be built")
+                self._native = False
+            else:
+                self._native = (lib, _NativeVocab(lib, self.vocabs.token_vocab), _NativeVocab(lib, self.vocabs.path_vocab),
+                                _NativeVocab(lib, self.vocabs.target_vocab))
+        return bool(self._native)
+
+    def _native_parse(self, data: bytes):
+        """bytes of complete lines -> (ReaderInputTensors of all rows, keep mask, target strings or None)."""
+        lib, tok, pth, tgt = self._native
+        Cn = self.config.MAX_CONTEXTS
+        cap = data.count(b"\n") + 1
+        src = np.empty((cap, Cn), dtype=np.int32)
+        path = np.empty((cap, Cn), dtype=np.int32)
+        dst = np.empty((cap, Cn), dtype=np.int32)
+        mask = np.empty((cap, Cn), dtype=np.float32)
+        target = np.empty(cap, dtype=np.int32)
+        keep = np.zeros(cap, dtype=np.uint8)
+        toff = np.empty(cap, dtype=np.int64)
+        tlen = np.empty(cap, dtype=np.int32)
+        err = C.c_int32(0)
+        mode = 0 if self.estimator_action.is_train else 1
+        threads = max(1, int(self.config.READER_NUM_PARALLEL_BATCHES or 1))
+        n = lib.c2v_parse_chunk(data, len(data), Cn, tok.h, pth.h, tgt.h, mode, threads, cap, src.ctypes.data,
+                                path.ctypes.data, dst.ctypes.data, mask.ctypes.data, target.ctypes.data, keep.ctypes.data,
+                                toff.ctypes.data, tlen.ctypes.data, C.byref(err))
+        if n < 0:
+            if err.value == 2:
+                raise ValueError("a context has more than 3 comma-separated parts (line %d of the chunk)" % (-n - 1))
+            raise ValueError("Expect %d fields but have a different number in record (line %d of the chunk)" % (Cn + 1, -n - 1))
+        sel = keep[:n].astype(bool)
+        strings = None
+        if self.estimator_action.is_evaluate:
+            oov = self._tgt_oov_word
+            strings = [data[o:o + l].decode("utf-8") if l else oov for o, l, k in zip(toff[:n], tlen[:n], sel) if k]
+        return (src[:n][sel], path[:n][sel], dst[:n][sel], mask[:n][sel], target[:n][sel]), strings
+
+    def _native_chunks(self):
+        """Complete-line byte chunks of the data file, one pass per epoch like _raw_lines."""
+        action = self.estimator_action
+        path = self.config.data_path(is_evaluating=action.is_evaluate)
+        chunk_bytes = 8 << 20
+        passes = 1
+        if action.is_train and not self.repeat_endlessly and self.config.NUM_TRAIN_EPOCHS > 1:
+            passes = self.config.NUM_TRAIN_EPOCHS
+        p = 0
+        while self.repeat_endlessly or p < passes:
+            p += 1
+            with open(path, "rb") as f:
+                tail = b""
+                while True:
+                    buf = f.read(chunk_bytes)
+                    if not buf:
+                        break
+                    buf = tail + buf
+                    cut = buf.rfind(b"\n")
+                    if cut < 0:
+                        tail = buf
+                        continue
+                    tail = buf[cut + 1:]
+                    yield buf[:cut + 1]
+                if tail.strip(b"\r\n"):
+                    yield tail
+
+    def _iterate_batches_native(self):
+        action = self.estimator_action
+        B = self.config.batch_size(is_evaluating=action.is_evaluate)
+        former = self.model_input_tensors_former
+        names = ("path_source_token_indices", "path_indices", "path_target_token_indices", "context_valid_mask", "target_index")
+
+        def emit(arrs, strings):
+            return former.to_model_input_form(ReaderInputTensors(target_string=strings, **dict(zip(names, arrs))))
+
+        if action.is_evaluate:
+            pend, pend_s = None, []
+            for chunk in self._native_chunks():
+                arrs, strings = self._native_parse(chunk)
+                pend = arrs if pend is None else tuple(np.concatenate([a, b]) for a, b in zip(pend, arrs))
+                pend_s += strings
+                while pend[0].shape[0] >= B:
+                    yield emit(tuple(a[:B] for a in pend), pend_s[:B])
+                    pend, pend_s = tuple(a[B:] for a in pend), pend_s[B:]
+            if pend is not None and pend[0].shape[0]:
+                yield emit(pend, pend_s)
+            return
+        # train: a pool of at least SHUFFLE_BUFFER_SIZE rows; every batch is a uniform draw without
+        # replacement from the pool (tf.data's shuffle(buffer) draws the same way, one row at a time)
+        S = max(int(self.config.SHUFFLE_BUFFER_SIZE), 1)
+        pool = None
+        for chunk in self._native_chunks():
+            arrs, _ = self._native_parse(chunk)
+            pool = arrs if pool is None else tuple(np.concatenate([a, b]) for a, b in zip(pool, arrs))
+            while pool[0].shape[0] >= S + B:
+                n = pool[0].shape[0]
+                pick = self._rng.choice(n, size=B, replace=False)
+                yield emit(tuple(a[pick] for a in pool), None)
+                rest = np.ones(n, dtype=bool)
+                rest[pick] = False
+                pool = tuple(a[rest] for a in pool)
+        if pool is not None:
+            n = pool[0].shape[0]
+            order = self._rng.permutation(n)
+            for lo in range(0, n, B):
+                pick = order[lo:lo + B]
+                yield emit(tuple(a[pick] for a in pool), None)
+
     def _iterate_batches(self, input_data_rows):
         action = self.estimator_action
+        if input_data_rows is None and self._native_ready():
+            yield from self._iterate_batches_native()
+            return
         lines = self._raw_lines(input_data_rows)
         if action.is_train:
             lines = self._shuffled(lines)

@@ -1,0 +1,118 @@
+"""The native (C++) tensoriser against the pure-Python reader: identical rows, masks, filtering,
+target strings and error behaviour on generated `.c2v` files, including padding, OOV words, empty
+pieces, short contexts and malformed lines."""
+import pickle
+
+import numpy as np
+import pytest
+
+from code2vec_b200 import vocabularies as V
+from code2vec_b200.config import Config
+from code2vec_b200.path_context_reader import EstimatorAction, PathContextReader, load_native_tensoriser
+
+
+class _Former:
+    def to_model_input_form(self, t):
+        return t
+
+    def from_model_input_form(self, row):
+        return row
+
+
+def _setup(tmp_path, lines, separate=False, C=6, batch=4, epochs=1):
+    rng = np.random.default_rng(0)
+    prefix = str(tmp_path / "ds")
+    tok = {"t%d" % i: int(rng.integers(1, 50)) for i in range(30)}
+    pth = {str(100 + i): int(rng.integers(1, 50)) for i in range(20)}
+    tgt = {"name|%d" % i: int(rng.integers(1, 50)) for i in range(10)}
+    with open(prefix + ".dict.c2v", "wb") as f:
+        for d in (tok, pth, tgt):
+            pickle.dump(d, f)
+        pickle.dump(len(lines), f)
+    with open(prefix + ".train.c2v", "w") as f:
+        f.write("".join(l + "\n" for l in lines))
+    cfg = Config(set_defaults=True)
+    cfg.VERBOSE_MODE = 0
+    cfg.TRAIN_DATA_PATH_PREFIX = prefix
+    cfg.TEST_DATA_PATH = prefix + ".train.c2v"
+    cfg.MAX_CONTEXTS = C
+    cfg.TRAIN_BATCH_SIZE = cfg.TEST_BATCH_SIZE = batch
+    cfg.NUM_TRAIN_EPOCHS = epochs
+    cfg.SHUFFLE_BUFFER_SIZE = 8
+    cfg.SEPARATE_OOV_AND_PAD = separate
+    cfg.READER_NUM_PARALLEL_BATCHES = 3
+    return cfg, V.Code2VecVocabs(cfg)
+
+
+def _random_lines(n, C, seed):
+    rng = np.random.default_rng(seed)
+    out = []
+    for _ in range(n):
+        target = ["name|%d" % rng.integers(0, 12), "", "unknown"][int(rng.choice(3, p=[0.8, 0.05, 0.15]))]
+        k = int(rng.integers(0, C + 1))
+        ctxs = []
+        for _ in range(k):
+            kind = rng.integers(0, 10)
+            s, p, t = "t%d" % rng.integers(0, 36), str(100 + rng.integers(0, 25)), "t%d" % rng.integers(0, 36)
+            if kind == 0:
+                ctxs.append("%s,%s" % (s, p))
+            elif kind == 1:
+                ctxs.append(",,")
+            elif kind == 2:
+                ctxs.append("%s,,%s" % (s, t))
+            elif kind == 3:
+                ctxs.append("zzz,999,yyy")
+            else:
+                ctxs.append("%s,%s,%s" % (s, p, t))
+        out.append(" ".join([target] + ctxs + [""] * (C - k)))
+    return out
+
+
+pytestmark = pytest.mark.skipif(load_native_tensoriser() is None, reason="g++ build of the native tensoriser failed")
+
+
+@pytest.mark.parametrize("separate", [False, True])
+def test_native_evaluate_matches_python_reader(tmp_path, separate):
+    C = 6
+    lines = _random_lines(57, C, seed=3)
+    cfg, vs = _setup(tmp_path, lines, separate=separate, C=C, batch=5)
+    py = PathContextReader(vs, cfg, _Former(), EstimatorAction.Evaluate, use_native=False)
+    nat = PathContextReader(vs, cfg, _Former(), EstimatorAction.Evaluate, use_native=True)
+    a, b = list(py.get_dataset()), list(nat.get_dataset())
+    assert len(a) == len(b) and len(a) > 3
+    for x, y in zip(a, b):
+        for name in ("path_source_token_indices", "path_indices", "path_target_token_indices", "context_valid_mask", "target_index"):
+            u, v = getattr(x, name), getattr(y, name)
+            assert u.dtype == v.dtype and np.array_equal(u, v), name
+        assert list(x.target_string) == list(y.target_string)
+
+
+def test_native_train_filter_and_epochs(tmp_path):
+    C = 6
+    lines = _random_lines(40, C, seed=5)
+    cfg, vs = _setup(tmp_path, lines, C=C, batch=4, epochs=3)
+    py = PathContextReader(vs, cfg, _Former(), EstimatorAction.Train, use_native=False, shuffle_seed=1)
+    nat = PathContextReader(vs, cfg, _Former(), EstimatorAction.Train, use_native=True, shuffle_seed=1)
+
+    def rows(ds):
+        out = []
+        for b in ds:
+            for i in range(b.path_indices.shape[0]):
+                out.append((int(b.target_index[i]),) + tuple(b.path_source_token_indices[i]) + tuple(b.path_indices[i])
+                           + tuple(b.path_target_token_indices[i]) + tuple(b.context_valid_mask[i]))
+        return out
+    ra, rb = rows(py.get_dataset()), rows(nat.get_dataset())
+    assert len(ra) == len(rb) and len(ra) % 3 == 0 and len(ra) > 0
+    assert sorted(ra) == sorted(rb)                       # same multiset of rows (order is shuffled)
+    assert all(r[0] > 0 for r in rb)                      # train drops OOV targets
+
+
+def test_native_errors_match_python(tmp_path):
+    C = 4
+    good = " ".join(["name|1", "t1,100,t2", "", "", ""])
+    for bad in ("name|1 t1,100,t2", " ".join(["name|1", "a,b,c,d", "", "", ""])):
+        cfg, vs = _setup(tmp_path, [good, bad], C=C, batch=2)
+        for native in (False, True):
+            r = PathContextReader(vs, cfg, _Former(), EstimatorAction.Evaluate, use_native=native)
+            with pytest.raises(ValueError):
+                list(r.get_dataset())
