@@ -26,6 +26,7 @@ thread_local std::string g_create_error = "";
 constexpr size_t kAlign = 256;
 inline size_t align_up(size_t x, size_t a = kAlign) { return (x + a - 1) / a * a; }
 
+constexpr int kLrTableCap = 1 << 22;   // lazy Adam: per-step learning rates kept on the device (4 M steps)
 constexpr int kSplitDv = 18;   // split-K slices for dv = P . Y      (K = |Y|)
 constexpr int kSplitDw = 48;   // split-K slices for dW = X'^T . dU  (K = B*C)
 
@@ -33,6 +34,7 @@ constexpr int kSplitDw = 48;   // split-K slices for dW = X'^T . dU  (K = B*C)
 struct Workspace {
   size_t H, Xg, alpha, v, dv, S, loss_b, lse, loss, part, da_part, lse_part, dl;
   size_t st_src, st_pth, st_tgt, st_mask, st_target, st_topk_idx, st_topk_val, st_code, st_attn;
+  size_t stamp_tok, stamp_path, last_tok, last_path, lr_tab;     // lazy Adam bookkeeping
   size_t total;
   size_t ldS;
 };
@@ -80,6 +82,11 @@ Workspace carve(const c2v_dims& d) {
   w.st_topk_val = take(B * (size_t)d.top_k * 4);
   w.st_code = take(B * D * 4);
   w.st_attn = take(N * 4);
+  w.stamp_tok = take((size_t)d.token_vocab * 4);
+  w.stamp_path = take((size_t)d.path_vocab * 4);
+  w.last_tok = take((size_t)d.token_vocab * 4);
+  w.last_path = take((size_t)d.path_vocab * 4);
+  w.lr_tab = take((size_t)kLrTableCap * 4);
   w.total = off;
   return w;
 }
@@ -89,9 +96,10 @@ Workspace carve(const c2v_dims& d) {
 // Phases of a pass, for per-kernel timing (option "profile"): CUDA events bracket each phase on
 // the launching stream; c2v_phase_stats() resolves them.
 enum Phase { PH_CTX_FWD = 0, PH_ATTN_FWD, PH_LOGITS, PH_XENT, PH_DV, PH_DY, PH_ATTN_BWD, PH_DW, PH_DX_SCATTER,
-             PH_ADAM, PH_TOPK, PH_SAMPLED, PH_GATHER, PH_DX_GEMM, PH_COUNT };
+             PH_ADAM, PH_TOPK, PH_SAMPLED, PH_GATHER, PH_DX_GEMM, PH_ADAM_CATCHUP, PH_COUNT };
 const char* const kPhaseNames[PH_COUNT] = {"ctx_fwd", "attn_fwd", "logits", "xent", "dv", "dY", "attn_bwd", "dW",
-                                           "dx_scatter", "adam", "topk", "sampled_softmax", "gather", "dx_gemm"};
+                                           "dx_scatter", "adam", "topk", "sampled_softmax", "gather", "dx_gemm",
+                                           "adam_catchup"};
 struct PhaseLog {
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pending;
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> free_list;
@@ -111,6 +119,12 @@ struct c2v_engine {
   ShardedTable th_tok{}, th_path{}, gr_tok{}, gr_path{};   // how kernels reach the two embedding tables
   int table_world = 1;       // > 1: tables are row-sharded over peers (c2v_bind_table_shards)
   float grad_scale = 1.f;
+  // lazy-but-exact dense Adam for the embedding tables (option "lazy_adam")
+  int lazy = 0;
+  int64_t adam_t_done = 0;   // Adam steps applied so far
+  int32_t mark_epoch = 0;
+  float hp_lr = 0.f, hp_b1 = 0.f, hp_b2 = 0.f, hp_eps = 0.f;
+  bool hp_set = false;
   bool has_theta, has_grad, has_adam;
   bool emb_grads_clean;      // token/path gradient tables are known to be all-zero
   int math_mode;
@@ -246,9 +260,47 @@ ContextSource make_source(c2v_engine* e, const int32_t* src, const int32_t* pth,
   return cs;
 }
 
+// Lazy Adam: stamp the rows this batch references and replay their pending zero-gradient steps so the
+// gather below reads exactly what a dense Adam would have left there.
+int prepare_rows(c2v_engine* e, cudaStream_t st, const ContextSource& cs) {
+  if (!e->lazy) return C2V_OK;
+  PhaseTimer pt(e, PH_ADAM_CATCHUP, st);
+  const c2v_dims& d = e->dims;
+  int32_t* stamp_tok = wsp<int32_t>(e, e->ws.stamp_tok);
+  int32_t* stamp_path = wsp<int32_t>(e, e->ws.stamp_path);
+  e->mark_epoch++;
+  C2V_LAUNCH(e, (mark_rows_kernel<<<(cs.rows + 255) / 256, 256, 0, st>>>(cs.src, cs.pth, cs.tgt, cs.rows, stamp_tok, stamp_path,
+                                                                        e->mark_epoch)));
+  if (e->adam_t_done > 0) {
+    const float* lr_tab = wsp<float>(e, e->ws.lr_tab);
+    C2V_LAUNCH(e, (adam_rows_kernel<ADAM_ROWS_CATCHUP><<<(d.token_vocab + 7) / 8, 256, 0, st>>>(
+                      e->theta.tok, e->grad.tok, e->am.tok, e->av.tok, d.token_vocab, d.embed_dim, stamp_tok, e->mark_epoch,
+                      wsp<int32_t>(e, e->ws.last_tok), (int32_t)e->adam_t_done, lr_tab, e->hp_b1, e->hp_b2, e->hp_eps)));
+    C2V_LAUNCH(e, (adam_rows_kernel<ADAM_ROWS_CATCHUP><<<(d.path_vocab + 7) / 8, 256, 0, st>>>(
+                      e->theta.path, e->grad.path, e->am.path, e->av.path, d.path_vocab, d.embed_dim, stamp_path, e->mark_epoch,
+                      wsp<int32_t>(e, e->ws.last_path), (int32_t)e->adam_t_done, lr_tab, e->hp_b1, e->hp_b2, e->hp_eps)));
+  }
+  return C2V_OK;
+}
+
+// Lazy Adam: bring every row of both embedding tables up to date (export, checkpoint, mode switches).
+int flush_rows(c2v_engine* e, cudaStream_t st) {
+  if (!e->lazy || e->adam_t_done == 0) return C2V_OK;
+  const c2v_dims& d = e->dims;
+  const float* lr_tab = wsp<float>(e, e->ws.lr_tab);
+  C2V_LAUNCH(e, (adam_rows_kernel<ADAM_ROWS_FLUSH><<<(d.token_vocab + 7) / 8, 256, 0, st>>>(
+                    e->theta.tok, e->grad.tok, e->am.tok, e->av.tok, d.token_vocab, d.embed_dim, nullptr, 0,
+                    wsp<int32_t>(e, e->ws.last_tok), (int32_t)e->adam_t_done, lr_tab, e->hp_b1, e->hp_b2, e->hp_eps)));
+  C2V_LAUNCH(e, (adam_rows_kernel<ADAM_ROWS_FLUSH><<<(d.path_vocab + 7) / 8, 256, 0, st>>>(
+                    e->theta.path, e->grad.path, e->am.path, e->av.path, d.path_vocab, d.embed_dim, nullptr, 0,
+                    wsp<int32_t>(e, e->ws.last_path), (int32_t)e->adam_t_done, lr_tab, e->hp_b1, e->hp_b2, e->hp_eps)));
+  return C2V_OK;
+}
+
 // H = tanh(X' . W)   (tensorflow_model.py:238-252)
 int run_ctx_fwd(c2v_engine* e, cudaStream_t st, const ContextSource& cs, const Dropout& dp, float* H) {
   const int D = e->dims.code_dim, K = 3 * e->dims.embed_dim;
+  { int rc0 = prepare_rows(e, st, cs); if (rc0) return rc0; }
   if (e->math_mode == C2V_MATH_TF32) {
     float* Xg = wsp<float>(e, e->ws.Xg);
     {
@@ -509,7 +561,27 @@ int adam_impl(c2v_engine* e, cudaStream_t st, float lr, float b1, float b2, floa
   float* M[5] = {e->am.tok, e->am.path, e->am.tgt, e->am.W, e->am.a};
   float* V[5] = {e->av.tok, e->av.path, e->av.tgt, e->av.W, e->av.a};
   PhaseTimer pt(e, PH_ADAM, st);
-  for (int i = 0; i < 5; ++i) {
+  int first_dense = 0;
+  if (e->lazy) {
+    if (t != e->adam_t_done + 1) return fail(e, C2V_ERR_STATE, "lazy Adam needs consecutive step counts (t == previous t + 1)");
+    if (t >= kLrTableCap) return fail(e, C2V_ERR_UNSUPPORTED, "lazy Adam learning-rate table exhausted");
+    if (e->hp_set && (lr != e->hp_lr || b1 != e->hp_b1 || b2 != e->hp_b2 || eps != e->hp_eps)) {
+      int rcf = flush_rows(e, st);                  // pending steps must use the old hyper-parameters
+      if (rcf) return rcf;
+    }
+    e->hp_lr = lr; e->hp_b1 = b1; e->hp_b2 = b2; e->hp_eps = eps; e->hp_set = true;
+    float* lr_tab = wsp<float>(e, e->ws.lr_tab);
+    C2V_LAUNCH(e, (set_float_kernel<<<1, 1, 0, st>>>(lr_tab + t, lr_t)));
+    C2V_LAUNCH(e, (adam_rows_kernel<ADAM_ROWS_UPDATE><<<(d.token_vocab + 7) / 8, 256, 0, st>>>(
+                      P[0], G[0], M[0], V[0], d.token_vocab, d.embed_dim, wsp<int32_t>(e, e->ws.stamp_tok), e->mark_epoch,
+                      wsp<int32_t>(e, e->ws.last_tok), (int32_t)t, lr_tab, b1, b2, eps)));
+    C2V_LAUNCH(e, (adam_rows_kernel<ADAM_ROWS_UPDATE><<<(d.path_vocab + 7) / 8, 256, 0, st>>>(
+                      P[1], G[1], M[1], V[1], d.path_vocab, d.embed_dim, wsp<int32_t>(e, e->ws.stamp_path), e->mark_epoch,
+                      wsp<int32_t>(e, e->ws.last_path), (int32_t)t, lr_tab, b1, b2, eps)));
+    first_dense = 2;
+  }
+  e->adam_t_done = t;
+  for (int i = first_dense; i < 5; ++i) {
     const size_t n4 = n[i] / 4;
     size_t blocks = (n4 + 255) / 256;
     if (blocks > 148 * 16) blocks = 148 * 16;
@@ -623,6 +695,42 @@ int c2v_set_option(c2v_engine* e, const char* key, int64_t value) {
   }
   if (!strcmp(key, "deterministic")) { e->deterministic = value ? 1 : 0; return C2V_OK; }
   if (!strcmp(key, "profile")) { e->profile = value ? 1 : 0; return C2V_OK; }
+  if (!strcmp(key, "lazy_adam")) {
+    if (!e->wbase || !e->has_theta || !e->has_grad || !e->has_adam)
+      return fail(e, C2V_ERR_STATE, "bind workspace, parameters, gradients and Adam state before lazy_adam");
+    if (value && e->table_world > 1) return fail(e, C2V_ERR_STATE, "lazy_adam is for replicated (single-GPU) tables");
+    C2V_CUDA(e, cudaSetDevice(e->device));
+    if (!value && e->lazy) {                              // bring every row up to date, then go dense
+      int rc = flush_rows(e, 0);
+      if (rc) return rc;
+      C2V_CUDA(e, cudaStreamSynchronize(0));
+    }
+    if (value && !e->lazy) {                              // all rows are current as of adam_t_done
+      const c2v_dims& d = e->dims;
+      C2V_LAUNCH(e, (fill_i32_kernel<<<256, 256>>>(wsp<int32_t>(e, e->ws.last_tok), (size_t)d.token_vocab, (int32_t)e->adam_t_done)));
+      C2V_LAUNCH(e, (fill_i32_kernel<<<256, 256>>>(wsp<int32_t>(e, e->ws.last_path), (size_t)d.path_vocab, (int32_t)e->adam_t_done)));
+      C2V_CUDA(e, cudaMemset(wsp<int32_t>(e, e->ws.stamp_tok), 0, (size_t)d.token_vocab * 4));
+      C2V_CUDA(e, cudaMemset(wsp<int32_t>(e, e->ws.stamp_path), 0, (size_t)d.path_vocab * 4));
+      e->mark_epoch = 0;
+      C2V_CUDA(e, cudaDeviceSynchronize());
+    }
+    e->lazy = value ? 1 : 0;
+    return C2V_OK;
+  }
+  if (!strcmp(key, "adam_step_count")) {                  // optimizer reset / checkpoint restore
+    C2V_CUDA(e, cudaSetDevice(e->device));
+    if (e->lazy) {
+      int rc = flush_rows(e, 0);
+      if (rc) return rc;
+      const c2v_dims& d = e->dims;
+      C2V_LAUNCH(e, (fill_i32_kernel<<<256, 256>>>(wsp<int32_t>(e, e->ws.last_tok), (size_t)d.token_vocab, (int32_t)value)));
+      C2V_LAUNCH(e, (fill_i32_kernel<<<256, 256>>>(wsp<int32_t>(e, e->ws.last_path), (size_t)d.path_vocab, (int32_t)value)));
+      C2V_CUDA(e, cudaDeviceSynchronize());
+    }
+    e->adam_t_done = value;
+    e->hp_set = false;
+    return C2V_OK;
+  }
   return fail(e, C2V_ERR_INVALID, std::string("unknown option: ") + key);
 }
 
@@ -631,6 +739,8 @@ int c2v_get_option(const c2v_engine* e, const char* key, int64_t* value) {
   if (!strcmp(key, "math_mode")) { *value = e->math_mode; return C2V_OK; }
   if (!strcmp(key, "deterministic")) { *value = e->deterministic; return C2V_OK; }
   if (!strcmp(key, "profile")) { *value = e->profile; return C2V_OK; }
+  if (!strcmp(key, "lazy_adam")) { *value = e->lazy; return C2V_OK; }
+  if (!strcmp(key, "adam_step_count")) { *value = e->adam_t_done; return C2V_OK; }
   return C2V_ERR_INVALID;
 }
 
@@ -754,6 +864,12 @@ int c2v_ipc_free(int device, void* dev_ptr) {
   C2V_CUDA((c2v_engine*)nullptr, cudaSetDevice(device));
   C2V_CUDA((c2v_engine*)nullptr, cudaFree(dev_ptr));
   return C2V_OK;
+}
+
+int c2v_sync_tables(c2v_engine* e, void* stream) {
+  if (!e) return C2V_ERR_INVALID;
+  C2V_CUDA(e, cudaSetDevice(e->device));
+  return flush_rows(e, (cudaStream_t)stream);
 }
 
 int c2v_set_event(c2v_engine* e, const char* name, void* cuda_event) {

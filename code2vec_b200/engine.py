@@ -77,6 +77,7 @@ _SIGNATURES = {
     "c2v_selftest_gemm": (C.c_int, [_P, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _P, C.c_size_t, _P, C.c_size_t,
                                     _P, C.c_size_t, _P]),
     "c2v_set_event": (C.c_int, [_P, C.c_char_p, _P]),
+    "c2v_sync_tables": (C.c_int, [_P, _P]),
     "c2v_launch_count": (C.c_int64, [_P]),
     "c2v_phase_count": (C.c_int, []),
     "c2v_phase_name": (C.c_char_p, [C.c_int]),
@@ -301,17 +302,24 @@ class PathAttentionEngine:
                 raise ValueError("parameter %s has shape %s, expected %s" % (k, tuple(src.shape), tuple(self.params[k].shape)))
             self.params[k].copy_(src)
 
+    def sync_tables(self):
+        """Lazy Adam: replay deferred updates so the parameter tensors can be read from outside the engine."""
+        self._check(self.lib.c2v_sync_tables(self.h, self._stream()))
+
     def export_params(self) -> Dict[str, np.ndarray]:
+        self.sync_tables()
         return {k: self.params[k].detach().cpu().numpy() for k in PARAM_NAMES}
 
     def export_grads(self) -> Dict[str, np.ndarray]:
         return {k: self.grads[k].detach().cpu().numpy() for k in PARAM_NAMES}
 
     def reset_optimizer(self):
+        self.sync_tables()
         for d in (self.adam_m, self.adam_v):
             for t in d.values():
                 t.zero_()
         self.adam_t = 0
+        self.set_option("adam_step_count", 0)
 
     def to_device(self, arr, dtype):
         torch = self.torch
@@ -391,6 +399,8 @@ class PathAttentionEngine:
         world, rank = dist.get_world_size(group), dist.get_rank(group)
         if world not in (1, 2, 4, 8):
             raise ValueError("table sharding needs a world size of 1, 2, 4 or 8")
+        if self.training and self.get_option("lazy_adam"):
+            self.set_option("lazy_adam", 0)          # flushes deferred updates; shards use the dense per-rank Adam
         d = self.dims.embed_dim
         rows = {"tok": (self.dims.token_vocab + world - 1) // world, "path": (self.dims.path_vocab + world - 1) // world}
         own, handles = {}, {}

@@ -101,7 +101,7 @@ def shard_bounds(n: int, rank: int, world: int):
 
 class Trainer:
     def __init__(self, engine: PathAttentionEngine, keep_prob: float = 0.75, seed: int = 0, group=None,
-                 adam: Optional[dict] = None, schedule: str = "table_sharded"):
+                 adam: Optional[dict] = None, schedule: str = "table_sharded", lazy_adam: bool = True):
         self.e = engine
         self.keep = float(keep_prob)
         self.seed = int(seed)
@@ -150,6 +150,8 @@ class Trainer:
             self._ev_tgt = torch.cuda.Event()
             with torch.cuda.device(engine.dev):
                 engine.set_event("target_grads_ready", self._ev_tgt)
+        if self.schedule == "single" and lazy_adam and engine.training:
+            engine.set_option("lazy_adam", 1)       # exact, see c2v_b200.h; the multi-GPU schedules stay dense
         self._loss_host = torch.zeros(1, dtype=torch.float32).pin_memory()
 
     # ---- inputs already resident on the device ----------------------------------------------

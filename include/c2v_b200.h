@@ -99,7 +99,11 @@ int c2v_bind_adam_state(c2v_engine* e, const c2v_tensors* m, const c2v_tensors* 
 
 /* Options: "math_mode" (c2v_math_mode), "deterministic" (0/1: 1 = fixed-order reductions for
  * the scatter-add of embedding gradients instead of float atomics), "profile" (0/1: per-phase
- * CUDA-event timing, read with c2v_phase_stats). */
+ * CUDA-event timing, read with c2v_phase_stats), "lazy_adam" (0/1, single-GPU replicated tables:
+ * the dense TF1 Adam update of an embedding row that received no gradient is deferred and replayed
+ * bit-exactly when the row is next read or updated -- same results as the dense update, a
+ * fraction of the memory traffic; c2v_sync_tables brings every row up to date),
+ * "adam_step_count" (the number of Adam steps already applied: optimizer reset / restore). */
 int c2v_set_option(c2v_engine* e, const char* key, int64_t value);
 int c2v_get_option(const c2v_engine* e, const char* key, int64_t* value);
 
@@ -150,6 +154,11 @@ int c2v_sampled_train_step(c2v_engine* e, const int32_t* src, const int32_t* pat
  * sparse apply is not lazy); theta -= lr_t*m/(sqrt(v)+eps).  t is the 1-based step count. */
 int c2v_adam_step(c2v_engine* e, float lr, float beta1, float beta2, float eps, int64_t t,
                   void* stream);
+
+/* With "lazy_adam" on: replay all deferred updates so that the bound token / path tables (and their
+ * Adam slots) hold exactly what the dense optimizer would hold after the steps applied so far.  Call
+ * before reading the parameter tensors from outside the engine (export, checkpoint).  No-op otherwise. */
+int c2v_sync_tables(c2v_engine* e, void* stream);
 
 /* The same update on one contiguous slice of caller-provided device arrays (count % 4 == 0,
  * 16-byte aligned): the sharded-optimizer path of a data-parallel run, where each rank owns
