@@ -110,20 +110,41 @@ def make_batches(w, n_batches, seed, full_bags=False):
     return [synthetic_batch(dims, w["batch"], seed=seed + 7919 * i, full_bags=full_bags) for i in range(n_batches)]
 
 
-def algorithmic_work(w, B):
-    """Per-launch algorithmic FLOPs / bytes of each phase."""
+def algorithmic_work(w, B, touched_rows=None, world=1):
+    """Per-step algorithmic FLOPs / bytes of each phase.
+
+    adam: the dense TF1 update streams theta, m, v in and out = 24 B per parameter.  With the
+    lazy-but-exact scheme (single GPU) only the rows the batch references are streamed: 24 B per
+    element in the catch-up pass + 24 B in the update pass, the dense part being the target table,
+    TRANSFORM and ATTENTION.  Under table sharding each rank updates 1/world of every table."""
     d, D, C, Y = w["embed_dim"], w["code_dim"], w["max_contexts"], w["target_vocab"]
     N = B * C
-    n_params = (w["token_vocab"] + w["path_vocab"]) * d + Y * D + 3 * d * D + D
+    emb = (w["token_vocab"] + w["path_vocab"]) * d
+    rest = Y * D + 3 * d * D + D
     proj = 2.0 * N * 3 * d * D
     logit = 2.0 * B * D * Y
+    if touched_rows is not None:
+        adam, catchup = 24.0 * (rest + touched_rows * d), 24.0 * touched_rows * d
+    else:
+        adam, catchup = 24.0 * (emb + rest) / world, 0.0
     return {
-        "ctx_fwd": ("tensor", proj), "dW": ("tensor", proj), "dx_scatter": ("tensor", proj),
+        "ctx_fwd": ("tensor", proj), "dW": ("tensor", proj), "dx_gemm": ("tensor", proj),
         "logits": ("tensor", logit), "dv": ("tensor", logit), "dY": ("tensor", logit),
-        "adam": ("hbm", 24.0 * n_params),                       # theta, m, v read + written
+        "adam": ("hbm", adam), "adam_catchup": ("hbm", catchup),
         "attn_fwd": ("hbm", 4.0 * N * D), "attn_bwd": ("hbm", 3 * 4.0 * N * D),
         "xent": ("hbm", 2 * 4.0 * B * Y),
+        "gather": ("hbm", N * (3 * d * 4 + 16) + 4.0 * N * 3 * d),      # table rows + indices/mask in, X' out
+        "dx_scatter": ("hbm", 4.0 * N * 3 * d + 2 * 4.0 * N * 3 * d),   # dX' in, read-modify-write of the table rows
     }
+
+
+def ncu_traffic():
+    """DRAM bytes per launch measured by `ncu --set full` (profiles/r01_traffic.json), keyed by phase."""
+    p = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    try:
+        return json.load(open(p))
+    except Exception:
+        return {}
 
 
 # ================================ our arm ========================================================
@@ -221,11 +242,16 @@ def run_ours(args):
     value = contexts / (ms * 1e-3)
     e2e_value = contexts / (ms_e2e * 1e-3)
     peaks = _peaks()
-    work = algorithmic_work(w, B)
+    touched = None
+    if trainer.schedule == "single" and eng.get_option("lazy_adam"):
+        touched = float(np.mean([len(np.unique(np.concatenate([b[0].ravel(), b[2].ravel()]))) + len(np.unique(b[1]))
+                                 for b in host]))
+    work = algorithmic_work(w, B, touched_rows=touched, world=world if trainer.schedule == "table_sharded" else 1)
+    traffic = ncu_traffic()
     phase_out = {}
     dominant, dom_ms = None, -1.0
     for name, (tot_ms, n) in phases.items():
-        avg = tot_ms / max(n, 1)
+        avg = tot_ms / K                      # per step (a phase may be several launches)
         entry = {"ms": round(avg, 4), "share": round(tot_ms / ms, 4)}
         if name in work:
             kind, amount = work[name]
@@ -243,13 +269,14 @@ def run_ours(args):
             ach = amount / (dom_ms * 1e-3) / 1e12
             peak = peaks["tensor_sustained"]
             roofline = {"kernel": dominant, "bound": "tensor", "achieved": round(ach, 2), "peak": peak, "unit": "TFLOP/s",
-                        "frac": round(ach / peak, 4), "traffic": None,
+                        "frac": round(ach / peak, 4), "traffic": traffic.get(dominant),
                         "peak_source": peaks["source"] + " bf16 dense (sustained); tf32 tcgen05 peak is half of it"}
         else:
             ach = amount / (dom_ms * 1e-3) / 1e9
             peak = peaks["hbm"]
             roofline = {"kernel": dominant, "bound": "hbm", "achieved": round(ach, 1), "peak": peak, "unit": "GB/s",
-                        "frac": round(ach / peak, 4), "traffic": None, "peak_source": peaks["source"] + " copy bandwidth"}
+                        "frac": round(ach / peak, 4), "traffic": traffic.get(dominant),
+                        "peak_source": peaks["source"] + " copy bandwidth"}
 
     cpu = None
     if world == 1 and not args.no_cpu_baseline:

@@ -114,6 +114,7 @@ class Code2VecModel(Code2VecModelBase):
     # ---- checkpoint: header (json) + raw little-endian float32 tensors -------------------------
     def _save_inner_model(self, path: str, release: bool = False):
         e = self.engine
+        e.sync_tables()                                  # lazy Adam: replay deferred row updates before reading the tensors
         tensors = [("theta/" + k, e.params[k]) for k in PARAM_NAMES]
         with_optimizer = (not release) and e.adam_m is not None
         if with_optimizer:
@@ -271,6 +272,7 @@ class Code2VecModel(Code2VecModelBase):
 
     def _get_vocab_embedding_as_np_array(self, vocab_type: VocabType) -> np.ndarray:
         assert vocab_type in VocabType
+        self.engine.sync_tables()
         return self.engine.params[self._param_of_vocab[vocab_type]].detach().cpu().numpy()
 
     # ---- logging helpers (tensorflow_model.py:411-437) ------------------------------------------------------

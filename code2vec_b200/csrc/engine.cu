@@ -273,10 +273,10 @@ int prepare_rows(c2v_engine* e, cudaStream_t st, const ContextSource& cs) {
                                                                         e->mark_epoch)));
   if (e->adam_t_done > 0) {
     const float* lr_tab = wsp<float>(e, e->ws.lr_tab);
-    C2V_LAUNCH(e, (adam_rows_kernel<ADAM_ROWS_CATCHUP><<<(d.token_vocab + 7) / 8, 256, 0, st>>>(
+    C2V_LAUNCH(e, (adam_rows_kernel<ADAM_ROWS_CATCHUP><<<e->num_sms * 8, 256, 0, st>>>(
                       e->theta.tok, e->grad.tok, e->am.tok, e->av.tok, d.token_vocab, d.embed_dim, stamp_tok, e->mark_epoch,
                       wsp<int32_t>(e, e->ws.last_tok), (int32_t)e->adam_t_done, lr_tab, e->hp_b1, e->hp_b2, e->hp_eps)));
-    C2V_LAUNCH(e, (adam_rows_kernel<ADAM_ROWS_CATCHUP><<<(d.path_vocab + 7) / 8, 256, 0, st>>>(
+    C2V_LAUNCH(e, (adam_rows_kernel<ADAM_ROWS_CATCHUP><<<e->num_sms * 8, 256, 0, st>>>(
                       e->theta.path, e->grad.path, e->am.path, e->av.path, d.path_vocab, d.embed_dim, stamp_path, e->mark_epoch,
                       wsp<int32_t>(e, e->ws.last_path), (int32_t)e->adam_t_done, lr_tab, e->hp_b1, e->hp_b2, e->hp_eps)));
   }
@@ -288,10 +288,10 @@ int flush_rows(c2v_engine* e, cudaStream_t st) {
   if (!e->lazy || e->adam_t_done == 0) return C2V_OK;
   const c2v_dims& d = e->dims;
   const float* lr_tab = wsp<float>(e, e->ws.lr_tab);
-  C2V_LAUNCH(e, (adam_rows_kernel<ADAM_ROWS_FLUSH><<<(d.token_vocab + 7) / 8, 256, 0, st>>>(
+  C2V_LAUNCH(e, (adam_rows_kernel<ADAM_ROWS_FLUSH><<<e->num_sms * 8, 256, 0, st>>>(
                     e->theta.tok, e->grad.tok, e->am.tok, e->av.tok, d.token_vocab, d.embed_dim, nullptr, 0,
                     wsp<int32_t>(e, e->ws.last_tok), (int32_t)e->adam_t_done, lr_tab, e->hp_b1, e->hp_b2, e->hp_eps)));
-  C2V_LAUNCH(e, (adam_rows_kernel<ADAM_ROWS_FLUSH><<<(d.path_vocab + 7) / 8, 256, 0, st>>>(
+  C2V_LAUNCH(e, (adam_rows_kernel<ADAM_ROWS_FLUSH><<<e->num_sms * 8, 256, 0, st>>>(
                     e->theta.path, e->grad.path, e->am.path, e->av.path, d.path_vocab, d.embed_dim, nullptr, 0,
                     wsp<int32_t>(e, e->ws.last_path), (int32_t)e->adam_t_done, lr_tab, e->hp_b1, e->hp_b2, e->hp_eps)));
   return C2V_OK;
@@ -572,10 +572,10 @@ int adam_impl(c2v_engine* e, cudaStream_t st, float lr, float b1, float b2, floa
     e->hp_lr = lr; e->hp_b1 = b1; e->hp_b2 = b2; e->hp_eps = eps; e->hp_set = true;
     float* lr_tab = wsp<float>(e, e->ws.lr_tab);
     C2V_LAUNCH(e, (set_float_kernel<<<1, 1, 0, st>>>(lr_tab + t, lr_t)));
-    C2V_LAUNCH(e, (adam_rows_kernel<ADAM_ROWS_UPDATE><<<(d.token_vocab + 7) / 8, 256, 0, st>>>(
+    C2V_LAUNCH(e, (adam_rows_kernel<ADAM_ROWS_UPDATE><<<e->num_sms * 8, 256, 0, st>>>(
                       P[0], G[0], M[0], V[0], d.token_vocab, d.embed_dim, wsp<int32_t>(e, e->ws.stamp_tok), e->mark_epoch,
                       wsp<int32_t>(e, e->ws.last_tok), (int32_t)t, lr_tab, b1, b2, eps)));
-    C2V_LAUNCH(e, (adam_rows_kernel<ADAM_ROWS_UPDATE><<<(d.path_vocab + 7) / 8, 256, 0, st>>>(
+    C2V_LAUNCH(e, (adam_rows_kernel<ADAM_ROWS_UPDATE><<<e->num_sms * 8, 256, 0, st>>>(
                       P[1], G[1], M[1], V[1], d.path_vocab, d.embed_dim, wsp<int32_t>(e, e->ws.stamp_path), e->mark_epoch,
                       wsp<int32_t>(e, e->ws.last_path), (int32_t)t, lr_tab, b1, b2, eps)));
     first_dense = 2;

@@ -651,52 +651,71 @@ __global__ void set_float_kernel(float* p, float v) { *p = v; }
 
 enum { ADAM_ROWS_CATCHUP = 0, ADAM_ROWS_UPDATE = 1, ADAM_ROWS_FLUSH = 2 };
 
+// Persistent grid: every warp scans 32 rows at a time (one coalesced read of their stamps and
+// `last` values), then the whole warp walks the rows that need work, one 128-bit access per lane
+// and array.
 template <int MODE>
 __global__ void __launch_bounds__(256)
 adam_rows_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, int rows, int d,
                  const int32_t* __restrict__ stamp, int32_t epoch, int32_t* __restrict__ last, int32_t t_done,
                  const float* __restrict__ lr_tab, float b1, float b2, float eps) {
-  const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
-  if (row >= rows) return;
-  if (MODE != ADAM_ROWS_FLUSH && stamp[row] != epoch) return;
-  const int32_t from = last[row];
-  if (MODE != ADAM_ROWS_UPDATE && from >= t_done) return;
+  const int lane = threadIdx.x & 31;
+  const int warp_global = (blockIdx.x * 256 + threadIdx.x) >> 5;
+  const int total_warps = (gridDim.x * 256) >> 5;
   const float omb1 = __fsub_rn(1.f, b1), omb2 = __fsub_rn(1.f, b2);
-  for (int j = lane * 4; j < d; j += 128) {
-    const size_t o = (size_t)row * d + j;
-    float4 P = *reinterpret_cast<float4*>(p + o), M = *reinterpret_cast<float4*>(m + o), V = *reinterpret_cast<float4*>(v + o);
-    float* pp = reinterpret_cast<float*>(&P);
-    float* mm = reinterpret_cast<float*>(&M);
-    float* vv = reinterpret_cast<float*>(&V);
-    // pending zero-gradient steps: m*b1 + (1-b1)*0, v*b2 + (1-b2)*(0*0) -- the dense kernel's exact operations
-    const int32_t upto = (MODE == ADAM_ROWS_UPDATE) ? t_done - 1 : t_done;
-    for (int32_t s = from + 1; s <= upto; ++s) {
-      const float lr_s = lr_tab[s];
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        mm[q] = __fadd_rn(__fmul_rn(mm[q], b1), __fmul_rn(omb1, 0.f));
-        vv[q] = __fadd_rn(__fmul_rn(vv[q], b2), __fmul_rn(omb2, 0.f));
-        pp[q] = __fsub_rn(pp[q], __fdiv_rn(__fmul_rn(lr_s, mm[q]), __fadd_rn(__fsqrt_rn(vv[q]), eps)));
+  const int32_t upto = (MODE == ADAM_ROWS_UPDATE) ? t_done - 1 : t_done;
+  const float lr_t = (MODE == ADAM_ROWS_UPDATE) ? lr_tab[t_done] : 0.f;
+  for (int base = warp_global * 32; base < rows; base += total_warps * 32) {
+    const int r = base + lane;
+    int32_t from_l = 0;
+    bool hit = false;
+    if (r < rows) {
+      hit = (MODE == ADAM_ROWS_FLUSH) || (stamp[r] == epoch);
+      if (hit) {
+        from_l = last[r];
+        if (MODE != ADAM_ROWS_UPDATE && from_l >= t_done) hit = false;
       }
     }
-    if (MODE == ADAM_ROWS_UPDATE) {
-      const float4 G = *reinterpret_cast<const float4*>(g + o);
-      const float* gg = reinterpret_cast<const float*>(&G);
-      const float lr_t = lr_tab[t_done];
+    unsigned todo = __ballot_sync(0xffffffffu, hit);
+    while (todo) {
+      const int b = __ffs(todo) - 1;
+      todo &= todo - 1;
+      const int row = base + b;
+      const int32_t from = __shfl_sync(0xffffffffu, from_l, b);
+      for (int j = lane * 4; j < d; j += 128) {
+        const size_t o = (size_t)row * d + j;
+        float4 P = *reinterpret_cast<float4*>(p + o), M = *reinterpret_cast<float4*>(m + o), V = *reinterpret_cast<float4*>(v + o);
+        float* pp = reinterpret_cast<float*>(&P);
+        float* mm = reinterpret_cast<float*>(&M);
+        float* vv = reinterpret_cast<float*>(&V);
+        // pending zero-gradient steps: m*b1 + (1-b1)*0, v*b2 + (1-b2)*(0*0) -- the dense kernel's exact operations
+        for (int32_t s = from + 1; s <= upto; ++s) {
+          const float lr_s = lr_tab[s];
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        mm[q] = __fadd_rn(__fmul_rn(mm[q], b1), __fmul_rn(omb1, gg[q]));
-        vv[q] = __fadd_rn(__fmul_rn(vv[q], b2), __fmul_rn(omb2, __fmul_rn(gg[q], gg[q])));
-        pp[q] = __fsub_rn(pp[q], __fdiv_rn(__fmul_rn(lr_t, mm[q]), __fadd_rn(__fsqrt_rn(vv[q]), eps)));
+          for (int q = 0; q < 4; ++q) {
+            mm[q] = __fadd_rn(__fmul_rn(mm[q], b1), __fmul_rn(omb1, 0.f));
+            vv[q] = __fadd_rn(__fmul_rn(vv[q], b2), __fmul_rn(omb2, 0.f));
+            pp[q] = __fsub_rn(pp[q], __fdiv_rn(__fmul_rn(lr_s, mm[q]), __fadd_rn(__fsqrt_rn(vv[q]), eps)));
+          }
+        }
+        if (MODE == ADAM_ROWS_UPDATE) {
+          const float4 G = *reinterpret_cast<const float4*>(g + o);
+          const float* gg = reinterpret_cast<const float*>(&G);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            mm[q] = __fadd_rn(__fmul_rn(mm[q], b1), __fmul_rn(omb1, gg[q]));
+            vv[q] = __fadd_rn(__fmul_rn(vv[q], b2), __fmul_rn(omb2, __fmul_rn(gg[q], gg[q])));
+            pp[q] = __fsub_rn(pp[q], __fdiv_rn(__fmul_rn(lr_t, mm[q]), __fadd_rn(__fsqrt_rn(vv[q]), eps)));
+          }
+          *reinterpret_cast<float4*>(g + o) = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        *reinterpret_cast<float4*>(p + o) = P;
+        *reinterpret_cast<float4*>(m + o) = M;
+        *reinterpret_cast<float4*>(v + o) = V;
       }
-      *reinterpret_cast<float4*>(g + o) = make_float4(0.f, 0.f, 0.f, 0.f);
     }
-    *reinterpret_cast<float4*>(p + o) = P;
-    *reinterpret_cast<float4*>(m + o) = M;
-    *reinterpret_cast<float4*>(v + o) = V;
+    if (hit) last[r] = t_done;
   }
-  __syncwarp();
-  if (lane == 0) last[row] = t_done;
 }
 
 }  // namespace c2v
