@@ -584,7 +584,8 @@ adam_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m,
 // so the three projection GEMMs can be fed by TMA; and its inverse, the scatter-add of dX' rows
 // into the embedding gradient tables.  One warp per context row, 128-bit accesses.
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) gather_ctx_kernel(ContextSource cs, Dropout dp, float* __restrict__ Xg) {
+__global__ void __launch_bounds__(256)
+gather_ctx_kernel(const __grid_constant__ ContextSource cs, const __grid_constant__ Dropout dp, float* __restrict__ Xg) {
   const int n = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (n >= cs.rows) return;
   const int K3 = 3 * cs.d;
@@ -598,8 +599,9 @@ __global__ void __launch_bounds__(256) gather_ctx_kernel(ContextSource cs, Dropo
 }
 
 __global__ void __launch_bounds__(256)
-scatter_dx_kernel(ContextSource cs, Dropout dp, const float* __restrict__ mask, const float* __restrict__ dXg,
-                  ShardedTable g_tok, ShardedTable g_path, float grad_scale) {
+scatter_dx_kernel(const __grid_constant__ ContextSource cs, const __grid_constant__ Dropout dp, const float* __restrict__ mask,
+                  const float* __restrict__ dXg, const __grid_constant__ ShardedTable g_tok,
+                  const __grid_constant__ ShardedTable g_path, float grad_scale) {
   const int n = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (n >= cs.rows) return;
   if (mask[n] == 0.f) return;                 // masked contexts carry exact zeros

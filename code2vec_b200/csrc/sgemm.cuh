@@ -148,7 +148,8 @@ struct ScatterDx {
 // C[M,N] (+)= A[M,K] . B[K,N] over k in [z*kchunk, min(K,(z+1)*kchunk)), z = blockIdx.z.
 template <class AL, class BL, class EP>
 __global__ void __launch_bounds__(NT, 2)
-sgemm_kernel(int M, int N, int K, int kchunk, AL al, BL bl, EP ep) {
+sgemm_kernel(int M, int N, int K, int kchunk, const __grid_constant__ AL al, const __grid_constant__ BL bl,
+             const __grid_constant__ EP ep) {
   __shared__ __align__(16) float As[2][BK][LDT];
   __shared__ __align__(16) float Bs[2][BK][LDT];
   const int tid = threadIdx.x;
