@@ -437,6 +437,51 @@ int context_backward(c2v_engine* e, cudaStream_t st, const ContextSource& cs, co
   return C2V_OK;
 }
 
+// Given P = dL/dlogits in the S slab:  dv = P . Ytab  (split-K over |Y|, fixed-order reduction) and
+// dYtab = P^T . v  into the bound target-table gradient.
+int target_grad_gemms(c2v_engine* e, cudaStream_t st, const float* v, int B, float* dv) {
+  const int D = e->dims.code_dim, Y = e->dims.target_vocab;
+  float* S = wsp<float>(e, e->ws.S);
+  float* part = wsp<float>(e, e->ws.part);
+  int rc;
+  if (e->math_mode == C2V_MATH_TF32 && (reinterpret_cast<uintptr_t>(v) % 16 == 0)) {
+    {
+      PhaseTimer pt(e, PH_DV, st);
+      umma::Operand opA{S, e->ws.ldS, false};
+      umma::Operand opB{e->theta.tgt, (size_t)D, true};
+      const int ks = umma::effective_splits(Y, kSplitDv);
+      umma::EpiStore ep{part, (size_t)D, (size_t)B * D};
+      C2V_LAUNCH(e, C2V_CUDA(e, (umma::launch<192, 5>(st, B, D, Y, kSplitDv, opA, opB, ep, e->num_sms))));
+      if ((rc = launch_colsum(e, st, part, (size_t)B * D, ks, B * D, dv))) return rc;
+    }
+    {
+      PhaseTimer pt(e, PH_DY, st);
+      umma::Operand opA{S, e->ws.ldS, true};
+      umma::Operand opB{v, (size_t)D, true};
+      umma::EpiStore ep{e->grad.tgt, (size_t)D, 0};
+      C2V_LAUNCH(e, C2V_CUDA(e, (umma::launch<192, 5>(st, Y, D, B, 1, opA, opB, ep, e->num_sms))));
+    }
+    return C2V_OK;
+  }
+  {
+    PhaseTimer pt(e, PH_DV, st);
+    simt::RowsK al{S, e->ws.ldS};
+    simt::ColsX bl{e->theta.tgt, (size_t)D};
+    const int ks = simt::effective_ksplit(Y, kSplitDv);
+    simt::StoreC ep{part, (size_t)D, (size_t)B * D};
+    C2V_LAUNCH(e, C2V_CUDA(e, simt::launch(st, B, D, Y, kSplitDv, al, bl, ep)));
+    if ((rc = launch_colsum(e, st, part, (size_t)B * D, ks, B * D, dv))) return rc;
+  }
+  {
+    PhaseTimer pt(e, PH_DY, st);
+    simt::ColsX al{S, e->ws.ldS};
+    simt::ColsX bl{v, (size_t)D};
+    simt::StoreC ep{e->grad.tgt, (size_t)D, 0};
+    C2V_LAUNCH(e, C2V_CUDA(e, simt::launch(st, Y, D, B, 1, al, bl, ep)));
+  }
+  return C2V_OK;
+}
+
 int train_step_impl(c2v_engine* e, cudaStream_t st, const int32_t* src, const int32_t* pth, const int32_t* tgt,
                     const float* mask, const int32_t* target, int B, float keep, uint64_t seed, uint64_t step,
                     const float* ext_mask, float* loss_out) {
@@ -452,7 +497,6 @@ int train_step_impl(c2v_engine* e, cudaStream_t st, const int32_t* src, const in
   float* S = wsp<float>(e, e->ws.S);
   float* loss_b = wsp<float>(e, e->ws.loss_b);
   float* lse = wsp<float>(e, e->ws.lse);
-  float* part = wsp<float>(e, e->ws.part);
   int rc;
   if ((rc = run_ctx_fwd(e, st, cs, dp, H))) return rc;
   if ((rc = launch_attn_fwd(e, st, H, mask, B, alpha, v))) return rc;
@@ -472,42 +516,7 @@ int train_step_impl(c2v_engine* e, cudaStream_t st, const int32_t* src, const in
     }
     C2V_LAUNCH(e, (loss_reduce_kernel<<<1, 256, 0, st>>>(loss_b, B, invB, loss_out)));
   }
-  if (e->math_mode == C2V_MATH_TF32) {
-    {  // dv = P . Ytab   (split-K over |Y|, fixed-order reduction of the slices)
-      PhaseTimer pt(e, PH_DV, st);
-      umma::Operand opA{S, e->ws.ldS, false};
-      umma::Operand opB{e->theta.tgt, (size_t)D, true};
-      const int ks = umma::effective_splits(Y, kSplitDv);
-      umma::EpiStore ep{part, (size_t)D, (size_t)B * D};
-      C2V_LAUNCH(e, C2V_CUDA(e, (umma::launch<192, 5>(st, B, D, Y, kSplitDv, opA, opB, ep, e->num_sms))));
-      if ((rc = launch_colsum(e, st, part, (size_t)B * D, ks, B * D, dv))) return rc;
-    }
-    {  // dYtab = P^T . v
-      PhaseTimer pt(e, PH_DY, st);
-      umma::Operand opA{S, e->ws.ldS, true};
-      umma::Operand opB{v, (size_t)D, true};
-      umma::EpiStore ep{e->grad.tgt, (size_t)D, 0};
-      C2V_LAUNCH(e, C2V_CUDA(e, (umma::launch<192, 5>(st, Y, D, B, 1, opA, opB, ep, e->num_sms))));
-    }
-    if (e->ev_tgt_ready) C2V_CUDA(e, cudaEventRecord(e->ev_tgt_ready, st));
-    return context_backward(e, st, cs, mask, B, dp, dv);
-  }
-  {  // dv = P . Ytab   (K = |Y| split, fixed-order reduction)
-    PhaseTimer pt(e, PH_DV, st);
-    simt::RowsK al{S, e->ws.ldS};
-    simt::ColsX bl{e->theta.tgt, (size_t)D};
-    const int ks = simt::effective_ksplit(Y, kSplitDv);
-    simt::StoreC ep{part, (size_t)D, (size_t)B * D};
-    C2V_LAUNCH(e, C2V_CUDA(e, simt::launch(st, B, D, Y, kSplitDv, al, bl, ep)));
-    if ((rc = launch_colsum(e, st, part, (size_t)B * D, ks, B * D, dv))) return rc;
-  }
-  {  // dYtab = P^T . v
-    PhaseTimer pt(e, PH_DY, st);
-    simt::ColsX al{S, e->ws.ldS};
-    simt::ColsX bl{v, (size_t)D};
-    simt::StoreC ep{e->grad.tgt, (size_t)D, 0};
-    C2V_LAUNCH(e, C2V_CUDA(e, simt::launch(st, Y, D, B, 1, al, bl, ep)));
-  }
+  if ((rc = target_grad_gemms(e, st, v, B, dv))) return rc;
   if (e->ev_tgt_ready) C2V_CUDA(e, cudaEventRecord(e->ev_tgt_ready, st));
   return context_backward(e, st, cs, mask, B, dp, dv);
 }
@@ -695,6 +704,11 @@ int c2v_set_option(c2v_engine* e, const char* key, int64_t value) {
   }
   if (!strcmp(key, "deterministic")) { e->deterministic = value ? 1 : 0; return C2V_OK; }
   if (!strcmp(key, "profile")) { e->profile = value ? 1 : 0; return C2V_OK; }
+  if (!strcmp(key, "grad_scale_inverse")) {               // scatter-add scale = 1 / value (1 = unscaled)
+    if (value < 1) return fail(e, C2V_ERR_INVALID, "grad_scale_inverse must be >= 1");
+    e->grad_scale = 1.0f / (float)value;
+    return C2V_OK;
+  }
   if (!strcmp(key, "lazy_adam")) {
     if (!e->wbase || !e->has_theta || !e->has_grad || !e->has_adam)
       return fail(e, C2V_ERR_STATE, "bind workspace, parameters, gradients and Adam state before lazy_adam");
@@ -864,6 +878,82 @@ int c2v_ipc_free(int device, void* dev_ptr) {
   C2V_CUDA((c2v_engine*)nullptr, cudaSetDevice(device));
   C2V_CUDA((c2v_engine*)nullptr, cudaFree(dev_ptr));
   return C2V_OK;
+}
+
+// ---- phase-split training step: the fully sharded schedule (target table row-sharded too) ------------
+int c2v_context_forward(c2v_engine* e, const int32_t* src, const int32_t* path, const int32_t* tgt, const float* mask,
+                        int32_t B, float keep_prob, uint64_t seed, uint64_t step, const float* dropout_mask,
+                        float* code_vec, void* stream) {
+  int rc = check_batch(e, B);
+  if (rc) return rc;
+  if (!src || !path || !tgt || !mask || !code_vec) return fail(e, C2V_ERR_INVALID, "NULL argument");
+  if (!(keep_prob > 0.f) || keep_prob > 1.f) return fail(e, C2V_ERR_INVALID, "keep_prob must be in (0, 1]");
+  C2V_CUDA(e, cudaSetDevice(e->device));
+  const Dropout dp = make_dropout(e->dims, keep_prob, seed, step, dropout_mask);
+  return forward_impl(e, (cudaStream_t)stream, src, path, tgt, mask, B, dp, code_vec, wsp<float>(e, e->ws.alpha));
+}
+
+int c2v_target_forward(c2v_engine* e, const float* code_all, int32_t Bt, const int32_t* target, int32_t row_offset,
+                       float* row_max, float* row_sum, float* true_logit, void* stream) {
+  int rc = check_batch(e, Bt);
+  if (rc) return rc;
+  if (!code_all || !target || !row_max || !row_sum || !true_logit) return fail(e, C2V_ERR_INVALID, "NULL argument");
+  C2V_CUDA(e, cudaSetDevice(e->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  float* S = wsp<float>(e, e->ws.S);
+  const int Y = e->dims.target_vocab;
+  const bool fused = (e->math_mode == C2V_MATH_TF32) && (reinterpret_cast<uintptr_t>(code_all) % 16 == 0);
+  if ((rc = run_logits(e, st, code_all, Bt, S, fused))) return rc;
+  PhaseTimer pt(e, PH_XENT, st);
+  C2V_LAUNCH(e, (row_maxsum_kernel<<<Bt, 256, 0, st>>>(fused ? wsp<float2>(e, e->ws.lse_part) : nullptr,
+                                                       2 * ((Y + 255) / 256), S, e->ws.ldS, Y, target, row_offset, row_max,
+                                                       row_sum, true_logit)));
+  return C2V_OK;
+}
+
+int c2v_lse_combine(c2v_engine* e, const float* maxes, const float* sums, int32_t world, int32_t Bt, const float* true_logit,
+                    float inv_batch, float* lse_out, float* loss_out, void* stream) {
+  if (!e || !maxes || !sums || !true_logit || !lse_out || !loss_out) return C2V_ERR_INVALID;
+  if (Bt < 1 || Bt > e->dims.max_batch || world < 1) return fail(e, C2V_ERR_INVALID, "bad size");
+  C2V_CUDA(e, cudaSetDevice(e->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  float* loss_b = wsp<float>(e, e->ws.loss_b);
+  C2V_LAUNCH(e, (lse_combine_kernel<<<(Bt + 255) / 256, 256, 0, st>>>(maxes, sums, world, Bt, true_logit, lse_out, loss_b)));
+  C2V_LAUNCH(e, (loss_reduce_kernel<<<1, 256, 0, st>>>(loss_b, Bt, inv_batch, loss_out)));
+  return C2V_OK;
+}
+
+int c2v_target_backward(c2v_engine* e, const float* code_all, int32_t Bt, const float* lse, const int32_t* target,
+                        int32_t row_offset, float inv_batch, float* dv_partial, void* stream) {
+  int rc = check_batch(e, Bt);
+  if (rc) return rc;
+  if (!code_all || !lse || !target || !dv_partial) return fail(e, C2V_ERR_INVALID, "NULL argument");
+  if (!e->has_grad) return fail(e, C2V_ERR_STATE, "gradients not bound (c2v_bind_grads)");
+  C2V_CUDA(e, cudaSetDevice(e->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  float* S = wsp<float>(e, e->ws.S);
+  {
+    PhaseTimer pt(e, PH_XENT, st);
+    const int chunks = (int)((e->ws.ldS / 4 + 256 * 8 - 1) / (256 * 8));
+    C2V_LAUNCH(e, (softmax_grad_kernel<<<dim3(chunks, Bt), 256, 0, st>>>(S, e->ws.ldS, e->dims.target_vocab, lse, target,
+                                                                       inv_batch, row_offset)));
+  }
+  if ((rc = target_grad_gemms(e, st, code_all, Bt, dv_partial))) return rc;
+  if (e->ev_tgt_ready) C2V_CUDA(e, cudaEventRecord(e->ev_tgt_ready, st));
+  return C2V_OK;
+}
+
+int c2v_context_backward(c2v_engine* e, const int32_t* src, const int32_t* path, const int32_t* tgt, const float* mask,
+                         int32_t B, float keep_prob, uint64_t seed, uint64_t step, const float* dropout_mask,
+                         const float* dv, void* stream) {
+  int rc = check_batch(e, B);
+  if (rc) return rc;
+  if (!src || !path || !tgt || !mask || !dv) return fail(e, C2V_ERR_INVALID, "NULL argument");
+  if (!e->has_grad) return fail(e, C2V_ERR_STATE, "gradients not bound (c2v_bind_grads)");
+  C2V_CUDA(e, cudaSetDevice(e->device));
+  const Dropout dp = make_dropout(e->dims, keep_prob, seed, step, dropout_mask);
+  ContextSource cs = make_source(e, src, path, tgt, B);
+  return context_backward(e, (cudaStream_t)stream, cs, mask, B, dp, dv);
 }
 
 int c2v_sync_tables(c2v_engine* e, void* stream) {

@@ -294,11 +294,11 @@ xent_combine_kernel(const float2* __restrict__ partial, int n_tiles, const float
 // S <- (softmax(S) - onehot(target)) * inv_batch in place, padding columns zeroed.  grid (chunks, B).
 __global__ void __launch_bounds__(256)
 softmax_grad_kernel(float* __restrict__ S, size_t ldS, int Y, const float* __restrict__ lse, const int32_t* __restrict__ target,
-                    float inv_batch) {
+                    float inv_batch, int row0 = 0) {
   const int b = blockIdx.y;
   float* row = S + (size_t)b * ldS;
   const float l = lse[b];
-  const int y = target[b];
+  const int y = target[b] - row0;                    // outside [0, Y): the target row lives on another rank
   const int n4 = (int)(ldS >> 2);
   for (int q = blockIdx.x * 256 + threadIdx.x; q < n4; q += gridDim.x * 256) {
     const int j = 4 * q;
@@ -397,6 +397,58 @@ sampled_softmax_bwd_kernel(const float* __restrict__ v, const float* __restrict_
       atomicAdd(dst + i, acc);
     }
   }
+}
+
+// Fully sharded schedule: this rank holds a row slice of the target table, so a row of S covers only
+// its local classes.  row_maxsum_kernel: (max, sum exp) over the local columns -- from the logits
+// epilogue's partial slots when present, else by scanning the row -- and the local true logit
+// (S[b, t] if the example's target row lives here, else 0).  lse_combine_kernel folds the ranks'
+// partials into the global log-sum-exp and the per-example loss.
+__global__ void __launch_bounds__(256)
+row_maxsum_kernel(const float2* __restrict__ partial, int slots, const float* __restrict__ S, size_t ldS, int Y,
+                  const int32_t* __restrict__ target, int row0, float* __restrict__ row_max, float* __restrict__ row_sum,
+                  float* __restrict__ true_logit) {
+  __shared__ float red[32];
+  const int b = blockIdx.x;
+  const float* row = S + (size_t)b * ldS;
+  float m = -INFINITY, s = 0.f;
+  if (partial) {
+    const float2* p = partial + (size_t)b * slots;
+    for (int i = threadIdx.x; i < slots; i += 256) m = fmaxf(m, p[i].x);
+    m = block_max(m, red);
+    for (int i = threadIdx.x; i < slots; i += 256) {
+      const float2 v = p[i];
+      if (v.x > -INFINITY) s += v.y * expf(v.x - m);
+    }
+  } else {
+    for (int j = threadIdx.x; j < Y; j += 256) m = fmaxf(m, row[j]);
+    m = block_max(m, red);
+    for (int j = threadIdx.x; j < Y; j += 256) s += expf(row[j] - m);
+  }
+  s = block_sum(s, red);
+  if (threadIdx.x == 0) {
+    row_max[b] = m;
+    row_sum[b] = s;
+    const int t = target[b] - row0;                  // local row of the example's target, if it lives here
+    true_logit[b] = (t >= 0 && t < Y) ? row[t] : 0.f;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+lse_combine_kernel(const float* __restrict__ maxes, const float* __restrict__ sums, int world, int Bt,
+                   const float* __restrict__ true_logit, float* __restrict__ lse_out, float* __restrict__ loss_b) {
+  const int b = blockIdx.x * 256 + threadIdx.x;
+  if (b >= Bt) return;
+  float m = -INFINITY;
+  for (int r = 0; r < world; ++r) m = fmaxf(m, maxes[(size_t)r * Bt + b]);
+  float s = 0.f;
+  for (int r = 0; r < world; ++r) {
+    const float mr = maxes[(size_t)r * Bt + b];
+    if (mr > -INFINITY) s += sums[(size_t)r * Bt + b] * expf(mr - m);
+  }
+  const float lse = m + logf(s);
+  lse_out[b] = lse;
+  loss_b[b] = lse - true_logit[b];
 }
 
 // loss = (sum_b loss_b) * inv_batch, fixed summation order.

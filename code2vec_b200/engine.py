@@ -78,6 +78,11 @@ _SIGNATURES = {
                                     _P, C.c_size_t, _P]),
     "c2v_set_event": (C.c_int, [_P, C.c_char_p, _P]),
     "c2v_sync_tables": (C.c_int, [_P, _P]),
+    "c2v_context_forward": (C.c_int, [_P, _P, _P, _P, _P, _I32, C.c_float, C.c_uint64, C.c_uint64, _P, _P, _P]),
+    "c2v_target_forward": (C.c_int, [_P, _P, _I32, _P, _I32, _P, _P, _P, _P]),
+    "c2v_lse_combine": (C.c_int, [_P, _P, _P, _I32, _I32, _P, C.c_float, _P, _P, _P]),
+    "c2v_target_backward": (C.c_int, [_P, _P, _I32, _P, _P, _I32, C.c_float, _P, _P]),
+    "c2v_context_backward": (C.c_int, [_P, _P, _P, _P, _P, _I32, C.c_float, C.c_uint64, C.c_uint64, _P, _P, _P]),
     "c2v_launch_count": (C.c_int64, [_P]),
     "c2v_phase_count": (C.c_int, []),
     "c2v_phase_name": (C.c_char_p, [C.c_int]),
@@ -386,6 +391,32 @@ class PathAttentionEngine:
         self.adam_t = int(t)
         self._check(self.lib.c2v_adam_step_range(self.h, theta.data_ptr(), grad.data_ptr(), m.data_ptr(), v.data_ptr(),
                                                  n, lr, beta1, beta2, eps, int(t), 1 if zero_grad else 0, self._stream()))
+
+    # ---- phase-split step (fully sharded schedule) ------------------------------------------------
+    def context_forward(self, src, path, tgt, mask, code_out, keep=1.0, seed=0, step=0, dropout_mask=None):
+        self._check(self.lib.c2v_context_forward(self.h, src.data_ptr(), path.data_ptr(), tgt.data_ptr(), mask.data_ptr(),
+                                                 src.shape[0], float(keep), int(seed), int(step), _ptr(dropout_mask),
+                                                 code_out.data_ptr(), self._stream()))
+
+    def target_forward(self, code_all, target_all, row_offset, row_max, row_sum, true_logit):
+        self._check(self.lib.c2v_target_forward(self.h, code_all.data_ptr(), code_all.shape[0], target_all.data_ptr(),
+                                                int(row_offset), row_max.data_ptr(), row_sum.data_ptr(),
+                                                true_logit.data_ptr(), self._stream()))
+
+    def lse_combine(self, maxes, sums, true_logit, lse_out, loss_out):
+        world, Bt = maxes.shape
+        self._check(self.lib.c2v_lse_combine(self.h, maxes.data_ptr(), sums.data_ptr(), world, Bt, true_logit.data_ptr(),
+                                             1.0 / Bt, lse_out.data_ptr(), loss_out.data_ptr(), self._stream()))
+
+    def target_backward(self, code_all, lse, target_all, row_offset, dv_partial):
+        Bt = code_all.shape[0]
+        self._check(self.lib.c2v_target_backward(self.h, code_all.data_ptr(), Bt, lse.data_ptr(), target_all.data_ptr(),
+                                                 int(row_offset), 1.0 / Bt, dv_partial.data_ptr(), self._stream()))
+
+    def context_backward(self, src, path, tgt, mask, dv, keep=1.0, seed=0, step=0, dropout_mask=None):
+        self._check(self.lib.c2v_context_backward(self.h, src.data_ptr(), path.data_ptr(), tgt.data_ptr(), mask.data_ptr(),
+                                                  src.shape[0], float(keep), int(seed), int(step), _ptr(dropout_mask),
+                                                  dv.data_ptr(), self._stream()))
 
     # ---- row-sharded embedding tables over peer memory (data-parallel runs) ----------------------
     def enable_table_sharding(self, group=None):

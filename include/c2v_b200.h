@@ -103,7 +103,8 @@ int c2v_bind_adam_state(c2v_engine* e, const c2v_tensors* m, const c2v_tensors* 
  * the dense TF1 Adam update of an embedding row that received no gradient is deferred and replayed
  * bit-exactly when the row is next read or updated -- same results as the dense update, a
  * fraction of the memory traffic; c2v_sync_tables brings every row up to date),
- * "adam_step_count" (the number of Adam steps already applied: optimizer reset / restore). */
+ * "adam_step_count" (the number of Adam steps already applied: optimizer reset / restore),
+ * "grad_scale_inverse" (n: embedding scatter-adds are scaled by 1/n). */
 int c2v_set_option(c2v_engine* e, const char* key, int64_t value);
 int c2v_get_option(const c2v_engine* e, const char* key, int64_t* value);
 
@@ -154,6 +155,42 @@ int c2v_sampled_train_step(c2v_engine* e, const int32_t* src, const int32_t* pat
  * sparse apply is not lazy); theta -= lr_t*m/(sqrt(v)+eps).  t is the 1-based step count. */
 int c2v_adam_step(c2v_engine* e, float lr, float beta1, float beta2, float eps, int64_t t,
                   void* stream);
+
+/* ---- Phase-split train step for the fully sharded schedule (BASELINE config 5) -----------------------
+ * The target table is row-sharded too: this engine is created with target_vocab = the number of
+ * LOCAL rows and max_batch = the GLOBAL batch Bt.  Between the phases the caller moves only small
+ * tensors: all-gather of code vectors [Bt, D], all-gather of per-row (max, sum exp) [Bt] and an
+ * all-reduce of the true logits [Bt], reduce-scatter of dv [Bt, D] -- never a [*, Y] slab and
+ * never a table gradient.
+ *   c2v_context_forward : training forward of the local examples (dropout as c2v_train_step) ->
+ *                         code_vec [B, D]; activations stay in the workspace for the backward pass.
+ *   c2v_target_forward  : S = code_all . Ytab_local^T for all Bt examples; row_max / row_sum [Bt] =
+ *                         max and sum exp(. - max) over the local classes; this engine's rows are
+ *                         global rows [row_offset, row_offset + target_vocab): true_logit [Bt] =
+ *                         S[b, target[b] - row_offset] if that row lives here, else 0
+ *                         (target = global class ids of all Bt examples).
+ *   c2v_lse_combine     : the ranks' partials maxes / sums [world, Bt] (after all-gather) and the
+ *                         all-reduced true logits -> lse [Bt], mean loss (inv_batch = 1/Bt).
+ *   c2v_target_backward : S <- (exp(S - lse) - onehot(target - row_offset)) * inv_batch; dv_partial [Bt, D] =
+ *                         P . Ytab_local; the bound target gradient (local rows) = P^T . code_all.
+ *   c2v_context_backward: rest of the backward pass of the local examples given dv [B, D]
+ *                         (after the reduce-scatter): attention, TRANSFORM / ATTENTION gradients,
+ *                         scatter-add into the (sharded) embedding gradient tables. */
+int c2v_context_forward(c2v_engine* e, const int32_t* src, const int32_t* path, const int32_t* tgt,
+                        const float* mask, int32_t B, float keep_prob, uint64_t seed, uint64_t step,
+                        const float* dropout_mask, float* code_vec, void* stream);
+int c2v_target_forward(c2v_engine* e, const float* code_all, int32_t Bt, const int32_t* target,
+                       int32_t row_offset, float* row_max, float* row_sum, float* true_logit,
+                       void* stream);
+int c2v_lse_combine(c2v_engine* e, const float* maxes, const float* sums, int32_t world, int32_t Bt,
+                    const float* true_logit, float inv_batch, float* lse_out, float* loss_out,
+                    void* stream);
+int c2v_target_backward(c2v_engine* e, const float* code_all, int32_t Bt, const float* lse,
+                        const int32_t* target, int32_t row_offset, float inv_batch, float* dv_partial,
+                        void* stream);
+int c2v_context_backward(c2v_engine* e, const int32_t* src, const int32_t* path, const int32_t* tgt,
+                         const float* mask, int32_t B, float keep_prob, uint64_t seed, uint64_t step,
+                         const float* dropout_mask, const float* dv, void* stream);
 
 /* With "lazy_adam" on: replay all deferred updates so that the bound token / path tables (and their
  * Adam slots) hold exactly what the dense optimizer would hold after the steps applied so far.  Call
