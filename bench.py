@@ -169,8 +169,12 @@ def run_ours(args):
     if args.batch:
         w["batch"] = args.batch
     B, C = w["batch"], w["max_contexts"]
-    eng = PathAttentionEngine(EngineDims(w["token_vocab"], w["path_vocab"], w["target_vocab"], w["embed_dim"],
-                                         w["code_dim"], C, B, 10), device=local_rank, training=True)
+    gdims = EngineDims(w["token_vocab"], w["path_vocab"], w["target_vocab"], w["embed_dim"], w["code_dim"], C, B, 10)
+    if world > 1 and args.dp_schedule == "fully_sharded":
+        from code2vec_b200.trainer import make_fully_sharded_engine
+        eng = make_fully_sharded_engine(gdims, B, device=local_rank)
+    else:
+        eng = PathAttentionEngine(gdims, device=local_rank, training=True)
     eng.init_params(seed=4321)                       # replicated: same seed on every rank
     if args.math == "tf32":
         eng.set_option("math_mode", 1)
@@ -391,7 +395,7 @@ def main():
     ap.add_argument("--math", default=os.environ.get("C2V_MATH", "tf32"), choices=["fp32", "tf32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--dp-schedule", default=os.environ.get("C2V_DP_SCHEDULE", "table_sharded"),
-                    choices=["table_sharded", "sharded", "allreduce"])
+                    choices=["fully_sharded", "table_sharded", "sharded", "allreduce"])
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

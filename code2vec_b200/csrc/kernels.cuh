@@ -642,11 +642,25 @@ gather_ctx_kernel(const __grid_constant__ ContextSource cs, const __grid_constan
   if (n >= cs.rows) return;
   const int K3 = 3 * cs.d;
   float* dst = Xg + (size_t)n * K3;
-  for (int j = lane * 4; j < K3; j += 128) {
-    float4 x = __ldg(reinterpret_cast<const float4*>(ctx_ptr(cs, n, j)));
-    const float4 m = dropout_mult4(dp, n, j >> 2);
-    x.x *= m.x; x.y *= m.y; x.z *= m.z; x.w *= m.w;
-    *reinterpret_cast<float4*>(dst + j) = x;
+  // all loads of the row are issued before any is consumed: with peer (NVLink) shards each load is a
+  // multi-microsecond round trip, so memory-level parallelism per warp is what sets the bandwidth
+  constexpr int kU = 6;                          // covers 3d <= 768 in one batch
+  for (int j0 = lane * 4; j0 < K3; j0 += 128 * kU) {
+    float4 x[kU];
+#pragma unroll
+    for (int u = 0; u < kU; ++u) {
+      const int j = j0 + u * 128;
+      if (j < K3) x[u] = __ldg(reinterpret_cast<const float4*>(ctx_ptr(cs, n, j)));
+    }
+#pragma unroll
+    for (int u = 0; u < kU; ++u) {
+      const int j = j0 + u * 128;
+      if (j < K3) {
+        const float4 m = dropout_mult4(dp, n, j >> 2);
+        x[u].x *= m.x; x[u].y *= m.y; x[u].z *= m.z; x[u].w *= m.w;
+        *reinterpret_cast<float4*>(dst + j) = x[u];
+      }
+    }
   }
 }
 

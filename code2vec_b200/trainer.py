@@ -28,6 +28,16 @@ leaving every replica with bit-identical parameters:
                 the all-gather of the updated target table is issued after the local Adam, so its
                 completion means every shard is updated (the next gather may run).
 
+  "fully_sharded" : (BASELINE config 5) nothing big is replicated.  Embedding tables as in
+                "table_sharded"; the target table is row-sharded in contiguous blocks and each rank's
+                engine is built for its LOCAL target rows and the GLOBAL batch (make_fully_sharded_engine).
+                A step is phase-split (c2v_context_forward / c2v_target_forward / c2v_lse_combine /
+                c2v_target_backward / c2v_context_backward) and moves only small tensors between the
+                phases: all-gather of code vectors [Bt, D] and targets, all-gather of the per-row
+                (max, sum exp) partials and all-reduce of the true logits [Bt], reduce-scatter of dv
+                [Bt, D].  No logits slab and no table gradient ever crosses NVLink; each rank's Adam
+                covers 1/world of all three tables.
+
 torch.distributed (NCCL over NVLink/NVSwitch; gloo in the CPU tests of the host logic) is plumbing;
 all arithmetic stays in the engine's kernels.
 """
@@ -92,6 +102,26 @@ def all_gather_flat(flat, shard, group=None, async_op=False):
     return None
 
 
+def target_row_block(n_targets: int, rank: int, world: int):
+    """Contiguous block [row0, row1) of target-table rows owned by `rank` in the fully sharded schedule."""
+    per = (n_targets + world - 1) // world
+    row0 = min(rank * per, n_targets)
+    return row0, min(row0 + per, n_targets)
+
+
+def make_fully_sharded_engine(dims, local_batch: int, device: int, group=None, training: bool = True):
+    """Engine for the fully sharded schedule: `dims` are the GLOBAL model dims (EngineDims); the returned
+    engine holds this rank's block of target rows and is sized for the global batch."""
+    from dataclasses import replace
+    dist = _dist()
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    row0, row1 = target_row_block(dims.target_vocab, rank, world)
+    local = replace(dims, target_vocab=max(row1 - row0, 1), max_batch=local_batch * world)
+    eng = PathAttentionEngine(local, device=device, training=training)
+    eng.global_target_vocab, eng.target_row0, eng.local_batch = dims.target_vocab, row0, local_batch
+    return eng
+
+
 def shard_bounds(n: int, rank: int, world: int):
     """Contiguous slice [lo, hi) of n items owned by `rank` (sizes differ by at most 1)."""
     base, rem = divmod(n, world)
@@ -112,8 +142,23 @@ class Trainer:
         self.world = dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
         self.rank = dist.get_rank(group) if self.world > 1 else 0
         self.schedule = schedule if self.world > 1 else "single"
-        if self.schedule == "table_sharded" and self.world not in (2, 4, 8):
+        if self.schedule in ("table_sharded", "fully_sharded") and self.world not in (2, 4, 8):
             self.schedule = "sharded"
+        if self.schedule == "fully_sharded":
+            if not hasattr(engine, "target_row0"):
+                raise ValueError("the fully_sharded schedule needs an engine from make_fully_sharded_engine()")
+            with torch.cuda.device(engine.dev):
+                engine.enable_table_sharding(group)
+            engine.set_option("grad_scale_inverse", 1)     # dv already carries the 1/global-batch factor
+            Bl, Bt, D = engine.local_batch, engine.local_batch * self.world, engine.dims.code_dim
+            f32, i32, dev = torch.float32, torch.int32, engine.dev
+            z = lambda shape, dt=f32: torch.zeros(shape, dtype=dt, device=dev)
+            self._fs = dict(v_local=z((Bl, D)), v_all=z((Bt, D)), tgt_all=z((Bt,), i32), rmax=z((Bt,)), rsum=z((Bt,)),
+                            tlogit=z((Bt,)), maxes=z((self.world, Bt)), sums=z((self.world, Bt)), lse=z((Bt,)),
+                            dv_part=z((Bt, D)), dv_local=z((Bl, D)), loss=z((1,)), token=z((1,)))
+            layout, total = engine.flat_layout()
+            small0 = [off for k, off, n in layout if k == "W"][0]
+            self._small = (small0, total)
         B, C = engine.dims.max_batch, engine.dims.max_contexts
         self._dev = None
         if self.world > 1:
@@ -157,6 +202,8 @@ class Trainer:
     # ---- inputs already resident on the device ----------------------------------------------
     def step_device(self, src, path, tgt, mask, target):
         """Forward+backward, gradient exchange, Adam.  Returns the device loss tensor (no sync)."""
+        if self.schedule == "fully_sharded":
+            return self._fully_sharded_step(src, path, tgt, mask, target)
         e = self.e
         t = e.adam_t + 1
         # dropout stream position (seed, t); replicas use different seeds so their masks differ
@@ -168,9 +215,41 @@ class Trainer:
             e.adam_step(t=t, **self.adam)
         elif self.schedule == "table_sharded":
             self._table_sharded_update(t)
+        elif self.schedule == "fully_sharded":
+            raise RuntimeError("fully_sharded uses step_device_fully_sharded (phase-split step)")
         else:
             self._sharded_update(t)
         return loss
+
+    def _fully_sharded_step(self, src, path, tgt, mask, target):
+        e, dist, fs = self.e, _dist(), self._fs
+        t = e.adam_t + 1
+        B, W = int(src.shape[0]), self.world
+        if B != e.local_batch:
+            raise ValueError("fully_sharded needs the same local batch (%d) on every rank" % e.local_batch)
+        seed = self.seed + self.rank
+        e.context_forward(src, path, tgt, mask, fs["v_local"], keep=self.keep, seed=seed, step=t)
+        dist.all_gather_into_tensor(fs["v_all"], fs["v_local"], group=self.group)
+        dist.all_gather_into_tensor(fs["tgt_all"], target, group=self.group)
+        e.target_forward(fs["v_all"], fs["tgt_all"], e.target_row0, fs["rmax"], fs["rsum"], fs["tlogit"])
+        dist.all_gather_into_tensor(fs["maxes"].view(-1), fs["rmax"], group=self.group)
+        dist.all_gather_into_tensor(fs["sums"].view(-1), fs["rsum"], group=self.group)
+        dist.all_reduce(fs["tlogit"], op=dist.ReduceOp.SUM, group=self.group)
+        e.lse_combine(fs["maxes"], fs["sums"], fs["tlogit"], fs["lse"], fs["loss"])
+        e.target_backward(fs["v_all"], fs["lse"], fs["tgt_all"], e.target_row0, fs["dv_part"])
+        dist.reduce_scatter_tensor(fs["dv_local"], fs["dv_part"], op=dist.ReduceOp.SUM, group=self.group)
+        e.context_backward(src, path, tgt, mask, fs["dv_local"], keep=self.keep, seed=seed, step=t)
+        s0, s1 = self._small
+        # sum (not mean): dv already carries 1/global batch.  Completion == every rank's scatter-add has landed.
+        dist.all_reduce(e.flat_grads[s0:s1], op=dist.ReduceOp.SUM, group=self.group)
+        for name in ("tok", "path"):
+            e.adam_step_range(e.shard_params[name], e.shard_grads[name], e.shard_m[name], e.shard_v[name], t,
+                              zero_grad=True, **self.adam)
+        e.adam_step_range(e.params["tgt"], e.grads["tgt"], e.adam_m["tgt"], e.adam_v["tgt"], t, **self.adam)
+        e.adam_step_range(e.flat_params[s0:s1], e.flat_grads[s0:s1], e.flat_m[s0:s1], e.flat_v[s0:s1], t, **self.adam)
+        # every shard must be updated before any rank's next gather reads it
+        dist.all_reduce(fs["token"], group=self.group)
+        return fs["loss"]
 
     def _table_sharded_update(self, t: int):
         e, torch = self.e, self.e.torch

@@ -23,10 +23,17 @@ def _worker(rank, world, port, schedule, math_mode, out_dir):
     torch.cuda.set_device(rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
     from code2vec_b200.engine import EngineDims, PathAttentionEngine
-    from code2vec_b200.trainer import Trainer
-    eng = PathAttentionEngine(EngineDims(DIMS.token_vocab, DIMS.path_vocab, DIMS.target_vocab, DIMS.embed_dim,
-                                         DIMS.code_dim, DIMS.max_contexts, B_LOCAL, 10), device=rank, training=True)
-    eng.load_params(O.init_params(DIMS, seed=4321))
+    from code2vec_b200.trainer import Trainer, make_fully_sharded_engine, target_row_block
+    gdims = EngineDims(DIMS.token_vocab, DIMS.path_vocab, DIMS.target_vocab, DIMS.embed_dim, DIMS.code_dim,
+                       DIMS.max_contexts, B_LOCAL, 10)
+    full = O.init_params(DIMS, seed=4321)
+    if schedule == "fully_sharded":
+        eng = make_fully_sharded_engine(gdims, B_LOCAL, device=rank)
+        r0, r1 = target_row_block(DIMS.target_vocab, rank, world)
+        eng.load_params(dict(full, tgt=full["tgt"][r0:r1]))
+    else:
+        eng = PathAttentionEngine(gdims, device=rank, training=True)
+        eng.load_params(full)
     eng.set_option("math_mode", math_mode)
     tr = Trainer(eng, keep_prob=1.0, seed=0, schedule=schedule)
     src, pth, tgt, mask, target = O.synthetic_batch(DIMS, B_LOCAL * world, seed=77)
@@ -35,14 +42,14 @@ def _worker(rank, world, port, schedule, math_mode, out_dir):
     for _ in range(3):
         losses.append(tr.step_host(src[lo:hi], pth[lo:hi], tgt[lo:hi], mask[lo:hi], target[lo:hi]))
     out = eng.export_params()
-    if schedule == "table_sharded":
+    if schedule in ("table_sharded", "fully_sharded"):
         sh = eng.export_table_shards()
         out["tok_shard"], out["path_shard"] = sh["tok"], sh["path"]
     np.savez(os.path.join(out_dir, "rank%d.npz" % rank), losses=np.array(losses), **out)
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("schedule", ["allreduce", "sharded", "table_sharded"])
+@pytest.mark.parametrize("schedule", ["allreduce", "sharded", "table_sharded", "fully_sharded"])
 def test_two_rank_data_parallel_matches_single_engine(tmp_path, schedule):
     import torch
     if torch.cuda.device_count() < 2:
@@ -52,7 +59,7 @@ def test_two_rank_data_parallel_matches_single_engine(tmp_path, schedule):
     mp.spawn(_worker, args=(world, port, schedule, 0, str(tmp_path)), nprocs=world, join=True)
     r0 = np.load(str(tmp_path / "rank0.npz"))
     r1 = np.load(str(tmp_path / "rank1.npz"))
-    replicated = ("tgt", "W", "a") if schedule == "table_sharded" else O.PARAM_NAMES
+    replicated = {"table_sharded": ("tgt", "W", "a"), "fully_sharded": ("W", "a")}.get(schedule, O.PARAM_NAMES)
     for k in replicated:
         assert np.array_equal(r0[k], r1[k]), "replicas diverged on %s" % k
     # single engine on the global batch (mean loss over 2*B_LOCAL == average of the two local means)
@@ -64,7 +71,13 @@ def test_two_rank_data_parallel_matches_single_engine(tmp_path, schedule):
     ref = eng.export_params()
     for k in replicated:
         assert np.abs(r0[k] - ref[k]).max() < 5e-5, k
-    if schedule == "table_sharded":
+    if schedule == "fully_sharded":
+        from code2vec_b200.trainer import target_row_block
+        for r, res in ((0, r0), (1, r1)):
+            lo, hi = target_row_block(DIMS.target_vocab, r, 2)
+            assert np.abs(res["tgt"][:hi - lo] - ref["tgt"][lo:hi]).max() < 5e-5, r
+        assert abs(float(r0["losses"][0]) - float(r1["losses"][0])) < 1e-6      # the loss is global here
+    if schedule in ("table_sharded", "fully_sharded"):
         # row r of the global table lives on rank r % 2 at local row r // 2
         for r, res in ((0, r0), (1, r1)):
             for name, shard in (("tok", res["tok_shard"]), ("path", res["path_shard"])):
