@@ -170,6 +170,8 @@ def run_ours(args):
         w["batch"] = args.batch
     B, C = w["batch"], w["max_contexts"]
     gdims = EngineDims(w["token_vocab"], w["path_vocab"], w["target_vocab"], w["embed_dim"], w["code_dim"], C, B, 10)
+    if world not in (2, 4, 8) and args.dp_schedule in ("fully_sharded", "table_sharded"):
+        args.dp_schedule = "sharded"              # peer-memory table sharding needs a power-of-two world <= 8
     if world > 1 and args.dp_schedule == "fully_sharded":
         from code2vec_b200.trainer import make_fully_sharded_engine
         eng = make_fully_sharded_engine(gdims, B, device=local_rank)
@@ -394,7 +396,7 @@ def main():
     ap.add_argument("--batch", type=int, default=0)
     ap.add_argument("--math", default=os.environ.get("C2V_MATH", "tf32"), choices=["fp32", "tf32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--dp-schedule", default=os.environ.get("C2V_DP_SCHEDULE", "table_sharded"),
+    ap.add_argument("--dp-schedule", default=os.environ.get("C2V_DP_SCHEDULE", "fully_sharded"),
                     choices=["fully_sharded", "table_sharded", "sharded", "allreduce"])
     args = ap.parse_args()
     if args.impl == "reference":

@@ -449,9 +449,13 @@ int target_grad_gemms(c2v_engine* e, cudaStream_t st, const float* v, int B, flo
       PhaseTimer pt(e, PH_DV, st);
       umma::Operand opA{S, e->ws.ldS, false};
       umma::Operand opB{e->theta.tgt, (size_t)D, true};
-      const int ks = umma::effective_splits(Y, kSplitDv);
+      // enough split-K slices to fill the SMs about twice; few when the batch already gives many tiles
+      const int tiles = ((B + 127) / 128) * ((D + 191) / 192);
+      int want = (2 * e->num_sms + tiles - 1) / tiles;
+      if (want > kSplitDv) want = kSplitDv;
+      const int ks = umma::effective_splits(Y, want);
       umma::EpiStore ep{part, (size_t)D, (size_t)B * D};
-      C2V_LAUNCH(e, C2V_CUDA(e, (umma::launch<192, 5>(st, B, D, Y, kSplitDv, opA, opB, ep, e->num_sms))));
+      C2V_LAUNCH(e, C2V_CUDA(e, (umma::launch<192, 5>(st, B, D, Y, want, opA, opB, ep, e->num_sms))));
       if ((rc = launch_colsum(e, st, part, (size_t)B * D, ks, B * D, dv))) return rc;
     }
     {
