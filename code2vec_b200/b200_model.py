@@ -88,6 +88,12 @@ class Code2VecModel(Code2VecModelBase):
         import torch
         device = int(os.environ.get("LOCAL_RANK", "0")) if torch.cuda.device_count() > 1 else 0
         self.engine = PathAttentionEngine(self._engine_dims(), device=device, training=self.config.is_training)
+        # arithmetic of the big matrix products: tensor cores (tf32 operands, fp32 accumulate) for training
+        # steps, the reference's own fp32 FMA class for evaluate()/predict() so that top-k is decided on
+        # fp32 logits.  C2V_MATH=fp32|tf32 forces one mode for both.
+        forced = os.environ.get("C2V_MATH", "").lower()
+        self._math_train = {"fp32": 0, "tf32": 1}.get(forced, 1)
+        self._math_eval = {"fp32": 0, "tf32": 1}.get(forced, 0)
         if self.config.is_training:
             self.trainer = Trainer(self.engine, keep_prob=self.config.DROPOUT_KEEP_RATE, seed=int(time.time()) & 0x7FFFFFFF)
 
@@ -178,6 +184,7 @@ class Code2VecModel(Code2VecModelBase):
         for batch in _prefetch(train_reader.get_dataset()):
             t = _TrainInputFormer().from_model_input_form(batch)
             batch_num += 1
+            self.engine.set_option("math_mode", self._math_train)
             batch_loss = self.trainer.step_host(t.path_source_token_indices, t.path_indices, t.path_target_token_indices,
                                                 t.context_valid_mask, t.target_index)
             sum_loss += batch_loss
@@ -214,6 +221,7 @@ class Code2VecModel(Code2VecModelBase):
             self.log("Releasing model, output model: %s" % release_name)
             self._save_inner_model(release_name, release=True)
             return None                            # as the reference does after --release (:132-136)
+        self.engine.set_option("math_mode", self._math_eval)
         special = self.vocabs.target_vocab.special_words
         subtokens_metric = SubtokensEvaluationMetric(partial(common.filter_impossible_names, special))
         topk_metric = TopKAccuracyEvaluationMetric(cfg.TOP_K_WORDS_CONSIDERED_DURING_PREDICTION,
@@ -255,6 +263,7 @@ class Code2VecModel(Code2VecModelBase):
             self.predict_reader = PathContextReader(vocabs=self.vocabs, model_input_tensors_former=_EvaluateInputFormer(),
                                                     config=self.config, estimator_action=EstimatorAction.Predict)
         results: List[ModelPredictionResults] = []
+        self.engine.set_option("math_mode", self._math_eval)
         for line in predict_data_lines:
             t = _EvaluateInputFormer().from_model_input_form(self.predict_reader.process_input_row(line))
             idx, scores, code_vectors, attn = self.engine.predict_batch_host(
