@@ -16,6 +16,7 @@
 #include "kernels.cuh"
 #include "sgemm.cuh"
 #include "umma_gemm.cuh"
+#include "umma_gemm2.cuh"
 
 using namespace c2v;
 
@@ -128,6 +129,7 @@ struct c2v_engine {
   bool has_theta, has_grad, has_adam;
   bool emb_grads_clean;      // token/path gradient tables are known to be all-zero
   int math_mode;
+  int cta_pair = 0;          // 1: tcgen05 GEMMs run as CTA pairs (cta_group::2, UMMA 256 x BN)
   int num_sms;
   cudaEvent_t ev_tgt_ready = nullptr;   // recorded after dY (caller-owned)
   int deterministic;
@@ -173,6 +175,10 @@ struct PhaseTimer {
       return fail((e), C2V_ERR_CUDA, std::string("kernel launch failed: ") + cudaGetErrorString(_c)); \
     (e)->launches++;                                                                              \
   } while (0)
+
+// tcgen05 GEMM launchers: single-CTA (UMMA 128 x BN) or CTA-pair (UMMA 256 x BN) by engine option
+#define C2V_UMMA_192(...) (e->cta_pair ? umma::launch2<192, 7>(__VA_ARGS__) : umma::launch<192, 5>(__VA_ARGS__))
+#define C2V_UMMA_256(...) (e->cta_pair ? umma::launch2<256, 6>(__VA_ARGS__) : umma::launch<256, 4>(__VA_ARGS__))
 
 template <class T> T* wsp(c2v_engine* e, size_t off) { return reinterpret_cast<T*>(e->wbase + off); }
 
@@ -311,7 +317,7 @@ int run_ctx_fwd(c2v_engine* e, cudaStream_t st, const ContextSource& cs, const D
     umma::Operand opA{Xg, (size_t)K, false};
     umma::Operand opB{e->theta.W, (size_t)D, true};
     umma::EpiTanhStore ep{H, (size_t)D};
-    C2V_LAUNCH(e, C2V_CUDA(e, (umma::launch<192, 5>(st, cs.rows, D, K, 1, opA, opB, ep, e->num_sms))));
+    C2V_LAUNCH(e, C2V_CUDA(e, (C2V_UMMA_192(st, cs.rows, D, K, 1, opA, opB, ep, e->num_sms))));
     return C2V_OK;
   }
   PhaseTimer pt(e, PH_CTX_FWD, st);
@@ -332,10 +338,10 @@ int run_logits(c2v_engine* e, cudaStream_t st, const float* v, int B, float* S, 
     umma::Operand opB{e->theta.tgt, (size_t)D, false};
     if (with_lse) {
       umma::EpiStoreLse ep{S, e->ws.ldS, wsp<float2>(e, e->ws.lse_part), 2 * ((Y + 255) / 256)};
-      C2V_LAUNCH(e, C2V_CUDA(e, (umma::launch<256, 4>(st, B, Y, D, 1, opA, opB, ep, e->num_sms))));
+      C2V_LAUNCH(e, C2V_CUDA(e, (C2V_UMMA_256(st, B, Y, D, 1, opA, opB, ep, e->num_sms))));
     } else {
       umma::EpiStore ep{S, e->ws.ldS, 0};
-      C2V_LAUNCH(e, C2V_CUDA(e, (umma::launch<256, 4>(st, B, Y, D, 1, opA, opB, ep, e->num_sms))));
+      C2V_LAUNCH(e, C2V_CUDA(e, (C2V_UMMA_256(st, B, Y, D, 1, opA, opB, ep, e->num_sms))));
     }
     return C2V_OK;
   }
@@ -390,7 +396,7 @@ int context_backward(c2v_engine* e, cudaStream_t st, const ContextSource& cs, co
       umma::Operand opB{H, (size_t)D, true};
       const int ks = umma::effective_splits(N, kSplitDw);
       umma::EpiStore ep{part, (size_t)D, (size_t)K3 * D};
-      C2V_LAUNCH(e, C2V_CUDA(e, (umma::launch<192, 5>(st, K3, D, N, kSplitDw, opA, opB, ep, e->num_sms))));
+      C2V_LAUNCH(e, C2V_CUDA(e, (C2V_UMMA_192(st, K3, D, N, kSplitDw, opA, opB, ep, e->num_sms))));
       rc = launch_colsum(e, st, part, (size_t)K3 * D, ks, K3 * D, e->grad.W);
       if (rc) return rc;
     }
@@ -399,7 +405,7 @@ int context_backward(c2v_engine* e, cudaStream_t st, const ContextSource& cs, co
       umma::Operand opA{H, (size_t)D, false};
       umma::Operand opB{e->theta.W, (size_t)D, false};
       umma::EpiStore ep{Xg, (size_t)K3, 0};
-      C2V_LAUNCH(e, C2V_CUDA(e, (umma::launch<192, 5>(st, N, K3, D, 1, opA, opB, ep, e->num_sms))));
+      C2V_LAUNCH(e, C2V_CUDA(e, (C2V_UMMA_192(st, N, K3, D, 1, opA, opB, ep, e->num_sms))));
     }
     if (!e->emb_grads_clean && e->table_world == 1) {
       C2V_CUDA(e, cudaMemsetAsync(e->grad.tok, 0, (size_t)e->dims.token_vocab * d * 4, st));
@@ -455,7 +461,7 @@ int target_grad_gemms(c2v_engine* e, cudaStream_t st, const float* v, int B, flo
       if (want > kSplitDv) want = kSplitDv;
       const int ks = umma::effective_splits(Y, want);
       umma::EpiStore ep{part, (size_t)D, (size_t)B * D};
-      C2V_LAUNCH(e, C2V_CUDA(e, (umma::launch<192, 5>(st, B, D, Y, want, opA, opB, ep, e->num_sms))));
+      C2V_LAUNCH(e, C2V_CUDA(e, (C2V_UMMA_192(st, B, D, Y, want, opA, opB, ep, e->num_sms))));
       if ((rc = launch_colsum(e, st, part, (size_t)B * D, ks, B * D, dv))) return rc;
     }
     {
@@ -463,7 +469,7 @@ int target_grad_gemms(c2v_engine* e, cudaStream_t st, const float* v, int B, flo
       umma::Operand opA{S, e->ws.ldS, true};
       umma::Operand opB{v, (size_t)D, true};
       umma::EpiStore ep{e->grad.tgt, (size_t)D, 0};
-      C2V_LAUNCH(e, C2V_CUDA(e, (umma::launch<192, 5>(st, Y, D, B, 1, opA, opB, ep, e->num_sms))));
+      C2V_LAUNCH(e, C2V_CUDA(e, (C2V_UMMA_192(st, Y, D, B, 1, opA, opB, ep, e->num_sms))));
     }
     return C2V_OK;
   }
@@ -708,6 +714,7 @@ int c2v_set_option(c2v_engine* e, const char* key, int64_t value) {
   }
   if (!strcmp(key, "deterministic")) { e->deterministic = value ? 1 : 0; return C2V_OK; }
   if (!strcmp(key, "profile")) { e->profile = value ? 1 : 0; return C2V_OK; }
+  if (!strcmp(key, "cta_pair")) { e->cta_pair = value ? 1 : 0; return C2V_OK; }
   if (!strcmp(key, "grad_scale_inverse")) {               // scatter-add scale = 1 / value (1 = unscaled)
     if (value < 1) return fail(e, C2V_ERR_INVALID, "grad_scale_inverse must be >= 1");
     e->grad_scale = 1.0f / (float)value;
@@ -758,6 +765,7 @@ int c2v_get_option(const c2v_engine* e, const char* key, int64_t* value) {
   if (!strcmp(key, "deterministic")) { *value = e->deterministic; return C2V_OK; }
   if (!strcmp(key, "profile")) { *value = e->profile; return C2V_OK; }
   if (!strcmp(key, "lazy_adam")) { *value = e->lazy; return C2V_OK; }
+  if (!strcmp(key, "cta_pair")) { *value = e->cta_pair; return C2V_OK; }
   if (!strcmp(key, "adam_step_count")) { *value = e->adam_t_done; return C2V_OK; }
   return C2V_ERR_INVALID;
 }
@@ -1064,8 +1072,8 @@ int c2v_selftest_gemm(c2v_engine* e, int32_t a_mn, int32_t b_mn, int32_t bn, int
   umma::Operand opB{Bm, ldb, b_mn != 0};
   if (!umma::operand_ok(opA) || !umma::operand_ok(opB)) return fail(e, C2V_ERR_INVALID, "operand not TMA-compatible");
   umma::EpiStore ep{C, ldc, (size_t)M * ldc};
-  if (bn == 256) C2V_LAUNCH(e, C2V_CUDA(e, (umma::launch<256, 4>(st, M, N, K, splits, opA, opB, ep, e->num_sms))));
-  else if (bn == 192) C2V_LAUNCH(e, C2V_CUDA(e, (umma::launch<192, 5>(st, M, N, K, splits, opA, opB, ep, e->num_sms))));
+  if (bn == 256) C2V_LAUNCH(e, C2V_CUDA(e, (C2V_UMMA_256(st, M, N, K, splits, opA, opB, ep, e->num_sms))));
+  else if (bn == 192) C2V_LAUNCH(e, C2V_CUDA(e, (C2V_UMMA_192(st, M, N, K, splits, opA, opB, ep, e->num_sms))));
   else return fail(e, C2V_ERR_INVALID, "bn must be 192 or 256");
   return umma::effective_splits(K, splits);
 }

@@ -14,12 +14,15 @@ pytestmark = pytest.mark.gpu
 TINY = O.Dims(token_vocab=101, path_vocab=51, target_vocab=101, embed_dim=32, code_dim=96, max_contexts=20)
 
 
+@pytest.mark.parametrize("cta_pair", [0, 1])
 @pytest.mark.parametrize("a_mn,b_mn", [(False, False), (False, True), (True, False), (True, True)])
 @pytest.mark.parametrize("M,N,K,bn,splits", [(128, 192, 32, 192, 1), (256, 384, 384, 192, 1), (300, 200, 100, 192, 1),
                                               (1024, 1000, 384, 256, 1), (130, 384, 4100, 192, 7), (384, 384, 2000, 192, 48)])
-def test_umma_gemm_matches_float64(a_mn, b_mn, M, N, K, bn, splits):
+def test_umma_gemm_matches_float64(a_mn, b_mn, M, N, K, bn, splits, cta_pair):
+    """cta_pair = 1: the tcgen05.mma.cta_group::2 kernel (UMMA 256 x BN over two SMs, umma_gemm2.cuh)."""
     import torch
     eng, _ = make_engine(TINY, max_batch=8)
+    eng.set_option("cta_pair", cta_pair)
     rng = np.random.default_rng(M * 7 + N * 3 + K)
     A = rng.standard_normal((M, K)).astype(np.float32)
     B = rng.standard_normal((K, N)).astype(np.float32)
