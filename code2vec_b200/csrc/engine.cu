@@ -253,6 +253,12 @@ int launch_attn_bwd(c2v_engine* e, cudaStream_t st, float* H, const float* alpha
 }
 
 int launch_colsum(c2v_engine* e, cudaStream_t st, const float* in, size_t stride, int R, int n, float* out) {
+  if (R <= 64 && n % 4 == 0 && stride % 4 == 0) {          // split-K slices: few rows, many columns
+    size_t blocks = ((size_t)n / 4 + 255) / 256;
+    if (blocks > (size_t)e->num_sms * 16) blocks = (size_t)e->num_sms * 16;
+    C2V_LAUNCH(e, (slice_sum_kernel<<<(unsigned)blocks, 256, 0, st>>>(in, stride, R, (size_t)n / 4, out)));
+    return C2V_OK;
+  }
   C2V_LAUNCH(e, (colsum_kernel<<<(n + 31) / 32, dim3(32, 32), 0, st>>>(in, stride, R, n, out)));
   return C2V_OK;
 }

@@ -480,6 +480,21 @@ __global__ void __launch_bounds__(1024) colsum_kernel(const float* __restrict__ 
   if (y == 0 && j < n) out[j] = t[0][x];
 }
 
+// out[i] = sum_{r<R} in[r*stride + i] for the few, long slices a split-K GEMM leaves behind
+// (R <= ~64, n up to millions): one float4 column per thread, slices added in fixed order.
+__global__ void __launch_bounds__(256)
+slice_sum_kernel(const float* __restrict__ in, size_t stride, int R, size_t n4, float* __restrict__ out) {
+  const size_t step = (size_t)gridDim.x * 256;
+  for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < n4; i += step) {
+    float4 acc = reinterpret_cast<const float4*>(in)[i];
+    for (int r = 1; r < R; ++r) {
+      const float4 x = *reinterpret_cast<const float4*>(in + (size_t)r * stride + 4 * i);
+      acc.x += x.x; acc.y += x.y; acc.z += x.z; acc.w += x.w;
+    }
+    reinterpret_cast<float4*>(out)[i] = acc;
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // tf.nn.top_k over a row of scores: sorted descending, ties -> lower index   [TF-lib]
 // (tensorflow_model.py:299-304); normalize: softmax over the k values (:305-306).

@@ -17,9 +17,9 @@ def bench(M, N, K, a_mn, b_mn, bn, splits, pair, reps=10):
     ms = e0.elapsed_time(e1) / reps
     print("M=%d N=%d K=%d a_mn=%d b_mn=%d bn=%d splits=%d pair=%d : %.3f ms  %.0f TFLOP/s (incl. slice sum)" % (M, N, K, a_mn, b_mn, bn, splits, pair, ms, 2.0*M*N*K/ms/1e9))
 for pair in (0, 1):
-    print("--- logits-like"); bench(1024, 261246, 384, False, False, 256, 1, pair)
+    print("--- logits-like"); bench(1024, 261248, 384, False, False, 256, 1, pair)
     print("--- dv-like N=1"); [bench(1024, 384, 261246, False, True, 192, s, pair) for s in (18,)]
     print("--- dv-like N=8 shard"); [bench(8192, 384, 32656, False, True, 192, s, pair) for s in (1, 3, 6, 18)]
-    print("--- dY-like"); bench(261246, 384, 1024, True, True, 192, 1, pair)
+    print("--- dY-like"); bench(261248, 384, 1024, True, True, 192, 1, pair)
     print("--- ctx-like"); bench(204800, 384, 384, False, True, 192, 1, pair)
     print("--- dW-like"); bench(384, 384, 204800, True, True, 192, 48, pair)
