@@ -659,7 +659,7 @@ gather_ctx_kernel(const __grid_constant__ ContextSource cs, const __grid_constan
   float* dst = Xg + (size_t)n * K3;
   // all loads of the row are issued before any is consumed: with peer (NVLink) shards each load is a
   // multi-microsecond round trip, so memory-level parallelism per warp is what sets the bandwidth
-  constexpr int kU = 6;                          // covers 3d <= 768 in one batch
+  constexpr int kU = 3;                          // covers 3d <= 384 (d = 128) in one batch
   for (int j0 = lane * 4; j0 < K3; j0 += 128 * kU) {
     float4 x[kU];
 #pragma unroll
