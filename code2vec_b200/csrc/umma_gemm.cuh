@@ -104,6 +104,24 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
         "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
       : "r"(taddr));
 }
+// 64 consecutive columns in one round trip: r0 = columns [c, c+32), r1 = [c+32, c+64)
+__device__ __forceinline__ void tmem_ld64(uint32_t taddr, uint32_t (&a)[32], uint32_t (&b)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x64.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, "
+      "%32, %33, %34, %35, %36, %37, %38, %39, %40, %41, %42, %43, %44, %45, %46, %47, "
+      "%48, %49, %50, %51, %52, %53, %54, %55, %56, %57, %58, %59, %60, %61, %62, %63}, [%64];"
+      : "=r"(a[0]), "=r"(a[1]), "=r"(a[2]), "=r"(a[3]), "=r"(a[4]), "=r"(a[5]), "=r"(a[6]), "=r"(a[7]), "=r"(a[8]),
+        "=r"(a[9]), "=r"(a[10]), "=r"(a[11]), "=r"(a[12]), "=r"(a[13]), "=r"(a[14]), "=r"(a[15]), "=r"(a[16]),
+        "=r"(a[17]), "=r"(a[18]), "=r"(a[19]), "=r"(a[20]), "=r"(a[21]), "=r"(a[22]), "=r"(a[23]), "=r"(a[24]),
+        "=r"(a[25]), "=r"(a[26]), "=r"(a[27]), "=r"(a[28]), "=r"(a[29]), "=r"(a[30]), "=r"(a[31]),
+        "=r"(b[0]), "=r"(b[1]), "=r"(b[2]), "=r"(b[3]), "=r"(b[4]), "=r"(b[5]), "=r"(b[6]), "=r"(b[7]), "=r"(b[8]),
+        "=r"(b[9]), "=r"(b[10]), "=r"(b[11]), "=r"(b[12]), "=r"(b[13]), "=r"(b[14]), "=r"(b[15]), "=r"(b[16]),
+        "=r"(b[17]), "=r"(b[18]), "=r"(b[19]), "=r"(b[20]), "=r"(b[21]), "=r"(b[22]), "=r"(b[23]), "=r"(b[24]),
+        "=r"(b[25]), "=r"(b[26]), "=r"(b[27]), "=r"(b[28]), "=r"(b[29]), "=r"(b[30]), "=r"(b[31])
+      : "r"(taddr));
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // ---- descriptors ----------------------------------------------------------------------------------
@@ -216,6 +234,31 @@ struct EpiStoreLse {
     st.sum += (a0 + a1) + (a2 + a3);
   }
 };
+
+// Drains this warp's share of one accumulator: columns [col0, col0 + ncols) of TMEM lane quadrant q,
+// 64 columns per tcgen05.ld round trip (the loads contend with the tensor core's own accumulator
+// traffic, so fewer and wider round trips are what keeps the epilogue off the critical path).
+template <class Epi>
+__device__ __forceinline__ void drain_accumulator(const Epi& epi, typename Epi::State& est, uint32_t taddr, int col0, int ncols,
+                                                  int m, int n_tile0, int M, int N, int sp) {
+  int c = col0;
+#pragma unroll 1
+  for (; c + 64 <= col0 + ncols; c += 64) {
+    uint32_t r0[32], r1[32];
+    tmem_ld64(taddr + c, r0, r1);
+    tmem_ld_wait();
+    const int n = n_tile0 + c;
+    if (m < M && n < N) epi(m, n, r0, N - n, sp, est);
+    if (m < M && n + 32 < N) epi(m, n + 32, r1, N - n - 32, sp, est);
+  }
+  if (c < col0 + ncols) {
+    uint32_t r[32];
+    tmem_ld32(taddr + c, r);
+    tmem_ld_wait();
+    const int n = n_tile0 + c;
+    if (m < M && n < N) epi(m, n, r, N - n, sp, est);
+  }
+}
 
 // ---- kernel -------------------------------------------------------------------------------------------
 struct GemmShape {
@@ -370,15 +413,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN;
       typename Epi::State est;
       epi.begin(est);
-#pragma unroll 1
-      for (int cc = 0; cc < kChunksPerHalf; ++cc) {
-        const int c = half * kChunksPerHalf + cc;
-        uint32_t r[32];
-        tmem_ld32(taddr + c * 32, r);
-        tmem_ld_wait();
-        const int n = nt * BN + c * 32;
-        if (m < gs.M && n < gs.N) epi(m, n, r, gs.N - n, sp, est);
-      }
+      drain_accumulator(epi, est, taddr, half * kChunksPerHalf * 32, kChunksPerHalf * 32, m, nt * BN, gs.M, gs.N, sp);
       epi.end(m, 2 * nt + half, sp, m < gs.M, est);
       tc_fence_before();
       __syncwarp();

@@ -207,15 +207,7 @@ umma_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN;
       typename Epi::State est;
       epi.begin(est);
-#pragma unroll 1
-      for (int cc = 0; cc < kChunksPerHalf; ++cc) {
-        const int c = half * kChunksPerHalf + cc;
-        uint32_t r[32];
-        tmem_ld32(taddr + c * 32, r);
-        tmem_ld_wait();
-        const int n = nt * BN + c * 32;
-        if (m < gs.M && n < gs.N) epi(m, n, r, gs.N - n, sp, est);
-      }
+      drain_accumulator(epi, est, taddr, half * kChunksPerHalf * 32, kChunksPerHalf * 32, m, nt * BN, gs.M, gs.N, sp);
       epi.end(m, 2 * nt + half, sp, m < gs.M, est);
       tc_fence_before();
       __syncwarp();
