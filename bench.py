@@ -105,9 +105,9 @@ class ClockSampler:
 
 
 def make_batches(w, n_batches, seed, full_bags=False):
-    from oracle.path_attention_oracle import Dims, synthetic_batch   # synthetic-input generator only
-    dims = Dims(w["token_vocab"], w["path_vocab"], w["target_vocab"], w["embed_dim"], w["code_dim"], w["max_contexts"])
-    return [synthetic_batch(dims, w["batch"], seed=seed + 7919 * i, full_bags=full_bags) for i in range(n_batches)]
+    from code2vec_b200.synthetic import synthetic_batch
+    return [synthetic_batch(w["token_vocab"], w["path_vocab"], w["target_vocab"], w["max_contexts"], w["batch"],
+                            seed=seed + 7919 * i, full_bags=full_bags) for i in range(n_batches)]
 
 
 def algorithmic_work(w, B, touched_rows=None, world=1):

@@ -718,7 +718,11 @@ int c2v_set_option(c2v_engine* e, const char* key, int64_t value) {
     e->math_mode = (int)value;
     return C2V_OK;
   }
-  if (!strcmp(key, "deterministic")) { e->deterministic = value ? 1 : 0; return C2V_OK; }
+  if (!strcmp(key, "deterministic")) {
+    if (value) return fail(e, C2V_ERR_UNSUPPORTED, "deterministic (sorted) embedding scatter-add is not built; float atomics only");
+    e->deterministic = 0;
+    return C2V_OK;
+  }
   if (!strcmp(key, "profile")) { e->profile = value ? 1 : 0; return C2V_OK; }
   if (!strcmp(key, "cta_pair")) { e->cta_pair = value ? 1 : 0; return C2V_OK; }
   if (!strcmp(key, "grad_scale_inverse")) {               // scatter-add scale = 1 / value (1 = unscaled)

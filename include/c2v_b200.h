@@ -97,8 +97,9 @@ int c2v_bind_params(c2v_engine* e, const c2v_tensors* theta);         /* tf.get_
 int c2v_bind_grads(c2v_engine* e, const c2v_tensors* grads);          /* autodiff outputs of minimize(), :232   */
 int c2v_bind_adam_state(c2v_engine* e, const c2v_tensors* m, const c2v_tensors* v);  /* Adam slots, :232       */
 
-/* Options: "math_mode" (c2v_math_mode), "deterministic" (0/1: 1 = fixed-order reductions for
- * the scatter-add of embedding gradients instead of float atomics), "profile" (0/1: per-phase
+/* Options: "math_mode" (c2v_math_mode), "deterministic" (reserved: only 0 is accepted -- the
+ * embedding scatter-add uses float atomics; every other reduction is fixed-order), "cta_pair"
+ * (0/1: run the tcgen05 GEMMs as CTA pairs, tcgen05.mma.cta_group::2), "profile" (0/1: per-phase
  * CUDA-event timing, read with c2v_phase_stats), "lazy_adam" (0/1, single-GPU replicated tables:
  * the dense TF1 Adam update of an embedding row that received no gradient is deferred and replayed
  * bit-exactly when the row is next read or updated -- same results as the dense update, a

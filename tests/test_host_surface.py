@@ -253,3 +253,14 @@ def test_reader_filter_batching_and_epochs(tmp_path):
     assert n == 3 * 3                                                         # 3 valid rows x 3 epochs
     assert all(int(t) > 0 for b in batches for t in b.target_index)
     assert [b.path_indices.shape[0] for b in batches] == [2, 2, 2, 2, 1]
+
+
+def test_product_synthetic_generator_matches_the_oracles():
+    from code2vec_b200.synthetic import synthetic_batch
+    from oracle import path_attention_oracle as O
+    dims = O.Dims(1001, 501, 777, 32, 96, 20)
+    for kw in (dict(), dict(full_bags=True), dict(zipf=True)):
+        a = synthetic_batch(1001, 501, 777, 20, 16, seed=5, **kw)
+        b = O.synthetic_batch(dims, 16, seed=5, **kw)
+        for x, y in zip(a, b):
+            assert x.dtype == y.dtype and np.array_equal(x, y)
