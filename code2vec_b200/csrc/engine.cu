@@ -177,7 +177,7 @@ struct PhaseTimer {
   } while (0)
 
 // tcgen05 GEMM launchers: single-CTA (UMMA 128 x BN) or CTA-pair (UMMA 256 x BN) by engine option
-#define C2V_UMMA_192(...) (e->cta_pair ? umma::launch2<192, 7>(__VA_ARGS__) : umma::launch<192, 5>(__VA_ARGS__))
+#define C2V_UMMA_192(...) (e->cta_pair ? umma::launch2<192, 6>(__VA_ARGS__) : umma::launch<192, 4>(__VA_ARGS__))
 #define C2V_UMMA_256(...) (e->cta_pair ? umma::launch2<256, 6>(__VA_ARGS__) : umma::launch<256, 4>(__VA_ARGS__))
 
 template <class T> T* wsp(c2v_engine* e, size_t off) { return reinterpret_cast<T*>(e->wbase + off); }

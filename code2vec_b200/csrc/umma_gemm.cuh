@@ -147,8 +147,16 @@ __host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N, bool a_mn, 
 }
 
 // ---- epilogues ---------------------------------------------------------------------------------------
-// Per output tile each epilogue thread owns one row m: begin(state); then for every 32-column
-// chunk operator()(m, n0, 32 accumulators, nvalid columns, split, state); then end(...).
+// Each epilogue warp owns 32 accumulator rows (its TMEM lane quadrant) and a range of columns.  A
+// functor supplies:  State / begin / end  -- per-(row, tile) state and its publication;
+//                    observe(m, n0, 32 raw accumulators, nvalid, state) -- row-wise math (log-sum-exp);
+//                    map(x)    -- the element-wise transform applied on the way out (identity, tanh);
+//                    out(split), ldc -- where the tile goes.
+// The store itself is done by drain_accumulator: TMEM -> registers (thread = row) -> a 4 KB
+// XOR-swizzled shared-memory transpose per warp -> global stores in which every instruction writes
+// four complete 128-byte row segments.  (Storing straight from the TMEM register layout makes each
+// store instruction touch 32 different lines: 8x the LSU wavefronts, and that -- not the tensor
+// pipe -- was what bounded the short-K GEMMs.)
 struct EpiNoState {};
 
 struct EpiStore {
@@ -158,19 +166,9 @@ struct EpiStore {
   size_t split_stride;
   __device__ __forceinline__ void begin(State&) const {}
   __device__ __forceinline__ void end(int, int, int, bool, State&) const {}
-  __device__ __forceinline__ void operator()(int m, int n, const uint32_t (&r)[32], int nvalid, int split, State&) const {
-    float* p = C + (size_t)split * split_stride + (size_t)m * ldc + n;
-    if (nvalid >= 32) {
-#pragma unroll
-      for (int j = 0; j < 32; j += 4)
-        *reinterpret_cast<float4*>(p + j) = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]),
-                                                        __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
-    } else {
-#pragma unroll
-      for (int j = 0; j < 32; ++j)
-        if (j < nvalid) p[j] = __uint_as_float(r[j]);
-    }
-  }
+  __device__ __forceinline__ void observe(int, int, const uint32_t (&)[32], int, State&) const {}
+  __device__ __forceinline__ float map(float x) const { return x; }
+  __device__ __forceinline__ float* out(int split) const { return C + (size_t)split * split_stride; }
 };
 struct EpiTanhStore {
   using State = EpiNoState;
@@ -178,25 +176,14 @@ struct EpiTanhStore {
   size_t ldc;
   __device__ __forceinline__ void begin(State&) const {}
   __device__ __forceinline__ void end(int, int, int, bool, State&) const {}
-  __device__ __forceinline__ void operator()(int m, int n, const uint32_t (&r)[32], int nvalid, int, State&) const {
-    float* p = C + (size_t)m * ldc + n;
-    if (nvalid >= 32) {
-#pragma unroll
-      for (int j = 0; j < 32; j += 4)
-        *reinterpret_cast<float4*>(p + j) = make_float4(fast_tanh(__uint_as_float(r[j])), fast_tanh(__uint_as_float(r[j + 1])),
-                                                        fast_tanh(__uint_as_float(r[j + 2])), fast_tanh(__uint_as_float(r[j + 3])));
-    } else {
-#pragma unroll
-      for (int j = 0; j < 32; ++j)
-        if (j < nvalid) p[j] = fast_tanh(__uint_as_float(r[j]));
-    }
-  }
+  __device__ __forceinline__ void observe(int, int, const uint32_t (&)[32], int, State&) const {}
+  __device__ __forceinline__ float map(float x) const { return fast_tanh(x); }
+  __device__ __forceinline__ float* out(int) const { return C; }
 };
 
-// Logits epilogue: stores the tile of S and folds the row-wise (max, sum exp) of this tile's columns
-// into a per-(row, n-tile) partial, so the cross entropy needs no extra pass over S for its
+// Logits epilogue: stores the tile of S and folds the row-wise (max, sum exp) of this warp's columns
+// into a per-(row, half tile) partial, so the cross entropy needs no extra pass over S for its
 // log-sum-exp (tensorflow_model.py:227-230).
-struct LsePartial { float mx, sum; };
 struct EpiStoreLse {
   struct State { float mx, sum; };
   float* C;
@@ -207,21 +194,13 @@ struct EpiStoreLse {
   __device__ __forceinline__ void end(int m, int slot, int, bool row_ok, State& st) const {
     if (row_ok) partial[(size_t)m * slots + slot] = make_float2(st.mx, st.sum);
   }
-  __device__ __forceinline__ void operator()(int m, int n, const uint32_t (&r)[32], int nvalid, int, State& st) const {
-    float* p = C + (size_t)m * ldc + n;
+  __device__ __forceinline__ float map(float x) const { return x; }
+  __device__ __forceinline__ float* out(int) const { return C; }
+  __device__ __forceinline__ void observe(int, int, const uint32_t (&r)[32], int nvalid, State& st) const {
     float cm = -INFINITY;
-    if (nvalid >= 32) {
 #pragma unroll
-      for (int j = 0; j < 32; j += 4)
-        *reinterpret_cast<float4*>(p + j) = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]),
-                                                        __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
-#pragma unroll
-      for (int j = 0; j < 32; ++j) cm = fmaxf(cm, __uint_as_float(r[j]));
-    } else {
-#pragma unroll
-      for (int j = 0; j < 32; ++j)
-        if (j < nvalid) { p[j] = __uint_as_float(r[j]); cm = fmaxf(cm, __uint_as_float(r[j])); }
-    }
+    for (int j = 0; j < 32; ++j)
+      if (j < nvalid) cm = fmaxf(cm, __uint_as_float(r[j]));
     if (cm > st.mx) { st.sum *= __expf(st.mx - cm); st.mx = cm; }
     float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
 #pragma unroll
@@ -235,12 +214,48 @@ struct EpiStoreLse {
   }
 };
 
-// Drains this warp's share of one accumulator: columns [col0, col0 + ncols) of TMEM lane quadrant q,
-// 64 columns per tcgen05.ld round trip (the loads contend with the tensor core's own accumulator
-// traffic, so fewer and wider round trips are what keeps the epilogue off the critical path).
+constexpr int kEpiStageBytes = 32 * 32 * 4;      // one 32 x 32 fp32 block per epilogue warp
+
+// One 32-column chunk: registers (thread = row) -> swizzled smem -> coalesced global stores.
+template <class Epi>
+__device__ __forceinline__ void store_chunk(const Epi& epi, const uint32_t (&r)[32], float* stage, int lane, int m_base, int n,
+                                            int M, int N, float* cbase, size_t ldc) {
+#pragma unroll
+  for (int j4 = 0; j4 < 8; ++j4) {
+    const int pos = j4 ^ (lane & 7);
+    *reinterpret_cast<float4*>(stage + lane * 32 + pos * 4) =
+        make_float4(epi.map(__uint_as_float(r[4 * j4])), epi.map(__uint_as_float(r[4 * j4 + 1])),
+                    epi.map(__uint_as_float(r[4 * j4 + 2])), epi.map(__uint_as_float(r[4 * j4 + 3])));
+  }
+  __syncwarp();
+  const int col4 = lane & 7;
+  const int gn = n + col4 * 4;
+#pragma unroll
+  for (int it = 0; it < 8; ++it) {
+    const int row = it * 4 + (lane >> 3);
+    const float4 v = *reinterpret_cast<const float4*>(stage + row * 32 + ((col4 ^ (row & 7)) * 4));
+    const int gm = m_base + row;
+    if (gm < M && gn < N) {
+      float* p = cbase + (size_t)gm * ldc + gn;
+      if (gn + 3 < N) {
+        *reinterpret_cast<float4*>(p) = v;
+      } else {
+        p[0] = v.x;
+        if (gn + 1 < N) p[1] = v.y;
+        if (gn + 2 < N) p[2] = v.z;
+      }
+    }
+  }
+  __syncwarp();
+}
+
+// Drains this warp's share of one accumulator: columns [col0, col0 + ncols) of the tile, rows
+// m_base .. m_base + 31 (this thread's row is m_base + lane); 64 columns per tcgen05.ld round trip.
 template <class Epi>
 __device__ __forceinline__ void drain_accumulator(const Epi& epi, typename Epi::State& est, uint32_t taddr, int col0, int ncols,
-                                                  int m, int n_tile0, int M, int N, int sp) {
+                                                  int m_base, int lane, int n_tile0, int M, int N, int sp, float* stage) {
+  const int m = m_base + lane;
+  float* cbase = epi.out(sp);
   int c = col0;
 #pragma unroll 1
   for (; c + 64 <= col0 + ncols; c += 64) {
@@ -248,15 +263,24 @@ __device__ __forceinline__ void drain_accumulator(const Epi& epi, typename Epi::
     tmem_ld64(taddr + c, r0, r1);
     tmem_ld_wait();
     const int n = n_tile0 + c;
-    if (m < M && n < N) epi(m, n, r0, N - n, sp, est);
-    if (m < M && n + 32 < N) epi(m, n + 32, r1, N - n - 32, sp, est);
+    if (n < N) {
+      if (m < M) epi.observe(m, n, r0, N - n, est);
+      store_chunk(epi, r0, stage, lane, m_base, n, M, N, cbase, epi.ldc);
+    }
+    if (n + 32 < N) {
+      if (m < M) epi.observe(m, n + 32, r1, N - n - 32, est);
+      store_chunk(epi, r1, stage, lane, m_base, n + 32, M, N, cbase, epi.ldc);
+    }
   }
   if (c < col0 + ncols) {
     uint32_t r[32];
     tmem_ld32(taddr + c, r);
     tmem_ld_wait();
     const int n = n_tile0 + c;
-    if (m < M && n < N) epi(m, n, r, N - n, sp, est);
+    if (n < N) {
+      if (m < M) epi.observe(m, n, r, N - n, est);
+      store_chunk(epi, r, stage, lane, m_base, n, M, N, cbase, epi.ldc);
+    }
   }
 }
 
@@ -273,8 +297,10 @@ struct SmemLayout {
   static constexpr int kABytes = BM * BK * 4;          // 16 KB
   static constexpr int kBBytes = BN * BK * 4;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kBarOffset = STAGES * kStageBytes;
+  static constexpr int kEpiStageOffset = STAGES * kStageBytes;                 // 8 x 4 KB store-transpose blocks
+  static constexpr int kBarOffset = kEpiStageOffset + kEpiWarps * kEpiStageBytes;
   static constexpr int kTotal = kBarOffset + 256 + 1024;   // barriers + tmem ptr, + slack for 1024-B alignment
+  static_assert(kTotal <= 232448, "exceeds the 227 KB of shared memory a CTA can opt into");
 };
 
 template <int BN, int STAGES, bool A_MN, bool B_MN, class Epi>
@@ -413,7 +439,8 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN;
       typename Epi::State est;
       epi.begin(est);
-      drain_accumulator(epi, est, taddr, half * kChunksPerHalf * 32, kChunksPerHalf * 32, m, nt * BN, gs.M, gs.N, sp);
+      drain_accumulator(epi, est, taddr, half * kChunksPerHalf * 32, kChunksPerHalf * 32, mt * BM + q * 32, lane, nt * BN,
+                        gs.M, gs.N, sp, reinterpret_cast<float*>(smem + L::kEpiStageOffset + (warp - kEpiWarp0) * kEpiStageBytes));
       epi.end(m, 2 * nt + half, sp, m < gs.M, est);
       tc_fence_before();
       __syncwarp();
@@ -505,7 +532,8 @@ inline int effective_splits(int K, int splits) {
   return (total_kblocks + per - 1) / per;
 }
 
-// Runtime dispatch over operand majors.  BN = 256 uses 4 stages (192 KB), BN = 192 uses 5 (200 KB).
+// Runtime dispatch over operand majors.  BN = 256 and BN = 192 both run 4 stages (192 / 160 KB) next to
+// the 32 KB of epilogue transpose blocks.
 template <int BN, int STAGES, class Epi>
 inline cudaError_t launch(cudaStream_t st, int M, int N, int K, int splits, const Operand& A, const Operand& B, const Epi& epi,
                           int num_sms) {

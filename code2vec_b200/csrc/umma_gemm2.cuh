@@ -67,8 +67,10 @@ struct SmemLayout2 {
   static constexpr int kABytes = BM * BK * 4;              // this CTA's 128 rows of A
   static constexpr int kBBytes = (BN / 2) * BK * 4;        // this CTA's half of the B tile
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kBarOffset = STAGES * kStageBytes;
+  static constexpr int kEpiStageOffset = STAGES * kStageBytes;
+  static constexpr int kBarOffset = kEpiStageOffset + kEpiWarps * kEpiStageBytes;
   static constexpr int kTotal = kBarOffset + 256 + 1024;
+  static_assert(kTotal <= 232448, "exceeds the 227 KB of shared memory a CTA can opt into");
 };
 
 template <int BN, int STAGES, bool A_MN, bool B_MN, class Epi>
@@ -207,7 +209,9 @@ umma_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN;
       typename Epi::State est;
       epi.begin(est);
-      drain_accumulator(epi, est, taddr, half * kChunksPerHalf * 32, kChunksPerHalf * 32, m, nt * BN, gs.M, gs.N, sp);
+      drain_accumulator(epi, est, taddr, half * kChunksPerHalf * 32, kChunksPerHalf * 32,
+                        mt * (2 * BM) + (int)cta * BM + q * 32, lane, nt * BN, gs.M, gs.N, sp,
+                        reinterpret_cast<float*>(smem + L::kEpiStageOffset + (warp - kEpiWarp0) * kEpiStageBytes));
       epi.end(m, 2 * nt + half, sp, m < gs.M, est);
       tc_fence_before();
       __syncwarp();
@@ -253,7 +257,7 @@ inline cudaError_t launch2_cfg(cudaStream_t st, int M, int N, int K, int splits,
   return cudaGetLastError();
 }
 
-// BN = 256 -> 6 stages of 32 KB, BN = 192 -> 7 stages of 28 KB (per CTA).
+// BN = 256 -> 6 stages of 32 KB, BN = 192 -> 6 stages of 28 KB (per CTA), plus 32 KB of epilogue blocks.
 template <int BN, int STAGES, class Epi>
 inline cudaError_t launch2(cudaStream_t st, int M, int N, int K, int splits, const Operand& A, const Operand& B, const Epi& epi,
                            int num_sms) {
