@@ -180,8 +180,7 @@ def run_ours(args):
     eng.init_params(seed=4321)                       # replicated: same seed on every rank
     if args.math == "tf32":
         eng.set_option("math_mode", 1)
-    if args.cta_pair:
-        eng.set_option("cta_pair", 1)
+    eng.set_option("cta_pair", args.cta_pair)
     trainer = Trainer(eng, keep_prob=KEEP_PROB, seed=99, schedule=args.dp_schedule)
 
     n_batches = 4
@@ -398,8 +397,8 @@ def main():
     ap.add_argument("--batch", type=int, default=0)
     ap.add_argument("--math", default=os.environ.get("C2V_MATH", "tf32"), choices=["fp32", "tf32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--cta-pair", type=int, default=int(os.environ.get("C2V_CTA_PAIR", "0")),
-                    help="1: run the tcgen05 GEMMs as CTA pairs (cta_group::2)")
+    ap.add_argument("--cta-pair", type=int, default=int(os.environ.get("C2V_CTA_PAIR", "2")),
+                    help="tcgen05 GEMMs as CTA pairs (cta_group::2): 0 never, 1 always, 2 auto (default)")
     ap.add_argument("--dp-schedule", default=os.environ.get("C2V_DP_SCHEDULE", "fully_sharded"),
                     choices=["fully_sharded", "table_sharded", "sharded", "allreduce"])
     args = ap.parse_args()

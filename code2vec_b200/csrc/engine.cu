@@ -129,7 +129,7 @@ struct c2v_engine {
   bool has_theta, has_grad, has_adam;
   bool emb_grads_clean;      // token/path gradient tables are known to be all-zero
   int math_mode;
-  int cta_pair = 0;          // 1: tcgen05 GEMMs run as CTA pairs (cta_group::2, UMMA 256 x BN)
+  int cta_pair = 2;          // tcgen05 GEMMs as CTA pairs (cta_group::2, UMMA 256 x BN): 0 never, 1 always, 2 auto
   int num_sms;
   cudaEvent_t ev_tgt_ready = nullptr;   // recorded after dY (caller-owned)
   int deterministic;
@@ -176,9 +176,14 @@ struct PhaseTimer {
     (e)->launches++;                                                                              \
   } while (0)
 
-// tcgen05 GEMM launchers: single-CTA (UMMA 128 x BN) or CTA-pair (UMMA 256 x BN) by engine option
-#define C2V_UMMA_192(...) (e->cta_pair ? umma::launch2<192, 6>(__VA_ARGS__) : umma::launch<192, 4>(__VA_ARGS__))
-#define C2V_UMMA_256(...) (e->cta_pair ? umma::launch2<256, 6>(__VA_ARGS__) : umma::launch<256, 4>(__VA_ARGS__))
+// tcgen05 GEMM launchers: single-CTA (UMMA 128 x BN) or CTA-pair (UMMA 256 x BN).  Option "cta_pair":
+// 0 = never, 1 = always, 2 = auto (default): pairs wherever they measured faster on B200 -- every GEMM
+// except the two whose work items are few and long (dW: 3x2 tiles x split-K; dY: 1024-deep K), where the
+// halved item count costs more than the halved B traffic saves (profiles/r01_bench_*).
+#define C2V_PAIR(site_default) (e->cta_pair == 1 || (e->cta_pair == 2 && (site_default)))
+#define C2V_UMMA_192(...) (C2V_PAIR(true) ? umma::launch2<192, 6>(__VA_ARGS__) : umma::launch<192, 4>(__VA_ARGS__))
+#define C2V_UMMA_192_SINGLE(...) (C2V_PAIR(false) ? umma::launch2<192, 6>(__VA_ARGS__) : umma::launch<192, 4>(__VA_ARGS__))
+#define C2V_UMMA_256(...) (C2V_PAIR(true) ? umma::launch2<256, 6>(__VA_ARGS__) : umma::launch<256, 4>(__VA_ARGS__))
 
 template <class T> T* wsp(c2v_engine* e, size_t off) { return reinterpret_cast<T*>(e->wbase + off); }
 
@@ -402,7 +407,7 @@ int context_backward(c2v_engine* e, cudaStream_t st, const ContextSource& cs, co
       umma::Operand opB{H, (size_t)D, true};
       const int ks = umma::effective_splits(N, kSplitDw);
       umma::EpiStore ep{part, (size_t)D, (size_t)K3 * D};
-      C2V_LAUNCH(e, C2V_CUDA(e, (C2V_UMMA_192(st, K3, D, N, kSplitDw, opA, opB, ep, e->num_sms))));
+      C2V_LAUNCH(e, C2V_CUDA(e, (C2V_UMMA_192_SINGLE(st, K3, D, N, kSplitDw, opA, opB, ep, e->num_sms))));
       rc = launch_colsum(e, st, part, (size_t)K3 * D, ks, K3 * D, e->grad.W);
       if (rc) return rc;
     }
@@ -475,7 +480,7 @@ int target_grad_gemms(c2v_engine* e, cudaStream_t st, const float* v, int B, flo
       umma::Operand opA{S, e->ws.ldS, true};
       umma::Operand opB{v, (size_t)D, true};
       umma::EpiStore ep{e->grad.tgt, (size_t)D, 0};
-      C2V_LAUNCH(e, C2V_CUDA(e, (C2V_UMMA_192(st, Y, D, B, 1, opA, opB, ep, e->num_sms))));
+      C2V_LAUNCH(e, C2V_CUDA(e, (C2V_UMMA_192_SINGLE(st, Y, D, B, 1, opA, opB, ep, e->num_sms))));
     }
     return C2V_OK;
   }
@@ -724,7 +729,11 @@ int c2v_set_option(c2v_engine* e, const char* key, int64_t value) {
     return C2V_OK;
   }
   if (!strcmp(key, "profile")) { e->profile = value ? 1 : 0; return C2V_OK; }
-  if (!strcmp(key, "cta_pair")) { e->cta_pair = value ? 1 : 0; return C2V_OK; }
+  if (!strcmp(key, "cta_pair")) {
+    if (value < 0 || value > 2) return fail(e, C2V_ERR_INVALID, "cta_pair must be 0 (never), 1 (always) or 2 (auto)");
+    e->cta_pair = (int)value;
+    return C2V_OK;
+  }
   if (!strcmp(key, "grad_scale_inverse")) {               // scatter-add scale = 1 / value (1 = unscaled)
     if (value < 1) return fail(e, C2V_ERR_INVALID, "grad_scale_inverse must be >= 1");
     e->grad_scale = 1.0f / (float)value;

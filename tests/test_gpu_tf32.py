@@ -32,10 +32,12 @@ def test_tf32_forward_and_topk(dims, B):
     assert np.array_equal(idx.cpu().numpy()[clear, 0], idx_ref[clear, 0])
 
 
+@pytest.mark.parametrize("cta_pair", [0, 1, 2])
 @pytest.mark.parametrize("dims,B", [(TINY, 64), (ODD, 37), (MID, 48)])
-def test_tf32_train_step(dims, B):
+def test_tf32_train_step(dims, B, cta_pair):
     eng, params = make_engine(dims, max_batch=B)
     eng.set_option("math_mode", 1)
+    eng.set_option("cta_pair", cta_pair)
     src, pth, tgt, mask, target = O.synthetic_batch(dims, B, seed=21)
     src[0, 0] = tgt[0, 0] = src[1, 0] = 3
     dm = O.dropout_keep_mask(seed=5, step=2, n_rows=B * dims.max_contexts, ctx_dim=dims.ctx_dim, keep=0.75)
