@@ -371,23 +371,14 @@ class PathContextReader:
         # train: a pool of at least SHUFFLE_BUFFER_SIZE rows; every batch is a uniform draw without
         # replacement from the pool (tf.data's shuffle(buffer) draws the same way, one row at a time)
         S = max(int(self.config.SHUFFLE_BUFFER_SIZE), 1)
-        pool = None
+        pool = _RowPool()
         for chunk in self._native_chunks():
             arrs, _ = self._native_parse(chunk)
-            pool = arrs if pool is None else tuple(np.concatenate([a, b]) for a, b in zip(pool, arrs))
-            while pool[0].shape[0] >= S + B:
-                n = pool[0].shape[0]
-                pick = self._rng.choice(n, size=B, replace=False)
-                yield emit(tuple(a[pick] for a in pool), None)
-                rest = np.ones(n, dtype=bool)
-                rest[pick] = False
-                pool = tuple(a[rest] for a in pool)
-        if pool is not None:
-            n = pool[0].shape[0]
-            order = self._rng.permutation(n)
-            for lo in range(0, n, B):
-                pick = order[lo:lo + B]
-                yield emit(tuple(a[pick] for a in pool), None)
+            pool.append(arrs)
+            while pool.n >= S + B:
+                yield emit(pool.take(B, self._rng), None)
+        while pool.n > 0:
+            yield emit(pool.take(min(B, pool.n), self._rng), None)
 
     def _iterate_batches(self, input_data_rows):
         action = self.estimator_action
@@ -411,6 +402,48 @@ class PathContextReader:
                 rows = []
         if rows:
             yield self.model_input_tensors_former.to_model_input_form(self._stack(rows))
+
+
+class _RowPool:
+    """Shuffle pool over parallel row arrays: O(rows appended) to add, O(batch) to draw -- drawn rows are
+    replaced by rows from the tail, nothing else moves."""
+
+    def __init__(self):
+        self.arrays = None
+        self.n = 0
+
+    def append(self, arrs):
+        k = arrs[0].shape[0]
+        if k == 0:
+            return
+        if self.arrays is None:
+            cap = max(2 * k, 1024)
+            self.arrays = [np.empty((cap,) + a.shape[1:], dtype=a.dtype) for a in arrs]
+        if self.n + k > self.arrays[0].shape[0]:
+            cap = max(2 * self.arrays[0].shape[0], self.n + k)
+            grown = [np.empty((cap,) + a.shape[1:], dtype=a.dtype) for a in self.arrays]
+            for g, a in zip(grown, self.arrays):
+                g[:self.n] = a[:self.n]
+            self.arrays = grown
+        for dst, a in zip(self.arrays, arrs):
+            dst[self.n:self.n + k] = a
+        self.n += k
+
+    def take(self, b: int, rng) -> tuple:
+        n = self.n
+        pick = rng.choice(n, size=b, replace=False) if b < n else rng.permutation(n)
+        out = tuple(a[pick] for a in self.arrays)
+        # fill the holes left below the new end with the surviving rows of the tail
+        new_n = n - b
+        chosen = np.zeros(n, dtype=bool)
+        chosen[pick] = True
+        holes = np.flatnonzero(chosen[:new_n])
+        movers = new_n + np.flatnonzero(~chosen[new_n:])
+        if holes.size:
+            for a in self.arrays:
+                a[holes] = a[movers]
+        self.n = new_n
+        return out
 
 
 class _BatchDataset:
