@@ -33,7 +33,7 @@ constexpr int kSplitDw = 48;   // split-K slices for dW = X'^T . dU  (K = B*C)
 
 // Carve-up of the caller-provided workspace (offsets in bytes).
 struct Workspace {
-  size_t H, Xg, alpha, v, dv, S, loss_b, lse, loss, part, da_part, lse_part, dl;
+  size_t H, Xg, dXg, alpha, v, dv, S, loss_b, lse, loss, part, da_part, lse_part, dl;
   size_t st_src, st_pth, st_tgt, st_mask, st_target, st_topk_idx, st_topk_val, st_code, st_attn;
   size_t stamp_tok, stamp_path, last_tok, last_path, lr_tab;     // lazy Adam bookkeeping
   size_t total;
@@ -60,7 +60,8 @@ Workspace carve(const c2v_dims& d) {
   size_t off = 0;
   auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes); return o; };
   w.H = take(N * D * 4);
-  w.Xg = take(N * X * 4);      // gathered context matrix X' (tf32 path), reused for dX'
+  w.Xg = take(N * X * 4);      // gathered context matrix X' (tf32 path), kept for dW
+  w.dXg = take(N * X * 4);     // dX' (tf32 path): its scatter-add overlaps the dW GEMM, which still reads X'
   w.alpha = take(N * 4);
   w.v = take(B * D * 4);
   w.dv = take(B * D * 4);
@@ -132,6 +133,8 @@ struct c2v_engine {
   int cta_pair = 2;          // tcgen05 GEMMs as CTA pairs (cta_group::2, UMMA 256 x BN): 0 never, 1 always, 2 auto
   int num_sms;
   cudaEvent_t ev_tgt_ready = nullptr;   // recorded after dY (caller-owned)
+  cudaStream_t side = nullptr;          // engine-owned: the embedding scatter-add runs here, next to the dW GEMM
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   int deterministic;
   int64_t launches;
   std::string err;
@@ -401,6 +404,27 @@ int context_backward(c2v_engine* e, cudaStream_t st, const ContextSource& cs, co
   if (rc) return rc;
   if (e->math_mode == C2V_MATH_TF32) {
     float* Xg = wsp<float>(e, e->ws.Xg);
+    float* dXg = wsp<float>(e, e->ws.dXg);
+    {  // dX' = dU . W^T
+      PhaseTimer pt(e, PH_DX_GEMM, st);
+      umma::Operand opA{H, (size_t)D, false};
+      umma::Operand opB{e->theta.W, (size_t)D, false};
+      umma::EpiStore ep{dXg, (size_t)K3, 0};
+      C2V_LAUNCH(e, C2V_CUDA(e, (C2V_UMMA_192(st, N, K3, D, 1, opA, opB, ep, e->num_sms))));
+    }
+    if (!e->emb_grads_clean && e->table_world == 1) {
+      C2V_CUDA(e, cudaMemsetAsync(e->grad.tok, 0, (size_t)e->dims.token_vocab * d * 4, st));
+      C2V_CUDA(e, cudaMemsetAsync(e->grad.path, 0, (size_t)e->dims.path_vocab * d * 4, st));
+    }
+    // fork: the scatter-add of dX' rows (memory / NVLink bound, no shared memory) runs on the engine's
+    // side stream while the dW GEMM (tensor bound) runs on the caller's stream; join before returning.
+    C2V_CUDA(e, cudaEventRecord(e->ev_fork, st));
+    C2V_CUDA(e, cudaStreamWaitEvent(e->side, e->ev_fork, 0));
+    {
+      PhaseTimer pt(e, PH_DX_SCATTER, e->side);
+      C2V_LAUNCH(e, (scatter_dx_kernel<<<(N + 7) / 8, 256, 0, e->side>>>(cs, dp, mask, dXg, e->gr_tok, e->gr_path, e->grad_scale)));
+    }
+    C2V_CUDA(e, cudaEventRecord(e->ev_join, e->side));
     {  // dW = X'^T . dU on the gathered X' kept from the forward pass
       PhaseTimer pt(e, PH_DW, st);
       umma::Operand opA{Xg, (size_t)K3, true};
@@ -411,21 +435,7 @@ int context_backward(c2v_engine* e, cudaStream_t st, const ContextSource& cs, co
       rc = launch_colsum(e, st, part, (size_t)K3 * D, ks, K3 * D, e->grad.W);
       if (rc) return rc;
     }
-    {  // dX' = dU . W^T, written over X' (no longer needed)
-      PhaseTimer pt(e, PH_DX_GEMM, st);
-      umma::Operand opA{H, (size_t)D, false};
-      umma::Operand opB{e->theta.W, (size_t)D, false};
-      umma::EpiStore ep{Xg, (size_t)K3, 0};
-      C2V_LAUNCH(e, C2V_CUDA(e, (C2V_UMMA_192(st, N, K3, D, 1, opA, opB, ep, e->num_sms))));
-    }
-    if (!e->emb_grads_clean && e->table_world == 1) {
-      C2V_CUDA(e, cudaMemsetAsync(e->grad.tok, 0, (size_t)e->dims.token_vocab * d * 4, st));
-      C2V_CUDA(e, cudaMemsetAsync(e->grad.path, 0, (size_t)e->dims.path_vocab * d * 4, st));
-    }
-    {
-      PhaseTimer pt(e, PH_DX_SCATTER, st);
-      C2V_LAUNCH(e, (scatter_dx_kernel<<<(N + 7) / 8, 256, 0, st>>>(cs, dp, mask, Xg, e->gr_tok, e->gr_path, e->grad_scale)));
-    }
+    C2V_CUDA(e, cudaStreamWaitEvent(st, e->ev_join, 0));
     e->emb_grads_clean = false;
     return C2V_OK;
   }
@@ -663,6 +673,13 @@ int c2v_create(const c2v_dims* dims, int device, c2v_engine** out) {
   e->emb_grads_clean = false;
   e->math_mode = C2V_MATH_FP32;
   e->num_sms = prop.multiProcessorCount;
+  cudaSetDevice(device);
+  if (cudaStreamCreateWithFlags(&e->side, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&e->ev_join, cudaEventDisableTiming) != cudaSuccess) {
+    delete e;
+    return fail(nullptr, C2V_ERR_CUDA, "could not create the engine's side stream / events");
+  }
   e->deterministic = 0;
   e->launches = 0;
   *out = e;
@@ -671,6 +688,10 @@ int c2v_create(const c2v_dims* dims, int device, c2v_engine** out) {
 
 void c2v_destroy(c2v_engine* e) {
   if (!e) return;
+  cudaSetDevice(e->device);
+  if (e->ev_fork) cudaEventDestroy(e->ev_fork);
+  if (e->ev_join) cudaEventDestroy(e->ev_join);
+  if (e->side) cudaStreamDestroy(e->side);
   for (auto& L : e->phase) {
     for (auto& ev : L.pending) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
     for (auto& ev : L.free_list) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
