@@ -294,15 +294,16 @@ class PathContextReader:
         """bytes of complete lines -> (ReaderInputTensors of all rows, keep mask, target strings or None)."""
         lib, tok, pth, tgt = self._native
         Cn = self.config.MAX_CONTEXTS
-        cap = data.count(b"\n") + 1
-        src = np.empty((cap, Cn), dtype=np.int32)
-        path = np.empty((cap, Cn), dtype=np.int32)
-        dst = np.empty((cap, Cn), dtype=np.int32)
-        mask = np.empty((cap, Cn), dtype=np.float32)
-        target = np.empty(cap, dtype=np.int32)
-        keep = np.zeros(cap, dtype=np.uint8)
-        toff = np.empty(cap, dtype=np.int64)
-        tlen = np.empty(cap, dtype=np.int32)
+        cap = len(data) // (Cn + 1) + 1              # a line is at least MAX_CONTEXTS spaces + a newline long
+        bufs = getattr(self, "_parse_bufs", None)
+        if bufs is None or bufs[0].shape[0] < cap:   # scratch reused across chunks (no page faults per chunk)
+            bufs = (np.empty((cap, Cn), dtype=np.int32), np.empty((cap, Cn), dtype=np.int32),
+                    np.empty((cap, Cn), dtype=np.int32), np.empty((cap, Cn), dtype=np.float32),
+                    np.empty(cap, dtype=np.int32), np.zeros(cap, dtype=np.uint8), np.empty(cap, dtype=np.int64),
+                    np.empty(cap, dtype=np.int32))
+            self._parse_bufs = bufs
+        src, path, dst, mask, target, keep, toff, tlen = bufs
+        cap = src.shape[0]
         err = C.c_int32(0)
         mode = 0 if self.estimator_action.is_train else 1
         threads = max(1, int(self.config.READER_NUM_PARALLEL_BATCHES or 1))
@@ -332,20 +333,27 @@ class PathContextReader:
         while self.repeat_endlessly or p < passes:
             p += 1
             with open(path, "rb") as f:
-                tail = b""
+                size = chunk_bytes
                 while True:
-                    buf = f.read(chunk_bytes)
+                    start = f.tell()
+                    buf = f.read(size)
                     if not buf:
                         break
-                    buf = tail + buf
+                    at_eof = len(buf) < size
                     cut = buf.rfind(b"\n")
                     if cut < 0:
-                        tail = buf
+                        if at_eof:
+                            if buf.strip(b"\r\n"):
+                                yield buf
+                            break
+                        f.seek(start)                # a line longer than the chunk: retry with a bigger one
+                        size *= 2
                         continue
-                    tail = buf[cut + 1:]
+                    if at_eof:
+                        yield buf                    # includes a last line without a trailing newline
+                        break
+                    f.seek(start + cut + 1)          # re-read the partial last line with the next chunk
                     yield buf[:cut + 1]
-                if tail.strip(b"\r\n"):
-                    yield tail
 
     def _iterate_batches_native(self):
         action = self.estimator_action
