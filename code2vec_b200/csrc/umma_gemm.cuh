@@ -2,7 +2,7 @@
 // kind::tf32 operands (10-bit mantissa), fp32 accumulation in TMEM  (C2V_MATH_TF32).
 //
 // Persistent, warp-specialised, one CTA per SM:
-//   warp 0      : TMA producer   -- cp.async.bulk.tensor (SWIZZLE_128B) into a 4..5-stage smem ring
+//   warp 0      : TMA producer   -- cp.async.bulk.tensor (128-byte swizzle) into a 4-stage smem ring
 //   warp 1      : MMA issuer     -- one elected lane issues tcgen05.mma.cta_group::1.kind::tf32
 //                                   (UMMA 128 x BN x 8), tcgen05.commit frees smem stages / publishes
 //                                   the accumulator; also owns the TMEM allocation
