@@ -10,7 +10,7 @@ import numpy as np
 
 
 def synthetic_batch(token_vocab: int, path_vocab: int, target_vocab: int, max_contexts: int, batch: int, seed: int = 1234,
-                    full_bags: bool = False, zipf: bool = False):
+                    full_bags: bool = False, zipf: bool = False, normal_bags: bool = False):
     rng = np.random.default_rng(seed)
     B, C = batch, max_contexts
 
@@ -23,7 +23,12 @@ def synthetic_batch(token_vocab: int, path_vocab: int, target_vocab: int, max_co
     src = draw(token_vocab, (B, C))
     pth = draw(path_vocab, (B, C))
     tgt = draw(token_vocab, (B, C))
-    n_valid = np.full(B, C) if full_bags else rng.integers(1, C + 1, size=B)
+    if full_bags:
+        n_valid = np.full(B, C)
+    elif normal_bags:                      # SURVEY 8d second run: n_b ~ clip(N(0.6 C, 0.3 C), 1, C)
+        n_valid = np.clip(np.rint(rng.normal(0.6 * C, 0.3 * C, size=B)), 1, C).astype(np.int64)
+    else:
+        n_valid = rng.integers(1, C + 1, size=B)
     valid = np.arange(C)[None, :] < n_valid[:, None]
     src = np.where(valid, src, 0).astype(np.int32)
     pth = np.where(valid, pth, 0).astype(np.int32)
