@@ -133,7 +133,10 @@ struct c2v_engine {
   int cta_pair = 2;          // tcgen05 GEMMs as CTA pairs (cta_group::2, UMMA 256 x BN): 0 never, 1 always, 2 auto
   int num_sms;
   cudaEvent_t ev_tgt_ready = nullptr;   // recorded after dY (caller-owned)
-  cudaStream_t side = nullptr;          // engine-owned: the embedding scatter-add runs here, next to the dW GEMM
+  int dy_late = 1;                      // defer the dY GEMM into context_backward (overlaps the scatter-add)
+  const float* pending_dy_v = nullptr;  // code vectors of the deferred dY product
+  int pending_dy_B = 0;
+  cudaStream_t side = nullptr;          // engine-owned: the embedding scatter-add runs here, next to the dY / dW GEMMs
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   int deterministic;
   int64_t launches;
@@ -391,6 +394,8 @@ int topk_impl(c2v_engine* e, cudaStream_t st, const float* code_vec, int B, int3
 
 // Backward of everything below the code vector, given dv: gradients of a, W and the two
 // embedding tables.
+int run_dy(c2v_engine* e, cudaStream_t st, const float* v, int B);
+
 int context_backward(c2v_engine* e, cudaStream_t st, const ContextSource& cs, const float* mask, int B,
                      const Dropout& dp, const float* dv) {
   const int D = e->dims.code_dim, d = e->dims.embed_dim, K3 = 3 * d, N = cs.rows;
@@ -398,7 +403,13 @@ int context_backward(c2v_engine* e, cudaStream_t st, const ContextSource& cs, co
   float* alpha = wsp<float>(e, e->ws.alpha);
   float* da_part = wsp<float>(e, e->ws.da_part);
   float* part = wsp<float>(e, e->ws.part);
-  int rc = launch_attn_bwd(e, st, H, alpha, dv, B, da_part);          // H now holds dU
+  int rc;
+  if (e->pending_dy_v && e->math_mode != C2V_MATH_TF32) {   // fp32 path: nothing to overlap with, run it first
+    const float* pv = e->pending_dy_v;
+    e->pending_dy_v = nullptr;
+    if ((rc = run_dy(e, st, pv, e->pending_dy_B))) return rc;
+  }
+  rc = launch_attn_bwd(e, st, H, alpha, dv, B, da_part);          // H now holds dU
   if (rc) return rc;
   rc = launch_colsum(e, st, da_part, (size_t)D, B, D, e->grad.a);
   if (rc) return rc;
@@ -425,6 +436,11 @@ int context_backward(c2v_engine* e, cudaStream_t st, const ContextSource& cs, co
       C2V_LAUNCH(e, (scatter_dx_kernel<<<(N + 7) / 8, 256, 0, e->side>>>(cs, dp, mask, dXg, e->gr_tok, e->gr_path, e->grad_scale)));
     }
     C2V_CUDA(e, cudaEventRecord(e->ev_join, e->side));
+    if (e->pending_dy_v) {   // deferred dYtab = P^T . v, concurrent with the scatter-add
+      const float* pv = e->pending_dy_v;
+      e->pending_dy_v = nullptr;
+      if ((rc = run_dy(e, st, pv, e->pending_dy_B))) return rc;
+    }
     {  // dW = X'^T . dU on the gathered X' kept from the forward pass
       PhaseTimer pt(e, PH_DW, st);
       umma::Operand opA{Xg, (size_t)K3, true};
@@ -464,53 +480,66 @@ int context_backward(c2v_engine* e, cudaStream_t st, const ContextSource& cs, co
   return C2V_OK;
 }
 
-// Given P = dL/dlogits in the S slab:  dv = P . Ytab  (split-K over |Y|, fixed-order reduction) and
-// dYtab = P^T . v  into the bound target-table gradient.
-int target_grad_gemms(c2v_engine* e, cudaStream_t st, const float* v, int B, float* dv) {
+// Given P = dL/dlogits in the S slab:  dv = P . Ytab  (split-K over |Y|, fixed-order reduction).
+int run_dv(c2v_engine* e, cudaStream_t st, int B, float* dv) {
   const int D = e->dims.code_dim, Y = e->dims.target_vocab;
   float* S = wsp<float>(e, e->ws.S);
   float* part = wsp<float>(e, e->ws.part);
-  int rc;
-  if (e->math_mode == C2V_MATH_TF32 && (reinterpret_cast<uintptr_t>(v) % 16 == 0)) {
-    {
-      PhaseTimer pt(e, PH_DV, st);
-      umma::Operand opA{S, e->ws.ldS, false};
-      umma::Operand opB{e->theta.tgt, (size_t)D, true};
-      // enough split-K slices to fill the SMs about twice; few when the batch already gives many tiles
-      const int tiles = ((B + 127) / 128) * ((D + 191) / 192);
-      int want = (2 * e->num_sms + tiles - 1) / tiles;
-      if (want > kSplitDv) want = kSplitDv;
-      const int ks = umma::effective_splits(Y, want);
-      umma::EpiStore ep{part, (size_t)D, (size_t)B * D};
-      C2V_LAUNCH(e, C2V_CUDA(e, (C2V_UMMA_192(st, B, D, Y, want, opA, opB, ep, e->num_sms))));
-      if ((rc = launch_colsum(e, st, part, (size_t)B * D, ks, B * D, dv))) return rc;
-    }
-    {
-      PhaseTimer pt(e, PH_DY, st);
+  PhaseTimer pt(e, PH_DV, st);
+  if (e->math_mode == C2V_MATH_TF32) {
+    umma::Operand opA{S, e->ws.ldS, false};
+    umma::Operand opB{e->theta.tgt, (size_t)D, true};
+    // enough split-K slices to fill the SMs about twice; few when the batch already gives many tiles
+    const int tiles = ((B + 127) / 128) * ((D + 191) / 192);
+    int want = (2 * e->num_sms + tiles - 1) / tiles;
+    if (want > kSplitDv) want = kSplitDv;
+    const int ks = umma::effective_splits(Y, want);
+    umma::EpiStore ep{part, (size_t)D, (size_t)B * D};
+    C2V_LAUNCH(e, C2V_CUDA(e, (C2V_UMMA_192(st, B, D, Y, want, opA, opB, ep, e->num_sms))));
+    return launch_colsum(e, st, part, (size_t)B * D, ks, B * D, dv);
+  }
+  simt::RowsK al{S, e->ws.ldS};
+  simt::ColsX bl{e->theta.tgt, (size_t)D};
+  const int ks = simt::effective_ksplit(Y, kSplitDv);
+  simt::StoreC ep{part, (size_t)D, (size_t)B * D};
+  C2V_LAUNCH(e, C2V_CUDA(e, simt::launch(st, B, D, Y, kSplitDv, al, bl, ep)));
+  return launch_colsum(e, st, part, (size_t)B * D, ks, B * D, dv);
+}
+
+// dYtab = P^T . v  into the bound target-table gradient; then the caller's "target_grads_ready" event.
+int run_dy(c2v_engine* e, cudaStream_t st, const float* v, int B) {
+  const int D = e->dims.code_dim, Y = e->dims.target_vocab;
+  float* S = wsp<float>(e, e->ws.S);
+  {
+    PhaseTimer pt(e, PH_DY, st);
+    if (e->math_mode == C2V_MATH_TF32 && (reinterpret_cast<uintptr_t>(v) % 16 == 0)) {
       umma::Operand opA{S, e->ws.ldS, true};
       umma::Operand opB{v, (size_t)D, true};
       umma::EpiStore ep{e->grad.tgt, (size_t)D, 0};
       C2V_LAUNCH(e, C2V_CUDA(e, (C2V_UMMA_192_SINGLE(st, Y, D, B, 1, opA, opB, ep, e->num_sms))));
+    } else {
+      simt::ColsX al{S, e->ws.ldS};
+      simt::ColsX bl{v, (size_t)D};
+      simt::StoreC ep{e->grad.tgt, (size_t)D, 0};
+      C2V_LAUNCH(e, C2V_CUDA(e, simt::launch(st, Y, D, B, 1, al, bl, ep)));
     }
+  }
+  if (e->ev_tgt_ready) C2V_CUDA(e, cudaEventRecord(e->ev_tgt_ready, st));
+  return C2V_OK;
+}
+
+// The two target-table gradient products.  With option "dy_late" (default) only dv runs here and dY is
+// deferred into context_backward, where it overlaps the NVLink / L2-atomic bound scatter-add of the
+// embedding gradients (dY needs P and v only, not the context backward).
+int target_grad_gemms(c2v_engine* e, cudaStream_t st, const float* v, int B, float* dv) {
+  int rc = run_dv(e, st, B, dv);
+  if (rc) return rc;
+  if (e->dy_late) {
+    e->pending_dy_v = v;
+    e->pending_dy_B = B;
     return C2V_OK;
   }
-  {
-    PhaseTimer pt(e, PH_DV, st);
-    simt::RowsK al{S, e->ws.ldS};
-    simt::ColsX bl{e->theta.tgt, (size_t)D};
-    const int ks = simt::effective_ksplit(Y, kSplitDv);
-    simt::StoreC ep{part, (size_t)D, (size_t)B * D};
-    C2V_LAUNCH(e, C2V_CUDA(e, simt::launch(st, B, D, Y, kSplitDv, al, bl, ep)));
-    if ((rc = launch_colsum(e, st, part, (size_t)B * D, ks, B * D, dv))) return rc;
-  }
-  {
-    PhaseTimer pt(e, PH_DY, st);
-    simt::ColsX al{S, e->ws.ldS};
-    simt::ColsX bl{v, (size_t)D};
-    simt::StoreC ep{e->grad.tgt, (size_t)D, 0};
-    C2V_LAUNCH(e, C2V_CUDA(e, simt::launch(st, Y, D, B, 1, al, bl, ep)));
-  }
-  return C2V_OK;
+  return run_dy(e, st, v, B);
 }
 
 int train_step_impl(c2v_engine* e, cudaStream_t st, const int32_t* src, const int32_t* pth, const int32_t* tgt,
@@ -548,7 +577,6 @@ int train_step_impl(c2v_engine* e, cudaStream_t st, const int32_t* src, const in
     C2V_LAUNCH(e, (loss_reduce_kernel<<<1, 256, 0, st>>>(loss_b, B, invB, loss_out)));
   }
   if ((rc = target_grad_gemms(e, st, v, B, dv))) return rc;
-  if (e->ev_tgt_ready) C2V_CUDA(e, cudaEventRecord(e->ev_tgt_ready, st));
   return context_backward(e, st, cs, mask, B, dp, dv);
 }
 
@@ -750,6 +778,7 @@ int c2v_set_option(c2v_engine* e, const char* key, int64_t value) {
     return C2V_OK;
   }
   if (!strcmp(key, "profile")) { e->profile = value ? 1 : 0; return C2V_OK; }
+  if (!strcmp(key, "dy_late")) { e->dy_late = value ? 1 : 0; return C2V_OK; }
   if (!strcmp(key, "cta_pair")) {
     if (value < 0 || value > 2) return fail(e, C2V_ERR_INVALID, "cta_pair must be 0 (never), 1 (always) or 2 (auto)");
     e->cta_pair = (int)value;
@@ -806,6 +835,7 @@ int c2v_get_option(const c2v_engine* e, const char* key, int64_t* value) {
   if (!strcmp(key, "profile")) { *value = e->profile; return C2V_OK; }
   if (!strcmp(key, "lazy_adam")) { *value = e->lazy; return C2V_OK; }
   if (!strcmp(key, "cta_pair")) { *value = e->cta_pair; return C2V_OK; }
+  if (!strcmp(key, "dy_late")) { *value = e->dy_late; return C2V_OK; }
   if (!strcmp(key, "adam_step_count")) { *value = e->adam_t_done; return C2V_OK; }
   return C2V_ERR_INVALID;
 }
@@ -990,9 +1020,7 @@ int c2v_target_backward(c2v_engine* e, const float* code_all, int32_t Bt, const 
     C2V_LAUNCH(e, (softmax_grad_kernel<<<dim3(chunks, Bt), 256, 0, st>>>(S, e->ws.ldS, e->dims.target_vocab, lse, target,
                                                                        inv_batch, row_offset)));
   }
-  if ((rc = target_grad_gemms(e, st, code_all, Bt, dv_partial))) return rc;
-  if (e->ev_tgt_ready) C2V_CUDA(e, cudaEventRecord(e->ev_tgt_ready, st));
-  return C2V_OK;
+  return target_grad_gemms(e, st, code_all, Bt, dv_partial);
 }
 
 int c2v_context_backward(c2v_engine* e, const int32_t* src, const int32_t* path, const int32_t* tgt, const float* mask,

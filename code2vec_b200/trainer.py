@@ -183,6 +183,8 @@ class Trainer:
             self._ev_tgt = torch.cuda.Event()
             with torch.cuda.device(engine.dev):
                 engine.set_event("target_grads_ready", self._ev_tgt)
+        if self.schedule in ("sharded", "table_sharded"):
+            engine.set_option("dy_late", 0)     # these schedules start the target table's reduce-scatter right after dY
         if self.schedule == "sharded":
             (a0, a1), (b0, b1) = engine.bucket_bounds()
             w, r = self.world, self.rank

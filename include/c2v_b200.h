@@ -100,7 +100,9 @@ int c2v_bind_adam_state(c2v_engine* e, const c2v_tensors* m, const c2v_tensors* 
 /* Options: "math_mode" (c2v_math_mode), "deterministic" (reserved: only 0 is accepted -- the
  * embedding scatter-add uses float atomics; every other reduction is fixed-order), "cta_pair"
  * (tcgen05 GEMMs as CTA pairs, tcgen05.mma.cta_group::2: 0 never, 1 always, 2 auto = per GEMM,
- * wherever it measured faster; default 2), "profile" (0/1: per-phase
+ * wherever it measured faster; default 2), "dy_late" (0/1, default 1: the target-table gradient
+ * GEMM dY = P^T.v is issued inside the context backward pass so it overlaps the embedding
+ * scatter-add; with 0 it runs right after dv and "target_grads_ready" fires earlier), "profile" (0/1: per-phase
  * CUDA-event timing, read with c2v_phase_stats), "lazy_adam" (0/1, single-GPU replicated tables:
  * the dense TF1 Adam update of an embedding row that received no gradient is deferred and replayed
  * bit-exactly when the row is next read or updated -- same results as the dense update, a
