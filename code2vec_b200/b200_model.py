@@ -86,6 +86,11 @@ class Code2VecModel(Code2VecModelBase):
 
     def _make_engine(self):
         import torch
+        if int(os.environ.get("WORLD_SIZE", "1")) > 1:
+            # The multi-GPU schedules live in code2vec_b200.trainer (and bench.py drives them); wiring them into
+            # train() also needs per-rank data sharding and sharded checkpoints, which this backend does not do yet.
+            raise NotImplementedError("Code2VecModel.train()/evaluate() run one process on one GPU; "
+                                      "use code2vec_b200.trainer.Trainer for multi-GPU steps")
         device = int(os.environ.get("LOCAL_RANK", "0")) if torch.cuda.device_count() > 1 else 0
         self.engine = PathAttentionEngine(self._engine_dims(), device=device, training=self.config.is_training)
         # arithmetic of the big matrix products: tensor cores (tf32 operands, fp32 accumulate) for training
