@@ -113,26 +113,31 @@ def make_batches(w, n_batches, seed, bags="full", zipf=False):
             for i in range(n_batches)]
 
 
-def algorithmic_work(w, B, touched_rows=None, world=1):
+def algorithmic_work(w, B, touched_rows=None, world=1, fused_target_adam=False):
     """Per-step algorithmic FLOPs / bytes of each phase.
 
     adam: the dense TF1 update streams theta, m, v in and out = 24 B per parameter.  With the
     lazy-but-exact scheme (single GPU) only the rows the batch references are streamed: 24 B per
     element in the catch-up pass + 24 B in the update pass, the dense part being the target table,
-    TRANSFORM and ATTENTION.  Under table sharding each rank updates 1/world of every table."""
+    TRANSFORM and ATTENTION.  Under table sharding each rank updates 1/world of every table.
+    fused_target_adam: the target table's update runs in the dY epilogue, so its 24 B/param move
+    from "adam" to "dY", which then is HBM-bound (P^T read once + the update) rather than tensor-bound."""
     d, D, C, Y = w["embed_dim"], w["code_dim"], w["max_contexts"], w["target_vocab"]
     N = B * C
     emb = (w["token_vocab"] + w["path_vocab"]) * d
     rest = Y * D + 3 * d * D + D
     proj = 2.0 * N * 3 * d * D
     logit = 2.0 * B * D * Y
+    if fused_target_adam:
+        rest -= Y * D
     if touched_rows is not None:
         adam, catchup = 24.0 * (rest + touched_rows * d), 24.0 * touched_rows * d
     else:
         adam, catchup = 24.0 * (emb + rest) / world, 0.0
+    dy = ("hbm", 24.0 * Y * D + 4.0 * B * Y) if fused_target_adam else ("tensor", logit)
     return {
         "ctx_fwd": ("tensor", proj), "dW": ("tensor", proj), "dx_gemm": ("tensor", proj),
-        "logits": ("tensor", logit), "dv": ("tensor", logit), "dY": ("tensor", logit),
+        "logits": ("tensor", logit), "dv": ("tensor", logit), "dY": dy,
         "adam": ("hbm", adam), "adam_catchup": ("hbm", catchup),
         "attn_fwd": ("hbm", 4.0 * N * D), "attn_bwd": ("hbm", 3 * 4.0 * N * D),
         "xent": ("hbm", 2 * 4.0 * B * Y),
@@ -184,7 +189,7 @@ def run_ours(args):
     if args.math == "tf32":
         eng.set_option("math_mode", 1)
     eng.set_option("cta_pair", args.cta_pair)
-    trainer = Trainer(eng, keep_prob=KEEP_PROB, seed=99, schedule=args.dp_schedule)
+    trainer = Trainer(eng, keep_prob=KEEP_PROB, seed=99, schedule=args.dp_schedule, fuse_target_adam=not args.no_fuse_adam)
 
     n_batches = 4
     host = make_batches(w, n_batches, seed=1234 + 100003 * rank, bags=args.bags, zipf=args.zipf)
@@ -256,7 +261,9 @@ def run_ours(args):
     if trainer.schedule == "single" and eng.get_option("lazy_adam"):
         touched = float(np.mean([len(np.unique(np.concatenate([b[0].ravel(), b[2].ravel()]))) + len(np.unique(b[1]))
                                  for b in host]))
-    work = algorithmic_work(w, B, touched_rows=touched, world=world if trainer.schedule == "table_sharded" else 1)
+    fused = bool(getattr(trainer, "fuse_tgt", False)) and args.math == "tf32"
+    work = algorithmic_work(w, B, touched_rows=touched, world=world if trainer.schedule == "table_sharded" else 1,
+                            fused_target_adam=fused and world == 1)
     traffic = ncu_traffic()
     phase_out = {}
     dominant, dom_ms = None, -1.0
@@ -304,7 +311,7 @@ def run_ours(args):
                    "batch_per_gpu": B, "global_batch": B * world, "contexts_per_example": C,
                    "parallelism": "dp%d (%s)" % (world, trainer.schedule) if world > 1 else "single",
                    "l2": "no flush: >9 GB of parameter/optimizer traffic per step and 4 rotating input batches exceed the 126 MB L2",
-                   "math_mode": args.math, "last_loss": round(last_loss, 5),
+                   "math_mode": args.math, "fused_target_adam": fused, "last_loss": round(last_loss, 5),
                    "inputs": "%s bags, %s indices; all %d slots per example are counted in the metric" % (
                        args.bags, "zipf(1.2)" if args.zipf else "uniform", C),
                    "valid_context_fraction": round(float(np.mean([b[3].mean() for b in host])), 4)},
@@ -403,6 +410,8 @@ def main():
     ap.add_argument("--batch", type=int, default=0)
     ap.add_argument("--math", default=os.environ.get("C2V_MATH", "tf32"), choices=["fp32", "tf32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-fuse-adam", action="store_true",
+                    help="keep the target table's Adam update as a separate pass instead of the dY epilogue")
     ap.add_argument("--bags", default="full", choices=["full", "normal", "ragged"],
                     help="valid contexts per bag: full (default; worst case for HBM), normal ~N(120,60), ragged ~U{1..C}")
     ap.add_argument("--zipf", action="store_true", help="Zipfian instead of uniform indices (hot rows, L2 reuse)")

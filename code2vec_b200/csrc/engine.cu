@@ -138,6 +138,12 @@ struct c2v_engine {
   int pending_dy_B = 0;
   cudaStream_t side = nullptr;          // engine-owned: the embedding scatter-add runs here, next to the dY / dW GEMMs
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  // target-table Adam folded into the dY epilogue (c2v_arm_target_adam)
+  bool tgt_armed = false;               // the next tcgen05 dY product applies the update instead of storing dY
+  float tgt_lr = 0.f, tgt_b1 = 0.f, tgt_b2 = 0.f, tgt_eps = 0.f;
+  int64_t tgt_t = 0;
+  int fuse_tgt = 0;                     // option "fuse_target_adam": c2v_train_batch_host arms itself
+  int64_t tgt_fused_t = 0;              // step count whose target update has already been applied (0 = none)
   int deterministic;
   int64_t launches;
   std::string err;
@@ -515,8 +521,19 @@ int run_dy(c2v_engine* e, cudaStream_t st, const float* v, int B) {
     if (e->math_mode == C2V_MATH_TF32 && (reinterpret_cast<uintptr_t>(v) % 16 == 0)) {
       umma::Operand opA{S, e->ws.ldS, true};
       umma::Operand opB{v, (size_t)D, true};
-      umma::EpiStore ep{e->grad.tgt, (size_t)D, 0};
-      C2V_LAUNCH(e, C2V_CUDA(e, (C2V_UMMA_192_SINGLE(st, Y, D, B, 1, opA, opB, ep, e->num_sms))));
+      if (e->tgt_armed && e->has_adam) {
+        // dYtab never reaches memory: the epilogue applies TF1 Adam to the target table in place
+        const double lr_t = (double)e->tgt_lr * sqrt(1.0 - pow((double)e->tgt_b2, (double)e->tgt_t)) /
+                            (1.0 - pow((double)e->tgt_b1, (double)e->tgt_t));
+        umma::EpiAdam ep{e->theta.tgt, e->am.tgt, e->av.tgt, (size_t)D, (float)lr_t, e->tgt_b1, e->tgt_b2, e->tgt_eps,
+                         1.f - e->tgt_b1, 1.f - e->tgt_b2};
+        C2V_LAUNCH(e, C2V_CUDA(e, (C2V_UMMA_192_SINGLE(st, Y, D, B, 1, opA, opB, ep, e->num_sms))));
+        e->tgt_armed = false;
+        e->tgt_fused_t = e->tgt_t;
+      } else {
+        umma::EpiStore ep{e->grad.tgt, (size_t)D, 0};
+        C2V_LAUNCH(e, C2V_CUDA(e, (C2V_UMMA_192_SINGLE(st, Y, D, B, 1, opA, opB, ep, e->num_sms))));
+      }
     } else {
       simt::ColsX al{S, e->ws.ldS};
       simt::ColsX bl{v, (size_t)D};
@@ -619,6 +636,14 @@ int adam_impl(c2v_engine* e, cudaStream_t st, float lr, float b1, float b2, floa
   if (e->table_world > 1)
     return fail(e, C2V_ERR_STATE, "embedding tables are sharded: update each slice with c2v_adam_step_range");
   if (t < 1) return fail(e, C2V_ERR_INVALID, "Adam step count t must be >= 1");
+  e->tgt_armed = false;                 // an unconsumed arming (fp32 path, sampled softmax) falls back to the dense update
+  bool skip_tgt = false;
+  if (e->tgt_fused_t) {
+    if (e->tgt_fused_t != t || lr != e->tgt_lr || b1 != e->tgt_b1 || b2 != e->tgt_b2 || eps != e->tgt_eps)
+      return fail(e, C2V_ERR_STATE, "the target table was already updated by the armed dY epilogue with a different step count / hyper-parameters");
+    skip_tgt = true;
+    e->tgt_fused_t = 0;
+  }
   const double lr_t_d = (double)lr * sqrt(1.0 - pow((double)b2, (double)t)) / (1.0 - pow((double)b1, (double)t));
   const float lr_t = (float)lr_t_d;
   const c2v_dims& d = e->dims;
@@ -650,6 +675,7 @@ int adam_impl(c2v_engine* e, cudaStream_t st, float lr, float b1, float b2, floa
   }
   e->adam_t_done = t;
   for (int i = first_dense; i < 5; ++i) {
+    if (i == 2 && skip_tgt) continue;
     const size_t n4 = n[i] / 4;
     size_t blocks = (n4 + 255) / 256;
     if (blocks > 148 * 16) blocks = 148 * 16;
@@ -779,6 +805,7 @@ int c2v_set_option(c2v_engine* e, const char* key, int64_t value) {
   }
   if (!strcmp(key, "profile")) { e->profile = value ? 1 : 0; return C2V_OK; }
   if (!strcmp(key, "dy_late")) { e->dy_late = value ? 1 : 0; return C2V_OK; }
+  if (!strcmp(key, "fuse_target_adam")) { e->fuse_tgt = value ? 1 : 0; return C2V_OK; }
   if (!strcmp(key, "cta_pair")) {
     if (value < 0 || value > 2) return fail(e, C2V_ERR_INVALID, "cta_pair must be 0 (never), 1 (always) or 2 (auto)");
     e->cta_pair = (int)value;
@@ -811,6 +838,11 @@ int c2v_set_option(c2v_engine* e, const char* key, int64_t value) {
     e->lazy = value ? 1 : 0;
     return C2V_OK;
   }
+  if (!strcmp(key, "target_adam_fused_step")) {           // callers that run c2v_adam_step_range themselves acknowledge with 0
+    if (value) return fail(e, C2V_ERR_INVALID, "target_adam_fused_step can only be cleared (0)");
+    e->tgt_fused_t = 0;
+    return C2V_OK;
+  }
   if (!strcmp(key, "adam_step_count")) {                  // optimizer reset / checkpoint restore
     C2V_CUDA(e, cudaSetDevice(e->device));
     if (e->lazy) {
@@ -836,7 +868,9 @@ int c2v_get_option(const c2v_engine* e, const char* key, int64_t* value) {
   if (!strcmp(key, "lazy_adam")) { *value = e->lazy; return C2V_OK; }
   if (!strcmp(key, "cta_pair")) { *value = e->cta_pair; return C2V_OK; }
   if (!strcmp(key, "dy_late")) { *value = e->dy_late; return C2V_OK; }
+  if (!strcmp(key, "fuse_target_adam")) { *value = e->fuse_tgt; return C2V_OK; }
   if (!strcmp(key, "adam_step_count")) { *value = e->adam_t_done; return C2V_OK; }
+  if (!strcmp(key, "target_adam_fused_step")) { *value = e->tgt_fused_t; return C2V_OK; }
   return C2V_ERR_INVALID;
 }
 
@@ -896,6 +930,17 @@ int c2v_sampled_train_step(c2v_engine* e, const int32_t* src, const int32_t* pat
   C2V_CUDA(e, cudaSetDevice(e->device));
   return sampled_train_step_impl(e, (cudaStream_t)stream, src, path, tgt, mask, target, B, sampled, S, logq_true,
                                  logq_sampled, keep_prob, seed, step, dropout_mask, loss_out);
+}
+
+int c2v_arm_target_adam(c2v_engine* e, float lr, float beta1, float beta2, float eps, int64_t t) {
+  if (!e) return C2V_ERR_INVALID;
+  if (!e->has_theta || !e->has_adam) return fail(e, C2V_ERR_STATE, "parameters / Adam state not bound");
+  if (t < 1) return fail(e, C2V_ERR_INVALID, "Adam step count t must be >= 1");
+  if (e->tgt_fused_t)
+    return fail(e, C2V_ERR_STATE, "a fused target update is still unacknowledged: call c2v_adam_step (or clear target_adam_fused_step)");
+  e->tgt_lr = lr; e->tgt_b1 = beta1; e->tgt_b2 = beta2; e->tgt_eps = eps; e->tgt_t = t;
+  e->tgt_armed = true;
+  return C2V_OK;
 }
 
 int c2v_adam_step(c2v_engine* e, float lr, float beta1, float beta2, float eps, int64_t t, void* stream) {
@@ -1088,6 +1133,7 @@ int c2v_train_batch_host(c2v_engine* e, const int32_t* h_src, const int32_t* h_p
   C2V_CUDA(e, cudaMemcpyAsync(tgt, h_tgt, nb, cudaMemcpyHostToDevice, st));
   C2V_CUDA(e, cudaMemcpyAsync(mask, h_mask, nb, cudaMemcpyHostToDevice, st));
   C2V_CUDA(e, cudaMemcpyAsync(target, h_target, (size_t)B * 4, cudaMemcpyHostToDevice, st));
+  if (e->fuse_tgt && (rc = c2v_arm_target_adam(e, lr, beta1, beta2, eps, t))) return rc;
   // the Adam step count doubles as the dropout stream position
   if ((rc = train_step_impl(e, st, src, pth, tgt, mask, target, B, keep_prob, seed, (uint64_t)t, nullptr, loss))) return rc;
   if ((rc = adam_impl(e, st, lr, beta1, beta2, eps, t))) return rc;

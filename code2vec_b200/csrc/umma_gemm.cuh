@@ -151,7 +151,10 @@ __host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N, bool a_mn, 
 // functor supplies:  State / begin / end  -- per-(row, tile) state and its publication;
 //                    observe(m, n0, 32 raw accumulators, nvalid, state) -- row-wise math (log-sum-exp);
 //                    map(x)    -- the element-wise transform applied on the way out (identity, tanh);
-//                    out(split), ldc -- where the tile goes.
+//                    out(split), ldc -- where the tile goes;
+//                    Pre / prefetch / store4 / store1(base, offset, value) -- what "storing" an element
+//                    means (a plain write, or the optimizer update of the parameter the element is
+//                    the gradient of; prefetch issues that update's loads ahead of the arithmetic).
 // The store itself is done by drain_accumulator: TMEM -> registers (thread = row) -> a 4 KB
 // XOR-swizzled shared-memory transpose per warp -> global stores in which every instruction writes
 // four complete 128-byte row segments.  (Storing straight from the TMEM register layout makes each
@@ -169,6 +172,12 @@ struct EpiStore {
   __device__ __forceinline__ void observe(int, int, const uint32_t (&)[32], int, State&) const {}
   __device__ __forceinline__ float map(float x) const { return x; }
   __device__ __forceinline__ float* out(int split) const { return C + (size_t)split * split_stride; }
+  using Pre = EpiNoState;
+  static constexpr int kRowBatch = 8;
+  static constexpr bool kWideDrain = true;
+  __device__ __forceinline__ void prefetch(const float*, size_t, Pre&) const {}
+  __device__ __forceinline__ void store4(float* c, size_t off, float4 v, const Pre&) const { *reinterpret_cast<float4*>(c + off) = v; }
+  __device__ __forceinline__ void store1(float* c, size_t off, float x) const { c[off] = x; }
 };
 struct EpiTanhStore {
   using State = EpiNoState;
@@ -179,6 +188,12 @@ struct EpiTanhStore {
   __device__ __forceinline__ void observe(int, int, const uint32_t (&)[32], int, State&) const {}
   __device__ __forceinline__ float map(float x) const { return fast_tanh(x); }
   __device__ __forceinline__ float* out(int) const { return C; }
+  using Pre = EpiNoState;
+  static constexpr int kRowBatch = 8;
+  static constexpr bool kWideDrain = true;
+  __device__ __forceinline__ void prefetch(const float*, size_t, Pre&) const {}
+  __device__ __forceinline__ void store4(float* c, size_t off, float4 v, const Pre&) const { *reinterpret_cast<float4*>(c + off) = v; }
+  __device__ __forceinline__ void store1(float* c, size_t off, float x) const { c[off] = x; }
 };
 
 // Logits epilogue: stores the tile of S and folds the row-wise (max, sum exp) of this warp's columns
@@ -196,6 +211,12 @@ struct EpiStoreLse {
   }
   __device__ __forceinline__ float map(float x) const { return x; }
   __device__ __forceinline__ float* out(int) const { return C; }
+  using Pre = EpiNoState;
+  static constexpr int kRowBatch = 8;
+  static constexpr bool kWideDrain = true;
+  __device__ __forceinline__ void prefetch(const float*, size_t, Pre&) const {}
+  __device__ __forceinline__ void store4(float* c, size_t off, float4 v, const Pre&) const { *reinterpret_cast<float4*>(c + off) = v; }
+  __device__ __forceinline__ void store1(float* c, size_t off, float x) const { c[off] = x; }
   __device__ __forceinline__ void observe(int, int, const uint32_t (&r)[32], int nvalid, State& st) const {
     float cm = -INFINITY;
 #pragma unroll
@@ -211,6 +232,50 @@ struct EpiStoreLse {
       if (j + 3 < nvalid) a3 += __expf(__uint_as_float(r[j + 3]) - st.mx);
     }
     st.sum += (a0 + a1) + (a2 + a3);
+  }
+};
+
+// Target-table gradient epilogue with the optimizer folded in (option "fuse_target_adam"): the
+// accumulator element is dYtab[y, j]; instead of writing it out for adam_kernel to read back, the
+// epilogue applies TF1 Adam (tensorflow_model.py:232) to (theta, m, v) in place -- the
+// same correctly rounded fp32 operations in the same order as adam_kernel, so the result is
+// bit-identical; the gradient itself is never stored.
+struct EpiAdam {
+  using State = EpiNoState;
+  float* P;          // theta [M, ldc]; m and v have the same layout
+  float* Mo;
+  float* Vo;
+  size_t ldc;
+  float lr_t, b1, b2, eps, omb1, omb2;
+  __device__ __forceinline__ void begin(State&) const {}
+  __device__ __forceinline__ void end(int, int, int, bool, State&) const {}
+  __device__ __forceinline__ void observe(int, int, const uint32_t (&)[32], int, State&) const {}
+  __device__ __forceinline__ float map(float x) const { return x; }
+  __device__ __forceinline__ float* out(int) const { return P; }
+  __device__ __forceinline__ void upd(float& pp, float gg, float& mm, float& vv) const {
+    mm = __fadd_rn(__fmul_rn(mm, b1), __fmul_rn(omb1, gg));
+    vv = __fadd_rn(__fmul_rn(vv, b2), __fmul_rn(omb2, __fmul_rn(gg, gg)));
+    pp = __fsub_rn(pp, __fdiv_rn(__fmul_rn(lr_t, mm), __fadd_rn(__fsqrt_rn(vv), eps)));
+  }
+  struct Pre { float4 p, m, v; };
+  static constexpr int kRowBatch = 4;
+  static constexpr bool kWideDrain = false;      // 32 columns per tcgen05.ld: the update needs the registers
+  __device__ __forceinline__ void prefetch(const float* c, size_t off, Pre& q) const {
+    q.p = *reinterpret_cast<const float4*>(c + off);
+    q.m = *reinterpret_cast<const float4*>(Mo + off);
+    q.v = *reinterpret_cast<const float4*>(Vo + off);
+  }
+  __device__ __forceinline__ void store4(float* c, size_t off, float4 g, const Pre& q) const {
+    float4 p = q.p, m = q.m, v = q.v;
+    upd(p.x, g.x, m.x, v.x); upd(p.y, g.y, m.y, v.y); upd(p.z, g.z, m.z, v.z); upd(p.w, g.w, m.w, v.w);
+    *reinterpret_cast<float4*>(c + off) = p;
+    *reinterpret_cast<float4*>(Mo + off) = m;
+    *reinterpret_cast<float4*>(Vo + off) = v;
+  }
+  __device__ __forceinline__ void store1(float* c, size_t off, float g) const {
+    float p = c[off], m = Mo[off], v = Vo[off];
+    upd(p, g, m, v);
+    c[off] = p; Mo[off] = m; Vo[off] = v;
   }
 };
 
@@ -230,19 +295,31 @@ __device__ __forceinline__ void store_chunk(const Epi& epi, const uint32_t (&r)[
   __syncwarp();
   const int col4 = lane & 7;
   const int gn = n + col4 * 4;
+  // two passes per batch of rows so that a read-modify-write epilogue has kBatch rows' loads in flight
+  constexpr int kBatch = Epi::kRowBatch;
 #pragma unroll
-  for (int it = 0; it < 8; ++it) {
-    const int row = it * 4 + (lane >> 3);
-    const float4 v = *reinterpret_cast<const float4*>(stage + row * 32 + ((col4 ^ (row & 7)) * 4));
-    const int gm = m_base + row;
-    if (gm < M && gn < N) {
-      float* p = cbase + (size_t)gm * ldc + gn;
-      if (gn + 3 < N) {
-        *reinterpret_cast<float4*>(p) = v;
-      } else {
-        p[0] = v.x;
-        if (gn + 1 < N) p[1] = v.y;
-        if (gn + 2 < N) p[2] = v.z;
+  for (int it0 = 0; it0 < 8; it0 += kBatch) {
+    float4 v[kBatch];
+    typename Epi::Pre pre[kBatch];
+#pragma unroll
+    for (int i = 0; i < kBatch; ++i) {
+      const int row = (it0 + i) * 4 + (lane >> 3);
+      v[i] = *reinterpret_cast<const float4*>(stage + row * 32 + ((col4 ^ (row & 7)) * 4));
+      const int gm = m_base + row;
+      if (gm < M && gn + 3 < N) epi.prefetch(cbase, (size_t)gm * ldc + gn, pre[i]);
+    }
+#pragma unroll
+    for (int i = 0; i < kBatch; ++i) {
+      const int gm = m_base + (it0 + i) * 4 + (lane >> 3);
+      if (gm < M && gn < N) {
+        const size_t off = (size_t)gm * ldc + gn;
+        if (gn + 3 < N) {
+          epi.store4(cbase, off, v[i], pre[i]);
+        } else {
+          epi.store1(cbase, off, v[i].x);
+          if (gn + 1 < N) epi.store1(cbase, off + 1, v[i].y);
+          if (gn + 2 < N) epi.store1(cbase, off + 2, v[i].z);
+        }
       }
     }
   }
@@ -258,7 +335,7 @@ __device__ __forceinline__ void drain_accumulator(const Epi& epi, typename Epi::
   float* cbase = epi.out(sp);
   int c = col0;
 #pragma unroll 1
-  for (; c + 64 <= col0 + ncols; c += 64) {
+  for (; Epi::kWideDrain && c + 64 <= col0 + ncols; c += 64) {
     uint32_t r0[32], r1[32];
     tmem_ld64(taddr + c, r0, r1);
     tmem_ld_wait();
@@ -272,7 +349,8 @@ __device__ __forceinline__ void drain_accumulator(const Epi& epi, typename Epi::
       store_chunk(epi, r1, stage, lane, m_base, n + 32, M, N, cbase, epi.ldc);
     }
   }
-  if (c < col0 + ncols) {
+#pragma unroll 1
+  for (; c < col0 + ncols; c += 32) {
     uint32_t r[32];
     tmem_ld32(taddr + c, r);
     tmem_ld_wait();

@@ -64,6 +64,7 @@ _SIGNATURES = {
     "c2v_sampled_train_step": (C.c_int, [_P, _P, _P, _P, _P, _P, _I32, _P, _I32, _P, _P, C.c_float,
                                          C.c_uint64, C.c_uint64, _P, _P, _P]),
     "c2v_adam_step": (C.c_int, [_P, C.c_float, C.c_float, C.c_float, C.c_float, C.c_int64, _P]),
+    "c2v_arm_target_adam": (C.c_int, [_P, C.c_float, C.c_float, C.c_float, C.c_float, C.c_int64]),
     "c2v_adam_step_range": (C.c_int, [_P, _P, _P, _P, _P, C.c_size_t, C.c_float, C.c_float, C.c_float, C.c_float,
                                       C.c_int64, _I32, _P]),
     "c2v_bind_table_shards": (C.c_int, [_P, C.POINTER(c2v_table_shards), C.POINTER(c2v_table_shards), C.c_float]),
@@ -383,6 +384,11 @@ class PathAttentionEngine:
         else:
             self.adam_t = t
         self._check(self.lib.c2v_adam_step(self.h, lr, beta1, beta2, eps, int(t), self._stream()))
+
+    def arm_target_adam(self, t: int, lr=1e-3, beta1=0.9, beta2=0.999, eps=1e-8):
+        """The next train step's dY epilogue applies Adam step `t` to the target table (c2v_arm_target_adam);
+        the following adam_step(t) skips that table.  The target gradient buffer is then not written."""
+        self._check(self.lib.c2v_arm_target_adam(self.h, lr, beta1, beta2, eps, int(t)))
 
     def adam_step_range(self, theta, grad, m, v, t: int, lr=1e-3, beta1=0.9, beta2=0.999, eps=1e-8, zero_grad=False):
         """TF1 Adam on one contiguous slice (the sharded-optimizer path): flat tensors of equal length."""

@@ -131,7 +131,8 @@ def shard_bounds(n: int, rank: int, world: int):
 
 class Trainer:
     def __init__(self, engine: PathAttentionEngine, keep_prob: float = 0.75, seed: int = 0, group=None,
-                 adam: Optional[dict] = None, schedule: str = "table_sharded", lazy_adam: bool = True):
+                 adam: Optional[dict] = None, schedule: str = "table_sharded", lazy_adam: bool = True,
+                 fuse_target_adam: bool = True):
         self.e = engine
         self.keep = float(keep_prob)
         self.seed = int(seed)
@@ -199,6 +200,11 @@ class Trainer:
                 engine.set_event("target_grads_ready", self._ev_tgt)
         if self.schedule == "single" and lazy_adam and engine.training:
             engine.set_option("lazy_adam", 1)       # exact, see c2v_b200.h; the multi-GPU schedules stay dense
+        # target-table Adam inside the dY epilogue (bit-identical, see c2v_arm_target_adam): wherever the
+        # target gradient is complete on this rank without a collective
+        self.fuse_tgt = bool(fuse_target_adam) and self.schedule in ("single", "fully_sharded") and engine.training
+        if self.schedule == "single":
+            engine.set_option("fuse_target_adam", 1 if self.fuse_tgt else 0)     # for train_batch_host
         self._loss_host = torch.zeros(1, dtype=torch.float32).pin_memory()
 
     # ---- inputs already resident on the device ----------------------------------------------
@@ -208,6 +214,8 @@ class Trainer:
             return self._fully_sharded_step(src, path, tgt, mask, target)
         e = self.e
         t = e.adam_t + 1
+        if self.fuse_tgt:
+            e.arm_target_adam(t, **self.adam)
         # dropout stream position (seed, t); replicas use different seeds so their masks differ
         loss = e.train_step(src, path, tgt, mask, target, keep=self.keep, seed=self.seed + self.rank, step=t)
         if self.schedule == "single":
@@ -238,6 +246,8 @@ class Trainer:
         dist.all_gather_into_tensor(fs["sums"].view(-1), fs["rsum"], group=self.group)
         dist.all_reduce(fs["tlogit"], op=dist.ReduceOp.SUM, group=self.group)
         e.lse_combine(fs["maxes"], fs["sums"], fs["tlogit"], fs["lse"], fs["loss"])
+        if self.fuse_tgt:
+            e.arm_target_adam(t, **self.adam)
         e.target_backward(fs["v_all"], fs["lse"], fs["tgt_all"], e.target_row0, fs["dv_part"])
         dist.reduce_scatter_tensor(fs["dv_local"], fs["dv_part"], op=dist.ReduceOp.SUM, group=self.group)
         e.context_backward(src, path, tgt, mask, fs["dv_local"], keep=self.keep, seed=seed, step=t)
@@ -247,7 +257,10 @@ class Trainer:
         for name in ("tok", "path"):
             e.adam_step_range(e.shard_params[name], e.shard_grads[name], e.shard_m[name], e.shard_v[name], t,
                               zero_grad=True, **self.adam)
-        e.adam_step_range(e.params["tgt"], e.grads["tgt"], e.adam_m["tgt"], e.adam_v["tgt"], t, **self.adam)
+        if e.get_option("target_adam_fused_step") == t:
+            e.set_option("target_adam_fused_step", 0)       # the dY epilogue already applied this rank's target rows
+        else:
+            e.adam_step_range(e.params["tgt"], e.grads["tgt"], e.adam_m["tgt"], e.adam_v["tgt"], t, **self.adam)
         e.adam_step_range(e.flat_params[s0:s1], e.flat_grads[s0:s1], e.flat_m[s0:s1], e.flat_v[s0:s1], t, **self.adam)
         # every shard must be updated before any rank's next gather reads it
         dist.all_reduce(fs["token"], group=self.group)

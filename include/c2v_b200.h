@@ -108,7 +108,10 @@ int c2v_bind_adam_state(c2v_engine* e, const c2v_tensors* m, const c2v_tensors* 
  * bit-exactly when the row is next read or updated -- same results as the dense update, a
  * fraction of the memory traffic; c2v_sync_tables brings every row up to date),
  * "adam_step_count" (the number of Adam steps already applied: optimizer reset / restore),
- * "grad_scale_inverse" (n: embedding scatter-adds are scaled by 1/n). */
+ * "grad_scale_inverse" (n: embedding scatter-adds are scaled by 1/n), "fuse_target_adam" (0/1,
+ * default 0: c2v_train_batch_host arms c2v_arm_target_adam itself), "target_adam_fused_step"
+ * (read: the step count whose target-table update the dY epilogue has already applied, 0 = none;
+ * writing 0 acknowledges it for callers that drive c2v_adam_step_range themselves). */
 int c2v_set_option(c2v_engine* e, const char* key, int64_t value);
 int c2v_get_option(const c2v_engine* e, const char* key, int64_t* value);
 
@@ -159,6 +162,16 @@ int c2v_sampled_train_step(c2v_engine* e, const int32_t* src, const int32_t* pat
  * sparse apply is not lazy); theta -= lr_t*m/(sqrt(v)+eps).  t is the 1-based step count. */
 int c2v_adam_step(c2v_engine* e, float lr, float beta1, float beta2, float eps, int64_t t,
                   void* stream);
+
+/* Folds the TARGET_WORDS_VOCAB part of that update into the backward pass (tcgen05 path, full
+ * softmax): once armed, the next target-gradient product dY = P^T.v applies Adam step t to
+ * (theta, m, v) of the target table in its epilogue -- bit-identical to c2v_adam_step, but dY is
+ * never written (the bound target gradient buffer keeps stale values) and the 401 MB table is not
+ * re-read.  The following c2v_adam_step(t) with the same hyper-parameters skips the target table
+ * (different ones are an error).  If the step that follows cannot fuse (fp32 path, sampled
+ * softmax) the arming is dropped and c2v_adam_step updates the table as usual.  Same semantics as
+ * tensorflow_model.py:232; no reference statement of its own. */
+int c2v_arm_target_adam(c2v_engine* e, float lr, float beta1, float beta2, float eps, int64_t t);
 
 /* ---- Phase-split train step for the fully sharded schedule (BASELINE config 5) -----------------------
  * The target table is row-sharded too: this engine is created with target_vocab = the number of
