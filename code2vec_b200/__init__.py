@@ -6,3 +6,15 @@ reader interface lives beside it (``config.py``, ``vocabularies.py``, ``path_con
 ``model_base.py``, ``b200_model.py``).
 """
 __version__ = "0.1.0"
+
+
+def load_model_dynamically(config):
+    """The reference's backend factory (code2vec.py:7-13) for the two backends built here."""
+    if config.DL_FRAMEWORK == "b200":
+        from .b200_model import Code2VecModel
+    elif config.DL_FRAMEWORK == "b200-keras":
+        from .b200_keras_model import Code2VecModel
+    else:
+        raise ValueError("framework %r is the reference's own backend; this package provides 'b200' and 'b200-keras'"
+                         % (config.DL_FRAMEWORK,))
+    return Code2VecModel(config)

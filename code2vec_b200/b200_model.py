@@ -36,23 +36,37 @@ def _prefetch(iterable, depth: int = 8):
     import threading
     q: "queue.Queue" = queue.Queue(maxsize=depth)
     done = object()
+    stop = threading.Event()
+
+    def put(item) -> bool:
+        while not stop.is_set():
+            try:
+                q.put(item, timeout=0.1)
+                return True
+            except queue.Full:
+                continue
+        return False
 
     def run():
         try:
             for item in iterable:
-                q.put(item)
-            q.put(done)
+                if not put(item):
+                    return                    # the consumer went away (endless readers end here)
+            put(done)
         except BaseException as exc:          # surface reader errors in the consumer
-            q.put(exc)
+            put(exc)
 
     threading.Thread(target=run, daemon=True).start()
-    while True:
-        item = q.get()
-        if item is done:
-            return
-        if isinstance(item, BaseException):
-            raise item
-        yield item
+    try:
+        while True:
+            item = q.get()
+            if item is done:
+                return
+            if isinstance(item, BaseException):
+                raise item
+            yield item
+    finally:
+        stop.set()
 
 
 _CKPT_MAGIC = b"C2VB200\0"
@@ -60,6 +74,8 @@ _CKPT_SUFFIX = ".c2v_b200"
 
 
 class Code2VecModel(Code2VecModelBase):
+    _ADAM: Optional[dict] = None      # None = tf.compat.v1.train.AdamOptimizer() defaults (tensorflow_model.py:232)
+
     def __init__(self, config: Config):
         self.engine: Optional[PathAttentionEngine] = None
         self.trainer: Optional[Trainer] = None
@@ -100,7 +116,8 @@ class Code2VecModel(Code2VecModelBase):
         self._math_train = {"fp32": 0, "tf32": 1}.get(forced, 1)
         self._math_eval = {"fp32": 0, "tf32": 1}.get(forced, 0)
         if self.config.is_training:
-            self.trainer = Trainer(self.engine, keep_prob=self.config.DROPOUT_KEEP_RATE, seed=int(time.time()) & 0x7FFFFFFF)
+            self.trainer = Trainer(self.engine, keep_prob=self.config.DROPOUT_KEEP_RATE, seed=int(time.time()) & 0x7FFFFFFF,
+                                   adam=self._ADAM)
 
     def _create_inner_model(self):
         self._make_engine()
@@ -132,6 +149,7 @@ class Code2VecModel(Code2VecModelBase):
             tensors += [("adam_m/" + k, e.adam_m[k]) for k in PARAM_NAMES]
             tensors += [("adam_v/" + k, e.adam_v[k]) for k in PARAM_NAMES]
         meta = {"format": 1, "dims": vars(e.dims), "adam_t": int(e.adam_t) if with_optimizer else 0,
+                "epochs_trained": int(getattr(self, "nr_epochs_trained", 0)),
                 "tf_names": {"tok": "model/WORDS_VOCAB", "path": "model/PATHS_VOCAB", "tgt": "model/TARGET_WORDS_VOCAB",
                              "W": "model/TRANSFORM", "a": "model/ATTENTION"},
                 "tensors": []}
@@ -174,6 +192,8 @@ class Code2VecModel(Code2VecModelBase):
                 arr = np.frombuffer(f.read(ent["nbytes"]), dtype="<f4").reshape(ent["shape"])
                 dest[group][name].copy_(torch.from_numpy(arr.copy()))
             e.adam_t = int(meta.get("adam_t", 0))
+            if hasattr(self, "nr_epochs_trained"):           # the Keras-schedule backend resumes at this epoch
+                self.nr_epochs_trained = int(meta.get("epochs_trained", 0))
 
     # ---- train (tensorflow_model.py:40-112) ------------------------------------------------------
     def train(self):

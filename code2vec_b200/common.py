@@ -99,6 +99,11 @@ class common:
             return f.read().splitlines()
 
     @staticmethod
+    def chunks(seq, n):
+        """Successive slices of `seq` of length n (reference common.py:194-197)."""
+        return (seq[lo:lo + n] for lo in range(0, len(seq), n))
+
+    @staticmethod
     def split_to_batches(data_lines, batch_size):
         for lo in range(0, len(data_lines), batch_size):
             yield data_lines[lo:lo + batch_size]

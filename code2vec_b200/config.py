@@ -2,8 +2,9 @@
 
 Same attribute names, flags, derived properties and `verify()` errors as the reference's Config so
 that code written against it (the model base class, the reader, the vocabularies) runs unchanged;
-the one addition is the third value of `--framework`: ``b200`` (the CUDA path-attention engine),
-which is also the default here.
+the one addition is two more values of `--framework`: ``b200`` (the CUDA path-attention engine with
+the TensorFlow backend's numerics; the default here) and ``b200-keras`` (the same engine with the
+Keras backend's initialisers, optimizer epsilon, scores and evaluation schedule).
 """
 from __future__ import annotations
 
@@ -14,7 +15,7 @@ import sys
 from argparse import ArgumentParser
 from typing import Iterator, Optional, Tuple
 
-FRAMEWORKS = ("b200", "tensorflow", "keras")
+FRAMEWORKS = ("b200", "b200-keras", "tensorflow", "keras")
 
 # name -> default, in the groups the reference uses (config.py:46-70)
 _TRAINING_DEFAULTS = {
@@ -210,7 +211,7 @@ class Config:
             raise ValueError("Model load dir `{model_load_dir}` does not exist.".format(
                 model_load_dir=self.model_load_dir))
         if self.DL_FRAMEWORK not in set(FRAMEWORKS):
-            raise ValueError("config.DL_FRAMEWORK must be in {'b200', 'tensorflow', 'keras'}.")
+            raise ValueError("config.DL_FRAMEWORK must be in {'b200', 'b200-keras', 'tensorflow', 'keras'}.")
 
     def __iter__(self) -> Iterator[Tuple[str, object]]:
         """(name, value) of every non-callable public attribute -- the start-up config dump."""

@@ -385,6 +385,7 @@ int forward_impl(c2v_engine* e, cudaStream_t st, const int32_t* src, const int32
 }
 
 int topk_impl(c2v_engine* e, cudaStream_t st, const float* code_vec, int B, int32_t* idx, float* val, int normalize) {
+  if (normalize < 0 || normalize > 2) return fail(e, C2V_ERR_INVALID, "normalize must be 0 (logits), 1 (softmax over k) or 2 (full softmax)");
   float* S = wsp<float>(e, e->ws.S);
   int rc = run_logits(e, st, code_vec, B, S);
   if (rc) return rc;
@@ -395,6 +396,7 @@ int topk_impl(c2v_engine* e, cudaStream_t st, const float* code_vec, int B, int3
     C2V_LAUNCH(e, (topk_kernel<16><<<B, kTopkThreads, 0, st>>>(S, e->ws.ldS, Y, k, normalize, idx, val)));
   else
     C2V_LAUNCH(e, (topk_iter_kernel<<<B, kTopkThreads, 0, st>>>(S, e->ws.ldS, Y, k, normalize, idx, val)));
+  if (normalize == 2) C2V_LAUNCH(e, (topk_full_softmax_kernel<<<B, 256, 0, st>>>(S, e->ws.ldS, Y, k, val)));
   return C2V_OK;
 }
 

@@ -534,8 +534,9 @@ __device__ __forceinline__ ValIdx block_argbest(float v, int i, ValIdx* red) {
 }
 
 __device__ __forceinline__ void topk_finish(float* vals, int k, int normalize, float* val_out) {
-  // thread 0 only
-  if (normalize) {
+  // thread 0 only.  normalize: 0 raw logits; 1 softmax over the k values (tensorflow_model.py:305-306);
+  // 2 raw here, topk_full_softmax_kernel turns them into full-vocabulary probabilities afterwards.
+  if (normalize == 1) {
     float mx = vals[0], s = 0.f;
     for (int q = 0; q < k; ++q) s += expf(vals[q] - mx);
     for (int q = 0; q < k; ++q) val_out[q] = expf(vals[q] - mx) / s;
@@ -614,6 +615,24 @@ topk_iter_kernel(const float* __restrict__ S, size_t ldS, int Y, int k, int norm
     if (tid == 0) { idx_out[(size_t)blockIdx.x * k + r] = w.i; outv[r] = w.v; }
   }
   if (tid == 0) topk_finish(outv, k, normalize, val_out + (size_t)blockIdx.x * k);
+}
+
+// normalize == 2: the Keras backend's scores (keras_model.py:69-70, keras_topk_word_predictions_layer.py:30-35):
+// top-k of softmax(logits) over the WHOLE target vocabulary.  softmax is monotone, so the indices are
+// those of the logits; the k values become exp(l - max) / sum_j exp(l_j - max).
+__global__ void __launch_bounds__(256)
+topk_full_softmax_kernel(const float* __restrict__ S, size_t ldS, int Y, int k, float* __restrict__ val) {
+  __shared__ float red[32];
+  const float* row = S + (size_t)blockIdx.x * ldS;
+  float m = -INFINITY, s = 0.f;
+  for (int j = threadIdx.x; j < Y; j += 256) m = fmaxf(m, row[j]);
+  m = block_max(m, red);
+  for (int j = threadIdx.x; j < Y; j += 256) s += expf(row[j] - m);
+  s = block_sum(s, red);
+  if (threadIdx.x < k) {
+    float* v = val + (size_t)blockIdx.x * k + threadIdx.x;
+    *v = expf(*v - m) / s;
+  }
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -287,16 +287,23 @@ class PathAttentionEngine:
         return out
 
     # ---- parameters -----------------------------------------------------------------------
-    def init_params(self, seed: int = 4321):
-        """The reference's initialisers (tensorflow_model.py:205-220,249-250): tables
+    def init_params(self, seed: int = 4321, scheme: str = "tensorflow"):
+        """The reference's initialisers.  scheme "tensorflow" (tensorflow_model.py:205-220,249-250): tables
         U(+-sqrt(3/cols)) (variance_scaling fan_out uniform), TRANSFORM / ATTENTION glorot-uniform.
+        scheme "keras" (keras_model.py:46-70, keras_attention_layer.py:29-34): embeddings and the attention
+        vector U(+-0.05), both Dense kernels glorot-uniform (the output kernel is [D, |Y|] there).
         Drawn on the device with torch's generator (initialisation is not the hot path)."""
         torch = self.torch
         g = torch.Generator(device=self.dev)
         g.manual_seed(seed)
-        d, D = self.dims.embed_dim, self.dims.code_dim
-        lim = {"tok": (3.0 / d) ** 0.5, "path": (3.0 / d) ** 0.5, "tgt": (3.0 / D) ** 0.5,
-               "W": (6.0 / (3 * d + D)) ** 0.5, "a": (6.0 / (D + 1)) ** 0.5}
+        d, D, Y = self.dims.embed_dim, self.dims.code_dim, self.dims.target_vocab
+        if scheme == "tensorflow":
+            lim = {"tok": (3.0 / d) ** 0.5, "path": (3.0 / d) ** 0.5, "tgt": (3.0 / D) ** 0.5,
+                   "W": (6.0 / (3 * d + D)) ** 0.5, "a": (6.0 / (D + 1)) ** 0.5}
+        elif scheme == "keras":
+            lim = {"tok": 0.05, "path": 0.05, "tgt": (6.0 / (D + Y)) ** 0.5, "W": (6.0 / (3 * d + D)) ** 0.5, "a": 0.05}
+        else:
+            raise ValueError("unknown initialisation scheme: %r" % (scheme,))
         for k in PARAM_NAMES:
             self.params[k].uniform_(-lim[k], lim[k], generator=g)
 
@@ -351,7 +358,7 @@ class PathAttentionEngine:
         idx = torch.empty((B, k), dtype=torch.int32, device=self.dev)
         val = torch.empty((B, k), dtype=torch.float32, device=self.dev)
         self._check(self.lib.c2v_topk(self.h, code_vec.data_ptr(), B, idx.data_ptr(), val.data_ptr(),
-                                      1 if normalize else 0, self._stream()))
+                                      int(normalize), self._stream()))
         return idx, val
 
     def loss(self, code_vec, target):
@@ -524,7 +531,7 @@ class PathAttentionEngine:
         code = np.empty((B, self.dims.code_dim), dtype=np.float32) if want_code else None
         attn = np.empty((B, Cn), dtype=np.float32) if want_attention else None
         self._check(self.lib.c2v_predict_batch_host(
-            self.h, _host_ptr(src), _host_ptr(path), _host_ptr(tgt), _host_ptr(mask), B, 1 if normalize else 0,
+            self.h, _host_ptr(src), _host_ptr(path), _host_ptr(tgt), _host_ptr(mask), B, int(normalize),
             idx.ctypes.data, val.ctypes.data, None if code is None else code.ctypes.data,
             None if attn is None else attn.ctypes.data, self._stream()))
         return idx, val, code, attn

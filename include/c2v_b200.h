@@ -123,8 +123,11 @@ int c2v_forward(c2v_engine* e, const int32_t* src, const int32_t* path, const in
                 const float* mask, int32_t B, float* code_vec, float* attn, void* stream);
 
 /* scores = code_vec . TARGET_WORDS_VOCAB^T ; tf.nn.top_k(scores, k) sorted descending, ties to
- * the lower index; normalize != 0 applies softmax over the k values (predict)
- * (tensorflow_model.py:297-306).  idx: device int32 [B, k]; val: device float [B, k]. */
+ * the lower index (tensorflow_model.py:297-306).  normalize: 0 = raw scores (evaluate); 1 =
+ * softmax over the k values (TF backend's predict, :305-306); 2 = probabilities of the softmax
+ * over the whole target vocabulary (Keras backend: Dense(softmax) then top_k,
+ * keras_model.py:69-70, keras_topk_word_predictions_layer.py:30-35).
+ * idx: device int32 [B, k]; val: device float [B, k]. */
 int c2v_topk(c2v_engine* e, const float* code_vec, int32_t B, int32_t* idx, float* val,
              int32_t normalize, void* stream);
 

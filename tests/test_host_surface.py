@@ -264,3 +264,29 @@ def test_product_synthetic_generator_matches_the_oracles():
         b = O.synthetic_batch(dims, 16, seed=5, **kw)
         for x, y in zip(a, b):
             assert x.dtype == y.dtype and np.array_equal(x, y)
+
+
+# ---- the Keras-numerics backend's host pieces (keras_words_subtoken_metrics.py, code2vec.py:7-13) -------
+def test_keras_subtoken_counts_and_backend_factory():
+    from code2vec_b200 import load_model_dynamically
+    from code2vec_b200.b200_keras_model import SubtokenCounts
+    from code2vec_b200.config import Config
+    c = SubtokenCounts()
+    c.update("get|file|name", "get|name")           # tp 2, fp 0, fn 1
+    c.update("set|value", "get|value|value")        # tp 2 (duplicates count), fp 1, fn 1
+    assert (c.tp, c.fp, c.fn) == (4.0, 1.0, 2.0)
+    assert abs(c.precision - 4 / 5) < 1e-12 and abs(c.recall - 4 / 6) < 1e-12
+    p, r = 4 / 5, 4 / 6
+    assert abs(c.f1 - 2 * p * r / (p + r + 1e-7)) < 1e-12
+    empty = SubtokenCounts()
+    assert empty.precision == 0.0 and empty.recall == 0.0 and empty.f1 == 0.0      # divide_no_nan
+    cfg = Config(set_defaults=True)
+    cfg.DL_FRAMEWORK = "b200-keras"
+    cfg.TRAIN_DATA_PATH_PREFIX = "x"
+    cfg.verify()
+    cfg.DL_FRAMEWORK = "tensorflow"                 # the reference's own backends are not provided by this package
+    with pytest.raises(ValueError):
+        load_model_dynamically(cfg)
+    cfg.DL_FRAMEWORK = "pytorch"
+    with pytest.raises(ValueError):
+        cfg.verify()

@@ -182,3 +182,18 @@ def test_sampled_softmax_grads_match_autograd():
     assert abs(float(L.detach()) - loss) < 1e-12
     np.testing.assert_allclose(dv, tv.grad.numpy(), atol=1e-12)
     np.testing.assert_allclose(g_tgt, ty.grad.numpy(), atol=1e-12)
+
+
+def test_keras_numerics_in_the_oracle():
+    """Keras initialiser ranges and full-vocabulary softmax scores."""
+    dims = O.Dims(token_vocab=500, path_vocab=300, target_vocab=700, embed_dim=16, code_dim=48, max_contexts=9)
+    p = O.keras_init_params(dims, seed=1)
+    assert np.abs(p["tok"]).max() <= 0.05 and np.abs(p["path"]).max() <= 0.05 and np.abs(p["a"]).max() <= 0.05
+    assert np.abs(p["tgt"]).max() <= np.sqrt(6.0 / (48 + 700)) + 1e-7 and p["tgt"].shape == (700, 48)
+    src, pth, tgt, mask, _ = O.synthetic_batch(dims, 6, seed=2)
+    idx, probs, _, _, scores = O.evaluate_topk(p, src, pth, tgt, mask, k=5, normalize=2)
+    e = np.exp(scores.astype(np.float64) - scores.max(1, keepdims=True))
+    full = e / e.sum(1, keepdims=True)
+    assert np.abs(probs - np.take_along_axis(full, idx, 1)).max() < 1e-7
+    idx1, soft_k, _, _, _ = O.evaluate_topk(p, src, pth, tgt, mask, k=5, normalize=1)
+    assert np.array_equal(idx, idx1) and np.allclose(soft_k.sum(1), 1.0, atol=1e-6) and np.all(probs.sum(1) < 1.0)
