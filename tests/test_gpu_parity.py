@@ -13,12 +13,14 @@ pytestmark = pytest.mark.gpu
 TINY = O.Dims(token_vocab=1001, path_vocab=501, target_vocab=1001, embed_dim=32, code_dim=96, max_contexts=20)
 ODD = O.Dims(token_vocab=777, path_vocab=333, target_vocab=1537, embed_dim=20, code_dim=52, max_contexts=13)
 MID = O.Dims(token_vocab=5003, path_vocab=3001, target_vocab=4099, embed_dim=128, code_dim=384, max_contexts=200)
+# BASELINE config 5's model shape (d=256, D=768, 200 contexts) at a vocabulary the oracle finishes in seconds
+LARGE = O.Dims(token_vocab=3001, path_vocab=2003, target_vocab=2600, embed_dim=256, code_dim=768, max_contexts=200)
 
 GAP_EPS = 1e-6
 LOSS_TOL = 1e-4
 
 
-@pytest.mark.parametrize("dims,B", [(TINY, 64), (ODD, 37), (MID, 48)])
+@pytest.mark.parametrize("dims,B", [(TINY, 64), (ODD, 37), (MID, 48), (LARGE, 12)])
 def test_forward_matches_oracle(dims, B):
     eng, params = make_engine(dims, max_batch=B)
     src, pth, tgt, mask, _ = O.synthetic_batch(dims, B, seed=11)
@@ -43,7 +45,7 @@ def test_all_masked_bag_is_nan():
     assert np.all(np.isfinite(np.delete(code, 5, axis=0)))
 
 
-@pytest.mark.parametrize("dims,B,k", [(TINY, 64, 10), (ODD, 37, 10), (MID, 48, 10), (TINY, 16, 33)])
+@pytest.mark.parametrize("dims,B,k", [(TINY, 64, 10), (ODD, 37, 10), (MID, 48, 10), (TINY, 16, 33), (LARGE, 12, 10)])
 def test_topk_bit_exact(dims, B, k):
     eng, params = make_engine(dims, max_batch=B, top_k=k)
     src, pth, tgt, mask, _ = O.synthetic_batch(dims, B, seed=5)
@@ -76,7 +78,7 @@ def test_topk_ties_prefer_lower_index():
     assert idx[:, :3].tolist() == [[3, 7, 900]] * 4
 
 
-@pytest.mark.parametrize("dims,B", [(TINY, 64), (ODD, 37), (MID, 48)])
+@pytest.mark.parametrize("dims,B", [(TINY, 64), (ODD, 37), (MID, 48), (LARGE, 12)])
 def test_train_step_grads_match_oracle(dims, B):
     eng, params = make_engine(dims, max_batch=B)
     src, pth, tgt, mask, target = O.synthetic_batch(dims, B, seed=21)

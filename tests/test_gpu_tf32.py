@@ -12,9 +12,11 @@ pytestmark = pytest.mark.gpu
 TINY = O.Dims(token_vocab=1001, path_vocab=501, target_vocab=1001, embed_dim=32, code_dim=96, max_contexts=20)
 ODD = O.Dims(token_vocab=777, path_vocab=333, target_vocab=1537, embed_dim=20, code_dim=52, max_contexts=13)
 MID = O.Dims(token_vocab=5003, path_vocab=3001, target_vocab=4099, embed_dim=128, code_dim=384, max_contexts=200)
+# BASELINE config 5's model shape (d=256, D=768, 200 contexts) at a vocabulary the oracle finishes in seconds
+LARGE = O.Dims(token_vocab=3001, path_vocab=2003, target_vocab=2600, embed_dim=256, code_dim=768, max_contexts=200)
 
 
-@pytest.mark.parametrize("dims,B", [(TINY, 64), (ODD, 37), (MID, 48)])
+@pytest.mark.parametrize("dims,B", [(TINY, 64), (ODD, 37), (MID, 48), (LARGE, 12)])
 def test_tf32_forward_and_topk(dims, B):
     eng, params = make_engine(dims, max_batch=B)
     eng.set_option("math_mode", 1)
@@ -33,7 +35,7 @@ def test_tf32_forward_and_topk(dims, B):
 
 
 @pytest.mark.parametrize("cta_pair", [0, 1, 2])
-@pytest.mark.parametrize("dims,B", [(TINY, 64), (ODD, 37), (MID, 48)])
+@pytest.mark.parametrize("dims,B", [(TINY, 64), (ODD, 37), (MID, 48), (LARGE, 12)])
 def test_tf32_train_step(dims, B, cta_pair):
     eng, params = make_engine(dims, max_batch=B)
     eng.set_option("math_mode", 1)

@@ -17,7 +17,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 
-def main(n_lines=16384, C=200, n_tok=200000, n_path=150000, n_tgt=30000, threads=16):
+def main(n_lines=65536, C=200, n_tok=200000, n_path=150000, n_tgt=30000, threads=16):
     from code2vec_b200.b200_model import Code2VecModel
     from code2vec_b200.config import Config
     tmp = tempfile.mkdtemp()
@@ -50,15 +50,27 @@ def main(n_lines=16384, C=200, n_tok=200000, n_path=150000, n_tgt=30000, threads
     cfg.MAX_TOKEN_VOCAB_SIZE, cfg.MAX_PATH_VOCAB_SIZE, cfg.MAX_TARGET_VOCAB_SIZE = n_tok, n_path, n_tgt
     model = Code2VecModel(cfg)
     import torch
+    stamps = []
+    inner = model.trainer.step_host
+
+    def stamped(*a, **k):
+        out = inner(*a, **k)           # returns after the step's loss has reached the host
+        stamps.append(time.time())
+        return out
+
+    model.trainer.step_host = stamped
     torch.cuda.synchronize()
     t0 = time.time()
     model.train()
     torch.cuda.synchronize()
     dt = time.time() - t0
+    skip = max(len(stamps) // 4, 1)    # steady state: after the reader threads and the prefetch queue have filled
+    steady = (len(stamps) - 1 - skip) * cfg.TRAIN_BATCH_SIZE * C / max(stamps[-1] - stamps[skip], 1e-9)
     size_mb = os.path.getsize(prefix + ".train.c2v") / 1e6
     print(json.dumps({"what": "Code2VecModel.train() end to end (file -> native reader -> engine)", "examples": n_lines,
                       "contexts_per_example": C, "seconds": round(dt, 3), "examples_per_s": round(n_lines / dt, 1),
-                      "path_contexts_per_s": round(n_lines * C / dt, 1), "file_MB": round(size_mb, 1),
+                      "path_contexts_per_s": round(n_lines * C / dt, 1),
+                      "steady_state_path_contexts_per_s": round(steady, 1), "batches": len(stamps), "file_MB": round(size_mb, 1),
                       "text_MB_per_s": round(size_mb / dt, 1), "reader_threads": threads, "host_cores": os.cpu_count(),
                       "dataset_generation_s": round(gen_s, 1)}))
     model.close_session()
