@@ -123,6 +123,7 @@ struct c2v_engine {
   float grad_scale = 1.f;
   // lazy-but-exact dense Adam for the embedding tables (option "lazy_adam")
   int lazy = 0;
+  bool lazy_grads_pending = false;  // a train step's embedding gradients are in the tables and c2v_adam_step has not followed
   int64_t adam_t_done = 0;   // Adam steps applied so far
   int32_t mark_epoch = 0;
   float hp_lr = 0.f, hp_b1 = 0.f, hp_b2 = 0.f, hp_eps = 0.f;
@@ -431,7 +432,11 @@ int context_backward(c2v_engine* e, cudaStream_t st, const ContextSource& cs, co
       umma::EpiStore ep{dXg, (size_t)K3, 0};
       C2V_LAUNCH(e, C2V_CUDA(e, (C2V_UMMA_192(st, N, K3, D, 1, opA, opB, ep, e->num_sms))));
     }
-    if (!e->emb_grads_clean && e->table_world == 1) {
+    if (e->lazy) {
+      if (e->lazy_grads_pending)
+        return fail(e, C2V_ERR_STATE, "lazy_adam: every train step must be followed by c2v_adam_step before the next one");
+      e->lazy_grads_pending = true;
+    } else if (!e->emb_grads_clean && e->table_world == 1) {
       C2V_CUDA(e, cudaMemsetAsync(e->grad.tok, 0, (size_t)e->dims.token_vocab * d * 4, st));
       C2V_CUDA(e, cudaMemsetAsync(e->grad.path, 0, (size_t)e->dims.path_vocab * d * 4, st));
     }
@@ -474,7 +479,11 @@ int context_backward(c2v_engine* e, cudaStream_t st, const ContextSource& cs, co
     if (rc) return rc;
   }
   {  // dX' = dU . W^T -> dropout backward -> scatter-add into the embedding gradient tables
-    if (!e->emb_grads_clean && e->table_world == 1) {
+    if (e->lazy) {
+      if (e->lazy_grads_pending)
+        return fail(e, C2V_ERR_STATE, "lazy_adam: every train step must be followed by c2v_adam_step before the next one");
+      e->lazy_grads_pending = true;
+    } else if (!e->emb_grads_clean && e->table_world == 1) {
       C2V_CUDA(e, cudaMemsetAsync(e->grad.tok, 0, (size_t)e->dims.token_vocab * d * 4, st));
       C2V_CUDA(e, cudaMemsetAsync(e->grad.path, 0, (size_t)e->dims.path_vocab * d * 4, st));
     }
@@ -666,13 +675,10 @@ int adam_impl(c2v_engine* e, cudaStream_t st, float lr, float b1, float b2, floa
     }
     e->hp_lr = lr; e->hp_b1 = b1; e->hp_b2 = b2; e->hp_eps = eps; e->hp_set = true;
     float* lr_tab = wsp<float>(e, e->ws.lr_tab);
+    // the embedding rows' step t is deferred: their gradient rows keep this step's scatter-add until the
+    // rows are next referenced (prepare_rows) or flushed; only the learning rate of the step is recorded
     C2V_LAUNCH(e, (set_float_kernel<<<1, 1, 0, st>>>(lr_tab + t, lr_t)));
-    C2V_LAUNCH(e, (adam_rows_kernel<ADAM_ROWS_UPDATE><<<e->num_sms * 8, 256, 0, st>>>(
-                      P[0], G[0], M[0], V[0], d.token_vocab, d.embed_dim, wsp<int32_t>(e, e->ws.stamp_tok), e->mark_epoch,
-                      wsp<int32_t>(e, e->ws.last_tok), (int32_t)t, lr_tab, b1, b2, eps)));
-    C2V_LAUNCH(e, (adam_rows_kernel<ADAM_ROWS_UPDATE><<<e->num_sms * 8, 256, 0, st>>>(
-                      P[1], G[1], M[1], V[1], d.path_vocab, d.embed_dim, wsp<int32_t>(e, e->ws.stamp_path), e->mark_epoch,
-                      wsp<int32_t>(e, e->ws.last_path), (int32_t)t, lr_tab, b1, b2, eps)));
+    e->lazy_grads_pending = false;
     first_dense = 2;
   }
   e->adam_t_done = t;
@@ -685,7 +691,7 @@ int adam_impl(c2v_engine* e, cudaStream_t st, float lr, float b1, float b2, floa
     const int zero = (i < 2) ? 1 : 0;   // embedding gradient tables are cleared for the next scatter-add
     C2V_LAUNCH(e, (adam_kernel<<<(unsigned)blocks, 256, 0, st>>>(P[i], G[i], M[i], V[i], n4, lr_t, b1, b2, eps, zero)));
   }
-  e->emb_grads_clean = true;
+  e->emb_grads_clean = !e->lazy;     // lazy: the gradient tables hold deferred steps, cleared row by row as they are applied
   return C2V_OK;
 }
 
@@ -827,9 +833,16 @@ int c2v_set_option(c2v_engine* e, const char* key, int64_t value) {
       int rc = flush_rows(e, 0);
       if (rc) return rc;
       C2V_CUDA(e, cudaStreamSynchronize(0));
+      e->emb_grads_clean = !e->lazy_grads_pending;        // every applied gradient row was cleared on the way
+      e->lazy_grads_pending = false;
     }
     if (value && !e->lazy) {                              // all rows are current as of adam_t_done
       const c2v_dims& d = e->dims;
+      if (!e->emb_grads_clean) {                          // deferred steps read the gradient rows: they must start from zero
+        C2V_CUDA(e, cudaMemset(e->grad.tok, 0, (size_t)d.token_vocab * d.embed_dim * 4));
+        C2V_CUDA(e, cudaMemset(e->grad.path, 0, (size_t)d.path_vocab * d.embed_dim * 4));
+      }
+      e->lazy_grads_pending = false;
       C2V_LAUNCH(e, (fill_i32_kernel<<<256, 256>>>(wsp<int32_t>(e, e->ws.last_tok), (size_t)d.token_vocab, (int32_t)e->adam_t_done)));
       C2V_LAUNCH(e, (fill_i32_kernel<<<256, 256>>>(wsp<int32_t>(e, e->ws.last_path), (size_t)d.path_vocab, (int32_t)e->adam_t_done)));
       C2V_CUDA(e, cudaMemset(wsp<int32_t>(e, e->ws.stamp_tok), 0, (size_t)d.token_vocab * 4));

@@ -724,16 +724,17 @@ scatter_dx_kernel(const __grid_constant__ ContextSource cs, const __grid_constan
 // Lazy-but-exact dense Adam for the two embedding tables (single GPU).
 //
 // TF1's Adam is dense: every row decays m, v and moves theta on every step, gradient or not
-// (SURVEY A.3).  For a row with g == 0 that update depends only on (theta, m, v, step), so it can be
-// DEFERRED without changing a single bit: each row remembers the last step it is current for
-// (`last`), and the pending zero-gradient steps are replayed -- same fp32 operations, same order --
-// the next time the row is about to be read (forward gather) or updated with a real gradient.
+// (SURVEY A.3).  The update of a row depends only on (theta, m, v, g, step), and nothing reads a row
+// between two batches that reference it, so the whole update can be DEFERRED without changing a
+// single bit: each row remembers the last step it is current for (`last`); its gradient row keeps
+// the scatter-add of the step that last touched it (zeros otherwise); and the pending steps are
+// replayed -- same fp32 operations, same order: one step with that gradient, then zero-gradient
+// steps -- the next time the row is about to be read (forward gather of a batch that references it).
 // Per step only the rows of the current batch are touched (~25 % of the tables at B = 1024 x 200
-// uniform, far fewer on Zipfian data) instead of streaming 9 GB of theta / m / v.
-//   mark_rows_kernel     : stamp[row] = epoch for every row the batch references
-//   adam_rows_kernel<CATCHUP>: stamped rows  -> replay zero-gradient steps last+1 .. t_done
-//   adam_rows_kernel<UPDATE> : stamped rows  -> the real step t with the row's gradient (then cleared)
-//   adam_rows_kernel<FLUSH>  : all rows      -> replay up to t_done (before export / checkpoint)
+// uniform, far fewer on Zipfian data), ONCE, instead of streaming 9 GB of theta / m / v.
+//   mark_rows_kernel         : stamp[row] = epoch for every row the batch references
+//   adam_rows_kernel<CATCHUP>: stamped rows -> replay steps last+1 .. t_done, clear the gradient row
+//   adam_rows_kernel<FLUSH>  : all rows     -> the same (before export / checkpoint / mode switch)
 // lr_tab[s] holds lr_s = lr*sqrt(1-b2^s)/(1-b1^s) as computed on the host for the dense kernel.
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
@@ -751,11 +752,15 @@ __global__ void fill_i32_kernel(int32_t* __restrict__ p, size_t n, int32_t v) {
 }
 __global__ void set_float_kernel(float* p, float v) { *p = v; }
 
-enum { ADAM_ROWS_CATCHUP = 0, ADAM_ROWS_UPDATE = 1, ADAM_ROWS_FLUSH = 2 };
+enum { ADAM_ROWS_CATCHUP = 0, ADAM_ROWS_FLUSH = 2 };
 
 // Persistent grid: every warp scans 32 rows at a time (one coalesced read of their stamps and
 // `last` values), then the whole warp walks the rows that need work, one 128-bit access per lane
-// and array.
+// and array.  A row that is behind (last < t_done) replays steps last+1 .. t_done: the first of
+// them with whatever its gradient row holds -- the scatter-add of the step that last touched it,
+// or zeros -- and the rest with a zero gradient; the gradient row is cleared on the way.  So a
+// row the batch references costs one pass (theta, m, v, g in; theta, m, v, 0 out) per step instead
+// of a catch-up pass before the forward and an update pass after the backward.
 template <int MODE>
 __global__ void __launch_bounds__(256)
 adam_rows_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, int rows, int d,
@@ -765,8 +770,6 @@ adam_rows_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict
   const int warp_global = (blockIdx.x * 256 + threadIdx.x) >> 5;
   const int total_warps = (gridDim.x * 256) >> 5;
   const float omb1 = __fsub_rn(1.f, b1), omb2 = __fsub_rn(1.f, b2);
-  const int32_t upto = (MODE == ADAM_ROWS_UPDATE) ? t_done - 1 : t_done;
-  const float lr_t = (MODE == ADAM_ROWS_UPDATE) ? lr_tab[t_done] : 0.f;
   for (int base = warp_global * 32; base < rows; base += total_warps * 32) {
     const int r = base + lane;
     int32_t from_l = 0;
@@ -775,7 +778,7 @@ adam_rows_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict
       hit = (MODE == ADAM_ROWS_FLUSH) || (stamp[r] == epoch);
       if (hit) {
         from_l = last[r];
-        if (MODE != ADAM_ROWS_UPDATE && from_l >= t_done) hit = false;
+        if (from_l >= t_done) hit = false;
       }
     }
     unsigned todo = __ballot_sync(0xffffffffu, hit);
@@ -787,11 +790,22 @@ adam_rows_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict
       for (int j = lane * 4; j < d; j += 128) {
         const size_t o = (size_t)row * d + j;
         float4 P = *reinterpret_cast<float4*>(p + o), M = *reinterpret_cast<float4*>(m + o), V = *reinterpret_cast<float4*>(v + o);
+        const float4 G = *reinterpret_cast<const float4*>(g + o);
         float* pp = reinterpret_cast<float*>(&P);
         float* mm = reinterpret_cast<float*>(&M);
         float* vv = reinterpret_cast<float*>(&V);
-        // pending zero-gradient steps: m*b1 + (1-b1)*0, v*b2 + (1-b2)*(0*0) -- the dense kernel's exact operations
-        for (int32_t s = from + 1; s <= upto; ++s) {
+        const float* gg = reinterpret_cast<const float*>(&G);
+        {  // step from+1: the deferred gradient step (the dense kernel's exact operations)
+          const float lr_s = lr_tab[from + 1];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            mm[q] = __fadd_rn(__fmul_rn(mm[q], b1), __fmul_rn(omb1, gg[q]));
+            vv[q] = __fadd_rn(__fmul_rn(vv[q], b2), __fmul_rn(omb2, __fmul_rn(gg[q], gg[q])));
+            pp[q] = __fsub_rn(pp[q], __fdiv_rn(__fmul_rn(lr_s, mm[q]), __fadd_rn(__fsqrt_rn(vv[q]), eps)));
+          }
+        }
+        // the zero-gradient steps after it: m*b1 + (1-b1)*0, v*b2 + (1-b2)*(0*0)
+        for (int32_t s = from + 2; s <= t_done; ++s) {
           const float lr_s = lr_tab[s];
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
@@ -800,20 +814,11 @@ adam_rows_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict
             pp[q] = __fsub_rn(pp[q], __fdiv_rn(__fmul_rn(lr_s, mm[q]), __fadd_rn(__fsqrt_rn(vv[q]), eps)));
           }
         }
-        if (MODE == ADAM_ROWS_UPDATE) {
-          const float4 G = *reinterpret_cast<const float4*>(g + o);
-          const float* gg = reinterpret_cast<const float*>(&G);
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            mm[q] = __fadd_rn(__fmul_rn(mm[q], b1), __fmul_rn(omb1, gg[q]));
-            vv[q] = __fadd_rn(__fmul_rn(vv[q], b2), __fmul_rn(omb2, __fmul_rn(gg[q], gg[q])));
-            pp[q] = __fsub_rn(pp[q], __fdiv_rn(__fmul_rn(lr_t, mm[q]), __fadd_rn(__fsqrt_rn(vv[q]), eps)));
-          }
-          *reinterpret_cast<float4*>(g + o) = make_float4(0.f, 0.f, 0.f, 0.f);
-        }
         *reinterpret_cast<float4*>(p + o) = P;
         *reinterpret_cast<float4*>(m + o) = M;
         *reinterpret_cast<float4*>(v + o) = V;
+        if ((__float_as_uint(G.x) | __float_as_uint(G.y) | __float_as_uint(G.z) | __float_as_uint(G.w)) != 0u)
+          *reinterpret_cast<float4*>(g + o) = make_float4(0.f, 0.f, 0.f, 0.f);
       }
     }
     if (hit) last[r] = t_done;

@@ -104,9 +104,12 @@ int c2v_bind_adam_state(c2v_engine* e, const c2v_tensors* m, const c2v_tensors* 
  * GEMM dY = P^T.v is issued inside the context backward pass so it overlaps the embedding
  * scatter-add; with 0 it runs right after dv and "target_grads_ready" fires earlier), "profile" (0/1: per-phase
  * CUDA-event timing, read with c2v_phase_stats), "lazy_adam" (0/1, single-GPU replicated tables:
- * the dense TF1 Adam update of an embedding row that received no gradient is deferred and replayed
- * bit-exactly when the row is next read or updated -- same results as the dense update, a
- * fraction of the memory traffic; c2v_sync_tables brings every row up to date),
+ * the dense TF1 Adam update of an embedding row is deferred -- its gradient stays in the bound
+ * gradient table -- and replayed bit-exactly (one step with that gradient, then the zero-gradient
+ * steps) when a later batch references the row; same results as the dense update, one pass over
+ * the batch's rows per step instead of 9 GB of traffic.  While it is on, the token / path gradient
+ * tables are engine state (deferred steps), every c2v_train_step must be followed by
+ * c2v_adam_step with consecutive t, and c2v_sync_tables brings every row up to date),
  * "adam_step_count" (the number of Adam steps already applied: optimizer reset / restore),
  * "grad_scale_inverse" (n: embedding scatter-adds are scaled by 1/n), "fuse_target_adam" (0/1,
  * default 0: c2v_train_batch_host arms c2v_arm_target_adam itself), "target_adam_fused_step"
