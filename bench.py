@@ -117,9 +117,9 @@ def algorithmic_work(w, B, touched_rows=None, world=1, fused_target_adam=False):
     """Per-step algorithmic FLOPs / bytes of each phase.
 
     adam: the dense TF1 update streams theta, m, v in and out = 24 B per parameter.  With the
-    lazy-but-exact scheme (single GPU) only the rows the batch references are streamed: 24 B per
-    element in the catch-up pass + 24 B in the update pass, the dense part being the target table,
-    TRANSFORM and ATTENTION.  Under table sharding each rank updates 1/world of every table.
+    lazy-but-exact scheme (single GPU) only the rows the batch references are streamed, once: 32 B
+    per element (theta, m, v and the deferred gradient, in and out) in the catch-up pass; the dense
+    part is the target table (unless fused into dY), TRANSFORM and ATTENTION.  Under table sharding each rank updates 1/world of every table.
     fused_target_adam: the target table's update runs in the dY epilogue, so its 24 B/param move
     from "adam" to "dY", which then is HBM-bound (P^T read once + the update) rather than tensor-bound."""
     d, D, C, Y = w["embed_dim"], w["code_dim"], w["max_contexts"], w["target_vocab"]
@@ -131,7 +131,8 @@ def algorithmic_work(w, B, touched_rows=None, world=1, fused_target_adam=False):
     if fused_target_adam:
         rest -= Y * D
     if touched_rows is not None:
-        adam, catchup = 24.0 * (rest + touched_rows * d), 24.0 * touched_rows * d
+        # lazy Adam: one pass over the batch's rows (theta, m, v, g in and out); the dense kernels keep the rest
+        adam, catchup = 24.0 * rest, 32.0 * touched_rows * d
     else:
         adam, catchup = 24.0 * (emb + rest) / world, 0.0
     dy = ("hbm", 24.0 * Y * D + 4.0 * B * Y) if fused_target_adam else ("tensor", logit)
@@ -191,6 +192,8 @@ def run_ours(args):
     eng.set_option("cta_pair", args.cta_pair)
     trainer = Trainer(eng, keep_prob=KEEP_PROB, seed=99, schedule=args.dp_schedule, fuse_target_adam=not args.no_fuse_adam)
 
+    if args.dy_late >= 0:
+        eng.set_option("dy_late", args.dy_late)
     n_batches = 4
     host = make_batches(w, n_batches, seed=1234 + 100003 * rank, bags=args.bags, zipf=args.zipf)
     pinned = [[torch.from_numpy(a).pin_memory() for a in b] for b in host]
@@ -410,6 +413,8 @@ def main():
     ap.add_argument("--batch", type=int, default=0)
     ap.add_argument("--math", default=os.environ.get("C2V_MATH", "tf32"), choices=["fp32", "tf32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--dy-late", type=int, default=-1, choices=[-1, 0, 1],
+                    help="engine option dy_late (-1 = the schedule's default)")
     ap.add_argument("--no-fuse-adam", action="store_true",
                     help="keep the target table's Adam update as a separate pass instead of the dY epilogue")
     ap.add_argument("--bags", default="full", choices=["full", "normal", "ragged"],
