@@ -32,7 +32,7 @@ from typing import Iterable, List, Optional
 import numpy as np
 
 from .b200_model import Code2VecModel as _TFNumericsModel
-from .b200_model import _EvaluateInputFormer, _TrainInputFormer, _prefetch
+from .b200_model import _EvaluateInputFormer, _TrainInputFormer, _prefetch, _with_next
 from .common import common
 from .model_base import ModelEvaluationResults, ModelPredictionResults
 from .path_context_reader import EstimatorAction, ModelInputTensorsFormer, PathContextReader, ReaderInputTensors
@@ -107,7 +107,8 @@ class Code2VecModel(_TFNumericsModel):
         self.log("Starting training...")
         reader = PathContextReader(vocabs=self.vocabs, model_input_tensors_former=_TrainInputFormer(), config=cfg,
                                    estimator_action=EstimatorAction.Train, repeat_endlessly=True)
-        batches = _prefetch(reader.get_dataset())
+        batches = _with_next(_prefetch(reader.get_dataset()))
+        former = _TrainInputFormer()
         steps = cfg.train_steps_per_epoch
         last_saved_epoch = self.nr_epochs_trained
         avg_throughput = None
@@ -116,12 +117,15 @@ class Code2VecModel(_TFNumericsModel):
             window_loss, window_start, epoch_loss = 0.0, time.time(), 0.0
             for batch_idx in range(steps):
                 try:
-                    t = _TrainInputFormer().from_model_input_form(next(batches))
+                    batch, following = next(batches)
                 except StopIteration:
                     break
+                t = former.from_model_input_form(batch)
+                n = former.from_model_input_form(following) if following is not None else None
                 self.engine.set_option("math_mode", self._math_train)
-                loss = self.trainer.step_host(t.path_source_token_indices, t.path_indices, t.path_target_token_indices,
-                                              t.context_valid_mask, t.target_index)
+                loss = self.trainer.step_host(
+                    t.path_source_token_indices, t.path_indices, t.path_target_token_indices, t.context_valid_mask, t.target_index,
+                    next_batch=None if n is None else (n.path_source_token_indices, n.path_indices, n.path_target_token_indices))
                 window_loss += loss
                 epoch_loss += loss
                 done = batch_idx + 1

@@ -69,6 +69,19 @@ def _prefetch(iterable, depth: int = 8):
         stop.set()
 
 
+def _with_next(iterable):
+    """(item, following item or None) pairs: the one-batch lookahead behind the engine's next-batch hint."""
+    it = iter(iterable)
+    try:
+        cur = next(it)
+    except StopIteration:
+        return
+    for nxt in it:
+        yield cur, nxt
+        cur = nxt
+    yield cur, None
+
+
 _CKPT_MAGIC = b"C2VB200\0"
 _CKPT_SUFFIX = ".c2v_b200"
 
@@ -206,12 +219,17 @@ class Code2VecModel(Code2VecModelBase):
         train_reader = PathContextReader(vocabs=self.vocabs, model_input_tensors_former=_TrainInputFormer(),
                                          config=cfg, estimator_action=EstimatorAction.Train)
         self.log("Started reader...")
-        for batch in _prefetch(train_reader.get_dataset()):
-            t = _TrainInputFormer().from_model_input_form(batch)
+        former = _TrainInputFormer()
+        for batch, following in _with_next(_prefetch(train_reader.get_dataset())):
+            t = former.from_model_input_form(batch)
+            nxt = None
+            if following is not None:
+                n = former.from_model_input_form(following)
+                nxt = (n.path_source_token_indices, n.path_indices, n.path_target_token_indices)
             batch_num += 1
             self.engine.set_option("math_mode", self._math_train)
             batch_loss = self.trainer.step_host(t.path_source_token_indices, t.path_indices, t.path_target_token_indices,
-                                                t.context_valid_mask, t.target_index)
+                                                t.context_valid_mask, t.target_index, next_batch=nxt)
             sum_loss += batch_loss
             if batch_num % cfg.NUM_BATCHES_TO_LOG_PROGRESS == 0:
                 self._trace_training(sum_loss, batch_num, multi_batch_start_time)

@@ -35,6 +35,7 @@ constexpr int kSplitDw = 48;   // split-K slices for dW = X'^T . dU  (K = B*C)
 struct Workspace {
   size_t H, Xg, dXg, alpha, v, dv, S, loss_b, lse, loss, part, da_part, lse_part, dl;
   size_t st_src, st_pth, st_tgt, st_mask, st_target, st_topk_idx, st_topk_val, st_code, st_attn;
+  size_t nx_src, nx_pth, nx_tgt;                                  // indices of the hinted NEXT batch (host entry point)
   size_t stamp_tok, stamp_path, last_tok, last_path, lr_tab;     // lazy Adam bookkeeping
   size_t total;
   size_t ldS;
@@ -79,6 +80,9 @@ Workspace carve(const c2v_dims& d) {
   w.st_pth = take(N * 4);
   w.st_tgt = take(N * 4);
   w.st_mask = take(N * 4);
+  w.nx_src = take(N * 4);
+  w.nx_pth = take(N * 4);
+  w.nx_tgt = take(N * 4);
   w.st_target = take(B * 4);
   w.st_topk_idx = take(B * (size_t)d.top_k * 4);
   w.st_topk_val = take(B * (size_t)d.top_k * 4);
@@ -143,6 +147,15 @@ struct c2v_engine {
   bool tgt_armed = false;               // the next tcgen05 dY product applies the update instead of storing dY
   float tgt_lr = 0.f, tgt_b1 = 0.f, tgt_b2 = 0.f, tgt_eps = 0.f;
   int64_t tgt_t = 0;
+  int64_t armed_t = 0;                  // step whose hyper-parameters c2v_arm_target_adam declared (0 = none)
+  // next-batch hint (c2v_hint_next_batch): the deferred embedding-row updates of the NEXT batch's rows are
+  // applied on the side stream during this step's backward, next to the dY / dW GEMMs
+  const int32_t* hint_src = nullptr;
+  const int32_t* hint_pth = nullptr;
+  const int32_t* hint_tgt = nullptr;
+  int hint_B = 0;
+  int64_t early_t = 0;                  // step count the early catch-up already assumed applied (0 = none)
+  int64_t early_count = 0;              // how many steps used the hint (option "early_catchup_count", read-only)
   int fuse_tgt = 0;                     // option "fuse_target_adam": c2v_train_batch_host arms itself
   int64_t tgt_fused_t = 0;              // step count whose target update has already been applied (0 = none)
   int deterministic;
@@ -327,6 +340,43 @@ int flush_rows(c2v_engine* e, cudaStream_t st) {
   return C2V_OK;
 }
 
+// Lazy Adam + next-batch hint: once this step's scatter-add is queued on the side stream, the rows the NEXT
+// batch references can already be brought up to date through THIS step (its hyper-parameters are known
+// from c2v_arm_target_adam): their deferred updates then run next to the dY / dW GEMMs instead of at the
+// head of the next step.  Same kernels, same arithmetic, only earlier; anything not covered here is
+// handled by the next step's prepare_rows as usual.
+int early_catchup(c2v_engine* e, cudaStream_t side) {
+  const int32_t *hs = e->hint_src, *hp = e->hint_pth, *ht = e->hint_tgt;
+  const int hB = e->hint_B;
+  e->hint_src = e->hint_pth = e->hint_tgt = nullptr;          // one-shot
+  e->hint_B = 0;
+  if (!hs || !e->lazy || e->table_world > 1) return C2V_OK;
+  const int64_t t = e->armed_t;
+  if (t != e->adam_t_done + 1 || t >= kLrTableCap) return C2V_OK;
+  // pending steps were recorded under e->hp_*: only valid to run ahead if this step keeps them
+  if (!e->hp_set || e->tgt_lr != e->hp_lr || e->tgt_b1 != e->hp_b1 || e->tgt_b2 != e->hp_b2 || e->tgt_eps != e->hp_eps)
+    return C2V_OK;
+  const c2v_dims& d = e->dims;
+  const double lr_t = (double)e->tgt_lr * sqrt(1.0 - pow((double)e->tgt_b2, (double)t)) / (1.0 - pow((double)e->tgt_b1, (double)t));
+  float* lr_tab = wsp<float>(e, e->ws.lr_tab);
+  int32_t* stamp_tok = wsp<int32_t>(e, e->ws.stamp_tok);
+  int32_t* stamp_path = wsp<int32_t>(e, e->ws.stamp_path);
+  PhaseTimer pt(e, PH_ADAM_CATCHUP, side);
+  C2V_LAUNCH(e, (set_float_kernel<<<1, 1, 0, side>>>(lr_tab + t, (float)lr_t)));
+  e->mark_epoch++;
+  const int rows = hB * d.max_contexts;
+  C2V_LAUNCH(e, (mark_rows_kernel<<<(rows + 255) / 256, 256, 0, side>>>(hs, hp, ht, rows, stamp_tok, stamp_path, e->mark_epoch)));
+  C2V_LAUNCH(e, (adam_rows_kernel<ADAM_ROWS_CATCHUP><<<e->num_sms * 8, 256, 0, side>>>(
+                    e->theta.tok, e->grad.tok, e->am.tok, e->av.tok, d.token_vocab, d.embed_dim, stamp_tok, e->mark_epoch,
+                    wsp<int32_t>(e, e->ws.last_tok), (int32_t)t, lr_tab, e->hp_b1, e->hp_b2, e->hp_eps)));
+  C2V_LAUNCH(e, (adam_rows_kernel<ADAM_ROWS_CATCHUP><<<e->num_sms * 8, 256, 0, side>>>(
+                    e->theta.path, e->grad.path, e->am.path, e->av.path, d.path_vocab, d.embed_dim, stamp_path, e->mark_epoch,
+                    wsp<int32_t>(e, e->ws.last_path), (int32_t)t, lr_tab, e->hp_b1, e->hp_b2, e->hp_eps)));
+  e->early_t = t;
+  e->early_count++;
+  return C2V_OK;
+}
+
 // H = tanh(X' . W)   (tensorflow_model.py:238-252)
 int run_ctx_fwd(c2v_engine* e, cudaStream_t st, const ContextSource& cs, const Dropout& dp, float* H) {
   const int D = e->dims.code_dim, K = 3 * e->dims.embed_dim;
@@ -448,6 +498,7 @@ int context_backward(c2v_engine* e, cudaStream_t st, const ContextSource& cs, co
       PhaseTimer pt(e, PH_DX_SCATTER, e->side);
       C2V_LAUNCH(e, (scatter_dx_kernel<<<(N + 7) / 8, 256, 0, e->side>>>(cs, dp, mask, dXg, e->gr_tok, e->gr_path, e->grad_scale)));
     }
+    if ((rc = early_catchup(e, e->side))) return rc;
     C2V_CUDA(e, cudaEventRecord(e->ev_join, e->side));
     if (e->pending_dy_v) {   // deferred dYtab = P^T . v, concurrent with the scatter-add
       const float* pv = e->pending_dy_v;
@@ -648,12 +699,16 @@ int adam_impl(c2v_engine* e, cudaStream_t st, float lr, float b1, float b2, floa
     return fail(e, C2V_ERR_STATE, "embedding tables are sharded: update each slice with c2v_adam_step_range");
   if (t < 1) return fail(e, C2V_ERR_INVALID, "Adam step count t must be >= 1");
   e->tgt_armed = false;                 // an unconsumed arming (fp32 path, sampled softmax) falls back to the dense update
+  e->armed_t = 0;
+  e->hint_src = e->hint_pth = e->hint_tgt = nullptr;      // a hint the step could not use is dropped
   bool skip_tgt = false;
-  if (e->tgt_fused_t) {
-    if (e->tgt_fused_t != t || lr != e->tgt_lr || b1 != e->tgt_b1 || b2 != e->tgt_b2 || eps != e->tgt_eps)
-      return fail(e, C2V_ERR_STATE, "the target table was already updated by the armed dY epilogue with a different step count / hyper-parameters");
-    skip_tgt = true;
+  if (e->tgt_fused_t || e->early_t) {
+    const int64_t done_t = e->tgt_fused_t ? e->tgt_fused_t : e->early_t;
+    if (done_t != t || lr != e->tgt_lr || b1 != e->tgt_b1 || b2 != e->tgt_b2 || eps != e->tgt_eps)
+      return fail(e, C2V_ERR_STATE, "part of this Adam step was already applied inside the train step (c2v_arm_target_adam) with a different step count / hyper-parameters");
+    skip_tgt = e->tgt_fused_t != 0;
     e->tgt_fused_t = 0;
+    e->early_t = 0;
   }
   const double lr_t_d = (double)lr * sqrt(1.0 - pow((double)b2, (double)t)) / (1.0 - pow((double)b1, (double)t));
   const float lr_t = (float)lr_t_d;
@@ -886,6 +941,7 @@ int c2v_get_option(const c2v_engine* e, const char* key, int64_t* value) {
   if (!strcmp(key, "fuse_target_adam")) { *value = e->fuse_tgt; return C2V_OK; }
   if (!strcmp(key, "adam_step_count")) { *value = e->adam_t_done; return C2V_OK; }
   if (!strcmp(key, "target_adam_fused_step")) { *value = e->tgt_fused_t; return C2V_OK; }
+  if (!strcmp(key, "early_catchup_count")) { *value = e->early_count; return C2V_OK; }
   return C2V_ERR_INVALID;
 }
 
@@ -953,9 +1009,36 @@ int c2v_arm_target_adam(c2v_engine* e, float lr, float beta1, float beta2, float
   if (t < 1) return fail(e, C2V_ERR_INVALID, "Adam step count t must be >= 1");
   if (e->tgt_fused_t)
     return fail(e, C2V_ERR_STATE, "a fused target update is still unacknowledged: call c2v_adam_step (or clear target_adam_fused_step)");
+  if (e->early_t) return fail(e, C2V_ERR_STATE, "the previous armed step is still unacknowledged: call c2v_adam_step");
   e->tgt_lr = lr; e->tgt_b1 = beta1; e->tgt_b2 = beta2; e->tgt_eps = eps; e->tgt_t = t;
   e->tgt_armed = true;
+  e->armed_t = t;
   return C2V_OK;
+}
+
+int c2v_hint_next_batch(c2v_engine* e, const int32_t* src, const int32_t* path, const int32_t* tgt, int32_t B) {
+  int rc = check_batch(e, B);
+  if (rc) return rc;
+  if (!src || !path || !tgt) return fail(e, C2V_ERR_INVALID, "NULL argument");
+  e->hint_src = src; e->hint_pth = path; e->hint_tgt = tgt; e->hint_B = B;
+  return C2V_OK;
+}
+
+int c2v_hint_next_batch_host(c2v_engine* e, const int32_t* h_src, const int32_t* h_path, const int32_t* h_tgt, int32_t B,
+                             void* stream) {
+  int rc = check_batch(e, B);
+  if (rc) return rc;
+  if (!h_src || !h_path || !h_tgt) return fail(e, C2V_ERR_INVALID, "NULL argument");
+  C2V_CUDA(e, cudaSetDevice(e->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t nb = (size_t)B * e->dims.max_contexts * 4;
+  int32_t* src = wsp<int32_t>(e, e->ws.nx_src);
+  int32_t* pth = wsp<int32_t>(e, e->ws.nx_pth);
+  int32_t* tgt = wsp<int32_t>(e, e->ws.nx_tgt);
+  C2V_CUDA(e, cudaMemcpyAsync(src, h_src, nb, cudaMemcpyHostToDevice, st));
+  C2V_CUDA(e, cudaMemcpyAsync(pth, h_path, nb, cudaMemcpyHostToDevice, st));
+  C2V_CUDA(e, cudaMemcpyAsync(tgt, h_tgt, nb, cudaMemcpyHostToDevice, st));
+  return c2v_hint_next_batch(e, src, pth, tgt, B);
 }
 
 int c2v_adam_step(c2v_engine* e, float lr, float beta1, float beta2, float eps, int64_t t, void* stream) {

@@ -65,6 +65,8 @@ _SIGNATURES = {
                                          C.c_uint64, C.c_uint64, _P, _P, _P]),
     "c2v_adam_step": (C.c_int, [_P, C.c_float, C.c_float, C.c_float, C.c_float, C.c_int64, _P]),
     "c2v_arm_target_adam": (C.c_int, [_P, C.c_float, C.c_float, C.c_float, C.c_float, C.c_int64]),
+    "c2v_hint_next_batch": (C.c_int, [_P, _P, _P, _P, _I32]),
+    "c2v_hint_next_batch_host": (C.c_int, [_P, _P, _P, _P, _I32, _P]),
     "c2v_adam_step_range": (C.c_int, [_P, _P, _P, _P, _P, C.c_size_t, C.c_float, C.c_float, C.c_float, C.c_float,
                                       C.c_int64, _I32, _P]),
     "c2v_bind_table_shards": (C.c_int, [_P, C.POINTER(c2v_table_shards), C.POINTER(c2v_table_shards), C.c_float]),
@@ -396,6 +398,17 @@ class PathAttentionEngine:
         """The next train step's dY epilogue applies Adam step `t` to the target table (c2v_arm_target_adam);
         the following adam_step(t) skips that table.  The target gradient buffer is then not written."""
         self._check(self.lib.c2v_arm_target_adam(self.h, lr, beta1, beta2, eps, int(t)))
+
+    def hint_next_batch(self, src, path, tgt):
+        """Device index tensors [B, C] of the batch the next train step will use (c2v_hint_next_batch); the
+        caller keeps them alive until that step has been issued."""
+        self._check(self.lib.c2v_hint_next_batch(self.h, src.data_ptr(), path.data_ptr(), tgt.data_ptr(), int(src.shape[0])))
+
+    def hint_next_batch_host(self, src, path, tgt):
+        """Same from host arrays / pinned tensors (c2v_hint_next_batch_host)."""
+        src, path, tgt = (_as_host(x, np.int32) for x in (src, path, tgt))      # pageable sources are staged before the call returns
+        self._check(self.lib.c2v_hint_next_batch_host(self.h, _host_ptr(src), _host_ptr(path), _host_ptr(tgt),
+                                                      int(src.shape[0]), self._stream()))
 
     def adam_step_range(self, theta, grad, m, v, t: int, lr=1e-3, beta1=0.9, beta2=0.999, eps=1e-8, zero_grad=False):
         """TF1 Adam on one contiguous slice (the sharded-optimizer path): flat tensors of equal length."""

@@ -208,14 +208,18 @@ class Trainer:
         self._loss_host = torch.zeros(1, dtype=torch.float32).pin_memory()
 
     # ---- inputs already resident on the device ----------------------------------------------
-    def step_device(self, src, path, tgt, mask, target):
-        """Forward+backward, gradient exchange, Adam.  Returns the device loss tensor (no sync)."""
+    def step_device(self, src, path, tgt, mask, target, next_batch=None):
+        """Forward+backward, gradient exchange, Adam.  Returns the device loss tensor (no sync).
+        next_batch: optional (src, path, tgt) device tensors of the batch the NEXT call will get -- with lazy
+        Adam the deferred updates of its rows then overlap this step's backward GEMMs (c2v_hint_next_batch)."""
         if self.schedule == "fully_sharded":
             return self._fully_sharded_step(src, path, tgt, mask, target)
         e = self.e
         t = e.adam_t + 1
         if self.fuse_tgt:
             e.arm_target_adam(t, **self.adam)
+            if next_batch is not None and self.schedule == "single":
+                e.hint_next_batch(*next_batch[:3])
         # dropout stream position (seed, t); replicas use different seeds so their masks differ
         loss = e.train_step(src, path, tgt, mask, target, keep=self.keep, seed=self.seed + self.rank, step=t)
         if self.schedule == "single":
@@ -314,10 +318,13 @@ class Trainer:
                 wk.wait()
 
     # ---- inputs in host memory (what train() does per batch) ---------------------------------
-    def step_host(self, src, path, tgt, mask, target) -> float:
-        """One training step on HOST buffers (numpy / pinned tensors); returns the loss (synchronises)."""
+    def step_host(self, src, path, tgt, mask, target, next_batch=None) -> float:
+        """One training step on HOST buffers (numpy / pinned tensors); returns the loss (synchronises).
+        next_batch: optional host (src, path, tgt) of the following batch (see step_device)."""
         e = self.e
         if self.world == 1:
+            if next_batch is not None and self.fuse_tgt:
+                e.hint_next_batch_host(*next_batch[:3])
             return e.train_batch_host(src, path, tgt, mask, target, keep=self.keep, seed=self.seed, **self.adam)
         torch = e.torch
         B = int(src.shape[0])

@@ -114,7 +114,8 @@ int c2v_bind_adam_state(c2v_engine* e, const c2v_tensors* m, const c2v_tensors* 
  * "grad_scale_inverse" (n: embedding scatter-adds are scaled by 1/n), "fuse_target_adam" (0/1,
  * default 0: c2v_train_batch_host arms c2v_arm_target_adam itself), "target_adam_fused_step"
  * (read: the step count whose target-table update the dY epilogue has already applied, 0 = none;
- * writing 0 acknowledges it for callers that drive c2v_adam_step_range themselves). */
+ * writing 0 acknowledges it for callers that drive c2v_adam_step_range themselves),
+ * "early_catchup_count" (read-only: how many train steps used a c2v_hint_next_batch hint). */
 int c2v_set_option(c2v_engine* e, const char* key, int64_t value);
 int c2v_get_option(const c2v_engine* e, const char* key, int64_t* value);
 
@@ -178,6 +179,19 @@ int c2v_adam_step(c2v_engine* e, float lr, float beta1, float beta2, float eps, 
  * softmax) the arming is dropped and c2v_adam_step updates the table as usual.  Same semantics as
  * tensorflow_model.py:232; no reference statement of its own. */
 int c2v_arm_target_adam(c2v_engine* e, float lr, float beta1, float beta2, float eps, int64_t t);
+
+/* Next-batch hint for "lazy_adam" (one-shot, optional; tf.data's prefetch, path_context_reader.py:150,
+ * is what makes the next batch known in the reference too): the index arrays [B, C] of the batch
+ * the NEXT train step will run on.  If the current step is armed (c2v_arm_target_adam supplies the
+ * step's hyper-parameters) the deferred updates of that batch's embedding rows are applied during
+ * the current step's backward pass, on the engine's side stream next to the dY / dW GEMMs,
+ * instead of at the head of the next step.  Results are identical with or without the hint; a
+ * wrong hint only costs the overlap.  Device pointers must stay valid until the next train step
+ * has been issued; the _host variant copies from host memory into the engine's staging area. */
+int c2v_hint_next_batch(c2v_engine* e, const int32_t* src, const int32_t* path, const int32_t* tgt,
+                        int32_t B);
+int c2v_hint_next_batch_host(c2v_engine* e, const int32_t* h_src, const int32_t* h_path,
+                             const int32_t* h_tgt, int32_t B, void* stream);
 
 /* ---- Phase-split train step for the fully sharded schedule (BASELINE config 5) -----------------------
  * The target table is row-sharded too: this engine is created with target_vocab = the number of

@@ -83,3 +83,44 @@ def test_lazy_adam_through_host_entry_point_and_mode_switch():
     ia, va, ca, _ = eng.predict_batch_host(src, pth, tgt, mask)
     ib, vb, cb, _ = ref.predict_batch_host(src, pth, tgt, mask)
     assert np.abs(ca - cb).max() < 1e-5
+
+
+@pytest.mark.parametrize("entry", ["device", "host"])
+def test_next_batch_hint_runs_the_deferred_updates_early_and_changes_nothing(entry):
+    """Trainer("single") = lazy Adam + target Adam in the dY epilogue + next-batch hint (the deferred row
+    updates of batch t+1 run during step t's backward) against a plain dense engine: train_step + adam_step."""
+    import torch
+    from code2vec_b200.trainer import Trainer
+    batches = _batches()
+    fast, params0 = make_engine(DIMS, max_batch=B)
+    dense, _ = make_engine(DIMS, max_batch=B, params=params0)
+    for eng in (fast, dense):
+        eng.set_option("math_mode", 1)
+    tr = Trainer(fast, keep_prob=1.0, seed=3)
+    assert tr.schedule == "single" and tr.fuse_tgt and fast.get_option("lazy_adam") == 1
+    for s, (src, pth, tgt, mask, target) in enumerate(batches):
+        nxt = batches[s + 1][:3] if s + 1 < len(batches) else None
+        if entry == "device":
+            d = dev_batch(fast, src, pth, tgt, mask, target)
+            dn = None if nxt is None else dev_batch(fast, nxt[0], nxt[1], nxt[2], mask)[:3]
+            la = float(tr.step_device(*d, next_batch=dn).cpu()[0])
+        else:
+            la = tr.step_host(src, pth, tgt, mask, target, next_batch=nxt)
+        lb = float(dense.train_step(*dev_batch(dense, src, pth, tgt, mask, target), keep=1.0).cpu()[0])
+        dense.adam_step()
+        assert abs(la - lb) < 1e-5
+    # the first step cannot run ahead (no hyper-parameters on record yet), the last one has no next batch
+    assert fast.get_option("early_catchup_count") == STEPS - 2
+    a, b = fast.export_params(), dense.export_params()
+    assert np.array_equal(a["tgt"], b["tgt"])                    # epilogue Adam == adam_kernel, bit for bit
+    for k in O.PARAM_NAMES:
+        assert np.abs(a[k] - b[k]).max() < 2e-6, k
+    for name, cols in (("tok", (0, 2)), ("path", (1,))):
+        counts = np.zeros(a[name].shape[0], dtype=np.int64)
+        for batch in batches:
+            for c in cols:
+                np.add.at(counts, batch[c][batch[3] > 0], 1)
+        once = counts == 1
+        assert once.sum() > 50 and np.array_equal(a[name][once], b[name][once]), name
+    assert torch.allclose(fast.adam_m["tok"], dense.adam_m["tok"], atol=1e-7)
+    assert torch.allclose(fast.adam_v["path"], dense.adam_v["path"], atol=1e-9)
