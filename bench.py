@@ -194,8 +194,8 @@ def run_ours(args):
 
     if args.dy_late >= 0:
         eng.set_option("dy_late", args.dy_late)
-    # a training loop knows its next batch (the reader prefetches): hint it so lazy Adam can run ahead
-    nxt = (lambda seq, i: None) if args.no_hint else (lambda seq, i: seq[(i + 1) % n_batches])
+    # a training loop knows its next batch (the reader prefetches); --hint passes it on so lazy Adam can run ahead
+    nxt = (lambda seq, i: seq[(i + 1) % n_batches]) if args.hint else (lambda seq, i: None)
     n_batches = 4
     host = make_batches(w, n_batches, seed=1234 + 100003 * rank, bags=args.bags, zipf=args.zipf)
     pinned = [[torch.from_numpy(a).pin_memory() for a in b] for b in host]
@@ -305,7 +305,7 @@ def run_ours(args):
         cpu = cpu_baseline(w, host[0], steps=1)
 
     h2d = sum(int(a.nbytes) for a in host[0])
-    if world == 1 and not args.no_hint and fused:
+    if world == 1 and args.hint and fused:
         h2d += sum(int(a.nbytes) for a in host[0][:3])      # the next batch's index arrays are copied once more as the hint
     out = {
         "metric": "path-contexts/sec (train step, batch 1024x200)", "value": round(value, 1), "unit": "path-contexts/s",
@@ -318,7 +318,7 @@ def run_ours(args):
                    "batch_per_gpu": B, "global_batch": B * world, "contexts_per_example": C,
                    "parallelism": "dp%d (%s)" % (world, trainer.schedule) if world > 1 else "single",
                    "l2": "no flush: >9 GB of parameter/optimizer traffic per step and 4 rotating input batches exceed the 126 MB L2",
-                   "math_mode": args.math, "fused_target_adam": fused, "next_batch_hint": bool(world == 1 and not args.no_hint and fused), "last_loss": round(last_loss, 5),
+                   "math_mode": args.math, "fused_target_adam": fused, "next_batch_hint": bool(world == 1 and args.hint and fused), "last_loss": round(last_loss, 5),
                    "inputs": "%s bags, %s indices; all %d slots per example are counted in the metric" % (
                        args.bags, "zipf(1.2)" if args.zipf else "uniform", C),
                    "valid_context_fraction": round(float(np.mean([b[3].mean() for b in host])), 4)},
@@ -417,9 +417,10 @@ def main():
     ap.add_argument("--batch", type=int, default=0)
     ap.add_argument("--math", default=os.environ.get("C2V_MATH", "tf32"), choices=["fp32", "tf32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--dy-late", type=int, default=-1, choices=[-1, 0, 1],
+    ap.add_argument("--dy-late", type=int, default=-1, choices=[-1, 0, 1, 2],
                     help="engine option dy_late (-1 = the schedule's default)")
-    ap.add_argument("--no-hint", action="store_true", help="do not hint the next batch to the engine (c2v_hint_next_batch)")
+    ap.add_argument("--hint", action="store_true",
+                    help="hint the next batch to the engine (c2v_hint_next_batch); measured no gain on one GPU, off by default")
     ap.add_argument("--no-fuse-adam", action="store_true",
                     help="keep the target table's Adam update as a separate pass instead of the dY epilogue")
     ap.add_argument("--bags", default="full", choices=["full", "normal", "ragged"],

@@ -121,7 +121,7 @@ class Code2VecModel(_TFNumericsModel):
                 except StopIteration:
                     break
                 t = former.from_model_input_form(batch)
-                n = former.from_model_input_form(following) if following is not None else None
+                n = former.from_model_input_form(following) if (self._hint_next and following is not None) else None
                 self.engine.set_option("math_mode", self._math_train)
                 loss = self.trainer.step_host(
                     t.path_source_token_indices, t.path_indices, t.path_target_token_indices, t.context_valid_mask, t.target_index,

@@ -128,6 +128,8 @@ class Code2VecModel(Code2VecModelBase):
         forced = os.environ.get("C2V_MATH", "").lower()
         self._math_train = {"fp32": 0, "tf32": 1}.get(forced, 1)
         self._math_eval = {"fp32": 0, "tf32": 1}.get(forced, 0)
+        # C2V_HINT_NEXT=1: pass each next batch to the engine (c2v_hint_next_batch); no measured gain on one GPU
+        self._hint_next = os.environ.get("C2V_HINT_NEXT", "0") == "1"
         if self.config.is_training:
             self.trainer = Trainer(self.engine, keep_prob=self.config.DROPOUT_KEEP_RATE, seed=int(time.time()) & 0x7FFFFFFF,
                                    adam=self._ADAM)
@@ -223,7 +225,7 @@ class Code2VecModel(Code2VecModelBase):
         for batch, following in _with_next(_prefetch(train_reader.get_dataset())):
             t = former.from_model_input_form(batch)
             nxt = None
-            if following is not None:
+            if self._hint_next and following is not None:
                 n = former.from_model_input_form(following)
                 nxt = (n.path_source_token_indices, n.path_indices, n.path_target_token_indices)
             batch_num += 1

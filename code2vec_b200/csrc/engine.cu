@@ -138,11 +138,14 @@ struct c2v_engine {
   int cta_pair = 2;          // tcgen05 GEMMs as CTA pairs (cta_group::2, UMMA 256 x BN): 0 never, 1 always, 2 auto
   int num_sms;
   cudaEvent_t ev_tgt_ready = nullptr;   // recorded after dY (caller-owned)
-  int dy_late = 1;                      // defer the dY GEMM into context_backward (overlaps the scatter-add)
+  int dy_late = 1;                      // where dY = P^T.v runs: 0 after dv, 1 inside context_backward, 2 on side2 after dv
   const float* pending_dy_v = nullptr;  // code vectors of the deferred dY product
   int pending_dy_B = 0;
   cudaStream_t side = nullptr;          // engine-owned: the embedding scatter-add runs here, next to the dY / dW GEMMs
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  cudaStream_t side2 = nullptr;         // engine-owned: the dY (+ target Adam) GEMM with dy_late == 2
+  cudaEvent_t ev_fork2 = nullptr, ev_join2 = nullptr;
+  bool dy_in_flight = false;            // a dY launched on side2 has not been joined yet
   // target-table Adam folded into the dY epilogue (c2v_arm_target_adam)
   bool tgt_armed = false;               // the next tcgen05 dY product applies the update instead of storing dY
   float tgt_lr = 0.f, tgt_b1 = 0.f, tgt_b2 = 0.f, tgt_eps = 0.f;
@@ -516,6 +519,10 @@ int context_backward(c2v_engine* e, cudaStream_t st, const ContextSource& cs, co
       if (rc) return rc;
     }
     C2V_CUDA(e, cudaStreamWaitEvent(st, e->ev_join, 0));
+    if (e->dy_in_flight) {
+      C2V_CUDA(e, cudaStreamWaitEvent(st, e->ev_join2, 0));
+      e->dy_in_flight = false;
+    }
     e->emb_grads_clean = false;
     return C2V_OK;
   }
@@ -613,6 +620,16 @@ int run_dy(c2v_engine* e, cudaStream_t st, const float* v, int B) {
 int target_grad_gemms(c2v_engine* e, cudaStream_t st, const float* v, int B, float* dv) {
   int rc = run_dv(e, st, B, dv);
   if (rc) return rc;
+  if (e->dy_late == 2 && e->math_mode == C2V_MATH_TF32) {
+    // dY (and the target table's Adam step in its epilogue) is HBM-bound and independent of the context
+    // backward pass: it runs on its own stream from here until context_backward joins it
+    C2V_CUDA(e, cudaEventRecord(e->ev_fork2, st));
+    C2V_CUDA(e, cudaStreamWaitEvent(e->side2, e->ev_fork2, 0));
+    if ((rc = run_dy(e, e->side2, v, B))) return rc;
+    C2V_CUDA(e, cudaEventRecord(e->ev_join2, e->side2));
+    e->dy_in_flight = true;
+    return C2V_OK;
+  }
   if (e->dy_late) {
     e->pending_dy_v = v;
     e->pending_dy_B = B;
@@ -793,7 +810,10 @@ int c2v_create(const c2v_dims* dims, int device, c2v_engine** out) {
   cudaSetDevice(device);
   if (cudaStreamCreateWithFlags(&e->side, cudaStreamNonBlocking) != cudaSuccess ||
       cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
-      cudaEventCreateWithFlags(&e->ev_join, cudaEventDisableTiming) != cudaSuccess) {
+      cudaEventCreateWithFlags(&e->ev_join, cudaEventDisableTiming) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&e->side2, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaEventCreateWithFlags(&e->ev_fork2, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&e->ev_join2, cudaEventDisableTiming) != cudaSuccess) {
     delete e;
     return fail(nullptr, C2V_ERR_CUDA, "could not create the engine's side stream / events");
   }
@@ -809,6 +829,9 @@ void c2v_destroy(c2v_engine* e) {
   if (e->ev_fork) cudaEventDestroy(e->ev_fork);
   if (e->ev_join) cudaEventDestroy(e->ev_join);
   if (e->side) cudaStreamDestroy(e->side);
+  if (e->ev_fork2) cudaEventDestroy(e->ev_fork2);
+  if (e->ev_join2) cudaEventDestroy(e->ev_join2);
+  if (e->side2) cudaStreamDestroy(e->side2);
   for (auto& L : e->phase) {
     for (auto& ev : L.pending) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
     for (auto& ev : L.free_list) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
@@ -867,7 +890,11 @@ int c2v_set_option(c2v_engine* e, const char* key, int64_t value) {
     return C2V_OK;
   }
   if (!strcmp(key, "profile")) { e->profile = value ? 1 : 0; return C2V_OK; }
-  if (!strcmp(key, "dy_late")) { e->dy_late = value ? 1 : 0; return C2V_OK; }
+  if (!strcmp(key, "dy_late")) {
+    if (value < 0 || value > 2) return fail(e, C2V_ERR_INVALID, "dy_late must be 0, 1 or 2");
+    e->dy_late = (int)value;
+    return C2V_OK;
+  }
   if (!strcmp(key, "fuse_target_adam")) { e->fuse_tgt = value ? 1 : 0; return C2V_OK; }
   if (!strcmp(key, "cta_pair")) {
     if (value < 0 || value > 2) return fail(e, C2V_ERR_INVALID, "cta_pair must be 0 (never), 1 (always) or 2 (auto)");

@@ -299,25 +299,26 @@ __device__ __forceinline__ void store_chunk(const Epi& epi, const uint32_t (&r)[
   constexpr int kBatch = Epi::kRowBatch;
 #pragma unroll
   for (int it0 = 0; it0 < 8; it0 += kBatch) {
+    float4 v[kBatch];
     typename Epi::Pre pre[kBatch];
 #pragma unroll
     for (int i = 0; i < kBatch; ++i) {
-      const int gm = m_base + (it0 + i) * 4 + (lane >> 3);
+      const int row = (it0 + i) * 4 + (lane >> 3);
+      v[i] = *reinterpret_cast<const float4*>(stage + row * 32 + ((col4 ^ (row & 7)) * 4));
+      const int gm = m_base + row;
       if (gm < M && gn + 3 < N) epi.prefetch(cbase, (size_t)gm * ldc + gn, pre[i]);
     }
 #pragma unroll
     for (int i = 0; i < kBatch; ++i) {
-      const int row = (it0 + i) * 4 + (lane >> 3);
-      const int gm = m_base + row;
+      const int gm = m_base + (it0 + i) * 4 + (lane >> 3);
       if (gm < M && gn < N) {
-        const float4 v = *reinterpret_cast<const float4*>(stage + row * 32 + ((col4 ^ (row & 7)) * 4));
         const size_t off = (size_t)gm * ldc + gn;
         if (gn + 3 < N) {
-          epi.store4(cbase, off, v, pre[i]);
+          epi.store4(cbase, off, v[i], pre[i]);
         } else {
-          epi.store1(cbase, off, v.x);
-          if (gn + 1 < N) epi.store1(cbase, off + 1, v.y);
-          if (gn + 2 < N) epi.store1(cbase, off + 2, v.z);
+          epi.store1(cbase, off, v[i].x);
+          if (gn + 1 < N) epi.store1(cbase, off + 1, v[i].y);
+          if (gn + 2 < N) epi.store1(cbase, off + 2, v[i].z);
         }
       }
     }

@@ -100,9 +100,12 @@ int c2v_bind_adam_state(c2v_engine* e, const c2v_tensors* m, const c2v_tensors* 
 /* Options: "math_mode" (c2v_math_mode), "deterministic" (reserved: only 0 is accepted -- the
  * embedding scatter-add uses float atomics; every other reduction is fixed-order), "cta_pair"
  * (tcgen05 GEMMs as CTA pairs, tcgen05.mma.cta_group::2: 0 never, 1 always, 2 auto = per GEMM,
- * wherever it measured faster; default 2), "dy_late" (0/1, default 1: the target-table gradient
- * GEMM dY = P^T.v is issued inside the context backward pass so it overlaps the embedding
- * scatter-add; with 0 it runs right after dv and "target_grads_ready" fires earlier), "profile" (0/1: per-phase
+ * wherever it measured faster; default 2), "dy_late" (where the target-table gradient GEMM dY = P^T.v -- with the
+ * target table's Adam step in its epilogue when armed -- runs: 0 = right after dv on the caller's
+ * stream, "target_grads_ready" fires earliest; 1 = default: inside the context backward pass, next
+ * to the embedding scatter-add; 2 = on an engine-owned stream right after dv, joined before the
+ * step returns.  All three measure within 1 % of each other on one GPU: the persistent GEMM CTAs
+ * fill the register file, so kernels on other streams mostly wait for them), "profile" (0/1: per-phase
  * CUDA-event timing, read with c2v_phase_stats), "lazy_adam" (0/1, single-GPU replicated tables:
  * the dense TF1 Adam update of an embedding row is deferred -- its gradient stays in the bound
  * gradient table -- and replayed bit-exactly (one step with that gradient, then the zero-gradient
