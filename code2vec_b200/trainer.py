@@ -205,6 +205,9 @@ class Trainer:
         self.fuse_tgt = bool(fuse_target_adam) and self.schedule in ("single", "fully_sharded") and engine.training
         if self.schedule == "single":
             engine.set_option("fuse_target_adam", 1 if self.fuse_tgt else 0)     # for train_batch_host
+            # dY (+ the target table's Adam step) straight after dv: on one GPU it is HBM-bound like the scatter-add
+            # it would otherwise share the memory system with (dy_late 0/1/2 all measure within 1 %)
+            engine.set_option("dy_late", 0)
         self._loss_host = torch.zeros(1, dtype=torch.float32).pin_memory()
 
     # ---- inputs already resident on the device ----------------------------------------------
