@@ -194,6 +194,8 @@ def run_ours(args):
 
     if args.dy_late >= 0:
         eng.set_option("dy_late", args.dy_late)
+    if args.adam_rows_occ:
+        eng.set_option("adam_rows_occupancy", args.adam_rows_occ)
     # a training loop knows its next batch (the reader prefetches); --hint passes it on so lazy Adam can run ahead
     nxt = (lambda seq, i: seq[(i + 1) % n_batches]) if args.hint else (lambda seq, i: None)
     n_batches = 4
@@ -419,6 +421,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--dy-late", type=int, default=-1, choices=[-1, 0, 1, 2],
                     help="engine option dy_late (-1 = the schedule's default)")
+    ap.add_argument("--adam-rows-occ", type=int, default=0, choices=[0, 4, 5], help="engine option adam_rows_occupancy (0 = default)")
     ap.add_argument("--hint", action="store_true",
                     help="hint the next batch to the engine (c2v_hint_next_batch); measured no gain on one GPU, off by default")
     ap.add_argument("--no-fuse-adam", action="store_true",

@@ -127,6 +127,7 @@ struct c2v_engine {
   float grad_scale = 1.f;
   // lazy-but-exact dense Adam for the embedding tables (option "lazy_adam")
   int lazy = 0;
+  int adam_rows_occ = 4;
   bool lazy_grads_pending = false;  // a train step's embedding gradients are in the tables and c2v_adam_step has not followed
   int64_t adam_t_done = 0;   // Adam steps applied so far
   int32_t mark_epoch = 0;
@@ -203,6 +204,15 @@ struct PhaseTimer {
     if (_c != cudaSuccess)                                                                        \
       return fail((e), C2V_ERR_CUDA, std::string("kernel launch failed: ") + cudaGetErrorString(_c)); \
     (e)->launches++;                                                                              \
+  } while (0)
+
+// adam_rows_kernel as one wave of num_sms * occupancy blocks (option "adam_rows_occupancy": 4 or 5)
+#define C2V_ADAM_ROWS(e, MODE, stream, ...)                                                                    \
+  do {                                                                                                         \
+    if ((e)->adam_rows_occ == 5)                                                                               \
+      C2V_LAUNCH(e, (adam_rows_kernel<MODE, 5><<<(e)->num_sms * 5, 256, 0, stream>>>(__VA_ARGS__)));           \
+    else                                                                                                       \
+      C2V_LAUNCH(e, (adam_rows_kernel<MODE, 4><<<(e)->num_sms * 4, 256, 0, stream>>>(__VA_ARGS__)));           \
   } while (0)
 
 // tcgen05 GEMM launchers: single-CTA (UMMA 128 x BN) or CTA-pair (UMMA 256 x BN).  Option "cta_pair":
@@ -319,12 +329,12 @@ int prepare_rows(c2v_engine* e, cudaStream_t st, const ContextSource& cs) {
                                                                         e->mark_epoch)));
   if (e->adam_t_done > 0) {
     const float* lr_tab = wsp<float>(e, e->ws.lr_tab);
-    C2V_LAUNCH(e, (adam_rows_kernel<ADAM_ROWS_CATCHUP><<<e->num_sms * 8, 256, 0, st>>>(
-                      e->theta.tok, e->grad.tok, e->am.tok, e->av.tok, d.token_vocab, d.embed_dim, stamp_tok, e->mark_epoch,
-                      wsp<int32_t>(e, e->ws.last_tok), (int32_t)e->adam_t_done, lr_tab, e->hp_b1, e->hp_b2, e->hp_eps)));
-    C2V_LAUNCH(e, (adam_rows_kernel<ADAM_ROWS_CATCHUP><<<e->num_sms * 8, 256, 0, st>>>(
-                      e->theta.path, e->grad.path, e->am.path, e->av.path, d.path_vocab, d.embed_dim, stamp_path, e->mark_epoch,
-                      wsp<int32_t>(e, e->ws.last_path), (int32_t)e->adam_t_done, lr_tab, e->hp_b1, e->hp_b2, e->hp_eps)));
+    C2V_ADAM_ROWS(e, ADAM_ROWS_CATCHUP, st,
+                  e->theta.tok, e->grad.tok, e->am.tok, e->av.tok, d.token_vocab, d.embed_dim, stamp_tok, e->mark_epoch,
+                      wsp<int32_t>(e, e->ws.last_tok), (int32_t)e->adam_t_done, lr_tab, e->hp_b1, e->hp_b2, e->hp_eps);
+    C2V_ADAM_ROWS(e, ADAM_ROWS_CATCHUP, st,
+                  e->theta.path, e->grad.path, e->am.path, e->av.path, d.path_vocab, d.embed_dim, stamp_path, e->mark_epoch,
+                      wsp<int32_t>(e, e->ws.last_path), (int32_t)e->adam_t_done, lr_tab, e->hp_b1, e->hp_b2, e->hp_eps);
   }
   return C2V_OK;
 }
@@ -334,12 +344,12 @@ int flush_rows(c2v_engine* e, cudaStream_t st) {
   if (!e->lazy || e->adam_t_done == 0) return C2V_OK;
   const c2v_dims& d = e->dims;
   const float* lr_tab = wsp<float>(e, e->ws.lr_tab);
-  C2V_LAUNCH(e, (adam_rows_kernel<ADAM_ROWS_FLUSH><<<e->num_sms * 8, 256, 0, st>>>(
-                    e->theta.tok, e->grad.tok, e->am.tok, e->av.tok, d.token_vocab, d.embed_dim, nullptr, 0,
-                    wsp<int32_t>(e, e->ws.last_tok), (int32_t)e->adam_t_done, lr_tab, e->hp_b1, e->hp_b2, e->hp_eps)));
-  C2V_LAUNCH(e, (adam_rows_kernel<ADAM_ROWS_FLUSH><<<e->num_sms * 8, 256, 0, st>>>(
-                    e->theta.path, e->grad.path, e->am.path, e->av.path, d.path_vocab, d.embed_dim, nullptr, 0,
-                    wsp<int32_t>(e, e->ws.last_path), (int32_t)e->adam_t_done, lr_tab, e->hp_b1, e->hp_b2, e->hp_eps)));
+  C2V_ADAM_ROWS(e, ADAM_ROWS_FLUSH, st,
+                  e->theta.tok, e->grad.tok, e->am.tok, e->av.tok, d.token_vocab, d.embed_dim, nullptr, 0,
+                    wsp<int32_t>(e, e->ws.last_tok), (int32_t)e->adam_t_done, lr_tab, e->hp_b1, e->hp_b2, e->hp_eps);
+  C2V_ADAM_ROWS(e, ADAM_ROWS_FLUSH, st,
+                  e->theta.path, e->grad.path, e->am.path, e->av.path, d.path_vocab, d.embed_dim, nullptr, 0,
+                    wsp<int32_t>(e, e->ws.last_path), (int32_t)e->adam_t_done, lr_tab, e->hp_b1, e->hp_b2, e->hp_eps);
   return C2V_OK;
 }
 
@@ -369,12 +379,12 @@ int early_catchup(c2v_engine* e, cudaStream_t side) {
   e->mark_epoch++;
   const int rows = hB * d.max_contexts;
   C2V_LAUNCH(e, (mark_rows_kernel<<<(rows + 255) / 256, 256, 0, side>>>(hs, hp, ht, rows, stamp_tok, stamp_path, e->mark_epoch)));
-  C2V_LAUNCH(e, (adam_rows_kernel<ADAM_ROWS_CATCHUP><<<e->num_sms * 8, 256, 0, side>>>(
-                    e->theta.tok, e->grad.tok, e->am.tok, e->av.tok, d.token_vocab, d.embed_dim, stamp_tok, e->mark_epoch,
-                    wsp<int32_t>(e, e->ws.last_tok), (int32_t)t, lr_tab, e->hp_b1, e->hp_b2, e->hp_eps)));
-  C2V_LAUNCH(e, (adam_rows_kernel<ADAM_ROWS_CATCHUP><<<e->num_sms * 8, 256, 0, side>>>(
-                    e->theta.path, e->grad.path, e->am.path, e->av.path, d.path_vocab, d.embed_dim, stamp_path, e->mark_epoch,
-                    wsp<int32_t>(e, e->ws.last_path), (int32_t)t, lr_tab, e->hp_b1, e->hp_b2, e->hp_eps)));
+  C2V_ADAM_ROWS(e, ADAM_ROWS_CATCHUP, side,
+                  e->theta.tok, e->grad.tok, e->am.tok, e->av.tok, d.token_vocab, d.embed_dim, stamp_tok, e->mark_epoch,
+                    wsp<int32_t>(e, e->ws.last_tok), (int32_t)t, lr_tab, e->hp_b1, e->hp_b2, e->hp_eps);
+  C2V_ADAM_ROWS(e, ADAM_ROWS_CATCHUP, side,
+                  e->theta.path, e->grad.path, e->am.path, e->av.path, d.path_vocab, d.embed_dim, stamp_path, e->mark_epoch,
+                    wsp<int32_t>(e, e->ws.last_path), (int32_t)t, lr_tab, e->hp_b1, e->hp_b2, e->hp_eps);
   e->early_t = t;
   e->early_count++;
   return C2V_OK;
@@ -896,6 +906,11 @@ int c2v_set_option(c2v_engine* e, const char* key, int64_t value) {
     return C2V_OK;
   }
   if (!strcmp(key, "fuse_target_adam")) { e->fuse_tgt = value ? 1 : 0; return C2V_OK; }
+  if (!strcmp(key, "adam_rows_occupancy")) {
+    if (value != 4 && value != 5) return fail(e, C2V_ERR_INVALID, "adam_rows_occupancy must be 4 or 5");
+    e->adam_rows_occ = (int)value;
+    return C2V_OK;
+  }
   if (!strcmp(key, "cta_pair")) {
     if (value < 0 || value > 2) return fail(e, C2V_ERR_INVALID, "cta_pair must be 0 (never), 1 (always) or 2 (auto)");
     e->cta_pair = (int)value;

@@ -761,8 +761,10 @@ enum { ADAM_ROWS_CATCHUP = 0, ADAM_ROWS_FLUSH = 2 };
 // or zeros -- and the rest with a zero gradient; the gradient row is cleared on the way.  So a
 // row the batch references costs one pass (theta, m, v, g in; theta, m, v, 0 out) per step instead
 // of a catch-up pass before the forward and an update pass after the backward.
-template <int MODE>
-__global__ void __launch_bounds__(256)
+// OCC = resident blocks per SM the kernel is compiled for (4: 64 registers, no spills; 5: 48 registers,
+// a few spilled words); the persistent grid is launched as exactly one wave of num_sms * OCC blocks.
+template <int MODE, int OCC>
+__global__ void __launch_bounds__(256, OCC)
 adam_rows_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, int rows, int d,
                  const int32_t* __restrict__ stamp, int32_t epoch, int32_t* __restrict__ last, int32_t t_done,
                  const float* __restrict__ lr_tab, float b1, float b2, float eps) {
