@@ -1,9 +1,14 @@
-import sys, torch, time
-sys.path.insert(0, '/root/repo')
-from oracle import path_attention_oracle as O
-from tests.util import make_engine
-TINY = O.Dims(token_vocab=101, path_vocab=51, target_vocab=101, embed_dim=32, code_dim=96, max_contexts=20)
-eng, _ = make_engine(TINY, max_batch=8)
+"""Times the tcgen05 GEMM kernels alone (c2v_selftest_gemm) at the shapes of the train step."""
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from code2vec_b200.engine import EngineDims, PathAttentionEngine  # noqa: E402
+
+eng = PathAttentionEngine(EngineDims(101, 51, 101, 32, 96, 20, 8, 10), device=0, training=True)   # any engine: the GEMM self-test only needs a handle
+eng.init_params()
 def bench(M, N, K, a_mn, b_mn, bn, splits, pair, reps=10):
     eng.set_option("cta_pair", pair)
     A = torch.randn((K, M) if a_mn else (M, (K + 63)//64*64), device="cuda")
