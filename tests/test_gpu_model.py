@@ -123,3 +123,33 @@ def test_train_save_load_evaluate_predict(tmp_path, monkeypatch):
     assert m3.evaluate() is None
     assert os.path.getsize(save_path + ".release.c2v_b200") < os.path.getsize(save_path + ".c2v_b200")
     m3.close_session()
+
+
+def test_command_line_train_evaluate_predict(tmp_path, monkeypatch, capsys):
+    """`python -m code2vec_b200` = code2vec.py:16-38 with the reference's flags and defaults (d=128, 200 contexts)."""
+    import io
+    import sys
+    import tests.test_gpu_model as this
+    from code2vec_b200.__main__ import main
+    monkeypatch.setattr(this, "C", 200)               # the default MAX_CONTEXTS: lines carry 200 context fields
+    monkeypatch.chdir(tmp_path)
+    prefix, test_lines = _make_dataset(tmp_path)
+    save = str(tmp_path / "cli" / "saved")
+    assert main(["--data", prefix, "--test", prefix + ".test.c2v", "--save", save, "--framework", "b200",
+                 "--save_w2v", str(tmp_path / "tok.w2v"), "--save_t2v", str(tmp_path / "tgt.w2v")]) == 0
+    assert os.path.exists(save + ".c2v_b200") and os.path.exists(save + "_iter1.c2v_b200")
+    header = open(str(tmp_path / "tgt.w2v")).readline().split()
+    assert header[1] == "384"
+    # evaluate-only run from the saved model, then predictions from already-extracted lines
+    assert main(["--load", save, "--test", prefix + ".test.c2v", "--framework", "b200"]) == 0
+    lines_file = tmp_path / "extracted.txt"
+    lines_file.write_text("\n".join(line.rstrip() for line in test_lines[:2]) + "\n")
+    capsys.readouterr()
+    assert main(["--load", save, "--predict", "--export_code_vectors", "--predict_input", str(lines_file)]) == 0
+    out = capsys.readouterr().out
+    assert out.count("Original name:\t") == 2 and "predicted: [" in out and "Attention:" in out and "Code vector:" in out
+    first = test_lines[0].split(" ")[0]
+    assert ("Original name:\t" + first) in out
+    monkeypatch.setattr(sys, "stdin", io.StringIO(test_lines[2].rstrip() + "\n"))
+    assert main(["--load", save, "--predict", "--framework", "b200-keras"]) == 0       # same checkpoint, Keras scores
+    assert capsys.readouterr().out.count("Original name:\t") == 1

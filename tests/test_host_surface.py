@@ -290,3 +290,18 @@ def test_keras_subtoken_counts_and_backend_factory():
     cfg.DL_FRAMEWORK = "pytorch"
     with pytest.raises(ValueError):
         cfg.verify()
+
+
+def test_extractor_output_post_processing():
+    """code2vec_b200.__main__: what extractor.py:20-49 does to the JAR's output before model.predict()."""
+    from code2vec_b200.__main__ import java_string_hashcode, prepare_extracted_lines
+    # Java's "hello".hashCode() == 99162322; wrap-around to negative values for longer strings
+    assert java_string_hashcode("hello") == 99162322 and java_string_hashcode("") == 0
+    assert java_string_hashcode("(NameExpr0)^(MethodCallExpr)_(NameExpr2)") == -(2 ** 31) + (
+        sum(ord(c) * pow(31, i, 2 ** 32) for i, c in enumerate(reversed("(NameExpr0)^(MethodCallExpr)_(NameExpr2)"))) + 2 ** 31) % 2 ** 32
+    lines, unhash = prepare_extracted_lines(["get|x a,(A)^(B),b c,(C)_(D),d e,77,f", "", "solo"], 2)
+    h = str(java_string_hashcode("(A)^(B)"))
+    assert lines[0] == "get|x a,%s,b c,%s,d" % (h, java_string_hashcode("(C)_(D)"))     # first MAX_CONTEXTS contexts, no padding left
+    assert lines[1] == "solo" + "  " and unhash[h] == "(A)^(B)"
+    lines, unhash = prepare_extracted_lines(["m e,77,f"], 3)
+    assert lines == ["m e,77,f" + "  "] and unhash == {"77": "77"}                      # pre-hashed paths pass through
