@@ -321,6 +321,29 @@ class PathContextReader:
             strings = [data[o:o + l].decode("utf-8") if l else oov for o, l, k in zip(toff[:n], tlen[:n], sel) if k]
         return (src[:n][sel], path[:n][sel], dst[:n][sel], mask[:n][sel], target[:n][sel]), strings
 
+    def _native_parse_into(self, data: bytes, pool: "_RowPool"):
+        """Train path: rows are parsed straight into the tail of the shuffle pool (no scratch copy, no
+        selection copy); rows the filter drops are then overwritten by kept rows from the end."""
+        lib, tok, pth, tgt = self._native
+        Cn = self.config.MAX_CONTEXTS
+        cap = data.count(b"\n") + 1                  # complete lines in the chunk (+1: a last line without newline)
+        pool.reserve(cap, Cn)
+        small = getattr(self, "_parse_small", None)
+        if small is None or small[0].shape[0] < cap:
+            small = (np.zeros(cap, dtype=np.uint8), np.empty(cap, dtype=np.int64), np.empty(cap, dtype=np.int32))
+            self._parse_small = small
+        keep, toff, tlen = small
+        src, path, dst, mask, target = pool.tail_pointers()
+        err = C.c_int32(0)
+        threads = max(1, int(self.config.READER_NUM_PARALLEL_BATCHES or 1))
+        n = lib.c2v_parse_chunk(data, len(data), Cn, tok.h, pth.h, tgt.h, 0, threads, cap, src, path, dst, mask, target,
+                                keep.ctypes.data, toff.ctypes.data, tlen.ctypes.data, C.byref(err))
+        if n < 0:
+            if err.value == 2:
+                raise ValueError("a context has more than 3 comma-separated parts (line %d of the chunk)" % (-n - 1))
+            raise ValueError("Expect %d fields but have a different number in record (line %d of the chunk)" % (Cn + 1, -n - 1))
+        pool.commit(n, keep[:n])
+
     def _native_chunks(self):
         """Complete-line byte chunks of the data file, one pass per epoch like _raw_lines."""
         action = self.estimator_action
@@ -381,8 +404,7 @@ class PathContextReader:
         S = max(int(self.config.SHUFFLE_BUFFER_SIZE), 1)
         pool = _RowPool()
         for chunk in self._native_chunks():
-            arrs, _ = self._native_parse(chunk)
-            pool.append(arrs)
+            self._native_parse_into(chunk, pool)
             while pool.n >= S + B:
                 yield emit(pool.take(B, self._rng), None)
         while pool.n > 0:
@@ -436,6 +458,38 @@ class _RowPool:
         for dst, a in zip(self.arrays, arrs):
             dst[self.n:self.n + k] = a
         self.n += k
+
+    def reserve(self, k: int, contexts: int):
+        """Room for k more rows behind the current end (arrays are created on first use: three int32 index
+        matrices, the float32 mask, the int32 targets -- the reader's column order)."""
+        if self.arrays is None:
+            cap = max(2 * k, 1024)
+            self.arrays = [np.empty((cap, contexts), dtype=np.int32), np.empty((cap, contexts), dtype=np.int32),
+                           np.empty((cap, contexts), dtype=np.int32), np.empty((cap, contexts), dtype=np.float32),
+                           np.empty((cap,), dtype=np.int32)]
+        if self.n + k > self.arrays[0].shape[0]:
+            cap = max(2 * self.arrays[0].shape[0], self.n + k)
+            grown = [np.empty((cap,) + a.shape[1:], dtype=a.dtype) for a in self.arrays]
+            for g, a in zip(grown, self.arrays):
+                g[:self.n] = a[:self.n]
+            self.arrays = grown
+
+    def tail_pointers(self):
+        """Addresses of row `n` in every array: where a parser may write reserved rows."""
+        return tuple(a.ctypes.data + self.n * a.strides[0] for a in self.arrays)
+
+    def commit(self, k: int, keep):
+        """k rows were written behind the end; keep[i] == 0 marks rows to drop.  Dropped rows inside the new
+        extent are overwritten by kept rows from beyond it -- O(dropped) row moves."""
+        keep = np.asarray(keep[:k], dtype=bool)
+        kept = int(keep.sum())
+        if kept < k:
+            holes = self.n + np.flatnonzero(~keep[:kept])
+            movers = self.n + kept + np.flatnonzero(keep[kept:])
+            if holes.size:
+                for a in self.arrays:
+                    a[holes] = a[movers]
+        self.n += kept
 
     def take(self, b: int, rng) -> tuple:
         n = self.n
