@@ -326,7 +326,8 @@ class PathContextReader:
         selection copy); rows the filter drops are then overwritten by kept rows from the end."""
         lib, tok, pth, tgt = self._native
         Cn = self.config.MAX_CONTEXTS
-        cap = data.count(b"\n") + 1                  # complete lines in the chunk (+1: a last line without newline)
+        cap = len(data) // (Cn + 1) + 1              # a line is at least MAX_CONTEXTS spaces + a newline long; the
+        #                                              reserve is address space only -- pages are touched as rows land
         pool.reserve(cap, Cn)
         small = getattr(self, "_parse_small", None)
         if small is None or small[0].shape[0] < cap:
