@@ -31,7 +31,6 @@ from typing import Iterable, Iterator, List, NamedTuple, Optional
 import numpy as np
 
 import ctypes as C
-import os
 
 from .config import Config
 from .vocabularies import Code2VecVocabs

@@ -13,7 +13,7 @@ import os
 import pickle
 from argparse import Namespace
 from enum import Enum
-from typing import Dict, Iterable, NamedTuple, Optional, Sequence, Set
+from typing import Dict, Iterable, NamedTuple, Optional, Set
 
 import numpy as np
 

@@ -305,3 +305,44 @@ def test_extractor_output_post_processing():
     assert lines[1] == "solo" + "  " and unhash[h] == "(A)^(B)"
     lines, unhash = prepare_extracted_lines(["m e,77,f"], 3)
     assert lines == ["m e,77,f" + "  "] and unhash == {"77": "77"}                      # pre-hashed paths pass through
+
+
+def test_prefetch_and_lookahead_helpers():
+    """b200_model._prefetch (the role of tf.data's prefetch, path_context_reader.py:150) and _with_next."""
+    import threading
+    import time
+    from code2vec_b200.b200_model import _prefetch, _with_next
+    assert list(_with_next([])) == [] and list(_with_next([1])) == [(1, None)]
+    assert list(_with_next(iter("abc"))) == [("a", "b"), ("b", "c"), ("c", None)]
+    assert list(_prefetch(iter(range(50)), depth=3)) == list(range(50))
+
+    def failing():
+        yield 1
+        raise RuntimeError("reader broke")
+
+    got = []
+    with pytest.raises(RuntimeError, match="reader broke"):
+        for x in _prefetch(failing()):
+            got.append(x)
+    assert got == [1]
+    # an endless producer stops once the consumer goes away (the Keras-schedule train loop relies on this)
+    produced = []
+
+    def endless():
+        i = 0
+        while True:
+            produced.append(i)
+            yield i
+            i += 1
+
+    before = threading.active_count()
+    gen = _prefetch(endless(), depth=2)
+    assert [next(gen) for _ in range(3)] == [0, 1, 2]
+    gen.close()
+    deadline = time.time() + 5
+    while threading.active_count() > before and time.time() < deadline:
+        time.sleep(0.05)
+    assert threading.active_count() <= before
+    n = len(produced)
+    time.sleep(0.3)
+    assert len(produced) == n

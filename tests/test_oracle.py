@@ -2,7 +2,6 @@
 is pinned by (i) torch autograd on an independent statement of the forward graph, (ii) float64
 finite differences, (iii) semantic properties stated in the reference source."""
 import numpy as np
-import pytest
 
 from oracle import path_attention_oracle as O
 from oracle import torch_crosscheck as TC
