@@ -304,7 +304,7 @@ def run_ours(args):
 
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
-        cpu = cpu_baseline(w, host[0], steps=1)
+        cpu = cpu_baseline(w, host[0], steps=1, threads=args.cpu_threads or None)
 
     h2d = sum(int(a.nbytes) for a in host[0])
     if world == 1 and args.hint and fused:
@@ -339,13 +339,18 @@ def run_ours(args):
 
 
 # ================================ CPU arm ========================================================
+def default_cpu_threads():
+    """Intra-op threads of the CPU arm: every host core unless C2V_CPU_THREADS / --cpu-threads says otherwise."""
+    return int(os.environ.get("C2V_CPU_THREADS", "0")) or os.cpu_count() or 1
+
+
 def cpu_baseline(w, batch, steps=1, threads=None):
     """The oracle port of the reference graph (torch-CPU, all host threads): forward + backward +
     TF1 dense Adam on the same workload; `steps` full batches (bounded sample)."""
     import torch
     from oracle.path_attention_oracle import Dims, init_params
     from oracle.torch_crosscheck import TorchCpuTrainer
-    cores = threads or os.cpu_count() or 1
+    cores = threads or default_cpu_threads()
     dims = Dims(w["token_vocab"], w["path_vocab"], w["target_vocab"], w["embed_dim"], w["code_dim"], w["max_contexts"])
     params = init_params(dims, seed=4321)
     tr = TorchCpuTrainer(params, threads=cores)
@@ -379,7 +384,7 @@ def run_reference(args):
     import torch
     from oracle.path_attention_oracle import Dims, init_params
     from oracle.torch_crosscheck import TorchCpuTrainer
-    cores = os.cpu_count() or 1
+    cores = args.cpu_threads or default_cpu_threads()
     dims = Dims(w["token_vocab"], w["path_vocab"], w["target_vocab"], w["embed_dim"], w["code_dim"], w["max_contexts"])
     tr = TorchCpuTrainer(init_params(dims, seed=4321), threads=cores)
     src, pth, tgt, mask, target = batch
@@ -419,6 +424,7 @@ def main():
     ap.add_argument("--batch", type=int, default=0)
     ap.add_argument("--math", default=os.environ.get("C2V_MATH", "tf32"), choices=["fp32", "tf32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-threads", type=int, default=0, help="threads of the CPU arm (0 = all host cores)")
     ap.add_argument("--dy-late", type=int, default=-1, choices=[-1, 0, 1, 2],
                     help="engine option dy_late (-1 = the schedule's default)")
     ap.add_argument("--adam-rows-occ", type=int, default=0, choices=[0, 4, 5], help="engine option adam_rows_occupancy (0 = default)")
