@@ -340,8 +340,29 @@ def run_ours(args):
 
 # ================================ CPU arm ========================================================
 def default_cpu_threads():
-    """Intra-op threads of the CPU arm: every host core unless C2V_CPU_THREADS / --cpu-threads says otherwise."""
+    """Upper bound of the CPU arm's intra-op threads: every host core unless C2V_CPU_THREADS says otherwise."""
     return int(os.environ.get("C2V_CPU_THREADS", "0")) or os.cpu_count() or 1
+
+
+def pick_cpu_threads(tr, batch, limit):
+    """More threads are not always faster (two sockets x SMT: 128 threads ran the step at 9.0 s, 32 at 3.2 s on the
+    GPU boxes' Xeons), so the CPU arm gets the best of {all, 1/2, 1/4, 1/8} of the host threads, probed with one
+    step on a 64-example slice each (the dense Adam over all 383 M parameters is part of every probe)."""
+    import torch
+    src, pth, tgt, mask, target = (a[:64] for a in batch)
+    cands = sorted({max(1, limit // d) for d in (1, 2, 4, 8)}, reverse=True)
+    if limit <= 16 or len(cands) == 1:          # small hosts: every core helps, nothing to probe
+        torch.set_num_threads(limit)
+        return limit, {}
+    timing = {}
+    for c in cands:
+        torch.set_num_threads(c)
+        t0 = time.time()
+        tr.train_step(src, pth, tgt, mask, target, keep=1.0)
+        timing[c] = round(time.time() - t0, 3)
+    best = min(timing, key=timing.get)
+    torch.set_num_threads(best)
+    return best, timing
 
 
 def cpu_baseline(w, batch, steps=1, threads=None):
@@ -354,6 +375,9 @@ def cpu_baseline(w, batch, steps=1, threads=None):
     dims = Dims(w["token_vocab"], w["path_vocab"], w["target_vocab"], w["embed_dim"], w["code_dim"], w["max_contexts"])
     params = init_params(dims, seed=4321)
     tr = TorchCpuTrainer(params, threads=cores)
+    probed = {}
+    if not threads:
+        _, probed = pick_cpu_threads(tr, batch, cores)
     src, pth, tgt, mask, target = batch
     rng = np.random.default_rng(0)
     times = []
@@ -366,7 +390,8 @@ def cpu_baseline(w, batch, steps=1, threads=None):
     B, C = src.shape
     return {"value": round(B * C / sec, 1), "unit": "path-contexts/s", "cores": int(torch.get_num_threads()), "kind": "port",
             "sample": "%d full train step(s) of the same workload (B=%d x C=%d), torch-CPU restatement of "
-                      "tensorflow_model.py:197-265 incl. dense Adam; %.2f s/step" % (steps, B, C, sec)}
+                      "tensorflow_model.py:197-265 incl. dense Adam; %.2f s/step%s" % (
+                          steps, B, C, sec, "; threads = fastest of a 64-example probe %s (s)" % probed if probed else "")}
 
 
 def run_reference(args):
@@ -387,6 +412,9 @@ def run_reference(args):
     cores = args.cpu_threads or default_cpu_threads()
     dims = Dims(w["token_vocab"], w["path_vocab"], w["target_vocab"], w["embed_dim"], w["code_dim"], w["max_contexts"])
     tr = TorchCpuTrainer(init_params(dims, seed=4321), threads=cores)
+    probed = {}
+    if not args.cpu_threads:
+        _, probed = pick_cpu_threads(tr, batch, cores)
     src, pth, tgt, mask, target = batch
     rng = np.random.default_rng(0)
     def one():
@@ -401,7 +429,8 @@ def run_reference(args):
     B, C = src.shape
     value = B * C / sec
     sample = ("%d timed full-batch step(s) (of --steps %d; bounded) after %d warm-up, torch-CPU restatement of the "
-              "reference graph (TensorFlow not installable here), %d threads" % (k_eff, K, min(W, 1), torch.get_num_threads()))
+              "reference graph (TensorFlow not installable here), %d threads%s" % (
+                  k_eff, K, min(W, 1), torch.get_num_threads(), " (fastest of a 64-example probe %s s)" % probed if probed else ""))
     out = {"impl": "reference", "metric": "path-contexts/sec (train step, batch 1024x200)", "value": round(value, 1),
            "unit": "path-contexts/s", "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": round(sec * 1e3, 2),
            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
