@@ -807,25 +807,13 @@ adam_rows_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict
           }
         }
         // the zero-gradient steps after it: m*b1 + (1-b1)*0, v*b2 + (1-b2)*(0*0)
-        int32_t s = from + 2;
-        for (; s <= t_done; ++s) {
-          // a row left alone for long enough has m decayed to exactly +-0 (~1100 steps at beta1 = 0.9): from
-          // there on theta - lr*0/(sqrt(v)+eps) == theta, so only v still changes -- leave the expensive loop
-          if (__all_sync(0xffffffffu, (mm[0] == 0.f) & (mm[1] == 0.f) & (mm[2] == 0.f) & (mm[3] == 0.f))) break;
+        for (int32_t s = from + 2; s <= t_done; ++s) {
           const float lr_s = lr_tab[s];
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
             mm[q] = __fadd_rn(__fmul_rn(mm[q], b1), __fmul_rn(omb1, 0.f));
             vv[q] = __fadd_rn(__fmul_rn(vv[q], b2), __fmul_rn(omb2, 0.f));
             pp[q] = __fsub_rn(pp[q], __fdiv_rn(__fmul_rn(lr_s, mm[q]), __fadd_rn(__fsqrt_rn(vv[q]), eps)));
-          }
-        }
-        for (; s <= t_done; ++s) {            // m == 0 everywhere: v keeps decaying (until it is 0 too), theta rests
-          if (__all_sync(0xffffffffu, (vv[0] == 0.f) & (vv[1] == 0.f) & (vv[2] == 0.f) & (vv[3] == 0.f))) break;
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            mm[q] = __fadd_rn(__fmul_rn(mm[q], b1), __fmul_rn(omb1, 0.f));      // keeps the sign of a -0 as the dense kernel does
-            vv[q] = __fadd_rn(__fmul_rn(vv[q], b2), __fmul_rn(omb2, 0.f));
           }
         }
         *reinterpret_cast<float4*>(p + o) = P;

@@ -124,42 +124,3 @@ def test_next_batch_hint_runs_the_deferred_updates_early_and_changes_nothing(ent
         assert once.sum() > 50 and np.array_equal(a[name][once], b[name][once]), name
     assert torch.allclose(fast.adam_m["tok"], dense.adam_m["tok"], atol=1e-7)
     assert torch.allclose(fast.adam_v["path"], dense.adam_v["path"], atol=1e-9)
-
-
-def test_long_idle_rows_take_the_underflow_fast_paths_and_stay_bit_exact():
-    """A row left alone for ~1000 steps: its m decays to exactly 0 (after which theta rests and only v decays) and
-    then v does too.  adam_rows_kernel leaves the division / square-root loop at those points; the dense kernel
-    grinds through every step.  Same bits."""
-    import torch
-    hp = dict(lr=1e-2, beta1=0.5, beta2=0.9, eps=1e-8)          # small betas: m is 0 after ~150 idle steps, v after ~900
-    a = O.synthetic_batch(DIMS, B, seed=500)
-    b = O.synthetic_batch(DIMS, B, seed=501)
-    lazy, params0 = make_engine(DIMS, max_batch=B)
-    dense, _ = make_engine(DIMS, max_batch=B, params=params0)
-    lazy.set_option("lazy_adam", 1)
-    n_idle = 1000
-    plan = [a] + [b] * n_idle + [a]
-    dev = {id(x): (dev_batch(lazy, *x), dev_batch(dense, *x)) for x in (a, b)}
-    for batch in plan:
-        dl, dd = dev[id(batch)]
-        lazy.train_step(*dl, keep=1.0)
-        lazy.adam_step(**hp)
-        dense.train_step(*dd, keep=1.0)
-        dense.adam_step(**hp)
-    got, want = lazy.export_params(), dense.export_params()
-    for name, cols in (("tok", (0, 2)), ("path", (1,))):
-        in_a = np.zeros(got[name].shape[0], dtype=np.int64)
-        in_b = np.zeros_like(in_a)
-        for c in cols:
-            np.add.at(in_a, a[c][a[3] > 0], 1)
-            np.add.at(in_b, b[c][b[3] > 0], 1)
-        idle = (in_a == 1) & (in_b == 0)                        # one context in batch a, none in b: no atomic-order freedom
-        assert idle.sum() > 20, name
-        assert np.array_equal(got[name][idle], want[name][idle]), name
-        # the slots went all the way down: m is exactly 0 again, theta moved
-        m_l, m_d = getattr(lazy, "adam_m")[name].cpu().numpy(), getattr(dense, "adam_m")[name].cpu().numpy()
-        v_l, v_d = getattr(lazy, "adam_v")[name].cpu().numpy(), getattr(dense, "adam_v")[name].cpu().numpy()
-        assert np.array_equal(m_l[idle], m_d[idle]) and np.array_equal(v_l[idle], v_d[idle]), name
-        assert np.abs(got[name][idle] - params0[name][idle]).max() > 1e-3
-    for k in O.PARAM_NAMES:
-        assert np.abs(got[k] - want[k]).max() < 5e-6, k
