@@ -56,6 +56,21 @@ _ARG_FIELDS = {   # attribute -> (argparse dest, default when absent)
 }
 
 
+def _is_set(option: str) -> property:
+    """True when a path-like option was given (config.py:147-161)."""
+    return property(lambda self: bool(getattr(self, option)))
+
+
+def _batches_of(examples: str, batch: str) -> property:
+    """ceil(examples / batch), 0 while the batch size is unset (config.py:163-169)."""
+    return property(lambda self: math.ceil(getattr(self, examples) / getattr(self, batch)) if getattr(self, batch) else 0)
+
+
+def _only_if(flag: str, value) -> property:
+    """A derived path that exists only in the mode `flag` names, else None (config.py:177-230)."""
+    return property(lambda self: value(self) if getattr(self, flag) else None)
+
+
 class Config:
     @classmethod
     def arguments_parser(cls) -> ArgumentParser:
@@ -126,35 +141,26 @@ class Config:
             setattr(self, name, getattr(args, dest))
         self.DL_FRAMEWORK = args.dl_framework or "b200"
 
-    # ---- derived values (config.py:143-230) -------------------------------------------------
-    @property
-    def context_vector_size(self) -> int:
-        # a context = source-token embedding ++ path embedding ++ target-token embedding
-        return 2 * self.TOKEN_EMBEDDINGS_SIZE + self.PATH_EMBEDDINGS_SIZE
+    # ---- derived values (config.py:143-230): declared through the three helpers below the class ----
+    context_vector_size = property(
+        lambda self: 2 * self.TOKEN_EMBEDDINGS_SIZE + self.PATH_EMBEDDINGS_SIZE,
+        doc="width of one context: source-token, path and target-token embeddings side by side")
 
-    @property
-    def is_training(self) -> bool:
-        return bool(self.TRAIN_DATA_PATH_PREFIX)
+    is_training = _is_set("TRAIN_DATA_PATH_PREFIX")
+    is_loading = _is_set("MODEL_LOAD_PATH")
+    is_saving = _is_set("MODEL_SAVE_PATH")
+    is_testing = _is_set("TEST_DATA_PATH")
 
-    @property
-    def is_loading(self) -> bool:
-        return bool(self.MODEL_LOAD_PATH)
+    train_steps_per_epoch = _batches_of("NUM_TRAIN_EXAMPLES", "TRAIN_BATCH_SIZE")
+    test_steps = _batches_of("NUM_TEST_EXAMPLES", "TEST_BATCH_SIZE")
 
-    @property
-    def is_saving(self) -> bool:
-        return bool(self.MODEL_SAVE_PATH)
-
-    @property
-    def is_testing(self) -> bool:
-        return bool(self.TEST_DATA_PATH)
-
-    @property
-    def train_steps_per_epoch(self) -> int:
-        return math.ceil(self.NUM_TRAIN_EXAMPLES / self.TRAIN_BATCH_SIZE) if self.TRAIN_BATCH_SIZE else 0
-
-    @property
-    def test_steps(self) -> int:
-        return math.ceil(self.NUM_TEST_EXAMPLES / self.TEST_BATCH_SIZE) if self.TEST_BATCH_SIZE else 0
+    train_data_path = _only_if("is_training", lambda self: self.TRAIN_DATA_PATH_PREFIX + ".train.c2v")
+    word_freq_dict_path = _only_if("is_training", lambda self: self.TRAIN_DATA_PATH_PREFIX + ".dict.c2v")
+    entire_model_load_path = _only_if("is_loading", lambda self: self.get_entire_model_path(self.MODEL_LOAD_PATH))
+    model_weights_load_path = _only_if("is_loading", lambda self: self.get_model_weights_path(self.MODEL_LOAD_PATH))
+    entire_model_save_path = _only_if("is_saving", lambda self: self.get_entire_model_path(self.MODEL_SAVE_PATH))
+    model_weights_save_path = _only_if("is_saving", lambda self: self.get_model_weights_path(self.MODEL_SAVE_PATH))
+    model_load_dir = property(lambda self: self.MODEL_LOAD_PATH.rpartition("/")[0])
 
     def data_path(self, is_evaluating: bool = False):
         return self.TEST_DATA_PATH if is_evaluating else self.train_data_path
@@ -162,46 +168,19 @@ class Config:
     def batch_size(self, is_evaluating: bool = False):
         return self.TEST_BATCH_SIZE if is_evaluating else self.TRAIN_BATCH_SIZE
 
-    @property
-    def train_data_path(self) -> Optional[str]:
-        return "%s.train.c2v" % self.TRAIN_DATA_PATH_PREFIX if self.is_training else None
+    @staticmethod
+    def get_vocabularies_path_from_model_path(model_file_path: str) -> str:
+        """`dictionaries.bin` lives beside the model files."""
+        folder, slash, _ = model_file_path.rpartition("/")
+        return folder + slash + "dictionaries.bin"
 
-    @property
-    def word_freq_dict_path(self) -> Optional[str]:
-        return "%s.dict.c2v" % self.TRAIN_DATA_PATH_PREFIX if self.is_training else None
-
-    @classmethod
-    def get_vocabularies_path_from_model_path(cls, model_file_path: str) -> str:
-        # `dictionaries.bin` sits beside the model files
-        return "/".join(model_file_path.split("/")[:-1] + ["dictionaries.bin"])
-
-    @classmethod
-    def get_entire_model_path(cls, model_path: str) -> str:
+    @staticmethod
+    def get_entire_model_path(model_path: str) -> str:
         return model_path + "__entire-model"
 
-    @classmethod
-    def get_model_weights_path(cls, model_path: str) -> str:
+    @staticmethod
+    def get_model_weights_path(model_path: str) -> str:
         return model_path + "__only-weights"
-
-    @property
-    def model_load_dir(self):
-        return "/".join(self.MODEL_LOAD_PATH.split("/")[:-1])
-
-    @property
-    def entire_model_load_path(self) -> Optional[str]:
-        return self.get_entire_model_path(self.MODEL_LOAD_PATH) if self.is_loading else None
-
-    @property
-    def model_weights_load_path(self) -> Optional[str]:
-        return self.get_model_weights_path(self.MODEL_LOAD_PATH) if self.is_loading else None
-
-    @property
-    def entire_model_save_path(self) -> Optional[str]:
-        return self.get_entire_model_path(self.MODEL_SAVE_PATH) if self.is_saving else None
-
-    @property
-    def model_weights_save_path(self) -> Optional[str]:
-        return self.get_model_weights_path(self.MODEL_SAVE_PATH) if self.is_saving else None
 
     def verify(self):
         """Same failure conditions and messages as the reference (config.py:232-239)."""

@@ -120,12 +120,34 @@ WordFreqDictType = Dict[str, int]
 
 
 class Code2VecWordFreqDicts(NamedTuple):
+    """The three histograms of `<data>.dict.c2v`, in the order the file stores them (preprocess.py:12-20)."""
     token_to_count: WordFreqDictType
     path_to_count: WordFreqDictType
     target_to_count: WordFreqDictType
 
 
+class _Slot(NamedTuple):
+    """How one of the three vocabularies is wired: attribute on Code2VecVocabs, histogram field, size limit, log name."""
+    kind: VocabType
+    attr: str
+    histogram: str
+    limit: str
+    label: str
+
+
+_SLOTS = {
+    VocabType.Token: _Slot(VocabType.Token, "token_vocab", "token_to_count", "MAX_TOKEN_VOCAB_SIZE", "token"),
+    VocabType.Path: _Slot(VocabType.Path, "path_vocab", "path_to_count", "MAX_PATH_VOCAB_SIZE", "path"),
+    VocabType.Target: _Slot(VocabType.Target, "target_vocab", "target_to_count", "MAX_TARGET_VOCAB_SIZE", "target"),
+}
+_BUILD_ORDER = (VocabType.Token, VocabType.Path, VocabType.Target)      # creation and its log lines (vocabularies.py:188-202)
+_DISK_ORDER = (VocabType.Token, VocabType.Target, VocabType.Path)       # dictionaries.bin (vocabularies.py:211-218)
+
+
 class Code2VecVocabs:
+    """The token / path / target vocabularies of a model: built from the training histograms, or read
+    back from the `dictionaries.bin` stored next to a saved model (reference vocabularies.py:142-243)."""
+
     def __init__(self, config: Config):
         self.config = config
         self.token_vocab: Optional[Vocab] = None
@@ -134,69 +156,64 @@ class Code2VecVocabs:
         self._already_saved_in_paths: Set[str] = set()
         self._load_or_create()
 
+    # ---- which special words a vocabulary starts with (vocabularies.py:204-209) -----------------
+    def _get_special_words_by_vocab_type(self, vocab_type: VocabType) -> SpecialVocabWordsType:
+        if self.config.SEPARATE_OOV_AND_PAD:
+            return _SpecialVocabWords_OnlyOov if vocab_type is VocabType.Target else _SpecialVocabWords_SeparateOovPad
+        return _SpecialVocabWords_JoinedOovPad
+
+    # ---- construction --------------------------------------------------------------------------------
     def _load_or_create(self):
-        assert self.config.is_training or self.config.is_loading
-        if self.config.is_loading:
-            path = self.config.get_vocabularies_path_from_model_path(self.config.MODEL_LOAD_PATH)
-            if not os.path.isfile(path):
-                raise ValueError("Model dictionaries file is not found in model load dir. "
-                                 "Expecting file `{vocabularies_load_path}`.".format(vocabularies_load_path=path))
-            self._load_from_path(path)
-        else:
+        cfg = self.config
+        assert cfg.is_training or cfg.is_loading
+        if not cfg.is_loading:
             self._create_from_word_freq_dict()
+            return
+        stored = cfg.get_vocabularies_path_from_model_path(cfg.MODEL_LOAD_PATH)
+        if not os.path.isfile(stored):
+            raise ValueError("Model dictionaries file is not found in model load dir. "
+                             "Expecting file `{vocabularies_load_path}`.".format(vocabularies_load_path=stored))
+        self._load_from_path(stored)
 
     def _load_from_path(self, vocabularies_load_path: str):
         assert os.path.exists(vocabularies_load_path)
         self.config.log("Loading model vocabularies from: `%s` ... " % vocabularies_load_path)
-        with open(vocabularies_load_path, "rb") as f:     # order on disk: token, target, path
-            self.token_vocab = Vocab.load_from_file(VocabType.Token, f, self._get_special_words_by_vocab_type(VocabType.Token))
-            self.target_vocab = Vocab.load_from_file(VocabType.Target, f, self._get_special_words_by_vocab_type(VocabType.Target))
-            self.path_vocab = Vocab.load_from_file(VocabType.Path, f, self._get_special_words_by_vocab_type(VocabType.Path))
+        with open(vocabularies_load_path, "rb") as fh:
+            for kind in _DISK_ORDER:
+                setattr(self, _SLOTS[kind].attr, Vocab.load_from_file(kind, fh, self._get_special_words_by_vocab_type(kind)))
         self.config.log("Done loading model vocabularies.")
-        self._already_saved_in_paths.add(vocabularies_load_path)
-
-    def _create_from_word_freq_dict(self):
-        freq = self._load_word_freq_dict()
-        self.config.log("Word frequencies dictionaries loaded. Now creating vocabularies.")
-        self.token_vocab = Vocab.create_from_freq_dict(
-            VocabType.Token, freq.token_to_count, self.config.MAX_TOKEN_VOCAB_SIZE,
-            special_words=self._get_special_words_by_vocab_type(VocabType.Token))
-        self.config.log("Created token vocab. size: %d" % self.token_vocab.size)
-        self.path_vocab = Vocab.create_from_freq_dict(
-            VocabType.Path, freq.path_to_count, self.config.MAX_PATH_VOCAB_SIZE,
-            special_words=self._get_special_words_by_vocab_type(VocabType.Path))
-        self.config.log("Created path vocab. size: %d" % self.path_vocab.size)
-        self.target_vocab = Vocab.create_from_freq_dict(
-            VocabType.Target, freq.target_to_count, self.config.MAX_TARGET_VOCAB_SIZE,
-            special_words=self._get_special_words_by_vocab_type(VocabType.Target))
-        self.config.log("Created target vocab. size: %d" % self.target_vocab.size)
-
-    def _get_special_words_by_vocab_type(self, vocab_type: VocabType) -> SpecialVocabWordsType:
-        if not self.config.SEPARATE_OOV_AND_PAD:
-            return _SpecialVocabWords_JoinedOovPad
-        return _SpecialVocabWords_OnlyOov if vocab_type == VocabType.Target else _SpecialVocabWords_SeparateOovPad
-
-    def save(self, vocabularies_save_path: str):
-        if vocabularies_save_path in self._already_saved_in_paths:
-            return
-        with open(vocabularies_save_path, "wb") as f:
-            self.token_vocab.save_to_file(f)
-            self.target_vocab.save_to_file(f)
-            self.path_vocab.save_to_file(f)
-        self._already_saved_in_paths.add(vocabularies_save_path)
+        self._already_saved_in_paths.add(vocabularies_load_path)        # no need to write the same file back
 
     def _load_word_freq_dict(self) -> Code2VecWordFreqDicts:
-        assert self.config.is_training
-        self.config.log("Loading word frequencies dictionaries from: %s ... " % self.config.word_freq_dict_path)
-        with open(self.config.word_freq_dict_path, "rb") as f:     # token, path, target (+ count, unused)
-            token_to_count = pickle.load(f)
-            path_to_count = pickle.load(f)
-            target_to_count = pickle.load(f)
-        self.config.log("Done loading word frequencies dictionaries.")
-        return Code2VecWordFreqDicts(token_to_count, path_to_count, target_to_count)
+        cfg = self.config
+        assert cfg.is_training
+        cfg.log("Loading word frequencies dictionaries from: %s ... " % cfg.word_freq_dict_path)
+        with open(cfg.word_freq_dict_path, "rb") as fh:                  # a fourth pickle (the example count) follows
+            histograms = Code2VecWordFreqDicts(*(pickle.load(fh) for _ in Code2VecWordFreqDicts._fields))
+        cfg.log("Done loading word frequencies dictionaries.")
+        return histograms
 
+    def _create_from_word_freq_dict(self):
+        histograms = self._load_word_freq_dict()
+        self.config.log("Word frequencies dictionaries loaded. Now creating vocabularies.")
+        for kind in _BUILD_ORDER:
+            slot = _SLOTS[kind]
+            vocab = Vocab.create_from_freq_dict(kind, getattr(histograms, slot.histogram), getattr(self.config, slot.limit),
+                                                special_words=self._get_special_words_by_vocab_type(kind))
+            setattr(self, slot.attr, vocab)
+            self.config.log("Created %s vocab. size: %d" % (slot.label, vocab.size))
+
+    # ---- use -----------------------------------------------------------------------------------------
     def get(self, vocab_type: VocabType) -> Vocab:
         if not isinstance(vocab_type, VocabType):
             raise ValueError("`vocab_type` should be `VocabType.Token`, `VocabType.Target` or `VocabType.Path`.")
-        return {VocabType.Token: self.token_vocab, VocabType.Target: self.target_vocab,
-                VocabType.Path: self.path_vocab}[vocab_type]
+        return getattr(self, _SLOTS[vocab_type].attr)
+
+    def save(self, vocabularies_save_path: str):
+        """Writes `dictionaries.bin` once per destination (vocabularies.py:211-218)."""
+        if vocabularies_save_path in self._already_saved_in_paths:
+            return
+        with open(vocabularies_save_path, "wb") as fh:
+            for kind in _DISK_ORDER:
+                self.get(kind).save_to_file(fh)
+        self._already_saved_in_paths.add(vocabularies_save_path)
