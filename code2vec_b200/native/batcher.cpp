@@ -55,8 +55,46 @@ struct ParseJob {
   std::atomic<int> bad_kind{0};
 };
 
+// One pending vocabulary lookup of a line: the bytes of a context part, its hash, and -- once probed --
+// the slot that may hold it.
+struct Part {
+  const char* p;
+  uint32_t len;
+  int32_t result;              // filled in by resolve()
+  uint64_t h;
+  const Vocab::Slot* cand;     // first slot with the same hash and length (nullptr: an empty slot came first)
+};
+
+// Lookups are latency-bound (two dependent cache misses each: the slot, then the word's bytes; the tables
+// of a java14m-sized vocabulary are ~100 MB), so a line's ~600 lookups are issued as a software pipeline:
+// hash every part and prefetch its slot, then probe all slots and prefetch the candidates' bytes, then compare.
+inline void hash_and_prefetch(const Vocab& v, Part& q) {
+  q.h = hash_bytes(q.p, q.len);
+  __builtin_prefetch(&v.slots[q.h & v.mask]);
+}
+
+inline void probe(const Vocab& v, Part& q) {
+  q.cand = nullptr;
+  for (uint64_t i = q.h & v.mask;; i = (i + 1) & v.mask) {
+    const Vocab::Slot& s = v.slots[i];
+    if (s.h == 0) return;
+    if (s.h == q.h && (uint32_t)s.len == q.len) {
+      q.cand = &s;
+      __builtin_prefetch(v.bytes.data() + s.off);
+      return;
+    }
+  }
+}
+
+inline void resolve(const Vocab& v, Part& q) {
+  if (!q.cand) { q.result = v.oov; return; }
+  if (memcmp(v.bytes.data() + q.cand->off, q.p, q.len) == 0) { q.result = q.cand->idx; return; }
+  q.result = v.lookup(q.p, q.len);        // same hash and length, different word: take the plain path
+}
+
 // one line -> one row.  Returns 0 ok, 1 wrong field count, 2 context with more than 3 parts.
-int parse_line(const ParseJob& J, int64_t li) {
+// `parts` is per-thread scratch with room for 3 * C entries.
+int parse_line(const ParseJob& J, int64_t li, Part* parts) {
   const char* p = J.text + J.line_off[li];
   const char* end = J.text + J.line_off[li + 1];
   while (end > p && (end[-1] == '\n' || end[-1] == '\r')) --end;
@@ -74,8 +112,9 @@ int parse_line(const ParseJob& J, int64_t li) {
   J.tgt_len[li] = (int32_t)(fe - f);
   const int32_t ty = (fe == f) ? J.tgt->oov : J.tgt->lookup(f, fe - f);
   J.target[li] = ty;
+  // pass 1: split the contexts; a part that is absent keeps len == UINT32_MAX and resolves to PAD
+  constexpr uint32_t kAbsent = UINT32_MAX;
   int nfields = 1;
-  int32_t max_s = INT32_MIN, max_t = INT32_MIN, max_p = INT32_MIN;
   int c = 0;
   while (sp) {
     f = sp + 1;
@@ -83,31 +122,50 @@ int parse_line(const ParseJob& J, int64_t li) {
     fe = sp ? sp : end;
     ++nfields;
     if (c >= C) continue;       // keep counting fields for the error check
-    int32_t s = tpad, q = ppad, t = tpad;
+    Part* q = parts + 3 * c;
+    q[0].len = q[1].len = q[2].len = kAbsent;
     if (fe != f) {
       const char* c1 = (const char*)memchr(f, ',', fe - f);
       if (!c1) {
-        s = J.tok->lookup(f, fe - f);                    // missing parts stay PAD
+        q[0].p = f; q[0].len = (uint32_t)(fe - f);                      // missing parts stay PAD
       } else {
-        s = J.tok->lookup(f, c1 - f);
+        q[0].p = f; q[0].len = (uint32_t)(c1 - f);
         const char* c2 = (const char*)memchr(c1 + 1, ',', fe - (c1 + 1));
         if (!c2) {
-          q = J.pth->lookup(c1 + 1, fe - (c1 + 1));
+          q[1].p = c1 + 1; q[1].len = (uint32_t)(fe - (c1 + 1));
         } else {
-          q = J.pth->lookup(c1 + 1, c2 - (c1 + 1));
+          q[1].p = c1 + 1; q[1].len = (uint32_t)(c2 - (c1 + 1));
           if (memchr(c2 + 1, ',', fe - (c2 + 1))) return 2;
-          t = J.tok->lookup(c2 + 1, fe - (c2 + 1));
+          q[2].p = c2 + 1; q[2].len = (uint32_t)(fe - (c2 + 1));
         }
       }
+      if (q[0].len != kAbsent) hash_and_prefetch(*J.tok, q[0]);
+      if (q[1].len != kAbsent) hash_and_prefetch(*J.pth, q[1]);
+      if (q[2].len != kAbsent) hash_and_prefetch(*J.tok, q[2]);
     }
-    src[c] = s; pth[c] = q; dst[c] = t;
-    msk[c] = (s != tpad || t != tpad || q != ppad) ? 1.0f : 0.0f;
-    if (s > max_s) max_s = s;
-    if (t > max_t) max_t = t;
-    if (q > max_p) max_p = q;
     ++c;
   }
   if (nfields != C + 1) return 1;
+  // pass 2: probe the (prefetched) slots, prefetch the candidates' bytes; pass 3: compare
+  for (int i = 0; i < c; ++i) {
+    Part* q = parts + 3 * i;
+    if (q[0].len != kAbsent) probe(*J.tok, q[0]);
+    if (q[1].len != kAbsent) probe(*J.pth, q[1]);
+    if (q[2].len != kAbsent) probe(*J.tok, q[2]);
+  }
+  int32_t max_s = INT32_MIN, max_t = INT32_MIN, max_p = INT32_MIN;
+  for (int i = 0; i < c; ++i) {
+    Part* q = parts + 3 * i;
+    int32_t s = tpad, k = ppad, t = tpad;
+    if (q[0].len != kAbsent) { resolve(*J.tok, q[0]); s = q[0].result; }
+    if (q[1].len != kAbsent) { resolve(*J.pth, q[1]); k = q[1].result; }
+    if (q[2].len != kAbsent) { resolve(*J.tok, q[2]); t = q[2].result; }
+    src[i] = s; pth[i] = k; dst[i] = t;
+    msk[i] = (s != tpad || t != tpad || k != ppad) ? 1.0f : 0.0f;
+    if (s > max_s) max_s = s;
+    if (t > max_t) max_t = t;
+    if (k > max_p) max_p = k;
+  }
   // row filter (path_context_reader.py:153-177): reduce_max(indices) != PAD index, target > OOV (train)
   const bool any_valid = (max_s != tpad) || (max_t != tpad) || (max_p != ppad);
   uint8_t keep = 1;
@@ -177,8 +235,9 @@ int64_t c2v_parse_chunk(const char* text, int64_t len, int32_t max_contexts, con
   if ((int64_t)n_threads > n) n_threads = n > 0 ? (int)n : 1;
   auto work = [&](int t) {
     const int64_t lo = n * t / n_threads, hi = n * (t + 1) / n_threads;
+    std::vector<Part> parts((size_t)3 * (max_contexts > 0 ? max_contexts : 1));
     for (int64_t i = lo; i < hi; ++i) {
-      const int rc = parse_line(J, i);
+      const int rc = parse_line(J, i, parts.data());
       if (rc) {
         int64_t expect = -1;
         if (J.bad_line.compare_exchange_strong(expect, i)) J.bad_kind.store(rc);
