@@ -116,3 +116,21 @@ def test_native_errors_match_python(tmp_path):
             r = PathContextReader(vs, cfg, _Former(), EstimatorAction.Evaluate, use_native=native)
             with pytest.raises(ValueError):
                 list(r.get_dataset())
+
+
+@pytest.mark.parametrize("threads", [1, 5])
+def test_native_matches_python_on_a_larger_fuzz(tmp_path, threads):
+    """2000 generated lines (every field shape of _random_lines), 20 contexts, with the line range split over
+    1 and 5 parser threads: the pipelined lookups must give the Python reader's rows."""
+    C = 20
+    lines = _random_lines(2000, C, seed=11)
+    cfg, vs = _setup(tmp_path, lines, C=C, batch=64)
+    cfg.READER_NUM_PARALLEL_BATCHES = threads
+    py = PathContextReader(vs, cfg, _Former(), EstimatorAction.Evaluate, use_native=False)
+    nat = PathContextReader(vs, cfg, _Former(), EstimatorAction.Evaluate, use_native=True)
+    a, b = list(py.get_dataset()), list(nat.get_dataset())
+    assert len(a) == len(b) > 20
+    for x, y in zip(a, b):
+        for name in ("path_source_token_indices", "path_indices", "path_target_token_indices", "context_valid_mask", "target_index"):
+            assert np.array_equal(getattr(x, name), getattr(y, name)), name
+        assert list(x.target_string) == list(y.target_string)
