@@ -207,6 +207,10 @@ class Code2VecModel(Code2VecModelBase):
                 arr = np.frombuffer(f.read(ent["nbytes"]), dtype="<f4").reshape(ent["shape"])
                 dest[group][name].copy_(torch.from_numpy(arr.copy()))
             e.adam_t = int(meta.get("adam_t", 0))
+            if e.training:
+                # resuming: the engine's own step counter (lazy Adam needs consecutive steps and marks every row
+                # as current as of this step) has to agree with the restored optimizer state
+                e.set_option("adam_step_count", e.adam_t)
             if hasattr(self, "nr_epochs_trained"):           # the Keras-schedule backend resumes at this epoch
                 self.nr_epochs_trained = int(meta.get("epochs_trained", 0))
 
