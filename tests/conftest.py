@@ -21,8 +21,17 @@ def _cuda_ok():
         return False
 
 
+GPU_TEST_TIMEOUT_S = 300      # the whole GPU suite takes ~20 s; a hung kernel must not take the box with it
+
+
 def pytest_collection_modifyitems(config, items):
     if _cuda_ok():
+        # pytest-timeout, thread method: a test stuck inside a CUDA call (signals are not delivered there) is
+        # reported with a stack dump and the process exits, instead of hanging until the box's own limit
+        if config.pluginmanager.hasplugin("timeout"):
+            for item in items:
+                if "gpu" in item.keywords and item.get_closest_marker("timeout") is None:
+                    item.add_marker(pytest.mark.timeout(GPU_TEST_TIMEOUT_S, method="thread"))
         return
     skip = pytest.mark.skip(reason="no CUDA device in this container")
     for item in items:
