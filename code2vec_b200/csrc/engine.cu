@@ -128,6 +128,7 @@ struct c2v_engine {
   // lazy-but-exact dense Adam for the embedding tables (option "lazy_adam")
   int lazy = 0;
   int adam_rows_occ = 4;
+  int adam_rows_shortcut = 0;           // EXPERIMENTAL: adam_rows_shortcut_kernel (long-idle rows leave the div/sqrt loop early)
   bool lazy_grads_pending = false;  // a train step's embedding gradients are in the tables and c2v_adam_step has not followed
   int64_t adam_t_done = 0;   // Adam steps applied so far
   int32_t mark_epoch = 0;
@@ -209,7 +210,11 @@ struct PhaseTimer {
 // adam_rows_kernel as one wave of num_sms * occupancy blocks (option "adam_rows_occupancy": 4 or 5)
 #define C2V_ADAM_ROWS(e, MODE, stream, ...)                                                                    \
   do {                                                                                                         \
-    if ((e)->adam_rows_occ == 5)                                                                               \
+    if ((e)->adam_rows_shortcut && (e)->adam_rows_occ == 5)                                                    \
+      C2V_LAUNCH(e, (adam_rows_shortcut_kernel<MODE, 5><<<(e)->num_sms * 5, 256, 0, stream>>>(__VA_ARGS__)));  \
+    else if ((e)->adam_rows_shortcut)                                                                          \
+      C2V_LAUNCH(e, (adam_rows_shortcut_kernel<MODE, 4><<<(e)->num_sms * 4, 256, 0, stream>>>(__VA_ARGS__)));  \
+    else if ((e)->adam_rows_occ == 5)                                                                          \
       C2V_LAUNCH(e, (adam_rows_kernel<MODE, 5><<<(e)->num_sms * 5, 256, 0, stream>>>(__VA_ARGS__)));           \
     else                                                                                                       \
       C2V_LAUNCH(e, (adam_rows_kernel<MODE, 4><<<(e)->num_sms * 4, 256, 0, stream>>>(__VA_ARGS__)));           \
@@ -906,6 +911,7 @@ int c2v_set_option(c2v_engine* e, const char* key, int64_t value) {
     return C2V_OK;
   }
   if (!strcmp(key, "fuse_target_adam")) { e->fuse_tgt = value ? 1 : 0; return C2V_OK; }
+  if (!strcmp(key, "adam_rows_shortcut")) { e->adam_rows_shortcut = value ? 1 : 0; return C2V_OK; }
   if (!strcmp(key, "adam_rows_occupancy")) {
     if (value != 4 && value != 5) return fail(e, C2V_ERR_INVALID, "adam_rows_occupancy must be 4 or 5");
     e->adam_rows_occ = (int)value;

@@ -827,4 +827,86 @@ adam_rows_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict
   }
 }
 
+// EXPERIMENTAL (engine option "adam_rows_shortcut", off by default; not yet validated on a GPU -- see DESIGN.md
+// section 8): the same pass with two exits from the division / square-root loop for rows that were left alone
+// for a long time.  Once m has decayed to exactly +-0 (~1100 idle steps at beta1 = 0.9) theta - lr*0/(sqrt(v)+eps)
+// == theta, so only v still changes; once v is 0 too nothing changes.  tests/test_lazy_adam_model.py proves the
+// shortcut bit-exact on a numpy model.  The votes name exactly the lanes that hold a slice of the row
+// (`act`): with d < 128 the other lanes never reach them.
+template <int MODE, int OCC>
+__global__ void __launch_bounds__(256, OCC)
+adam_rows_shortcut_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, int rows, int d,
+                          const int32_t* __restrict__ stamp, int32_t epoch, int32_t* __restrict__ last, int32_t t_done,
+                          const float* __restrict__ lr_tab, float b1, float b2, float eps) {
+  const int lane = threadIdx.x & 31;
+  const int warp_global = (blockIdx.x * 256 + threadIdx.x) >> 5;
+  const int total_warps = (gridDim.x * 256) >> 5;
+  const float omb1 = __fsub_rn(1.f, b1), omb2 = __fsub_rn(1.f, b2);
+  for (int base = warp_global * 32; base < rows; base += total_warps * 32) {
+    const int r = base + lane;
+    int32_t from_l = 0;
+    bool hit = false;
+    if (r < rows) {
+      hit = (MODE == ADAM_ROWS_FLUSH) || (stamp[r] == epoch);
+      if (hit) {
+        from_l = last[r];
+        if (from_l >= t_done) hit = false;
+      }
+    }
+    unsigned todo = __ballot_sync(0xffffffffu, hit);
+    while (todo) {
+      const int b = __ffs(todo) - 1;
+      todo &= todo - 1;
+      const int row = base + b;
+      const int32_t from = __shfl_sync(0xffffffffu, from_l, b);
+      for (int j0 = 0; j0 < d; j0 += 128) {          // every lane walks the slices, so the ballot sees all 32
+        const int j = j0 + lane * 4;
+        const unsigned act = __ballot_sync(0xffffffffu, j < d);
+        if (j >= d) continue;
+        const size_t o = (size_t)row * d + j;
+        float4 P = *reinterpret_cast<float4*>(p + o), M = *reinterpret_cast<float4*>(m + o), V = *reinterpret_cast<float4*>(v + o);
+        const float4 G = *reinterpret_cast<const float4*>(g + o);
+        float* pp = reinterpret_cast<float*>(&P);
+        float* mm = reinterpret_cast<float*>(&M);
+        float* vv = reinterpret_cast<float*>(&V);
+        const float* gg = reinterpret_cast<const float*>(&G);
+        {
+          const float lr_s = lr_tab[from + 1];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            mm[q] = __fadd_rn(__fmul_rn(mm[q], b1), __fmul_rn(omb1, gg[q]));
+            vv[q] = __fadd_rn(__fmul_rn(vv[q], b2), __fmul_rn(omb2, __fmul_rn(gg[q], gg[q])));
+            pp[q] = __fsub_rn(pp[q], __fdiv_rn(__fmul_rn(lr_s, mm[q]), __fadd_rn(__fsqrt_rn(vv[q]), eps)));
+          }
+        }
+        int32_t s = from + 2;
+        for (; s <= t_done; ++s) {
+          if (__all_sync(act, (mm[0] == 0.f) & (mm[1] == 0.f) & (mm[2] == 0.f) & (mm[3] == 0.f))) break;
+          const float lr_s = lr_tab[s];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            mm[q] = __fadd_rn(__fmul_rn(mm[q], b1), __fmul_rn(omb1, 0.f));
+            vv[q] = __fadd_rn(__fmul_rn(vv[q], b2), __fmul_rn(omb2, 0.f));
+            pp[q] = __fsub_rn(pp[q], __fdiv_rn(__fmul_rn(lr_s, mm[q]), __fadd_rn(__fsqrt_rn(vv[q]), eps)));
+          }
+        }
+        for (; s <= t_done; ++s) {            // m == 0 in the whole row: theta rests, v keeps decaying until it is 0 too
+          if (__all_sync(act, (vv[0] == 0.f) & (vv[1] == 0.f) & (vv[2] == 0.f) & (vv[3] == 0.f))) break;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            mm[q] = __fadd_rn(__fmul_rn(mm[q], b1), __fmul_rn(omb1, 0.f));      // a -0 becomes +0, as in the dense kernel
+            vv[q] = __fadd_rn(__fmul_rn(vv[q], b2), __fmul_rn(omb2, 0.f));
+          }
+        }
+        *reinterpret_cast<float4*>(p + o) = P;
+        *reinterpret_cast<float4*>(m + o) = M;
+        *reinterpret_cast<float4*>(v + o) = V;
+        if ((__float_as_uint(G.x) | __float_as_uint(G.y) | __float_as_uint(G.z) | __float_as_uint(G.w)) != 0u)
+          *reinterpret_cast<float4*>(g + o) = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
+    if (hit) last[r] = t_done;
+  }
+}
+
 }  // namespace c2v

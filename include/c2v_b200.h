@@ -118,7 +118,10 @@ int c2v_bind_adam_state(c2v_engine* e, const c2v_tensors* m, const c2v_tensors* 
  * default 0: c2v_train_batch_host arms c2v_arm_target_adam itself), "target_adam_fused_step"
  * (read: the step count whose target-table update the dY epilogue has already applied, 0 = none;
  * writing 0 acknowledges it for callers that drive c2v_adam_step_range themselves),
- * "early_catchup_count" (read-only: how many train steps used a c2v_hint_next_batch hint). */
+ * "early_catchup_count" (read-only: how many train steps used a c2v_hint_next_batch hint),
+ * "adam_rows_occupancy" (4 or 5 resident blocks per SM for the lazy-Adam row pass; default 4),
+ * "adam_rows_shortcut" (EXPERIMENTAL, default 0, not yet validated on a GPU: rows idle for so long
+ * that m -- and later v -- have decayed to exactly zero leave the division / square-root loop). */
 int c2v_set_option(c2v_engine* e, const char* key, int64_t value);
 int c2v_get_option(const c2v_engine* e, const char* key, int64_t* value);
 
