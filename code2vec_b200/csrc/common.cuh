@@ -20,6 +20,25 @@ __device__ __forceinline__ float warp_max(float v) {
 }
 
 // ---------------------------------------------------------------------------------------------
+// 3xTF32 operand split (C2V_MATH_3XTF32): x = hi + lo + O(2^-22 |x|) with hi, lo representable in tf32
+// (10 explicit mantissa bits), both rounded to nearest so the tensor core's own handling of the low
+// 13 bits of a 32-bit operand never matters.  A fp32 product a.b is then issued as
+// a_lo.b_hi + a_hi.b_lo + a_hi.b_hi with fp32 accumulation; the dropped a_lo.b_lo term is O(2^-22 |a b|).
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float tf32_rna(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
+__device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
+  hi = tf32_rna(x);
+  lo = tf32_rna(x - hi);
+}
+__device__ __forceinline__ void split_tf32(const float4& x, float4& hi, float4& lo) {
+  split_tf32(x.x, hi.x, lo.x); split_tf32(x.y, hi.y, lo.y); split_tf32(x.z, hi.z, lo.z); split_tf32(x.w, hi.w, lo.w);
+}
+
+// ---------------------------------------------------------------------------------------------
 // Philox4x32-10 (Salmon et al., SC'11).  Counter-based, so the dropout mask of the forward pass
 // is regenerated -- not stored -- in the backward pass, and oracle/path_attention_oracle.py
 // (dropout_keep_mask) reproduces it bit for bit.

@@ -27,16 +27,17 @@ thread_local std::string g_create_error = "";
 constexpr size_t kAlign = 256;
 inline size_t align_up(size_t x, size_t a = kAlign) { return (x + a - 1) / a * a; }
 
-constexpr int kLrTableCap = 1 << 22;   // lazy Adam: per-step learning rates kept on the device (4 M steps)
 constexpr int kSplitDv = 18;   // split-K slices for dv = P . Y      (K = |Y|)
 constexpr int kSplitDw = 48;   // split-K slices for dW = X'^T . dU  (K = B*C)
 
 // Carve-up of the caller-provided workspace (offsets in bytes).
 struct Workspace {
   size_t H, Xg, dXg, alpha, v, dv, S, loss_b, lse, loss, part, da_part, lse_part, dl;
+  size_t Xg_lo, H_lo, S_lo, tgt_hi, tgt_lo, W_hi, W_lo, v_hi, v_lo;     // 3xTF32 operand splits
   size_t st_src, st_pth, st_tgt, st_mask, st_target, st_topk_idx, st_topk_val, st_code, st_attn;
   size_t nx_src, nx_pth, nx_tgt;                                  // indices of the hinted NEXT batch (host entry point)
   size_t stamp_tok, stamp_path, last_tok, last_path, lr_tab;     // lazy Adam bookkeeping
+  size_t stamp_tgt, last_tgt;                                    // ... of the target table (sampled softmax)
   size_t total;
   size_t ldS;
 };
@@ -92,7 +93,20 @@ Workspace carve(const c2v_dims& d) {
   w.stamp_path = take((size_t)d.path_vocab * 4);
   w.last_tok = take((size_t)d.token_vocab * 4);
   w.last_path = take((size_t)d.path_vocab * 4);
-  w.lr_tab = take((size_t)kLrTableCap * 4);
+  w.lr_tab = take((size_t)kLrRing * 4);
+  w.stamp_tgt = take((size_t)d.target_vocab * 4);
+  w.last_tgt = take((size_t)d.target_vocab * 4);
+  // 3xTF32 (C2V_MATH_3XTF32): low parts of the GEMM operands that are produced inside a step, and the
+  // (hi, lo) split of the operands that must keep their fp32 originals
+  w.Xg_lo = take(N * X * 4);
+  w.H_lo = take(N * D * 4);
+  w.S_lo = take(B * w.ldS * 4);
+  w.tgt_hi = take((size_t)d.target_vocab * D * 4);
+  w.tgt_lo = take((size_t)d.target_vocab * D * 4);
+  w.W_hi = take(X * D * 4);
+  w.W_lo = take(X * D * 4);
+  w.v_hi = take(B * D * 4);
+  w.v_lo = take(B * D * 4);
   w.total = off;
   return w;
 }
@@ -102,10 +116,10 @@ Workspace carve(const c2v_dims& d) {
 // Phases of a pass, for per-kernel timing (option "profile"): CUDA events bracket each phase on
 // the launching stream; c2v_phase_stats() resolves them.
 enum Phase { PH_CTX_FWD = 0, PH_ATTN_FWD, PH_LOGITS, PH_XENT, PH_DV, PH_DY, PH_ATTN_BWD, PH_DW, PH_DX_SCATTER,
-             PH_ADAM, PH_TOPK, PH_SAMPLED, PH_GATHER, PH_DX_GEMM, PH_ADAM_CATCHUP, PH_COUNT };
+             PH_ADAM, PH_TOPK, PH_SAMPLED, PH_GATHER, PH_DX_GEMM, PH_ADAM_CATCHUP, PH_SPLIT, PH_ADAM_SWEEP, PH_COUNT };
 const char* const kPhaseNames[PH_COUNT] = {"ctx_fwd", "attn_fwd", "logits", "xent", "dv", "dY", "attn_bwd", "dW",
                                            "dx_scatter", "adam", "topk", "sampled_softmax", "gather", "dx_gemm",
-                                           "adam_catchup"};
+                                           "adam_catchup", "split", "adam_sweep"};
 struct PhaseLog {
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pending;
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> free_list;
@@ -128,7 +142,12 @@ struct c2v_engine {
   // lazy-but-exact dense Adam for the embedding tables (option "lazy_adam")
   int lazy = 0;
   int adam_rows_occ = 4;
-  int adam_rows_shortcut = 0;           // EXPERIMENTAL: adam_rows_shortcut_kernel (long-idle rows leave the div/sqrt loop early)
+  int sweep_period = 32;                // lazy Adam: every step brings a 1/R slice of each table up to date, so no row
+                                        // is ever more than R steps behind (bounds the replay of rarely used rows and
+                                        // the cost of c2v_sync_tables); 0 = off
+  int64_t full_flush_t = 0;             // step count as of which every row was last known to be current
+  bool tgt_lazy = false;                // the target table's rows are updated lazily too (sampled softmax steps)
+  bool tgt_split_valid = false;         // 3xTF32: ws.tgt_hi / tgt_lo hold the split of the current target table
   bool lazy_grads_pending = false;  // a train step's embedding gradients are in the tables and c2v_adam_step has not followed
   int64_t adam_t_done = 0;   // Adam steps applied so far
   int32_t mark_epoch = 0;
@@ -210,15 +229,14 @@ struct PhaseTimer {
 // adam_rows_kernel as one wave of num_sms * occupancy blocks (option "adam_rows_occupancy": 4 or 5)
 #define C2V_ADAM_ROWS(e, MODE, stream, ...)                                                                    \
   do {                                                                                                         \
-    if ((e)->adam_rows_shortcut && (e)->adam_rows_occ == 5)                                                    \
-      C2V_LAUNCH(e, (adam_rows_shortcut_kernel<MODE, 5><<<(e)->num_sms * 5, 256, 0, stream>>>(__VA_ARGS__)));  \
-    else if ((e)->adam_rows_shortcut)                                                                          \
-      C2V_LAUNCH(e, (adam_rows_shortcut_kernel<MODE, 4><<<(e)->num_sms * 4, 256, 0, stream>>>(__VA_ARGS__)));  \
-    else if ((e)->adam_rows_occ == 5)                                                                          \
+    if ((e)->adam_rows_occ == 5)                                                                               \
       C2V_LAUNCH(e, (adam_rows_kernel<MODE, 5><<<(e)->num_sms * 5, 256, 0, stream>>>(__VA_ARGS__)));           \
     else                                                                                                       \
       C2V_LAUNCH(e, (adam_rows_kernel<MODE, 4><<<(e)->num_sms * 4, 256, 0, stream>>>(__VA_ARGS__)));           \
   } while (0)
+
+inline bool is_tc(const c2v_engine* e) { return e->math_mode != C2V_MATH_FP32; }          // tcgen05 GEMMs
+inline bool is_3x(const c2v_engine* e) { return e->math_mode == C2V_MATH_3XTF32; }        // ... as 3xTF32
 
 // tcgen05 GEMM launchers: single-CTA (UMMA 128 x BN) or CTA-pair (UMMA 256 x BN).  Option "cta_pair":
 // 0 = never, 1 = always, 2 = auto (default): pairs wherever they measured faster on B200 -- every GEMM
@@ -278,7 +296,8 @@ int launch_attn_fwd(c2v_engine* e, cudaStream_t st, const float* H, const float*
   return C2V_OK;
 }
 
-int launch_attn_bwd(c2v_engine* e, cudaStream_t st, float* H, const float* alpha, const float* dv, int B, float* da_part) {
+int launch_attn_bwd(c2v_engine* e, cudaStream_t st, float* H, const float* alpha, const float* dv, int B, float* da_part,
+                    float* H_lo) {
   const int C = e->dims.max_contexts, D = e->dims.code_dim;
   const size_t smem = ((size_t)((C + 3) & ~3) + 32 + (size_t)kAttnWarps * D) * sizeof(float);
   const float* a = e->theta.a;
@@ -287,7 +306,7 @@ int launch_attn_bwd(c2v_engine* e, cudaStream_t st, float* H, const float* alpha
   do {                                                                                                    \
     if (smem > 48 * 1024)                                                                                 \
       C2V_CUDA(e, cudaFuncSetAttribute(attn_bwd_kernel<NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-    C2V_LAUNCH(e, (attn_bwd_kernel<NV><<<B, kAttnThreads, smem, st>>>(H, alpha, dv, a, C, D, da_part)));  \
+    C2V_LAUNCH(e, (attn_bwd_kernel<NV><<<B, kAttnThreads, smem, st>>>(H, alpha, dv, a, C, D, da_part, H_lo))); \
   } while (0)
   switch ((D + 127) / 128) {
     case 1: C2V_AB(1); break;
@@ -355,6 +374,57 @@ int flush_rows(c2v_engine* e, cudaStream_t st) {
   C2V_ADAM_ROWS(e, ADAM_ROWS_FLUSH, st,
                   e->theta.path, e->grad.path, e->am.path, e->av.path, d.path_vocab, d.embed_dim, nullptr, 0,
                     wsp<int32_t>(e, e->ws.last_path), (int32_t)e->adam_t_done, lr_tab, e->hp_b1, e->hp_b2, e->hp_eps);
+  if (e->tgt_lazy)
+    C2V_ADAM_ROWS(e, ADAM_ROWS_FLUSH, st,
+                  e->theta.tgt, e->grad.tgt, e->am.tgt, e->av.tgt, d.target_vocab, d.code_dim, nullptr, 0,
+                    wsp<int32_t>(e, e->ws.last_tgt), (int32_t)e->adam_t_done, lr_tab, e->hp_b1, e->hp_b2, e->hp_eps);
+  e->full_flush_t = e->adam_t_done;
+  return C2V_OK;
+}
+
+// The target table leaves the lazily updated set (a full-softmax step, a full-vocabulary read): bring its rows
+// up to date first.  Its gradient rows are zero afterwards (cleared as they are applied).
+int end_target_lazy(c2v_engine* e, cudaStream_t st) {
+  if (!e->tgt_lazy) return C2V_OK;
+  if (e->adam_t_done > 0) {
+    const c2v_dims& d = e->dims;
+    C2V_ADAM_ROWS(e, ADAM_ROWS_FLUSH, st,
+                  e->theta.tgt, e->grad.tgt, e->am.tgt, e->av.tgt, d.target_vocab, d.code_dim, nullptr, 0,
+                    wsp<int32_t>(e, e->ws.last_tgt), (int32_t)e->adam_t_done, wsp<float>(e, e->ws.lr_tab), e->hp_b1, e->hp_b2,
+                    e->hp_eps);
+  }
+  e->tgt_lazy = false;
+  return C2V_OK;
+}
+
+// Lazy Adam sweep: rows [rows*ph/R, rows*(ph+1)/R) of every lazily updated table are brought up to date each
+// step (ph = t mod R), so a row is never more than R steps behind whatever the data looks like: the replay
+// of a rarely referenced row costs at most R iterations, and c2v_sync_tables at most R per row.
+int sweep_rows(c2v_engine* e, cudaStream_t st, int64_t t) {
+  const int R = e->sweep_period;
+  if (!e->lazy || R <= 0) return C2V_OK;
+  if (R == 1) return flush_rows(e, st);
+  PhaseTimer pt(e, PH_ADAM_SWEEP, st);
+  const c2v_dims& d = e->dims;
+  const float* lr_tab = wsp<float>(e, e->ws.lr_tab);
+  const int64_t ph = t % R;
+  auto slice = [&](float* p, float* g, float* m, float* v, int rows, int dim, int32_t* last) -> int {
+    const int64_t lo = (int64_t)rows * ph / R, hi = (int64_t)rows * (ph + 1) / R;
+    if (hi <= lo) return C2V_OK;
+    const size_t o = (size_t)lo * dim;
+    // a short slice: fewer blocks, so that its rows are spread over all of them
+    int blocks = (int)((hi - lo + 255) / 256);
+    if (blocks > e->num_sms * 4) blocks = e->num_sms * 4;
+    C2V_LAUNCH(e, (adam_rows_kernel<ADAM_ROWS_FLUSH, 4><<<blocks, 256, 0, st>>>(p + o, g + o, m + o, v + o, (int)(hi - lo), dim, nullptr, 0,
+                                                                             last + lo, (int32_t)t, lr_tab, e->hp_b1, e->hp_b2, e->hp_eps)));
+    return C2V_OK;
+  };
+  int rc;
+  if ((rc = slice(e->theta.tok, e->grad.tok, e->am.tok, e->av.tok, d.token_vocab, d.embed_dim, wsp<int32_t>(e, e->ws.last_tok)))) return rc;
+  if ((rc = slice(e->theta.path, e->grad.path, e->am.path, e->av.path, d.path_vocab, d.embed_dim, wsp<int32_t>(e, e->ws.last_path)))) return rc;
+  if (e->tgt_lazy &&
+      (rc = slice(e->theta.tgt, e->grad.tgt, e->am.tgt, e->av.tgt, d.target_vocab, d.code_dim, wsp<int32_t>(e, e->ws.last_tgt)))) return rc;
+  if (ph == R - 1) e->full_flush_t = t - R + 1;      // every row has been visited at or after step t - R + 1
   return C2V_OK;
 }
 
@@ -370,7 +440,7 @@ int early_catchup(c2v_engine* e, cudaStream_t side) {
   e->hint_B = 0;
   if (!hs || !e->lazy || e->table_world > 1) return C2V_OK;
   const int64_t t = e->armed_t;
-  if (t != e->adam_t_done + 1 || t >= kLrTableCap) return C2V_OK;
+  if (t != e->adam_t_done + 1) return C2V_OK;
   // pending steps were recorded under e->hp_*: only valid to run ahead if this step keeps them
   if (!e->hp_set || e->tgt_lr != e->hp_lr || e->tgt_b1 != e->hp_b1 || e->tgt_b2 != e->hp_b2 || e->tgt_eps != e->hp_eps)
     return C2V_OK;
@@ -380,7 +450,7 @@ int early_catchup(c2v_engine* e, cudaStream_t side) {
   int32_t* stamp_tok = wsp<int32_t>(e, e->ws.stamp_tok);
   int32_t* stamp_path = wsp<int32_t>(e, e->ws.stamp_path);
   PhaseTimer pt(e, PH_ADAM_CATCHUP, side);
-  C2V_LAUNCH(e, (set_float_kernel<<<1, 1, 0, side>>>(lr_tab + t, (float)lr_t)));
+  C2V_LAUNCH(e, (set_float_kernel<<<1, 1, 0, side>>>(lr_tab + (t & kLrRingMask), (float)lr_t)));
   e->mark_epoch++;
   const int rows = hB * d.max_contexts;
   C2V_LAUNCH(e, (mark_rows_kernel<<<(rows + 255) / 256, 256, 0, side>>>(hs, hp, ht, rows, stamp_tok, stamp_path, e->mark_epoch)));
@@ -395,20 +465,33 @@ int early_catchup(c2v_engine* e, cudaStream_t side) {
   return C2V_OK;
 }
 
+// 3xTF32: (hi, lo) tf32 split of a whole fp32 buffer into two workspace regions.
+int split_small(c2v_engine* e, cudaStream_t st, const float* x, size_t n, size_t off_hi, size_t off_lo) {
+  PhaseTimer pt(e, PH_SPLIT, st);
+  const size_t n4 = n / 4;                 // every split buffer here is a multiple of 4 floats (dims_ok)
+  size_t blocks = (n4 + 255) / 256;
+  if (blocks > (size_t)e->num_sms * 16) blocks = (size_t)e->num_sms * 16;
+  if (blocks < 1) blocks = 1;
+  C2V_LAUNCH(e, (split_tf32_kernel<<<(unsigned)blocks, 256, 0, st>>>(x, wsp<float>(e, off_hi), wsp<float>(e, off_lo), n4)));
+  return C2V_OK;
+}
+
 // H = tanh(X' . W)   (tensorflow_model.py:238-252)
 int run_ctx_fwd(c2v_engine* e, cudaStream_t st, const ContextSource& cs, const Dropout& dp, float* H) {
   const int D = e->dims.code_dim, K = 3 * e->dims.embed_dim;
   { int rc0 = prepare_rows(e, st, cs); if (rc0) return rc0; }
-  if (e->math_mode == C2V_MATH_TF32) {
+  if (is_tc(e)) {
     float* Xg = wsp<float>(e, e->ws.Xg);
+    const bool x3 = is_3x(e);
     {
       PhaseTimer pt(e, PH_GATHER, st);
-      C2V_LAUNCH(e, (gather_ctx_kernel<<<(cs.rows + 7) / 8, 256, 0, st>>>(cs, dp, Xg)));
+      C2V_LAUNCH(e, (gather_ctx_kernel<<<(cs.rows + 7) / 8, 256, 0, st>>>(cs, dp, Xg, x3 ? wsp<float>(e, e->ws.Xg_lo) : nullptr)));
     }
+    if (x3) { int rcs = split_small(e, st, e->theta.W, (size_t)K * D, e->ws.W_hi, e->ws.W_lo); if (rcs) return rcs; }
     PhaseTimer pt(e, PH_CTX_FWD, st);
-    umma::Operand opA{Xg, (size_t)K, false};
-    umma::Operand opB{e->theta.W, (size_t)D, true};
-    umma::EpiTanhStore ep{H, (size_t)D};
+    umma::Operand opA{Xg, (size_t)K, false, x3 ? wsp<float>(e, e->ws.Xg_lo) : nullptr};
+    umma::Operand opB{x3 ? wsp<float>(e, e->ws.W_hi) : e->theta.W, (size_t)D, true, x3 ? wsp<float>(e, e->ws.W_lo) : nullptr};
+    umma::EpiTanhStore ep{H, (size_t)D, x3 ? 1 : 0};
     C2V_LAUNCH(e, C2V_CUDA(e, (C2V_UMMA_192(st, cs.rows, D, K, 1, opA, opB, ep, e->num_sms))));
     return C2V_OK;
   }
@@ -424,12 +507,22 @@ int run_ctx_fwd(c2v_engine* e, cudaStream_t st, const ContextSource& cs, const D
 // with_lse (tf32 path only): also emit per-(row, 256-column tile) log-sum-exp partials into ws.lse_part.
 int run_logits(c2v_engine* e, cudaStream_t st, const float* v, int B, float* S, bool with_lse = false) {
   const int D = e->dims.code_dim, Y = e->dims.target_vocab;
-  PhaseTimer pt(e, PH_LOGITS, st);
-  if (e->math_mode == C2V_MATH_TF32 && (reinterpret_cast<uintptr_t>(v) % 16 == 0)) {
+  { int rcl = end_target_lazy(e, st); if (rcl) return rcl; }      // a pass over the whole table needs every row current
+  if (is_tc(e) && (reinterpret_cast<uintptr_t>(v) % 16 == 0)) {
+    const bool x3 = is_3x(e);
     umma::Operand opA{v, (size_t)D, false};
     umma::Operand opB{e->theta.tgt, (size_t)D, false};
+    if (x3) {      // fp32-faithful: both operands as tf32 (hi, lo) pairs; the table is re-split on every pass over it
+      int rcs;
+      if ((rcs = split_small(e, st, v, (size_t)B * D, e->ws.v_hi, e->ws.v_lo))) return rcs;
+      if ((rcs = split_small(e, st, e->theta.tgt, (size_t)Y * D, e->ws.tgt_hi, e->ws.tgt_lo))) return rcs;
+      e->tgt_split_valid = true;
+      opA.base = wsp<float>(e, e->ws.v_hi); opA.lo = wsp<float>(e, e->ws.v_lo);
+      opB.base = wsp<float>(e, e->ws.tgt_hi); opB.lo = wsp<float>(e, e->ws.tgt_lo);
+    }
+    PhaseTimer pt(e, PH_LOGITS, st);
     if (with_lse) {
-      umma::EpiStoreLse ep{S, e->ws.ldS, wsp<float2>(e, e->ws.lse_part), 2 * ((Y + 255) / 256)};
+      umma::EpiStoreLse ep{S, e->ws.ldS, wsp<float2>(e, e->ws.lse_part), 2 * ((Y + 255) / 256), x3 ? 1 : 0};
       C2V_LAUNCH(e, C2V_CUDA(e, (C2V_UMMA_256(st, B, Y, D, 1, opA, opB, ep, e->num_sms))));
     } else {
       umma::EpiStore ep{S, e->ws.ldS, 0};
@@ -437,6 +530,7 @@ int run_logits(c2v_engine* e, cudaStream_t st, const float* v, int B, float* S, 
     }
     return C2V_OK;
   }
+  PhaseTimer pt(e, PH_LOGITS, st);
   simt::RowsK al{v, (size_t)D};
   simt::RowsK bl{e->theta.tgt, (size_t)D};
   simt::StoreC ep{S, e->ws.ldS, 0};
@@ -481,22 +575,25 @@ int context_backward(c2v_engine* e, cudaStream_t st, const ContextSource& cs, co
   float* da_part = wsp<float>(e, e->ws.da_part);
   float* part = wsp<float>(e, e->ws.part);
   int rc;
-  if (e->pending_dy_v && e->math_mode != C2V_MATH_TF32) {   // fp32 path: nothing to overlap with, run it first
+  if (e->pending_dy_v && !is_tc(e)) {   // fp32 path: nothing to overlap with, run it first
     const float* pv = e->pending_dy_v;
     e->pending_dy_v = nullptr;
     if ((rc = run_dy(e, st, pv, e->pending_dy_B))) return rc;
   }
-  rc = launch_attn_bwd(e, st, H, alpha, dv, B, da_part);          // H now holds dU
+  const bool x3 = is_tc(e) && is_3x(e);
+  float* H_lo = x3 ? wsp<float>(e, e->ws.H_lo) : nullptr;
+  rc = launch_attn_bwd(e, st, H, alpha, dv, B, da_part, H_lo);    // H now holds dU (3xTF32: its high parts, H_lo the rest)
   if (rc) return rc;
   rc = launch_colsum(e, st, da_part, (size_t)D, B, D, e->grad.a);
   if (rc) return rc;
-  if (e->math_mode == C2V_MATH_TF32) {
+  if (is_tc(e)) {
     float* Xg = wsp<float>(e, e->ws.Xg);
     float* dXg = wsp<float>(e, e->ws.dXg);
     {  // dX' = dU . W^T
       PhaseTimer pt(e, PH_DX_GEMM, st);
-      umma::Operand opA{H, (size_t)D, false};
-      umma::Operand opB{e->theta.W, (size_t)D, false};
+      // 3xTF32: W's split was made by this step's forward pass (run_ctx_fwd) and W has not changed since
+      umma::Operand opA{H, (size_t)D, false, H_lo};
+      umma::Operand opB{x3 ? wsp<float>(e, e->ws.W_hi) : e->theta.W, (size_t)D, false, x3 ? wsp<float>(e, e->ws.W_lo) : nullptr};
       umma::EpiStore ep{dXg, (size_t)K3, 0};
       C2V_LAUNCH(e, C2V_CUDA(e, (C2V_UMMA_192(st, N, K3, D, 1, opA, opB, ep, e->num_sms))));
     }
@@ -525,8 +622,8 @@ int context_backward(c2v_engine* e, cudaStream_t st, const ContextSource& cs, co
     }
     {  // dW = X'^T . dU on the gathered X' kept from the forward pass
       PhaseTimer pt(e, PH_DW, st);
-      umma::Operand opA{Xg, (size_t)K3, true};
-      umma::Operand opB{H, (size_t)D, true};
+      umma::Operand opA{Xg, (size_t)K3, true, x3 ? wsp<float>(e, e->ws.Xg_lo) : nullptr};
+      umma::Operand opB{H, (size_t)D, true, H_lo};
       const int ks = umma::effective_splits(N, kSplitDw);
       umma::EpiStore ep{part, (size_t)D, (size_t)K3 * D};
       C2V_LAUNCH(e, C2V_CUDA(e, (C2V_UMMA_192_SINGLE(st, K3, D, N, kSplitDw, opA, opB, ep, e->num_sms))));
@@ -576,9 +673,18 @@ int run_dv(c2v_engine* e, cudaStream_t st, int B, float* dv) {
   float* S = wsp<float>(e, e->ws.S);
   float* part = wsp<float>(e, e->ws.part);
   PhaseTimer pt(e, PH_DV, st);
-  if (e->math_mode == C2V_MATH_TF32) {
+  if (is_tc(e)) {
     umma::Operand opA{S, e->ws.ldS, false};
     umma::Operand opB{e->theta.tgt, (size_t)D, true};
+    if (is_3x(e)) {      // P was written as its split by softmax_grad_kernel; the table's split dates from the logits pass
+      if (!e->tgt_split_valid) {
+        int rcs = split_small(e, st, e->theta.tgt, (size_t)Y * D, e->ws.tgt_hi, e->ws.tgt_lo);
+        if (rcs) return rcs;
+        e->tgt_split_valid = true;
+      }
+      opA.lo = wsp<float>(e, e->ws.S_lo);
+      opB.base = wsp<float>(e, e->ws.tgt_hi); opB.lo = wsp<float>(e, e->ws.tgt_lo);
+    }
     // enough split-K slices to fill the SMs about twice; few when the batch already gives many tiles
     const int tiles = ((B + 127) / 128) * ((D + 191) / 192);
     int want = (2 * e->num_sms + tiles - 1) / tiles;
@@ -602,9 +708,17 @@ int run_dy(c2v_engine* e, cudaStream_t st, const float* v, int B) {
   float* S = wsp<float>(e, e->ws.S);
   {
     PhaseTimer pt(e, PH_DY, st);
-    if (e->math_mode == C2V_MATH_TF32 && (reinterpret_cast<uintptr_t>(v) % 16 == 0)) {
+    if (is_3x(e) && (reinterpret_cast<uintptr_t>(v) % 16 != 0))
+      return fail(e, C2V_ERR_INVALID, "3xTF32: the code vectors must be 16-byte aligned");
+    if (is_tc(e) && (reinterpret_cast<uintptr_t>(v) % 16 == 0)) {
       umma::Operand opA{S, e->ws.ldS, true};
       umma::Operand opB{v, (size_t)D, true};
+      if (is_3x(e)) {
+        int rcs = split_small(e, st, v, (size_t)B * D, e->ws.v_hi, e->ws.v_lo);
+        if (rcs) return rcs;
+        opA.lo = wsp<float>(e, e->ws.S_lo);
+        opB.base = wsp<float>(e, e->ws.v_hi); opB.lo = wsp<float>(e, e->ws.v_lo);
+      }
       if (e->tgt_armed && e->has_adam) {
         // dYtab never reaches memory: the epilogue applies TF1 Adam to the target table in place
         const double lr_t = (double)e->tgt_lr * sqrt(1.0 - pow((double)e->tgt_b2, (double)e->tgt_t)) /
@@ -614,6 +728,7 @@ int run_dy(c2v_engine* e, cudaStream_t st, const float* v, int B) {
         C2V_LAUNCH(e, C2V_CUDA(e, (C2V_UMMA_192_SINGLE(st, Y, D, B, 1, opA, opB, ep, e->num_sms))));
         e->tgt_armed = false;
         e->tgt_fused_t = e->tgt_t;
+        e->tgt_split_valid = false;
       } else {
         umma::EpiStore ep{e->grad.tgt, (size_t)D, 0};
         C2V_LAUNCH(e, C2V_CUDA(e, (C2V_UMMA_192_SINGLE(st, Y, D, B, 1, opA, opB, ep, e->num_sms))));
@@ -635,7 +750,7 @@ int run_dy(c2v_engine* e, cudaStream_t st, const float* v, int B) {
 int target_grad_gemms(c2v_engine* e, cudaStream_t st, const float* v, int B, float* dv) {
   int rc = run_dv(e, st, B, dv);
   if (rc) return rc;
-  if (e->dy_late == 2 && e->math_mode == C2V_MATH_TF32) {
+  if (e->dy_late == 2 && is_tc(e)) {
     // dY (and the target table's Adam step in its epilogue) is HBM-bound and independent of the context
     // backward pass: it runs on its own stream from here until context_backward joins it
     C2V_CUDA(e, cudaEventRecord(e->ev_fork2, st));
@@ -658,7 +773,7 @@ int train_step_impl(c2v_engine* e, cudaStream_t st, const int32_t* src, const in
                     const float* ext_mask, float* loss_out) {
   if (!e->has_grad) return fail(e, C2V_ERR_STATE, "gradients not bound (c2v_bind_grads)");
   if (!(keep > 0.f) || keep > 1.f) return fail(e, C2V_ERR_INVALID, "keep_prob must be in (0, 1]");
-  const int D = e->dims.code_dim, Y = e->dims.target_vocab;
+  const int Y = e->dims.target_vocab;
   const Dropout dp = make_dropout(e->dims, keep, seed, step, ext_mask);
   ContextSource cs = make_source(e, src, pth, tgt, B);
   float* H = wsp<float>(e, e->ws.H);
@@ -671,7 +786,7 @@ int train_step_impl(c2v_engine* e, cudaStream_t st, const int32_t* src, const in
   int rc;
   if ((rc = run_ctx_fwd(e, st, cs, dp, H))) return rc;
   if ((rc = launch_attn_fwd(e, st, H, mask, B, alpha, v))) return rc;
-  const bool fused_lse = (e->math_mode == C2V_MATH_TF32);
+  const bool fused_lse = (is_tc(e));
   if ((rc = run_logits(e, st, v, B, S, fused_lse))) return rc;
   const float invB = 1.0f / (float)B;
   {
@@ -681,7 +796,8 @@ int train_step_impl(c2v_engine* e, cudaStream_t st, const int32_t* src, const in
       C2V_LAUNCH(e, (xent_combine_kernel<<<B, 256, 0, st>>>(wsp<float2>(e, e->ws.lse_part), n_tiles, S, e->ws.ldS, target,
                                                             loss_b, lse)));
       const int chunks = (int)((e->ws.ldS / 4 + 256 * 8 - 1) / (256 * 8));
-      C2V_LAUNCH(e, (softmax_grad_kernel<<<dim3(chunks, B), 256, 0, st>>>(S, e->ws.ldS, Y, lse, target, invB)));
+      C2V_LAUNCH(e, (softmax_grad_kernel<<<dim3(chunks, B), 256, 0, st>>>(S, e->ws.ldS, Y, lse, target, invB, 0,
+                                                                          is_3x(e) ? wsp<float>(e, e->ws.S_lo) : nullptr)));
     } else {
       C2V_LAUNCH(e, (xent_kernel<<<B, kXentThreads, 0, st>>>(S, e->ws.ldS, target, Y, invB, loss_b, lse, 1)));
     }
@@ -711,14 +827,38 @@ int sampled_train_step_impl(c2v_engine* e, cudaStream_t st, const int32_t* src, 
   if ((rc = run_ctx_fwd(e, st, cs, dp, H))) return rc;
   if ((rc = launch_attn_fwd(e, st, H, mask, B, alpha, v))) return rc;
   const float invB = 1.0f / (float)B;
+  if (e->lazy && e->has_adam && e->table_world == 1) {
+    // TF1 applies sampled-softmax gradients as IndexedSlices: every row of the table still decays m, v and moves
+    // (SURVEY A.3), exactly as for the embedding tables -- so the same deferred, bit-exact row replay applies, and
+    // a step touches only the B + S rows it reads instead of streaming 24 B x 100 M parameters.
+    PhaseTimer pt(e, PH_ADAM_CATCHUP, st);
+    const c2v_dims& d = e->dims;
+    int32_t* stamp = wsp<int32_t>(e, e->ws.stamp_tgt);
+    int32_t* last = wsp<int32_t>(e, e->ws.last_tgt);
+    if (!e->tgt_lazy) {          // the table joins the lazily updated set: every row is current as of adam_t_done
+      C2V_CUDA(e, cudaMemsetAsync(e->grad.tgt, 0, (size_t)d.target_vocab * D * 4, st));
+      C2V_LAUNCH(e, (fill_i32_kernel<<<256, 256, 0, st>>>(last, (size_t)d.target_vocab, (int32_t)e->adam_t_done)));
+      C2V_CUDA(e, cudaMemsetAsync(stamp, 0, (size_t)d.target_vocab * 4, st));
+      e->tgt_lazy = true;
+    }
+    e->mark_epoch++;
+    C2V_LAUNCH(e, (mark_list_kernel<<<(B + 255) / 256, 256, 0, st>>>(target, B, stamp, e->mark_epoch)));
+    C2V_LAUNCH(e, (mark_list_kernel<<<(S + 255) / 256, 256, 0, st>>>(sampled, S, stamp, e->mark_epoch)));
+    if (e->adam_t_done > 0)
+      C2V_ADAM_ROWS(e, ADAM_ROWS_CATCHUP, st,
+                    e->theta.tgt, e->grad.tgt, e->am.tgt, e->av.tgt, d.target_vocab, d.code_dim, stamp, e->mark_epoch, last,
+                    (int32_t)e->adam_t_done, wsp<float>(e, e->ws.lr_tab), e->hp_b1, e->hp_b2, e->hp_eps);
+  }
   {
     PhaseTimer pt(e, PH_SAMPLED, st);
     const size_t smem = ((size_t)D + S + 1) * sizeof(float);
     C2V_LAUNCH(e, (sampled_softmax_fwd_kernel<<<B, kSampledThreads, smem, st>>>(v, e->theta.tgt, target, sampled, S, logq_true,
                                                                                  logq_samp, D, invB, loss_b, dl, dv)));
     C2V_LAUNCH(e, (loss_reduce_kernel<<<1, 256, 0, st>>>(loss_b, B, invB, loss_out)));
-    // the target-table gradient is sparse here (B + S rows); the bound buffer is dense, so clear it first
-    C2V_CUDA(e, cudaMemsetAsync(e->grad.tgt, 0, (size_t)e->dims.target_vocab * D * 4, st));
+    // the target-table gradient is sparse here (B + S rows).  Lazy Adam: the rows were brought up to date (and
+    // their gradient rows cleared) before the forward kernel read them; the update of this step is deferred
+    // like an embedding row's.  Dense Adam: the bound buffer is dense, so it is cleared first.
+    if (!e->tgt_lazy) C2V_CUDA(e, cudaMemsetAsync(e->grad.tgt, 0, (size_t)e->dims.target_vocab * D * 4, st));
     C2V_LAUNCH(e, (sampled_softmax_bwd_kernel<<<B + S, kSampledThreads, 0, st>>>(v, dl, target, sampled, B, S, D, e->grad.tgt)));
   }
   if (e->ev_tgt_ready) C2V_CUDA(e, cudaEventRecord(e->ev_tgt_ready, st));
@@ -751,31 +891,39 @@ int adam_impl(c2v_engine* e, cudaStream_t st, float lr, float b1, float b2, floa
   float* G[5] = {e->grad.tok, e->grad.path, e->grad.tgt, e->grad.W, e->grad.a};
   float* M[5] = {e->am.tok, e->am.path, e->am.tgt, e->am.W, e->am.a};
   float* V[5] = {e->av.tok, e->av.path, e->av.tgt, e->av.W, e->av.a};
-  PhaseTimer pt(e, PH_ADAM, st);
   int first_dense = 0;
   if (e->lazy) {
     if (t != e->adam_t_done + 1) return fail(e, C2V_ERR_STATE, "lazy Adam needs consecutive step counts (t == previous t + 1)");
-    if (t >= kLrTableCap) return fail(e, C2V_ERR_UNSUPPORTED, "lazy Adam learning-rate table exhausted");
     if (e->hp_set && (lr != e->hp_lr || b1 != e->hp_b1 || b2 != e->hp_b2 || eps != e->hp_eps)) {
       int rcf = flush_rows(e, st);                  // pending steps must use the old hyper-parameters
+      if (rcf) return rcf;
+    }
+    // the learning rates of pending steps live in a ring: no row may fall a whole ring behind (only possible
+    // with the sweep switched off)
+    if (t - e->full_flush_t >= kLrRing - 2) {
+      int rcf = flush_rows(e, st);
       if (rcf) return rcf;
     }
     e->hp_lr = lr; e->hp_b1 = b1; e->hp_b2 = b2; e->hp_eps = eps; e->hp_set = true;
     float* lr_tab = wsp<float>(e, e->ws.lr_tab);
     // the embedding rows' step t is deferred: their gradient rows keep this step's scatter-add until the
-    // rows are next referenced (prepare_rows) or flushed; only the learning rate of the step is recorded
-    C2V_LAUNCH(e, (set_float_kernel<<<1, 1, 0, st>>>(lr_tab + t, lr_t)));
+    // rows are next referenced (prepare_rows), swept (sweep_rows) or flushed; only the learning rate of the
+    // step is recorded
+    C2V_LAUNCH(e, (set_float_kernel<<<1, 1, 0, st>>>(lr_tab + (t & kLrRingMask), lr_t)));
     e->lazy_grads_pending = false;
     first_dense = 2;
   }
   e->adam_t_done = t;
+  e->tgt_split_valid = false;
+  if (e->lazy) { int rcs = sweep_rows(e, st, t); if (rcs) return rcs; }
   for (int i = first_dense; i < 5; ++i) {
-    if (i == 2 && skip_tgt) continue;
+    if (i == 2 && (skip_tgt || e->tgt_lazy)) continue;     // lazy target rows: deferred like the embedding rows
     const size_t n4 = n[i] / 4;
     size_t blocks = (n4 + 255) / 256;
     if (blocks > 148 * 16) blocks = 148 * 16;
     if (blocks < 1) blocks = 1;
     const int zero = (i < 2) ? 1 : 0;   // embedding gradient tables are cleared for the next scatter-add
+    PhaseTimer pt(e, PH_ADAM, st);
     C2V_LAUNCH(e, (adam_kernel<<<(unsigned)blocks, 256, 0, st>>>(P[i], G[i], M[i], V[i], n4, lr_t, b1, b2, eps, zero)));
   }
   e->emb_grads_clean = !e->lazy;     // lazy: the gradient tables hold deferred steps, cleared row by row as they are applied
@@ -893,8 +1041,9 @@ int c2v_bind_adam_state(c2v_engine* e, const c2v_tensors* m, const c2v_tensors* 
 int c2v_set_option(c2v_engine* e, const char* key, int64_t value) {
   if (!e || !key) return C2V_ERR_INVALID;
   if (!strcmp(key, "math_mode")) {
-    if (value != C2V_MATH_FP32 && value != C2V_MATH_TF32) return fail(e, C2V_ERR_INVALID, "unknown math_mode");
-    if (value == C2V_MATH_TF32 && !umma::get_encode_fn())
+    if (value != C2V_MATH_FP32 && value != C2V_MATH_TF32 && value != C2V_MATH_3XTF32)
+      return fail(e, C2V_ERR_INVALID, "unknown math_mode");
+    if (value != C2V_MATH_FP32 && !umma::get_encode_fn())
       return fail(e, C2V_ERR_UNSUPPORTED, "cuTensorMapEncodeTiled not available from the driver");
     e->math_mode = (int)value;
     return C2V_OK;
@@ -911,7 +1060,11 @@ int c2v_set_option(c2v_engine* e, const char* key, int64_t value) {
     return C2V_OK;
   }
   if (!strcmp(key, "fuse_target_adam")) { e->fuse_tgt = value ? 1 : 0; return C2V_OK; }
-  if (!strcmp(key, "adam_rows_shortcut")) { e->adam_rows_shortcut = value ? 1 : 0; return C2V_OK; }
+  if (!strcmp(key, "adam_sweep_period")) {
+    if (value < 0 || value > kLrRing / 2) return fail(e, C2V_ERR_INVALID, "adam_sweep_period must be in [0, 32768]");
+    e->sweep_period = (int)value;
+    return C2V_OK;
+  }
   if (!strcmp(key, "adam_rows_occupancy")) {
     if (value != 4 && value != 5) return fail(e, C2V_ERR_INVALID, "adam_rows_occupancy must be 4 or 5");
     e->adam_rows_occ = (int)value;
@@ -938,6 +1091,7 @@ int c2v_set_option(c2v_engine* e, const char* key, int64_t value) {
       C2V_CUDA(e, cudaStreamSynchronize(0));
       e->emb_grads_clean = !e->lazy_grads_pending;        // every applied gradient row was cleared on the way
       e->lazy_grads_pending = false;
+      e->tgt_lazy = false;
     }
     if (value && !e->lazy) {                              // all rows are current as of adam_t_done
       const c2v_dims& d = e->dims;
@@ -951,6 +1105,8 @@ int c2v_set_option(c2v_engine* e, const char* key, int64_t value) {
       C2V_CUDA(e, cudaMemset(wsp<int32_t>(e, e->ws.stamp_tok), 0, (size_t)d.token_vocab * 4));
       C2V_CUDA(e, cudaMemset(wsp<int32_t>(e, e->ws.stamp_path), 0, (size_t)d.path_vocab * 4));
       e->mark_epoch = 0;
+      e->full_flush_t = e->adam_t_done;
+      e->tgt_lazy = false;
       C2V_CUDA(e, cudaDeviceSynchronize());
     }
     e->lazy = value ? 1 : 0;
@@ -970,6 +1126,8 @@ int c2v_set_option(c2v_engine* e, const char* key, int64_t value) {
       C2V_LAUNCH(e, (fill_i32_kernel<<<256, 256>>>(wsp<int32_t>(e, e->ws.last_tok), (size_t)d.token_vocab, (int32_t)value)));
       C2V_LAUNCH(e, (fill_i32_kernel<<<256, 256>>>(wsp<int32_t>(e, e->ws.last_path), (size_t)d.path_vocab, (int32_t)value)));
       C2V_CUDA(e, cudaDeviceSynchronize());
+      e->tgt_lazy = false;                                // flush_rows brought the target rows up to date as well
+      e->full_flush_t = value;
     }
     e->adam_t_done = value;
     e->hp_set = false;
@@ -984,6 +1142,7 @@ int c2v_get_option(const c2v_engine* e, const char* key, int64_t* value) {
   if (!strcmp(key, "deterministic")) { *value = e->deterministic; return C2V_OK; }
   if (!strcmp(key, "profile")) { *value = e->profile; return C2V_OK; }
   if (!strcmp(key, "lazy_adam")) { *value = e->lazy; return C2V_OK; }
+  if (!strcmp(key, "adam_sweep_period")) { *value = e->sweep_period; return C2V_OK; }
   if (!strcmp(key, "cta_pair")) { *value = e->cta_pair; return C2V_OK; }
   if (!strcmp(key, "dy_late")) { *value = e->dy_late; return C2V_OK; }
   if (!strcmp(key, "fuse_target_adam")) { *value = e->fuse_tgt; return C2V_OK; }
@@ -1019,11 +1178,20 @@ int c2v_loss(c2v_engine* e, const float* code_vec, const int32_t* target, int32_
   C2V_CUDA(e, cudaSetDevice(e->device));
   cudaStream_t st = (cudaStream_t)stream;
   float* S = wsp<float>(e, e->ws.S);
-  if ((rc = run_logits(e, st, code_vec, B, S))) return rc;
   const float invB = 1.0f / (float)B;
-  C2V_LAUNCH(e, (xent_kernel<<<B, kXentThreads, 0, st>>>(S, e->ws.ldS, target, e->dims.target_vocab, invB,
-                                                          wsp<float>(e, e->ws.loss_b), wsp<float>(e, e->ws.lse), 0)));
-  C2V_LAUNCH(e, (loss_reduce_kernel<<<1, 256, 0, st>>>(wsp<float>(e, e->ws.loss_b), B, invB, loss_out)));
+  const int Y = e->dims.target_vocab;
+  const bool fused = is_tc(e) && (reinterpret_cast<uintptr_t>(code_vec) % 16 == 0);
+  if ((rc = run_logits(e, st, code_vec, B, S, fused))) return rc;
+  {
+    PhaseTimer pt(e, PH_XENT, st);
+    if (fused)      // the logits epilogue already folded each tile into (max, sum exp) partials
+      C2V_LAUNCH(e, (xent_combine_kernel<<<B, 256, 0, st>>>(wsp<float2>(e, e->ws.lse_part), 2 * ((Y + 255) / 256), S, e->ws.ldS, target,
+                                                            wsp<float>(e, e->ws.loss_b), wsp<float>(e, e->ws.lse))));
+    else
+      C2V_LAUNCH(e, (xent_kernel<<<B, kXentThreads, 0, st>>>(S, e->ws.ldS, target, Y, invB, wsp<float>(e, e->ws.loss_b),
+                                                              wsp<float>(e, e->ws.lse), 0)));
+    C2V_LAUNCH(e, (loss_reduce_kernel<<<1, 256, 0, st>>>(wsp<float>(e, e->ws.loss_b), B, invB, loss_out)));
+  }
   return C2V_OK;
 }
 
@@ -1175,7 +1343,7 @@ int c2v_target_forward(c2v_engine* e, const float* code_all, int32_t Bt, const i
   cudaStream_t st = (cudaStream_t)stream;
   float* S = wsp<float>(e, e->ws.S);
   const int Y = e->dims.target_vocab;
-  const bool fused = (e->math_mode == C2V_MATH_TF32) && (reinterpret_cast<uintptr_t>(code_all) % 16 == 0);
+  const bool fused = (is_tc(e)) && (reinterpret_cast<uintptr_t>(code_all) % 16 == 0);
   if ((rc = run_logits(e, st, code_all, Bt, S, fused))) return rc;
   PhaseTimer pt(e, PH_XENT, st);
   C2V_LAUNCH(e, (row_maxsum_kernel<<<Bt, 256, 0, st>>>(fused ? wsp<float2>(e, e->ws.lse_part) : nullptr,
@@ -1208,8 +1376,8 @@ int c2v_target_backward(c2v_engine* e, const float* code_all, int32_t Bt, const 
   {
     PhaseTimer pt(e, PH_XENT, st);
     const int chunks = (int)((e->ws.ldS / 4 + 256 * 8 - 1) / (256 * 8));
-    C2V_LAUNCH(e, (softmax_grad_kernel<<<dim3(chunks, Bt), 256, 0, st>>>(S, e->ws.ldS, e->dims.target_vocab, lse, target,
-                                                                       inv_batch, row_offset)));
+    C2V_LAUNCH(e, (softmax_grad_kernel<<<dim3(chunks, Bt), 256, 0, st>>>(S, e->ws.ldS, e->dims.target_vocab, lse, target, inv_batch, row_offset,
+                                                                       (is_tc(e) && is_3x(e)) ? wsp<float>(e, e->ws.S_lo) : nullptr)));
   }
   return target_grad_gemms(e, st, code_all, Bt, dv_partial);
 }
@@ -1325,17 +1493,35 @@ int c2v_predict_batch_host(c2v_engine* e, const int32_t* h_src, const int32_t* h
 int c2v_selftest_gemm(c2v_engine* e, int32_t a_mn, int32_t b_mn, int32_t bn, int32_t M, int32_t N, int32_t K,
                       int32_t splits, const float* A, size_t lda, const float* Bm, size_t ldb, float* C, size_t ldc,
                       void* stream) {
+  return c2v_selftest_gemm3(e, a_mn, b_mn, bn, M, N, K, splits, A, nullptr, lda, Bm, nullptr, ldb, C, ldc, stream);
+}
+
+int c2v_selftest_gemm3(c2v_engine* e, int32_t a_mn, int32_t b_mn, int32_t bn, int32_t M, int32_t N, int32_t K,
+                       int32_t splits, const float* A, const float* A_lo, size_t lda, const float* Bm, const float* B_lo,
+                       size_t ldb, float* C, size_t ldc, void* stream) {
   if (!e || !A || !Bm || !C) return C2V_ERR_INVALID;
+  if ((A_lo != nullptr) != (B_lo != nullptr)) return fail(e, C2V_ERR_INVALID, "3xTF32 needs the low parts of both operands");
   C2V_CUDA(e, cudaSetDevice(e->device));
   cudaStream_t st = (cudaStream_t)stream;
-  umma::Operand opA{A, lda, a_mn != 0};
-  umma::Operand opB{Bm, ldb, b_mn != 0};
+  umma::Operand opA{A, lda, a_mn != 0, A_lo};
+  umma::Operand opB{Bm, ldb, b_mn != 0, B_lo};
   if (!umma::operand_ok(opA) || !umma::operand_ok(opB)) return fail(e, C2V_ERR_INVALID, "operand not TMA-compatible");
   umma::EpiStore ep{C, ldc, (size_t)M * ldc};
   if (bn == 256) C2V_LAUNCH(e, C2V_CUDA(e, (C2V_UMMA_256(st, M, N, K, splits, opA, opB, ep, e->num_sms))));
   else if (bn == 192) C2V_LAUNCH(e, C2V_CUDA(e, (C2V_UMMA_192(st, M, N, K, splits, opA, opB, ep, e->num_sms))));
   else return fail(e, C2V_ERR_INVALID, "bn must be 192 or 256");
   return umma::effective_splits(K, splits);
+}
+
+int c2v_selftest_split(c2v_engine* e, const float* x, float* hi, float* lo, size_t count, void* stream) {
+  if (!e || !x || !hi || !lo) return C2V_ERR_INVALID;
+  if (count % 4 || ((uintptr_t)x | (uintptr_t)hi | (uintptr_t)lo) % 16) return fail(e, C2V_ERR_INVALID, "count % 4 and 16-byte alignment");
+  C2V_CUDA(e, cudaSetDevice(e->device));
+  size_t blocks = (count / 4 + 255) / 256;
+  if (blocks > (size_t)e->num_sms * 16) blocks = (size_t)e->num_sms * 16;
+  if (blocks < 1) blocks = 1;
+  C2V_LAUNCH(e, (split_tf32_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(x, hi, lo, count / 4)));
+  return C2V_OK;
 }
 
 int64_t c2v_launch_count(const c2v_engine* e) { return e ? e->launches : 0; }

@@ -132,7 +132,8 @@ attn_fwd_kernel(const float* __restrict__ H, const float* __restrict__ a, const 
 template <int NV>
 __global__ void __launch_bounds__(kAttnThreads)
 attn_bwd_kernel(float* __restrict__ H, const float* __restrict__ alpha, const float* __restrict__ dv,
-                const float* __restrict__ a, int C, int D, float* __restrict__ da_part) {
+                const float* __restrict__ a, int C, int D, float* __restrict__ da_part, float* __restrict__ H_lo) {
+  // H_lo != nullptr (3xTF32): dU is written as its tf32 split, high parts over H and residuals into H_lo
   extern __shared__ float sm[];
   float* dal = sm;                      // [C]
   float* red = dal + ((C + 3) & ~3);    // [32]
@@ -178,7 +179,10 @@ attn_bwd_kernel(float* __restrict__ H, const float* __restrict__ alpha, const fl
 #pragma unroll
       for (int i = 0; i < NV; ++i) {
         const int j = i * 128 + lane * 4;
-        if (j < D) *reinterpret_cast<float4*>(h + j) = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (j < D) {
+          *reinterpret_cast<float4*>(h + j) = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (H_lo) *reinterpret_cast<float4*>(H_lo + ((size_t)b * C + c) * D + j) = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
       }
       continue;
     }
@@ -193,7 +197,14 @@ attn_bwd_kernel(float* __restrict__ H, const float* __restrict__ alpha, const fl
         du.y = (al * gv[i].y + dz * av[i].y) * (1.f - hv.y * hv.y);
         du.z = (al * gv[i].z + dz * av[i].z) * (1.f - hv.z * hv.z);
         du.w = (al * gv[i].w + dz * av[i].w) * (1.f - hv.w * hv.w);
-        *reinterpret_cast<float4*>(h + j) = du;
+        if (H_lo) {
+          float4 hi, lo;
+          split_tf32(du, hi, lo);
+          *reinterpret_cast<float4*>(h + j) = hi;
+          *reinterpret_cast<float4*>(H_lo + ((size_t)b * C + c) * D + j) = lo;
+        } else {
+          *reinterpret_cast<float4*>(h + j) = du;
+        }
         dacc[i].x += dz * hv.x; dacc[i].y += dz * hv.y; dacc[i].z += dz * hv.z; dacc[i].w += dz * hv.w;
       }
     }
@@ -294,7 +305,8 @@ xent_combine_kernel(const float2* __restrict__ partial, int n_tiles, const float
 // S <- (softmax(S) - onehot(target)) * inv_batch in place, padding columns zeroed.  grid (chunks, B).
 __global__ void __launch_bounds__(256)
 softmax_grad_kernel(float* __restrict__ S, size_t ldS, int Y, const float* __restrict__ lse, const int32_t* __restrict__ target,
-                    float inv_batch, int row0 = 0) {
+                    float inv_batch, int row0 = 0, float* __restrict__ S_lo = nullptr) {
+  // S_lo != nullptr (3xTF32): the gradient is written as its tf32 split (high parts over S, residuals into S_lo)
   const int b = blockIdx.y;
   float* row = S + (size_t)b * ldS;
   const float l = lse[b];
@@ -311,7 +323,27 @@ softmax_grad_kernel(float* __restrict__ S, size_t ldS, int Y, const float* __res
       if (y == j) x.x -= inv_batch; else if (y == j + 1) x.y -= inv_batch;
       else if (y == j + 2) x.z -= inv_batch; else x.w -= inv_batch;
     }
-    *reinterpret_cast<float4*>(row + j) = x;
+    if (S_lo) {
+      float4 hi, lo;
+      split_tf32(x, hi, lo);
+      *reinterpret_cast<float4*>(row + j) = hi;
+      *reinterpret_cast<float4*>(S_lo + (size_t)b * ldS + j) = lo;
+    } else {
+      *reinterpret_cast<float4*>(row + j) = x;
+    }
+  }
+}
+
+// x -> (hi, lo) tf32 split of a whole buffer (3xTF32: TRANSFORM, the code vectors, the target table).
+__global__ void __launch_bounds__(256)
+split_tf32_kernel(const float* __restrict__ x, float* __restrict__ hi, float* __restrict__ lo, size_t n4) {
+  const size_t step = (size_t)gridDim.x * 256;
+  for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < n4; i += step) {
+    const float4 v = reinterpret_cast<const float4*>(x)[i];
+    float4 h, l;
+    split_tf32(v, h, l);
+    reinterpret_cast<float4*>(hi)[i] = h;
+    reinterpret_cast<float4*>(lo)[i] = l;
   }
 }
 
@@ -671,7 +703,9 @@ adam_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m,
 // into the embedding gradient tables.  One warp per context row, 128-bit accesses.
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
-gather_ctx_kernel(const __grid_constant__ ContextSource cs, const __grid_constant__ Dropout dp, float* __restrict__ Xg) {
+gather_ctx_kernel(const __grid_constant__ ContextSource cs, const __grid_constant__ Dropout dp, float* __restrict__ Xg,
+                  float* __restrict__ Xlo) {
+  // Xlo != nullptr (3xTF32): X' is written as its tf32 split
   const int n = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (n >= cs.rows) return;
   const int K3 = 3 * cs.d;
@@ -692,7 +726,14 @@ gather_ctx_kernel(const __grid_constant__ ContextSource cs, const __grid_constan
       if (j < K3) {
         const float4 m = dropout_mult4(dp, n, j >> 2);
         x[u].x *= m.x; x[u].y *= m.y; x[u].z *= m.z; x[u].w *= m.w;
-        *reinterpret_cast<float4*>(dst + j) = x[u];
+        if (Xlo) {
+          float4 hi, lo;
+          split_tf32(x[u], hi, lo);
+          *reinterpret_cast<float4*>(dst + j) = hi;
+          *reinterpret_cast<float4*>(Xlo + (size_t)n * K3 + j) = lo;
+        } else {
+          *reinterpret_cast<float4*>(dst + j) = x[u];
+        }
       }
     }
   }
@@ -735,7 +776,7 @@ scatter_dx_kernel(const __grid_constant__ ContextSource cs, const __grid_constan
 //   mark_rows_kernel         : stamp[row] = epoch for every row the batch references
 //   adam_rows_kernel<CATCHUP>: stamped rows -> replay steps last+1 .. t_done, clear the gradient row
 //   adam_rows_kernel<FLUSH>  : all rows     -> the same (before export / checkpoint / mode switch)
-// lr_tab[s] holds lr_s = lr*sqrt(1-b2^s)/(1-b1^s) as computed on the host for the dense kernel.
+// lr_tab[s & kLrRingMask] holds lr_s = lr*sqrt(1-b2^s)/(1-b1^s) as computed on the host for the dense kernel.
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 mark_rows_kernel(const int32_t* __restrict__ src, const int32_t* __restrict__ pth, const int32_t* __restrict__ tgt, int n,
@@ -747,12 +788,25 @@ mark_rows_kernel(const int32_t* __restrict__ src, const int32_t* __restrict__ pt
   stamp_tok[tgt[i]] = epoch;
 }
 
+// stamp[idx[i]] = epoch: the rows a sampled-softmax step reads from the target table
+__global__ void __launch_bounds__(256)
+mark_list_kernel(const int32_t* __restrict__ idx, int n, int32_t* __restrict__ stamp, int32_t epoch) {
+  const int i = blockIdx.x * 256 + threadIdx.x;
+  if (i < n) stamp[idx[i]] = epoch;
+}
+
 __global__ void fill_i32_kernel(int32_t* __restrict__ p, size_t n, int32_t v) {
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) p[i] = v;
 }
 __global__ void set_float_kernel(float* p, float v) { *p = v; }
 
 enum { ADAM_ROWS_CATCHUP = 0, ADAM_ROWS_FLUSH = 2 };
+
+// lr_tab is a ring over the step count: entry s & kLrRingMask holds lr_s.  No row is ever more than the
+// ring's length behind: the engine sweeps a 1/R slice of every table per step (option "adam_sweep_period")
+// and otherwise flushes all rows before the ring wraps.
+constexpr int kLrRing = 1 << 16;
+constexpr int kLrRingMask = kLrRing - 1;
 
 // Persistent grid: every warp scans 32 rows at a time (one coalesced read of their stamps and
 // `last` values), then the whole warp walks the rows that need work, one 128-bit access per lane
@@ -798,7 +852,7 @@ adam_rows_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict
         float* vv = reinterpret_cast<float*>(&V);
         const float* gg = reinterpret_cast<const float*>(&G);
         {  // step from+1: the deferred gradient step (the dense kernel's exact operations)
-          const float lr_s = lr_tab[from + 1];
+          const float lr_s = lr_tab[(from + 1) & kLrRingMask];
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
             mm[q] = __fadd_rn(__fmul_rn(mm[q], b1), __fmul_rn(omb1, gg[q]));
@@ -808,94 +862,12 @@ adam_rows_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict
         }
         // the zero-gradient steps after it: m*b1 + (1-b1)*0, v*b2 + (1-b2)*(0*0)
         for (int32_t s = from + 2; s <= t_done; ++s) {
-          const float lr_s = lr_tab[s];
+          const float lr_s = lr_tab[s & kLrRingMask];
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
             mm[q] = __fadd_rn(__fmul_rn(mm[q], b1), __fmul_rn(omb1, 0.f));
             vv[q] = __fadd_rn(__fmul_rn(vv[q], b2), __fmul_rn(omb2, 0.f));
             pp[q] = __fsub_rn(pp[q], __fdiv_rn(__fmul_rn(lr_s, mm[q]), __fadd_rn(__fsqrt_rn(vv[q]), eps)));
-          }
-        }
-        *reinterpret_cast<float4*>(p + o) = P;
-        *reinterpret_cast<float4*>(m + o) = M;
-        *reinterpret_cast<float4*>(v + o) = V;
-        if ((__float_as_uint(G.x) | __float_as_uint(G.y) | __float_as_uint(G.z) | __float_as_uint(G.w)) != 0u)
-          *reinterpret_cast<float4*>(g + o) = make_float4(0.f, 0.f, 0.f, 0.f);
-      }
-    }
-    if (hit) last[r] = t_done;
-  }
-}
-
-// EXPERIMENTAL (engine option "adam_rows_shortcut", off by default; not yet validated on a GPU -- see DESIGN.md
-// section 8): the same pass with two exits from the division / square-root loop for rows that were left alone
-// for a long time.  Once m has decayed to exactly +-0 (~1100 idle steps at beta1 = 0.9) theta - lr*0/(sqrt(v)+eps)
-// == theta, so only v still changes; once v is 0 too nothing changes.  tests/test_lazy_adam_model.py proves the
-// shortcut bit-exact on a numpy model.  The votes name exactly the lanes that hold a slice of the row
-// (`act`): with d < 128 the other lanes never reach them.
-template <int MODE, int OCC>
-__global__ void __launch_bounds__(256, OCC)
-adam_rows_shortcut_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, int rows, int d,
-                          const int32_t* __restrict__ stamp, int32_t epoch, int32_t* __restrict__ last, int32_t t_done,
-                          const float* __restrict__ lr_tab, float b1, float b2, float eps) {
-  const int lane = threadIdx.x & 31;
-  const int warp_global = (blockIdx.x * 256 + threadIdx.x) >> 5;
-  const int total_warps = (gridDim.x * 256) >> 5;
-  const float omb1 = __fsub_rn(1.f, b1), omb2 = __fsub_rn(1.f, b2);
-  for (int base = warp_global * 32; base < rows; base += total_warps * 32) {
-    const int r = base + lane;
-    int32_t from_l = 0;
-    bool hit = false;
-    if (r < rows) {
-      hit = (MODE == ADAM_ROWS_FLUSH) || (stamp[r] == epoch);
-      if (hit) {
-        from_l = last[r];
-        if (from_l >= t_done) hit = false;
-      }
-    }
-    unsigned todo = __ballot_sync(0xffffffffu, hit);
-    while (todo) {
-      const int b = __ffs(todo) - 1;
-      todo &= todo - 1;
-      const int row = base + b;
-      const int32_t from = __shfl_sync(0xffffffffu, from_l, b);
-      for (int j0 = 0; j0 < d; j0 += 128) {          // every lane walks the slices, so the ballot sees all 32
-        const int j = j0 + lane * 4;
-        const unsigned act = __ballot_sync(0xffffffffu, j < d);
-        if (j >= d) continue;
-        const size_t o = (size_t)row * d + j;
-        float4 P = *reinterpret_cast<float4*>(p + o), M = *reinterpret_cast<float4*>(m + o), V = *reinterpret_cast<float4*>(v + o);
-        const float4 G = *reinterpret_cast<const float4*>(g + o);
-        float* pp = reinterpret_cast<float*>(&P);
-        float* mm = reinterpret_cast<float*>(&M);
-        float* vv = reinterpret_cast<float*>(&V);
-        const float* gg = reinterpret_cast<const float*>(&G);
-        {
-          const float lr_s = lr_tab[from + 1];
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            mm[q] = __fadd_rn(__fmul_rn(mm[q], b1), __fmul_rn(omb1, gg[q]));
-            vv[q] = __fadd_rn(__fmul_rn(vv[q], b2), __fmul_rn(omb2, __fmul_rn(gg[q], gg[q])));
-            pp[q] = __fsub_rn(pp[q], __fdiv_rn(__fmul_rn(lr_s, mm[q]), __fadd_rn(__fsqrt_rn(vv[q]), eps)));
-          }
-        }
-        int32_t s = from + 2;
-        for (; s <= t_done; ++s) {
-          if (__all_sync(act, (mm[0] == 0.f) & (mm[1] == 0.f) & (mm[2] == 0.f) & (mm[3] == 0.f))) break;
-          const float lr_s = lr_tab[s];
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            mm[q] = __fadd_rn(__fmul_rn(mm[q], b1), __fmul_rn(omb1, 0.f));
-            vv[q] = __fadd_rn(__fmul_rn(vv[q], b2), __fmul_rn(omb2, 0.f));
-            pp[q] = __fsub_rn(pp[q], __fdiv_rn(__fmul_rn(lr_s, mm[q]), __fadd_rn(__fsqrt_rn(vv[q]), eps)));
-          }
-        }
-        for (; s <= t_done; ++s) {            // m == 0 in the whole row: theta rests, v keeps decaying until it is 0 too
-          if (__all_sync(act, (vv[0] == 0.f) & (vv[1] == 0.f) & (vv[2] == 0.f) & (vv[3] == 0.f))) break;
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            mm[q] = __fadd_rn(__fmul_rn(mm[q], b1), __fmul_rn(omb1, 0.f));      // a -0 becomes +0, as in the dense kernel
-            vv[q] = __fadd_rn(__fmul_rn(vv[q], b2), __fmul_rn(omb2, 0.f));
           }
         }
         *reinterpret_cast<float4*>(p + o) = P;

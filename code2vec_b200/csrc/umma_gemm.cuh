@@ -183,10 +183,11 @@ struct EpiTanhStore {
   using State = EpiNoState;
   float* C;
   size_t ldc;
+  int precise;           // 1: tanhf (the fp32-faithful 3xTF32 mode); 0: the ex2.approx form
   __device__ __forceinline__ void begin(State&) const {}
   __device__ __forceinline__ void end(int, int, int, bool, State&) const {}
   __device__ __forceinline__ void observe(int, int, const uint32_t (&)[32], int, State&) const {}
-  __device__ __forceinline__ float map(float x) const { return fast_tanh(x); }
+  __device__ __forceinline__ float map(float x) const { return precise ? tanhf(x) : fast_tanh(x); }
   __device__ __forceinline__ float* out(int) const { return C; }
   using Pre = EpiNoState;
   static constexpr int kRowBatch = 8;
@@ -205,6 +206,8 @@ struct EpiStoreLse {
   size_t ldc;
   float2* partial;       // [M, slots]; slot = 2 * n_tile + column half
   int slots;
+  int precise;           // 1: expf (3xTF32 mode); 0: ex2.approx
+  __device__ __forceinline__ float ex(float x) const { return precise ? expf(x) : __expf(x); }
   __device__ __forceinline__ void begin(State& st) const { st.mx = -INFINITY; st.sum = 0.f; }
   __device__ __forceinline__ void end(int m, int slot, int, bool row_ok, State& st) const {
     if (row_ok) partial[(size_t)m * slots + slot] = make_float2(st.mx, st.sum);
@@ -222,14 +225,14 @@ struct EpiStoreLse {
 #pragma unroll
     for (int j = 0; j < 32; ++j)
       if (j < nvalid) cm = fmaxf(cm, __uint_as_float(r[j]));
-    if (cm > st.mx) { st.sum *= __expf(st.mx - cm); st.mx = cm; }
+    if (cm > st.mx) { st.sum *= ex(st.mx - cm); st.mx = cm; }
     float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
 #pragma unroll
     for (int j = 0; j < 32; j += 4) {
-      if (j + 0 < nvalid) a0 += __expf(__uint_as_float(r[j + 0]) - st.mx);
-      if (j + 1 < nvalid) a1 += __expf(__uint_as_float(r[j + 1]) - st.mx);
-      if (j + 2 < nvalid) a2 += __expf(__uint_as_float(r[j + 2]) - st.mx);
-      if (j + 3 < nvalid) a3 += __expf(__uint_as_float(r[j + 3]) - st.mx);
+      if (j + 0 < nvalid) a0 += ex(__uint_as_float(r[j + 0]) - st.mx);
+      if (j + 1 < nvalid) a1 += ex(__uint_as_float(r[j + 1]) - st.mx);
+      if (j + 2 < nvalid) a2 += ex(__uint_as_float(r[j + 2]) - st.mx);
+      if (j + 3 < nvalid) a3 += ex(__uint_as_float(r[j + 3]) - st.mx);
     }
     st.sum += (a0 + a1) + (a2 + a3);
   }
@@ -368,6 +371,7 @@ struct GemmShape {
   int m_tiles, n_tiles, splits;
   int kblocks_per_split;      // K blocks (of BK) per split-K slice
   int n_fastest;              // raster order of work items: 1 = consecutive items share the A tile
+  int terms;                  // 1 = plain tf32;  3 = 3xTF32: every K block is issued as A_lo.B_hi + A_hi.B_lo + A_hi.B_hi
 };
 
 template <int BN, int STAGES>
@@ -383,7 +387,8 @@ struct SmemLayout {
 
 template <int BN, int STAGES, bool A_MN, bool B_MN, class Epi>
 __global__ void __launch_bounds__(kThreads, 1)
-umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, GemmShape gs, Epi epi) {
+umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                 const __grid_constant__ CUtensorMap tmAlo, const __grid_constant__ CUtensorMap tmBlo, GemmShape gs, Epi epi) {
   using L = SmemLayout<BN, STAGES>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -435,25 +440,30 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const int kb0 = sp * gs.kblocks_per_split;
         const int kb1 = min(total_kblocks, kb0 + gs.kblocks_per_split);
         for (int kb = kb0; kb < kb1; ++kb) {
-          mbar_wait(&empty_bar[stage], phase ^ 1);
-          uint8_t* sa = smem + stage * L::kStageBytes;
-          uint8_t* sb = sa + L::kABytes;
-          mbar_expect_tx(&full_bar[stage], L::kStageBytes);
-          if (A_MN) {
-            // global A^T is [K rows, M contiguous]: boxes of {32 m, BK k-rows} (4 KB each)
+          for (int t = 0; t < gs.terms; ++t) {
+            // 3xTF32 term order: the two small cross terms first, then hi.hi
+            const CUtensorMap* mA = (gs.terms == 3 && t == 0) ? &tmAlo : &tmA;
+            const CUtensorMap* mB = (gs.terms == 3 && t == 1) ? &tmBlo : &tmB;
+            mbar_wait(&empty_bar[stage], phase ^ 1);
+            uint8_t* sa = smem + stage * L::kStageBytes;
+            uint8_t* sb = sa + L::kABytes;
+            mbar_expect_tx(&full_bar[stage], L::kStageBytes);
+            if (A_MN) {
+              // global A^T is [K rows, M contiguous]: boxes of {32 m, BK k-rows} (4 KB each)
 #pragma unroll
-            for (int c = 0; c < BM / 32; ++c) tma_load_2d(sa + c * (BK * 128), &tmA, &full_bar[stage], mt * BM + c * 32, kb * BK);
-          } else {
-            // global A is [M rows, K contiguous]: one box {BK k, BM rows}
-            tma_load_2d(sa, &tmA, &full_bar[stage], kb * BK, mt * BM);
-          }
-          if (B_MN) {
+              for (int c = 0; c < BM / 32; ++c) tma_load_2d(sa + c * (BK * 128), mA, &full_bar[stage], mt * BM + c * 32, kb * BK);
+            } else {
+              // global A is [M rows, K contiguous]: one box {BK k, BM rows}
+              tma_load_2d(sa, mA, &full_bar[stage], kb * BK, mt * BM);
+            }
+            if (B_MN) {
 #pragma unroll
-            for (int c = 0; c < BN / 32; ++c) tma_load_2d(sb + c * (BK * 128), &tmB, &full_bar[stage], nt * BN + c * 32, kb * BK);
-          } else {
-            tma_load_2d(sb, &tmB, &full_bar[stage], kb * BK, nt * BN);
+              for (int c = 0; c < BN / 32; ++c) tma_load_2d(sb + c * (BK * 128), mB, &full_bar[stage], nt * BN + c * 32, kb * BK);
+            } else {
+              tma_load_2d(sb, mB, &full_bar[stage], kb * BK, nt * BN);
+            }
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
           }
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
     }
@@ -483,19 +493,21 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + acc * BN;
         for (int kb = kb0; kb < kb1; ++kb) {
-          mbar_wait(&full_bar[stage], phase);
-          tc_fence_after();
-          const uint32_t sa = smem_u32(smem + stage * L::kStageBytes);
-          const uint32_t sb = sa + L::kABytes;
-          const uint64_t adesc = make_smem_desc(sa, a_lbo, a_sbo, a_lt);
-          const uint64_t bdesc = make_smem_desc(sb, b_lbo, b_sbo, b_lt);
+          for (int t = 0; t < gs.terms; ++t) {
+            mbar_wait(&full_bar[stage], phase);
+            tc_fence_after();
+            const uint32_t sa = smem_u32(smem + stage * L::kStageBytes);
+            const uint32_t sb = sa + L::kABytes;
+            const uint64_t adesc = make_smem_desc(sa, a_lbo, a_sbo, a_lt);
+            const uint64_t bdesc = make_smem_desc(sb, b_lbo, b_sbo, b_lt);
 #pragma unroll
-          for (int k = 0; k < BK / UMMA_K; ++k) {
-            mma_tf32(tmem_d, adesc + (uint64_t)((k * a_kstep) >> 4), bdesc + (uint64_t)((k * b_kstep) >> 4), idesc,
-                     (kb > kb0 || k > 0) ? 1u : 0u);
+            for (int k = 0; k < BK / UMMA_K; ++k) {
+              mma_tf32(tmem_d, adesc + (uint64_t)((k * a_kstep) >> 4), bdesc + (uint64_t)((k * b_kstep) >> 4), idesc,
+                       (kb > kb0 || t > 0 || k > 0) ? 1u : 0u);
+            }
+            tc_commit(&empty_bar[stage]);                       // frees the smem stage when the MMAs retire
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
           }
-          tc_commit(&empty_bar[stage]);                       // frees the smem stage when the MMAs retire
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
         tc_commit(&tfull_bar[acc]);                           // accumulator complete -> epilogue
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
@@ -548,8 +560,29 @@ inline EncodeTiledFn get_encode_fn() {
 }
 
 // 2-D fp32 tensor map over a row-major [rows, cols] matrix with row pitch ld (floats); box = {32 cols, box_rows}.
+// Encoded maps are kept in a small per-thread cache: a training step issues the same dozen (buffer, shape)
+// combinations every time, so after the first step no launch calls into the driver for a descriptor.
+struct TensorMapKey {
+  const float* base;
+  uint64_t rows, cols, ld;
+  uint32_t box_rows;
+  bool atom32;
+  bool operator==(const TensorMapKey& o) const {
+    return base == o.base && rows == o.rows && cols == o.cols && ld == o.ld && box_rows == o.box_rows && atom32 == o.atom32;
+  }
+};
+struct TensorMapCache {
+  static constexpr int kCap = 96;
+  TensorMapKey key[kCap];
+  CUtensorMap map[kCap];
+  int n = 0, next = 0;
+};
 inline bool make_tensor_map(CUtensorMap* map, const float* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows,
                             bool atom32) {
+  static thread_local TensorMapCache cache;
+  const TensorMapKey k{base, rows, cols, ld, box_rows, atom32};
+  for (int i = 0; i < cache.n; ++i)
+    if (cache.key[i] == k) { *map = cache.map[i]; return true; }
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) return false;
   cuuint64_t dims[2] = {cols, rows};
@@ -560,29 +593,45 @@ inline bool make_tensor_map(CUtensorMap* map, const float* base, uint64_t rows, 
                   CU_TENSOR_MAP_INTERLEAVE_NONE, atom32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  return r == CUDA_SUCCESS;
+  if (r != CUDA_SUCCESS) return false;
+  const int slot = (cache.n < TensorMapCache::kCap) ? cache.n++ : (cache.next++ % TensorMapCache::kCap);
+  cache.key[slot] = k;
+  cache.map[slot] = *map;
+  return true;
 }
 
 // Operand description: `major_mn == false`: element (x, k) at base[x*ld + k] (K contiguous);
 //                      `major_mn == true` : element (x, k) at base[k*ld + x] (M / N contiguous).
+// 3xTF32 (C2V_MATH_3XTF32): `base` holds the tf32-rounded high parts and `lo` (same layout) the tf32-rounded
+// residuals x - hi; both operands of a product must carry one, or neither.
 struct Operand {
   const float* base;
   size_t ld;
   bool major_mn;
+  const float* lo = nullptr;
 };
 
 template <int BN, int STAGES, bool A_MN, bool B_MN, class Epi>
 inline cudaError_t launch_cfg(cudaStream_t st, int M, int N, int K, int splits, const Operand& A, const Operand& B, const Epi& epi,
                               int num_sms) {
   using L = SmemLayout<BN, STAGES>;
-  CUtensorMap tmA, tmB;
-  const bool okA = A_MN ? make_tensor_map(&tmA, A.base, (uint64_t)K, (uint64_t)M, A.ld, BK, true)
-                        : make_tensor_map(&tmA, A.base, (uint64_t)M, (uint64_t)K, A.ld, BM, false);
-  const bool okB = B_MN ? make_tensor_map(&tmB, B.base, (uint64_t)K, (uint64_t)N, B.ld, BK, true)
-                        : make_tensor_map(&tmB, B.base, (uint64_t)N, (uint64_t)K, B.ld, BN, false);
-  if (!okA || !okB) return cudaErrorInvalidValue;
+  CUtensorMap tmA, tmB, tmAlo, tmBlo;
+  const bool three = A.lo != nullptr && B.lo != nullptr;
+  if ((A.lo != nullptr) != (B.lo != nullptr)) return cudaErrorInvalidValue;
+  auto mapA = [&](CUtensorMap* m, const float* base) {
+    return A_MN ? make_tensor_map(m, base, (uint64_t)K, (uint64_t)M, A.ld, BK, true)
+                : make_tensor_map(m, base, (uint64_t)M, (uint64_t)K, A.ld, BM, false);
+  };
+  auto mapB = [&](CUtensorMap* m, const float* base) {
+    return B_MN ? make_tensor_map(m, base, (uint64_t)K, (uint64_t)N, B.ld, BK, true)
+                : make_tensor_map(m, base, (uint64_t)N, (uint64_t)K, B.ld, BN, false);
+  };
+  if (!mapA(&tmA, A.base) || !mapB(&tmB, B.base)) return cudaErrorInvalidValue;
+  if (three) { if (!mapA(&tmAlo, A.lo) || !mapB(&tmBlo, B.lo)) return cudaErrorInvalidValue; }
+  else { tmAlo = tmA; tmBlo = tmB; }
   GemmShape gs;
   gs.M = M; gs.N = N; gs.K = K;
+  gs.terms = three ? 3 : 1;
   gs.m_tiles = (M + BM - 1) / BM;
   gs.n_tiles = (N + BN - 1) / BN;
   const int total_kblocks = (K + BK - 1) / BK;
@@ -597,7 +646,7 @@ inline cudaError_t launch_cfg(cudaStream_t st, int M, int N, int K, int splits, 
   if (e != cudaSuccess) return e;
   int grid = gs.m_tiles * gs.n_tiles * gs.splits;
   if (grid > num_sms) grid = num_sms;
-  kern<<<grid, kThreads, L::kTotal, st>>>(tmA, tmB, gs, epi);
+  kern<<<grid, kThreads, L::kTotal, st>>>(tmA, tmB, tmAlo, tmBlo, gs, epi);
   return cudaGetLastError();
 }
 

@@ -75,7 +75,8 @@ struct SmemLayout2 {
 
 template <int BN, int STAGES, bool A_MN, bool B_MN, class Epi>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
-umma_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, GemmShape gs, Epi epi) {
+umma_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                  const __grid_constant__ CUtensorMap tmAlo, const __grid_constant__ CUtensorMap tmBlo, GemmShape gs, Epi epi) {
   using L = SmemLayout2<BN, STAGES>;
   static_assert(BN % 64 == 0, "each CTA stages BN/2 columns of B in 32-element chunks");
   extern __shared__ uint8_t smem_raw[];
@@ -132,25 +133,29 @@ umma_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         const int m0 = mt * (2 * BM) + (int)cta * BM;             // this CTA's rows of A
         const int n0 = nt * BN + (int)cta * (BN / 2);             // this CTA's columns of B
         for (int kb = kb0; kb < kb1; ++kb) {
-          mbar_wait(&empty_bar[stage], phase ^ 1);
-          uint8_t* sa = smem + stage * L::kStageBytes;
-          uint8_t* sb = sa + L::kABytes;
-          const uint32_t leader_full = mapa_u32(smem_u32(&full_bar[stage]), 0);
-          if (A_MN) {
+          for (int t = 0; t < gs.terms; ++t) {
+            const CUtensorMap* mA = (gs.terms == 3 && t == 0) ? &tmAlo : &tmA;     // 3xTF32: lo.hi, hi.lo, hi.hi
+            const CUtensorMap* mB = (gs.terms == 3 && t == 1) ? &tmBlo : &tmB;
+            mbar_wait(&empty_bar[stage], phase ^ 1);
+            uint8_t* sa = smem + stage * L::kStageBytes;
+            uint8_t* sb = sa + L::kABytes;
+            const uint32_t leader_full = mapa_u32(smem_u32(&full_bar[stage]), 0);
+            if (A_MN) {
 #pragma unroll
-            for (int c = 0; c < BM / 32; ++c) tma_load_2d_pair(sa + c * (BK * 128), &tmA, leader_full, m0 + c * 32, kb * BK);
-          } else {
-            tma_load_2d_pair(sa, &tmA, leader_full, kb * BK, m0);
-          }
-          if (B_MN) {
+              for (int c = 0; c < BM / 32; ++c) tma_load_2d_pair(sa + c * (BK * 128), mA, leader_full, m0 + c * 32, kb * BK);
+            } else {
+              tma_load_2d_pair(sa, mA, leader_full, kb * BK, m0);
+            }
+            if (B_MN) {
 #pragma unroll
-            for (int c = 0; c < BN / 64; ++c) tma_load_2d_pair(sb + c * (BK * 128), &tmB, leader_full, n0 + c * 32, kb * BK);
-          } else {
-            tma_load_2d_pair(sb, &tmB, leader_full, kb * BK, n0);
+              for (int c = 0; c < BN / 64; ++c) tma_load_2d_pair(sb + c * (BK * 128), mB, leader_full, n0 + c * 32, kb * BK);
+            } else {
+              tma_load_2d_pair(sb, mB, leader_full, kb * BK, n0);
+            }
+            if (cta == 0) mbar_expect_tx(&full_bar[stage], 2 * L::kStageBytes);     // bytes of both CTAs land on this barrier
+            else mbar_arrive_cluster(leader_full);
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
           }
-          if (cta == 0) mbar_expect_tx(&full_bar[stage], 2 * L::kStageBytes);     // bytes of both CTAs land on this barrier
-          else mbar_arrive_cluster(leader_full);
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
     }
@@ -175,19 +180,21 @@ umma_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + acc * BN;
         for (int kb = kb0; kb < kb1; ++kb) {
-          mbar_wait(&full_bar[stage], phase);
-          tc_fence_after();
-          const uint32_t sa = smem_u32(smem + stage * L::kStageBytes);
-          const uint32_t sb = sa + L::kABytes;
-          const uint64_t adesc = make_smem_desc(sa, a_lbo, a_sbo, a_lt);
-          const uint64_t bdesc = make_smem_desc(sb, b_lbo, b_sbo, b_lt);
+          for (int t = 0; t < gs.terms; ++t) {
+            mbar_wait(&full_bar[stage], phase);
+            tc_fence_after();
+            const uint32_t sa = smem_u32(smem + stage * L::kStageBytes);
+            const uint32_t sb = sa + L::kABytes;
+            const uint64_t adesc = make_smem_desc(sa, a_lbo, a_sbo, a_lt);
+            const uint64_t bdesc = make_smem_desc(sb, b_lbo, b_sbo, b_lt);
 #pragma unroll
-          for (int k = 0; k < BK / UMMA_K; ++k) {
-            mma_tf32_pair(tmem_d, adesc + (uint64_t)((k * a_kstep) >> 4), bdesc + (uint64_t)((k * b_kstep) >> 4), idesc,
-                          (kb > kb0 || k > 0) ? 1u : 0u);
+            for (int k = 0; k < BK / UMMA_K; ++k) {
+              mma_tf32_pair(tmem_d, adesc + (uint64_t)((k * a_kstep) >> 4), bdesc + (uint64_t)((k * b_kstep) >> 4), idesc,
+                            (kb > kb0 || t > 0 || k > 0) ? 1u : 0u);
+            }
+            tc_commit_pair(&empty_bar[stage]);                  // frees this stage in both CTAs
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
           }
-          tc_commit_pair(&empty_bar[stage]);                  // frees this stage in both CTAs
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
         tc_commit_pair(&tfull_bar[acc]);                      // accumulator complete in both CTAs
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
@@ -232,14 +239,23 @@ template <int BN, int STAGES, bool A_MN, bool B_MN, class Epi>
 inline cudaError_t launch2_cfg(cudaStream_t st, int M, int N, int K, int splits, const Operand& A, const Operand& B, const Epi& epi,
                                int num_sms) {
   using L = SmemLayout2<BN, STAGES>;
-  CUtensorMap tmA, tmB;
-  const bool okA = A_MN ? make_tensor_map(&tmA, A.base, (uint64_t)K, (uint64_t)M, A.ld, BK, true)
-                        : make_tensor_map(&tmA, A.base, (uint64_t)M, (uint64_t)K, A.ld, BM, false);
-  const bool okB = B_MN ? make_tensor_map(&tmB, B.base, (uint64_t)K, (uint64_t)N, B.ld, BK, true)
-                        : make_tensor_map(&tmB, B.base, (uint64_t)N, (uint64_t)K, B.ld, BN / 2, false);
-  if (!okA || !okB) return cudaErrorInvalidValue;
+  CUtensorMap tmA, tmB, tmAlo, tmBlo;
+  const bool three = A.lo != nullptr && B.lo != nullptr;
+  if ((A.lo != nullptr) != (B.lo != nullptr)) return cudaErrorInvalidValue;
+  auto mapA = [&](CUtensorMap* m, const float* base) {
+    return A_MN ? make_tensor_map(m, base, (uint64_t)K, (uint64_t)M, A.ld, BK, true)
+                : make_tensor_map(m, base, (uint64_t)M, (uint64_t)K, A.ld, BM, false);
+  };
+  auto mapB = [&](CUtensorMap* m, const float* base) {
+    return B_MN ? make_tensor_map(m, base, (uint64_t)K, (uint64_t)N, B.ld, BK, true)
+                : make_tensor_map(m, base, (uint64_t)N, (uint64_t)K, B.ld, BN / 2, false);
+  };
+  if (!mapA(&tmA, A.base) || !mapB(&tmB, B.base)) return cudaErrorInvalidValue;
+  if (three) { if (!mapA(&tmAlo, A.lo) || !mapB(&tmBlo, B.lo)) return cudaErrorInvalidValue; }
+  else { tmAlo = tmA; tmBlo = tmB; }
   GemmShape gs;
   gs.M = M; gs.N = N; gs.K = K;
+  gs.terms = three ? 3 : 1;
   gs.m_tiles = (M + 2 * BM - 1) / (2 * BM);
   gs.n_tiles = (N + BN - 1) / BN;
   const int total_kblocks = (K + BK - 1) / BK;
@@ -253,7 +269,7 @@ inline cudaError_t launch2_cfg(cudaStream_t st, int M, int N, int K, int splits,
   if (e != cudaSuccess) return e;
   int pairs = gs.m_tiles * gs.n_tiles * gs.splits;
   if (pairs > num_sms / 2) pairs = num_sms / 2;
-  kern<<<2 * pairs, kThreads, L::kTotal, st>>>(tmA, tmB, gs, epi);
+  kern<<<2 * pairs, kThreads, L::kTotal, st>>>(tmA, tmB, tmAlo, tmBlo, gs, epi);
   return cudaGetLastError();
 }
 

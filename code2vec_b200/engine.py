@@ -19,6 +19,8 @@ PARAM_NAMES = ("tok", "path", "tgt", "W", "a")
 
 MATH_FP32 = 0
 MATH_TF32 = 1
+MATH_3XTF32 = 2
+MATH_MODES = {"fp32": MATH_FP32, "tf32": MATH_TF32, "3xtf32": MATH_3XTF32}
 
 
 class c2v_dims(C.Structure):
@@ -79,6 +81,9 @@ _SIGNATURES = {
     "c2v_predict_batch_host": (C.c_int, [_P, _P, _P, _P, _P, _I32, _I32, _P, _P, _P, _P, _P]),
     "c2v_selftest_gemm": (C.c_int, [_P, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _P, C.c_size_t, _P, C.c_size_t,
                                     _P, C.c_size_t, _P]),
+    "c2v_selftest_gemm3": (C.c_int, [_P, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _P, _P, C.c_size_t, _P, _P, C.c_size_t,
+                                     _P, C.c_size_t, _P]),
+    "c2v_selftest_split": (C.c_int, [_P, _P, _P, _P, C.c_size_t, _P]),
     "c2v_set_event": (C.c_int, [_P, C.c_char_p, _P]),
     "c2v_sync_tables": (C.c_int, [_P, _P]),
     "c2v_context_forward": (C.c_int, [_P, _P, _P, _P, _P, _I32, C.c_float, C.c_uint64, C.c_uint64, _P, _P, _P]),
@@ -244,9 +249,14 @@ class PathAttentionEngine:
         if getattr(self, "h", None):
             self.lib.c2v_destroy(self.h)
             self.h = None
+            # peers' shards first (unmap), then this rank's own allocations
             for p in getattr(self, "_ipc_opened", []):
                 self.lib.c2v_ipc_close(self.device, p)
             self._ipc_opened = []
+            self.shard_params = self.shard_grads = None          # views of the allocations freed below
+            for p in getattr(self, "_ipc_owned", []):
+                self.lib.c2v_ipc_free(self.device, p)
+            self._ipc_owned = []
 
     def __del__(self):
         try:
@@ -266,13 +276,27 @@ class PathAttentionEngine:
     def launch_count(self) -> int:
         return int(self.lib.c2v_launch_count(self.h))
 
-    def selftest_gemm(self, A, B, a_mn: bool, b_mn: bool, M: int, N: int, K: int, bn: int = 192, splits: int = 1):
+    def selftest_split(self, x):
+        """Test hook: the 3xTF32 operand split of a device tensor -> (hi, lo)."""
+        hi, lo = self.torch.empty_like(x), self.torch.empty_like(x)
+        self._check(self.lib.c2v_selftest_split(self.h, x.data_ptr(), hi.data_ptr(), lo.data_ptr(), x.numel(), self._stream()))
+        return hi, lo
+
+    def selftest_gemm(self, A, B, a_mn: bool, b_mn: bool, M: int, N: int, K: int, bn: int = 192, splits: int = 1,
+                      three: bool = False):
         """Test hook: C[M,N] = A.B on the tcgen05 path.  A is [M,K] (a_mn False) or [K,M] (True) row-major,
-        B is [N,K] (b_mn False) or [K,N] (True); returns C (slices summed on the host side of the test)."""
+        B is [N,K] (b_mn False) or [K,N] (True); returns C (slices summed on the host side of the test).
+        three: as 3xTF32 (operands split on the device first)."""
         torch = self.torch
         out = torch.zeros((max(splits, 1), M, N), dtype=torch.float32, device=self.dev)
-        rc = self.lib.c2v_selftest_gemm(self.h, int(a_mn), int(b_mn), bn, M, N, K, splits, A.data_ptr(), A.stride(0),
-                                        B.data_ptr(), B.stride(0), out.data_ptr(), N, self._stream())
+        if three:
+            (Ah, Al), (Bh, Bl) = self.selftest_split(A), self.selftest_split(B)
+            rc = self.lib.c2v_selftest_gemm3(self.h, int(a_mn), int(b_mn), bn, M, N, K, splits, Ah.data_ptr(), Al.data_ptr(),
+                                             A.stride(0), Bh.data_ptr(), Bl.data_ptr(), B.stride(0), out.data_ptr(), N,
+                                             self._stream())
+        else:
+            rc = self.lib.c2v_selftest_gemm(self.h, int(a_mn), int(b_mn), bn, M, N, K, splits, A.data_ptr(), A.stride(0),
+                                            B.data_ptr(), B.stride(0), out.data_ptr(), N, self._stream())
         if rc < 0:
             self._check(rc)
         return out[:rc].sum(dim=0)
@@ -322,6 +346,10 @@ class PathAttentionEngine:
         self._check(self.lib.c2v_sync_tables(self.h, self._stream()))
 
     def export_params(self) -> Dict[str, np.ndarray]:
+        if getattr(self, "table_world", 1) > 1:
+            # the token / path tables live in row shards (export_table_shards: this rank's rows); the replicated
+            # tensors of the same name are stale and are not handed out
+            return {k: self.params[k].detach().cpu().numpy() for k in ("tgt", "W", "a")}
         self.sync_tables()
         return {k: self.params[k].detach().cpu().numpy() for k in PARAM_NAMES}
 
@@ -523,14 +551,14 @@ class PathAttentionEngine:
                          lr=1e-3, beta1=0.9, beta2=0.999, eps=1e-8) -> float:
         """One reference `sess.run([optimizer, train_loss])` on HOST arrays (numpy or pinned torch
         tensors): H2D copies, train step, Adam, loss read-back -- all inside the C-ABI call."""
-        self.adam_t += 1
         loss = np.zeros(1, dtype=np.float32)
         B = int(src.shape[0])
         src, path, tgt, target = (_as_host(x, np.int32) for x in (src, path, tgt, target))
         mask = _as_host(mask, np.float32)
         self._check(self.lib.c2v_train_batch_host(
             self.h, _host_ptr(src), _host_ptr(path), _host_ptr(tgt), _host_ptr(mask), _host_ptr(target), B,
-            float(keep), int(seed), int(self.adam_t), lr, beta1, beta2, eps, loss.ctypes.data, self._stream()))
+            float(keep), int(seed), int(self.adam_t + 1), lr, beta1, beta2, eps, loss.ctypes.data, self._stream()))
+        self.adam_t += 1          # only once the step went through: a failed call leaves host and engine counters in step
         return float(loss[0])
 
     def predict_batch_host(self, src, path, tgt, mask, normalize: bool = False, want_code: bool = True,
@@ -550,10 +578,19 @@ class PathAttentionEngine:
         return idx, val, code, attn
 
 
+_TORCH_DTYPE_NAMES = {np.dtype(np.int32): "torch.int32", np.dtype(np.float32): "torch.float32"}
+
+
 def _as_host(a, dtype):
-    """numpy arrays are made contiguous/typed (no copy when already so); torch CPU tensors pass through."""
+    """numpy arrays are made contiguous/typed (no copy when already so); torch CPU tensors pass through, but only
+    with the element type the C entry point reads -- an int64 index tensor read as int32 would index the tables
+    out of range without any error."""
     if isinstance(a, np.ndarray):
         return np.ascontiguousarray(a, dtype=dtype)
+    if hasattr(a, "dtype") and hasattr(a, "data_ptr"):
+        want = _TORCH_DTYPE_NAMES[np.dtype(dtype)]
+        if str(a.dtype) != want:
+            raise TypeError("host tensor has dtype %s, the engine reads %s" % (a.dtype, want))
     return a
 
 

@@ -211,16 +211,22 @@ int32_t c2v_vocab_lookup(const void* v, const char* word, int64_t len) { return 
 // target [n] int32, keep [n] uint8 (row filter), tgt_off/tgt_len [n] (target field location).
 // Returns the number of lines (<= capacity), or -(line number + 1) on a malformed line with
 // *err_kind = 1 (field count) / 2 (context with > 3 parts), or INT64_MIN if capacity is too small.
+// Blank lines are skipped (they still count in the reported line number).
 int64_t c2v_parse_chunk(const char* text, int64_t len, int32_t max_contexts, const void* tok, const void* pth, const void* tgt,
                         int32_t mode, int32_t n_threads, int64_t capacity, int32_t* src, int32_t* path, int32_t* dst,
                         float* mask, int32_t* target, uint8_t* keep, int64_t* tgt_off, int32_t* tgt_len, int32_t* err_kind) {
-  std::vector<int64_t> off;
+  // blank lines ("" / "\n") are not records: the Python statement of the reader skips them too.  A record's span
+  // runs to the next record's start, so blank lines after it are trimmed with its own newline.
+  std::vector<int64_t> off, lineno;
   off.reserve(1024);
-  int64_t pos = 0;
+  lineno.reserve(1024);
+  int64_t pos = 0, line = 0;
   while (pos < len) {
-    off.push_back(pos);
     const char* nl = (const char*)memchr(text + pos, '\n', len - pos);
-    pos = nl ? (nl - text) + 1 : len;
+    const int64_t next = nl ? (nl - text) + 1 : len;
+    if (!(nl && nl == text + pos)) { off.push_back(pos); lineno.push_back(line); }
+    pos = next;
+    ++line;
   }
   off.push_back(len);
   const int64_t n = (int64_t)off.size() - 1;
@@ -254,7 +260,7 @@ int64_t c2v_parse_chunk(const char* text, int64_t len, int32_t max_contexts, con
   }
   if (J.bad_line.load() >= 0) {
     if (err_kind) *err_kind = J.bad_kind.load();
-    return -(J.bad_line.load() + 1);
+    return -(lineno[(size_t)J.bad_line.load()] + 1);
   }
   return n;
 }

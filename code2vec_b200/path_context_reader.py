@@ -60,6 +60,20 @@ def load_native_tensoriser():
     return _native_lib or None
 
 
+_INT64_MIN = -(1 << 63)
+
+
+def _raise_parse_error(n: int, kind: int, max_contexts: int):
+    """c2v_parse_chunk's negative return values as the reader's ValueErrors."""
+    if n == _INT64_MIN:
+        # more records than a chunk of that many bytes can hold well-formed lines: some line is far too short
+        raise ValueError("Expect %d fields but have a different number in record (a line of the chunk is too short)"
+                         % (max_contexts + 1))
+    if kind == 2:
+        raise ValueError("a context has more than 3 comma-separated parts (line %d of the chunk)" % (-n - 1))
+    raise ValueError("Expect %d fields but have a different number in record (line %d of the chunk)" % (max_contexts + 1, -n - 1))
+
+
 class _NativeVocab:
     def __init__(self, lib, vocab):
         self.lib = lib
@@ -310,9 +324,7 @@ class PathContextReader:
                                 path.ctypes.data, dst.ctypes.data, mask.ctypes.data, target.ctypes.data, keep.ctypes.data,
                                 toff.ctypes.data, tlen.ctypes.data, C.byref(err))
         if n < 0:
-            if err.value == 2:
-                raise ValueError("a context has more than 3 comma-separated parts (line %d of the chunk)" % (-n - 1))
-            raise ValueError("Expect %d fields but have a different number in record (line %d of the chunk)" % (Cn + 1, -n - 1))
+            _raise_parse_error(n, err.value, Cn)
         sel = keep[:n].astype(bool)
         strings = None
         if self.estimator_action.is_evaluate:
@@ -339,9 +351,7 @@ class PathContextReader:
         n = lib.c2v_parse_chunk(data, len(data), Cn, tok.h, pth.h, tgt.h, 0, threads, cap, src, path, dst, mask, target,
                                 keep.ctypes.data, toff.ctypes.data, tlen.ctypes.data, C.byref(err))
         if n < 0:
-            if err.value == 2:
-                raise ValueError("a context has more than 3 comma-separated parts (line %d of the chunk)" % (-n - 1))
-            raise ValueError("Expect %d fields but have a different number in record (line %d of the chunk)" % (Cn + 1, -n - 1))
+            _raise_parse_error(n, err.value, Cn)
         pool.commit(n, keep[:n])
 
     def _native_chunks(self):

@@ -238,6 +238,18 @@ class Trainer:
             self._sharded_update(t)
         return loss
 
+    def step_device_sampled(self, src, path, tgt, mask, target, sampled, logq_true, logq_sampled):
+        """BASELINE config 3: one training step with the sampled softmax (c2v_sampled_train_step) + Adam.  Single
+        GPU.  With lazy Adam the target table's rows are updated lazily too (only the B + S rows the step reads)."""
+        if self.schedule != "single":
+            raise RuntimeError("the sampled-softmax step is single-GPU")
+        e = self.e
+        t = e.adam_t + 1
+        loss = e.sampled_train_step(src, path, tgt, mask, target, sampled, logq_true, logq_sampled, keep=self.keep,
+                                    seed=self.seed, step=t)
+        e.adam_step(t=t, **self.adam)
+        return loss
+
     def _fully_sharded_step(self, src, path, tgt, mask, target):
         e, dist, fs = self.e, _dist(), self._fs
         t = e.adam_t + 1

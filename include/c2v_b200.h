@@ -72,8 +72,14 @@ typedef struct c2v_tensors {
  *   C2V_MATH_FP32  : fp32 FFMA on the SIMT pipe -- the reference's own arithmetic class
  *                    (cuBLAS/Eigen SGEMM); used for bit-level top-k parity.
  *   C2V_MATH_TF32  : tcgen05.mma kind::tf32 (fp32 storage, 10-bit mantissa operands, fp32
- *                    accumulate in TMEM) -- what TensorFlow itself runs on Ampere+ GPUs. */
-typedef enum c2v_math_mode { C2V_MATH_FP32 = 0, C2V_MATH_TF32 = 1 } c2v_math_mode;
+ *                    accumulate in TMEM) -- what TensorFlow itself runs on Ampere+ GPUs.
+ *   C2V_MATH_3XTF32: the same tensor-core kernels at fp32-equivalent accuracy: every operand is
+ *                    split into tf32 high and low parts (x = hi + lo up to 2^-22 |x|) and a product
+ *                    is issued as a_lo.b_hi + a_hi.b_lo + a_hi.b_hi into the same fp32 TMEM
+ *                    accumulator (the dropped a_lo.b_lo term is O(2^-22) relative); tanh / exp in the
+ *                    epilogues use the correctly rounded library forms.  The reference's arithmetic
+ *                    class (fp32 tf.matmul, tensorflow_model.py:226,252,297) on tensor cores. */
+typedef enum c2v_math_mode { C2V_MATH_FP32 = 0, C2V_MATH_TF32 = 1, C2V_MATH_3XTF32 = 2 } c2v_math_mode;
 
 int c2v_abi_version(void);
 
@@ -120,8 +126,11 @@ int c2v_bind_adam_state(c2v_engine* e, const c2v_tensors* m, const c2v_tensors* 
  * writing 0 acknowledges it for callers that drive c2v_adam_step_range themselves),
  * "early_catchup_count" (read-only: how many train steps used a c2v_hint_next_batch hint),
  * "adam_rows_occupancy" (4 or 5 resident blocks per SM for the lazy-Adam row pass; default 4),
- * "adam_rows_shortcut" (EXPERIMENTAL, default 0, not yet validated on a GPU: rows idle for so long
- * that m -- and later v -- have decayed to exactly zero leave the division / square-root loop). */
+ * "adam_sweep_period" (R, default 32, 0 = off: with lazy_adam every c2v_adam_step also brings rows
+ * [rows*(t mod R)/R, rows*(t mod R + 1)/R) of each lazily updated table up to date, so that no row is
+ * ever more than R steps behind -- this bounds the replay a rarely referenced row costs when a batch
+ * finally reads it, and the cost of c2v_sync_tables, whatever the index distribution; results are
+ * unchanged, the deferred steps are only applied earlier). */
 int c2v_set_option(c2v_engine* e, const char* key, int64_t value);
 int c2v_get_option(const c2v_engine* e, const char* key, int64_t* value);
 
@@ -304,6 +313,15 @@ int c2v_predict_batch_host(c2v_engine* e, const int32_t* h_src, const int32_t* h
 int c2v_selftest_gemm(c2v_engine* e, int32_t a_mn, int32_t b_mn, int32_t bn, int32_t M, int32_t N,
                       int32_t K, int32_t splits, const float* A, size_t lda, const float* B,
                       size_t ldb, float* C, size_t ldc, void* stream);
+
+/* The same product as 3xTF32 (C2V_MATH_3XTF32): A / A_lo and B / B_lo hold the tf32 high parts and
+ * residuals of the fp32 operands (same layout and pitch); c2v_selftest_split produces them
+ * (hi = rna_tf32(x), lo = rna_tf32(x - hi); count % 4 == 0, 16-byte aligned device pointers). */
+int c2v_selftest_gemm3(c2v_engine* e, int32_t a_mn, int32_t b_mn, int32_t bn, int32_t M, int32_t N,
+                       int32_t K, int32_t splits, const float* A, const float* A_lo, size_t lda,
+                       const float* B, const float* B_lo, size_t ldb, float* C, size_t ldc,
+                       void* stream);
+int c2v_selftest_split(c2v_engine* e, const float* x, float* hi, float* lo, size_t count, void* stream);
 
 /* Introspection for tests and bench: number of kernels the engine has launched so far. */
 int64_t c2v_launch_count(const c2v_engine* e);

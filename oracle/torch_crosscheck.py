@@ -88,5 +88,40 @@ class TorchCpuTrainer:
                 p.addcdiv_(self.m[k], self.v[k].sqrt().add_(eps), value=-lr_t)
         return float(L.detach())
 
+    def forward_loss(self, src, path, tgt, mask, target) -> float:
+        """Forward + full-softmax loss only (BASELINE configs[2]); no dropout, no gradient."""
+        with torch.no_grad():
+            v, _ = forward(self.tp, src, path, tgt, mask)
+            L, _ = loss(self.tp, v, target)
+        return float(L)
+
+    def sampled_train_step(self, src, path, tgt, mask, target, sampled, logq_true, logq_sampled, keep=1.0,
+                           dropout_mask=None) -> float:
+        """The sampled-softmax step of path_attention_oracle.sampled_softmax_loss_and_grads with torch autograd, then
+        the same dense Adam (TF1 applies IndexedSlices gradients to every row)."""
+        for t in self.tp.values():
+            t.grad = None
+        v, _ = forward(self.tp, src, path, tgt, mask, keep, dropout_mask)
+        target_t = torch.as_tensor(target, dtype=torch.long)
+        sampled_t = torch.as_tensor(sampled, dtype=torch.long)
+        Y = self.tp["tgt"]
+        l_true = (v * Y[target_t]).sum(dim=1) - torch.as_tensor(logq_true)
+        l_samp = v @ Y[sampled_t].t() - torch.as_tensor(logq_sampled)[None, :]
+        hit = sampled_t[None, :] == target_t[:, None]
+        l_samp = torch.where(hit, torch.full_like(l_samp, -1e9), l_samp)
+        logits = torch.cat([l_true[:, None], l_samp], dim=1)
+        L = torch.nn.functional.cross_entropy(logits, torch.zeros(v.shape[0], dtype=torch.long), reduction="sum") / v.shape[0]
+        L.backward()
+        lr, b1, b2, eps = self.hp
+        self.t += 1
+        lr_t = lr * (1.0 - b2 ** self.t) ** 0.5 / (1.0 - b1 ** self.t)
+        with torch.no_grad():
+            for k, p in self.tp.items():
+                g = p.grad
+                self.m[k].mul_(b1).add_(g, alpha=1.0 - b1)
+                self.v[k].mul_(b2).addcmul_(g, g, value=1.0 - b2)
+                p.addcdiv_(self.m[k], self.v[k].sqrt().add_(eps), value=-lr_t)
+        return float(L.detach())
+
     def numpy_params(self):
         return {k: t.detach().numpy() for k, t in self.tp.items()}

@@ -26,7 +26,7 @@ def test_reference_arm_prints_one_contract_line():
         assert key in d, key
     assert d["impl"] == "reference" and d["unit"] == "path-contexts/s" and d["higher_is_better"] is True
     assert d["vs_baseline"] is None and d["data"] == "synthetic" and d["steps"] == 2 and d["warmup"] == 1
-    assert d["config"]["workload"] == "tiny" and d["value"] > 0 and d["ms_per_step"] > 0
+    assert d["config"]["workload"].startswith("tiny") and d["value"] > 0 and d["ms_per_step"] > 0
     cb = d["cpu_baseline"]
     assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and "sample" in cb
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}

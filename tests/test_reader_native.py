@@ -134,3 +134,42 @@ def test_native_matches_python_on_a_larger_fuzz(tmp_path, threads):
         for name in ("path_source_token_indices", "path_indices", "path_target_token_indices", "context_valid_mask", "target_index"):
             assert np.array_equal(getattr(x, name), getattr(y, name)), name
         assert list(x.target_string) == list(y.target_string)
+
+
+def test_blank_lines_are_skipped_by_both_parsers(tmp_path):
+    """A blank line is not a record: the Python statement skips "" / "\\n" and the native tensoriser does the same
+    (whether a dataset loads must not depend on which of the two is in use)."""
+    C = 6
+    lines = _random_lines(23, C, seed=11)
+    with_blanks = []
+    for i, l in enumerate(lines):
+        with_blanks.append(l)
+        if i % 4 == 1:
+            with_blanks.append("")
+        if i % 9 == 2:
+            with_blanks += ["", ""]
+    cfg, vs = _setup(tmp_path, [""] + with_blanks + ["", ""], C=C, batch=5)
+    (tmp_path / "plain").mkdir()
+    cfg_plain, vs_plain = _setup(tmp_path / "plain", lines, C=C, batch=5)
+    got = {}
+    for native in (False, True):
+        r = PathContextReader(vs, cfg, _Former(), EstimatorAction.Evaluate, use_native=native)
+        got[native] = list(r.get_dataset())
+    plain = list(PathContextReader(vs_plain, cfg_plain, _Former(), EstimatorAction.Evaluate, use_native=True).get_dataset())
+    assert len(got[False]) == len(got[True]) == len(plain)
+    for x, y, z in zip(got[False], got[True], plain):
+        for name in ("path_source_token_indices", "path_indices", "path_target_token_indices", "context_valid_mask", "target_index"):
+            assert np.array_equal(getattr(x, name), getattr(y, name)) and np.array_equal(getattr(y, name), getattr(z, name)), name
+        assert list(x.target_string) == list(y.target_string) == list(z.target_string)
+
+
+def test_many_short_lines_raise_a_clear_error(tmp_path):
+    """More (malformed, short) lines than the chunk's size allows well-formed records: a ValueError about the field
+    count, not a nonsensical line number."""
+    C = 8
+    good = " ".join(["name|1", "t1,100,t2"] + [""] * (C - 1))
+    cfg, vs = _setup(tmp_path, [good] + ["x"] * 50, C=C, batch=2)
+    for native in (False, True):
+        r = PathContextReader(vs, cfg, _Former(), EstimatorAction.Evaluate, use_native=native)
+        with pytest.raises(ValueError, match="fields"):
+            list(r.get_dataset())
