@@ -146,6 +146,7 @@ struct c2v_engine {
                                         // is ever more than R steps behind (bounds the replay of rarely used rows and
                                         // the cost of c2v_sync_tables); 0 = off
   int64_t full_flush_t = 0;             // step count as of which every row was last known to be current
+  int rest_shortcut = 1;                // option "adam_rest_shortcut": replay_row may stop dividing once theta rests
   bool tgt_lazy = false;                // the target table's rows are updated lazily too (sampled softmax steps)
   bool tgt_split_valid = false;         // 3xTF32: ws.tgt_hi / tgt_lo hold the split of the current target table
   bool lazy_grads_pending = false;  // a train step's embedding gradients are in the tables and c2v_adam_step has not followed
@@ -235,6 +236,10 @@ struct PhaseTimer {
       C2V_LAUNCH(e, (adam_rows_kernel<MODE, 4><<<(e)->num_sms * 4, 256, 0, stream>>>(__VA_ARGS__)));           \
   } while (0)
 
+// the "theta rests" exit of the row replay (kernels.cuh, replay_row) is proven for these hyper-parameter ranges only
+inline int rest_ok(const c2v_engine* e) {
+  return (e->rest_shortcut && e->hp_b1 > 0.f && e->hp_b1 <= 0.95f && e->hp_b2 >= 0.99f && e->hp_b2 < 1.f && e->hp_eps > 0.f) ? 1 : 0;
+}
 inline bool is_tc(const c2v_engine* e) { return e->math_mode != C2V_MATH_FP32; }          // tcgen05 GEMMs
 inline bool is_3x(const c2v_engine* e) { return e->math_mode == C2V_MATH_3XTF32; }        // ... as 3xTF32
 
@@ -246,6 +251,10 @@ inline bool is_3x(const c2v_engine* e) { return e->math_mode == C2V_MATH_3XTF32;
 #define C2V_UMMA_192(...) (C2V_PAIR(true) ? umma::launch2<192, 6>(__VA_ARGS__) : umma::launch<192, 4>(__VA_ARGS__))
 #define C2V_UMMA_192_SINGLE(...) (C2V_PAIR(false) ? umma::launch2<192, 6>(__VA_ARGS__) : umma::launch<192, 4>(__VA_ARGS__))
 #define C2V_UMMA_256(...) (C2V_PAIR(true) ? umma::launch2<256, 6>(__VA_ARGS__) : umma::launch<256, 4>(__VA_ARGS__))
+// the same with the operand majors fixed at compile time (the fused-epilogue GEMMs each have one layout, so only
+// that instantiation is built): AMN / BMN = operand is M- resp. N-contiguous in memory
+#define C2V_UMMA_FIXED(BN, AMN, BMN, pair_default, EPI, ...)                                   \
+  (C2V_PAIR(pair_default) ? umma::launch2_cfg<BN, 6, AMN, BMN, EPI>(__VA_ARGS__) : umma::launch_cfg<BN, 4, AMN, BMN, EPI>(__VA_ARGS__))
 
 template <class T> T* wsp(c2v_engine* e, size_t off) { return reinterpret_cast<T*>(e->wbase + off); }
 
@@ -304,9 +313,15 @@ int launch_attn_bwd(c2v_engine* e, cudaStream_t st, float* H, const float* alpha
   PhaseTimer pt(e, PH_ATTN_BWD, st);
 #define C2V_AB(NV)                                                                                        \
   do {                                                                                                    \
-    if (smem > 48 * 1024)                                                                                 \
-      C2V_CUDA(e, cudaFuncSetAttribute(attn_bwd_kernel<NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-    C2V_LAUNCH(e, (attn_bwd_kernel<NV><<<B, kAttnThreads, smem, st>>>(H, alpha, dv, a, C, D, da_part, H_lo))); \
+    if (H_lo) {                                                                                           \
+      if (smem > 48 * 1024)                                                                               \
+        C2V_CUDA(e, cudaFuncSetAttribute(attn_bwd_kernel<NV, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+      C2V_LAUNCH(e, (attn_bwd_kernel<NV, true><<<B, kAttnThreads, smem, st>>>(H, alpha, dv, a, C, D, da_part, H_lo))); \
+    } else {                                                                                              \
+      if (smem > 48 * 1024)                                                                               \
+        C2V_CUDA(e, cudaFuncSetAttribute(attn_bwd_kernel<NV, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+      C2V_LAUNCH(e, (attn_bwd_kernel<NV, false><<<B, kAttnThreads, smem, st>>>(H, alpha, dv, a, C, D, da_part, nullptr))); \
+    }                                                                                                     \
   } while (0)
   switch ((D + 127) / 128) {
     case 1: C2V_AB(1); break;
@@ -355,11 +370,21 @@ int prepare_rows(c2v_engine* e, cudaStream_t st, const ContextSource& cs) {
     const float* lr_tab = wsp<float>(e, e->ws.lr_tab);
     C2V_ADAM_ROWS(e, ADAM_ROWS_CATCHUP, st,
                   e->theta.tok, e->grad.tok, e->am.tok, e->av.tok, d.token_vocab, d.embed_dim, stamp_tok, e->mark_epoch,
-                      wsp<int32_t>(e, e->ws.last_tok), (int32_t)e->adam_t_done, lr_tab, e->hp_b1, e->hp_b2, e->hp_eps);
+                      wsp<int32_t>(e, e->ws.last_tok), (int32_t)e->adam_t_done, lr_tab, e->hp_b1, e->hp_b2, e->hp_eps, rest_ok(e));
     C2V_ADAM_ROWS(e, ADAM_ROWS_CATCHUP, st,
                   e->theta.path, e->grad.path, e->am.path, e->av.path, d.path_vocab, d.embed_dim, stamp_path, e->mark_epoch,
-                      wsp<int32_t>(e, e->ws.last_path), (int32_t)e->adam_t_done, lr_tab, e->hp_b1, e->hp_b2, e->hp_eps);
+                      wsp<int32_t>(e, e->ws.last_path), (int32_t)e->adam_t_done, lr_tab, e->hp_b1, e->hp_b2, e->hp_eps, rest_ok(e));
   }
+  return C2V_OK;
+}
+
+// every row of one table that is behind step t: replay (one warp per row)
+int launch_sweep(c2v_engine* e, cudaStream_t st, float* p, float* g, float* m, float* v, int rows, int dim, int32_t* last, int64_t t) {
+  if (rows <= 0) return C2V_OK;
+  int blocks = (rows + 7) / 8;
+  if (blocks > e->num_sms * 4) blocks = e->num_sms * 4;
+  C2V_LAUNCH(e, (adam_sweep_kernel<4><<<blocks, 256, 0, st>>>(p, g, m, v, rows, dim, last, (int32_t)t, wsp<float>(e, e->ws.lr_tab), e->hp_b1,
+                                                             e->hp_b2, e->hp_eps, rest_ok(e))));
   return C2V_OK;
 }
 
@@ -368,16 +393,13 @@ int flush_rows(c2v_engine* e, cudaStream_t st) {
   if (!e->lazy || e->adam_t_done == 0) return C2V_OK;
   const c2v_dims& d = e->dims;
   const float* lr_tab = wsp<float>(e, e->ws.lr_tab);
-  C2V_ADAM_ROWS(e, ADAM_ROWS_FLUSH, st,
-                  e->theta.tok, e->grad.tok, e->am.tok, e->av.tok, d.token_vocab, d.embed_dim, nullptr, 0,
-                    wsp<int32_t>(e, e->ws.last_tok), (int32_t)e->adam_t_done, lr_tab, e->hp_b1, e->hp_b2, e->hp_eps);
-  C2V_ADAM_ROWS(e, ADAM_ROWS_FLUSH, st,
-                  e->theta.path, e->grad.path, e->am.path, e->av.path, d.path_vocab, d.embed_dim, nullptr, 0,
-                    wsp<int32_t>(e, e->ws.last_path), (int32_t)e->adam_t_done, lr_tab, e->hp_b1, e->hp_b2, e->hp_eps);
+  { int rcw = launch_sweep(e, st, e->theta.tok, e->grad.tok, e->am.tok, e->av.tok, d.token_vocab, d.embed_dim, wsp<int32_t>(e, e->ws.last_tok), e->adam_t_done);
+    if (rcw) return rcw; }
+  { int rcw = launch_sweep(e, st, e->theta.path, e->grad.path, e->am.path, e->av.path, d.path_vocab, d.embed_dim, wsp<int32_t>(e, e->ws.last_path), e->adam_t_done);
+    if (rcw) return rcw; }
   if (e->tgt_lazy)
-    C2V_ADAM_ROWS(e, ADAM_ROWS_FLUSH, st,
-                  e->theta.tgt, e->grad.tgt, e->am.tgt, e->av.tgt, d.target_vocab, d.code_dim, nullptr, 0,
-                    wsp<int32_t>(e, e->ws.last_tgt), (int32_t)e->adam_t_done, lr_tab, e->hp_b1, e->hp_b2, e->hp_eps);
+    { int rcw = launch_sweep(e, st, e->theta.tgt, e->grad.tgt, e->am.tgt, e->av.tgt, d.target_vocab, d.code_dim, wsp<int32_t>(e, e->ws.last_tgt), e->adam_t_done);
+    if (rcw) return rcw; }
   e->full_flush_t = e->adam_t_done;
   return C2V_OK;
 }
@@ -388,10 +410,8 @@ int end_target_lazy(c2v_engine* e, cudaStream_t st) {
   if (!e->tgt_lazy) return C2V_OK;
   if (e->adam_t_done > 0) {
     const c2v_dims& d = e->dims;
-    C2V_ADAM_ROWS(e, ADAM_ROWS_FLUSH, st,
-                  e->theta.tgt, e->grad.tgt, e->am.tgt, e->av.tgt, d.target_vocab, d.code_dim, nullptr, 0,
-                    wsp<int32_t>(e, e->ws.last_tgt), (int32_t)e->adam_t_done, wsp<float>(e, e->ws.lr_tab), e->hp_b1, e->hp_b2,
-                    e->hp_eps);
+    { int rcw = launch_sweep(e, st, e->theta.tgt, e->grad.tgt, e->am.tgt, e->av.tgt, d.target_vocab, d.code_dim, wsp<int32_t>(e, e->ws.last_tgt), e->adam_t_done);
+    if (rcw) return rcw; }
   }
   e->tgt_lazy = false;
   return C2V_OK;
@@ -412,12 +432,7 @@ int sweep_rows(c2v_engine* e, cudaStream_t st, int64_t t) {
     const int64_t lo = (int64_t)rows * ph / R, hi = (int64_t)rows * (ph + 1) / R;
     if (hi <= lo) return C2V_OK;
     const size_t o = (size_t)lo * dim;
-    // a short slice: fewer blocks, so that its rows are spread over all of them
-    int blocks = (int)((hi - lo + 255) / 256);
-    if (blocks > e->num_sms * 4) blocks = e->num_sms * 4;
-    C2V_LAUNCH(e, (adam_rows_kernel<ADAM_ROWS_FLUSH, 4><<<blocks, 256, 0, st>>>(p + o, g + o, m + o, v + o, (int)(hi - lo), dim, nullptr, 0,
-                                                                             last + lo, (int32_t)t, lr_tab, e->hp_b1, e->hp_b2, e->hp_eps)));
-    return C2V_OK;
+    return launch_sweep(e, st, p + o, g + o, m + o, v + o, (int)(hi - lo), dim, last + lo, t);
   };
   int rc;
   if ((rc = slice(e->theta.tok, e->grad.tok, e->am.tok, e->av.tok, d.token_vocab, d.embed_dim, wsp<int32_t>(e, e->ws.last_tok)))) return rc;
@@ -456,10 +471,10 @@ int early_catchup(c2v_engine* e, cudaStream_t side) {
   C2V_LAUNCH(e, (mark_rows_kernel<<<(rows + 255) / 256, 256, 0, side>>>(hs, hp, ht, rows, stamp_tok, stamp_path, e->mark_epoch)));
   C2V_ADAM_ROWS(e, ADAM_ROWS_CATCHUP, side,
                   e->theta.tok, e->grad.tok, e->am.tok, e->av.tok, d.token_vocab, d.embed_dim, stamp_tok, e->mark_epoch,
-                    wsp<int32_t>(e, e->ws.last_tok), (int32_t)t, lr_tab, e->hp_b1, e->hp_b2, e->hp_eps);
+                    wsp<int32_t>(e, e->ws.last_tok), (int32_t)t, lr_tab, e->hp_b1, e->hp_b2, e->hp_eps, rest_ok(e));
   C2V_ADAM_ROWS(e, ADAM_ROWS_CATCHUP, side,
                   e->theta.path, e->grad.path, e->am.path, e->av.path, d.path_vocab, d.embed_dim, stamp_path, e->mark_epoch,
-                    wsp<int32_t>(e, e->ws.last_path), (int32_t)t, lr_tab, e->hp_b1, e->hp_b2, e->hp_eps);
+                    wsp<int32_t>(e, e->ws.last_path), (int32_t)t, lr_tab, e->hp_b1, e->hp_b2, e->hp_eps, rest_ok(e));
   e->early_t = t;
   e->early_count++;
   return C2V_OK;
@@ -485,14 +500,20 @@ int run_ctx_fwd(c2v_engine* e, cudaStream_t st, const ContextSource& cs, const D
     const bool x3 = is_3x(e);
     {
       PhaseTimer pt(e, PH_GATHER, st);
-      C2V_LAUNCH(e, (gather_ctx_kernel<<<(cs.rows + 7) / 8, 256, 0, st>>>(cs, dp, Xg, x3 ? wsp<float>(e, e->ws.Xg_lo) : nullptr)));
+      if (x3) C2V_LAUNCH(e, (gather_ctx_kernel<true><<<(cs.rows + 7) / 8, 256, 0, st>>>(cs, dp, Xg, wsp<float>(e, e->ws.Xg_lo))));
+      else C2V_LAUNCH(e, (gather_ctx_kernel<false><<<(cs.rows + 7) / 8, 256, 0, st>>>(cs, dp, Xg, nullptr)));
     }
     if (x3) { int rcs = split_small(e, st, e->theta.W, (size_t)K * D, e->ws.W_hi, e->ws.W_lo); if (rcs) return rcs; }
     PhaseTimer pt(e, PH_CTX_FWD, st);
     umma::Operand opA{Xg, (size_t)K, false, x3 ? wsp<float>(e, e->ws.Xg_lo) : nullptr};
     umma::Operand opB{x3 ? wsp<float>(e, e->ws.W_hi) : e->theta.W, (size_t)D, true, x3 ? wsp<float>(e, e->ws.W_lo) : nullptr};
-    umma::EpiTanhStore ep{H, (size_t)D, x3 ? 1 : 0};
-    C2V_LAUNCH(e, C2V_CUDA(e, (C2V_UMMA_192(st, cs.rows, D, K, 1, opA, opB, ep, e->num_sms))));
+    if (x3) {
+      umma::EpiTanhStorePrecise ep{H, (size_t)D};
+      C2V_LAUNCH(e, C2V_CUDA(e, (C2V_UMMA_FIXED(192, false, true, true, umma::EpiTanhStorePrecise, st, cs.rows, D, K, 1, opA, opB, ep, e->num_sms))));
+    } else {
+      umma::EpiTanhStore ep{H, (size_t)D};
+      C2V_LAUNCH(e, C2V_CUDA(e, (C2V_UMMA_FIXED(192, false, true, true, umma::EpiTanhStore, st, cs.rows, D, K, 1, opA, opB, ep, e->num_sms))));
+    }
     return C2V_OK;
   }
   PhaseTimer pt(e, PH_CTX_FWD, st);
@@ -521,9 +542,12 @@ int run_logits(c2v_engine* e, cudaStream_t st, const float* v, int B, float* S, 
       opB.base = wsp<float>(e, e->ws.tgt_hi); opB.lo = wsp<float>(e, e->ws.tgt_lo);
     }
     PhaseTimer pt(e, PH_LOGITS, st);
-    if (with_lse) {
-      umma::EpiStoreLse ep{S, e->ws.ldS, wsp<float2>(e, e->ws.lse_part), 2 * ((Y + 255) / 256), x3 ? 1 : 0};
-      C2V_LAUNCH(e, C2V_CUDA(e, (C2V_UMMA_256(st, B, Y, D, 1, opA, opB, ep, e->num_sms))));
+    if (with_lse && x3) {
+      umma::EpiStoreLsePrecise ep{S, e->ws.ldS, wsp<float2>(e, e->ws.lse_part), 2 * ((Y + 255) / 256)};
+      C2V_LAUNCH(e, C2V_CUDA(e, (C2V_UMMA_FIXED(256, false, false, true, umma::EpiStoreLsePrecise, st, B, Y, D, 1, opA, opB, ep, e->num_sms))));
+    } else if (with_lse) {
+      umma::EpiStoreLse ep{S, e->ws.ldS, wsp<float2>(e, e->ws.lse_part), 2 * ((Y + 255) / 256)};
+      C2V_LAUNCH(e, C2V_CUDA(e, (C2V_UMMA_FIXED(256, false, false, true, umma::EpiStoreLse, st, B, Y, D, 1, opA, opB, ep, e->num_sms))));
     } else {
       umma::EpiStore ep{S, e->ws.ldS, 0};
       C2V_LAUNCH(e, C2V_CUDA(e, (C2V_UMMA_256(st, B, Y, D, 1, opA, opB, ep, e->num_sms))));
@@ -725,7 +749,7 @@ int run_dy(c2v_engine* e, cudaStream_t st, const float* v, int B) {
                             (1.0 - pow((double)e->tgt_b1, (double)e->tgt_t));
         umma::EpiAdam ep{e->theta.tgt, e->am.tgt, e->av.tgt, (size_t)D, (float)lr_t, e->tgt_b1, e->tgt_b2, e->tgt_eps,
                          1.f - e->tgt_b1, 1.f - e->tgt_b2};
-        C2V_LAUNCH(e, C2V_CUDA(e, (C2V_UMMA_192_SINGLE(st, Y, D, B, 1, opA, opB, ep, e->num_sms))));
+        C2V_LAUNCH(e, C2V_CUDA(e, (C2V_UMMA_FIXED(192, true, true, false, umma::EpiAdam, st, Y, D, B, 1, opA, opB, ep, e->num_sms))));
         e->tgt_armed = false;
         e->tgt_fused_t = e->tgt_t;
         e->tgt_split_valid = false;
@@ -796,8 +820,10 @@ int train_step_impl(c2v_engine* e, cudaStream_t st, const int32_t* src, const in
       C2V_LAUNCH(e, (xent_combine_kernel<<<B, 256, 0, st>>>(wsp<float2>(e, e->ws.lse_part), n_tiles, S, e->ws.ldS, target,
                                                             loss_b, lse)));
       const int chunks = (int)((e->ws.ldS / 4 + 256 * 8 - 1) / (256 * 8));
-      C2V_LAUNCH(e, (softmax_grad_kernel<<<dim3(chunks, B), 256, 0, st>>>(S, e->ws.ldS, Y, lse, target, invB, 0,
-                                                                          is_3x(e) ? wsp<float>(e, e->ws.S_lo) : nullptr)));
+      if (is_3x(e))
+        C2V_LAUNCH(e, (softmax_grad_kernel<true><<<dim3(chunks, B), 256, 0, st>>>(S, e->ws.ldS, Y, lse, target, invB, 0, wsp<float>(e, e->ws.S_lo))));
+      else
+        C2V_LAUNCH(e, (softmax_grad_kernel<false><<<dim3(chunks, B), 256, 0, st>>>(S, e->ws.ldS, Y, lse, target, invB, 0, nullptr)));
     } else {
       C2V_LAUNCH(e, (xent_kernel<<<B, kXentThreads, 0, st>>>(S, e->ws.ldS, target, Y, invB, loss_b, lse, 1)));
     }
@@ -847,7 +873,7 @@ int sampled_train_step_impl(c2v_engine* e, cudaStream_t st, const int32_t* src, 
     if (e->adam_t_done > 0)
       C2V_ADAM_ROWS(e, ADAM_ROWS_CATCHUP, st,
                     e->theta.tgt, e->grad.tgt, e->am.tgt, e->av.tgt, d.target_vocab, d.code_dim, stamp, e->mark_epoch, last,
-                    (int32_t)e->adam_t_done, wsp<float>(e, e->ws.lr_tab), e->hp_b1, e->hp_b2, e->hp_eps);
+                    (int32_t)e->adam_t_done, wsp<float>(e, e->ws.lr_tab), e->hp_b1, e->hp_b2, e->hp_eps, rest_ok(e));
   }
   {
     PhaseTimer pt(e, PH_SAMPLED, st);
@@ -859,7 +885,8 @@ int sampled_train_step_impl(c2v_engine* e, cudaStream_t st, const int32_t* src, 
     // their gradient rows cleared) before the forward kernel read them; the update of this step is deferred
     // like an embedding row's.  Dense Adam: the bound buffer is dense, so it is cleared first.
     if (!e->tgt_lazy) C2V_CUDA(e, cudaMemsetAsync(e->grad.tgt, 0, (size_t)e->dims.target_vocab * D * 4, st));
-    C2V_LAUNCH(e, (sampled_softmax_bwd_kernel<<<B + S, kSampledThreads, 0, st>>>(v, dl, target, sampled, B, S, D, e->grad.tgt)));
+    C2V_LAUNCH(e, (sampled_softmax_bwd_kernel<<<B + S * ((B + kSampledChunk - 1) / kSampledChunk), kSampledThreads, 0, st>>>(
+        v, dl, target, sampled, B, S, D, e->grad.tgt)));
   }
   if (e->ev_tgt_ready) C2V_CUDA(e, cudaEventRecord(e->ev_tgt_ready, st));
   return context_backward(e, st, cs, mask, B, dp, dv);
@@ -1060,6 +1087,7 @@ int c2v_set_option(c2v_engine* e, const char* key, int64_t value) {
     return C2V_OK;
   }
   if (!strcmp(key, "fuse_target_adam")) { e->fuse_tgt = value ? 1 : 0; return C2V_OK; }
+  if (!strcmp(key, "adam_rest_shortcut")) { e->rest_shortcut = value ? 1 : 0; return C2V_OK; }
   if (!strcmp(key, "adam_sweep_period")) {
     if (value < 0 || value > kLrRing / 2) return fail(e, C2V_ERR_INVALID, "adam_sweep_period must be in [0, 32768]");
     e->sweep_period = (int)value;
@@ -1143,6 +1171,7 @@ int c2v_get_option(const c2v_engine* e, const char* key, int64_t* value) {
   if (!strcmp(key, "profile")) { *value = e->profile; return C2V_OK; }
   if (!strcmp(key, "lazy_adam")) { *value = e->lazy; return C2V_OK; }
   if (!strcmp(key, "adam_sweep_period")) { *value = e->sweep_period; return C2V_OK; }
+  if (!strcmp(key, "adam_rest_shortcut")) { *value = e->rest_shortcut; return C2V_OK; }
   if (!strcmp(key, "cta_pair")) { *value = e->cta_pair; return C2V_OK; }
   if (!strcmp(key, "dy_late")) { *value = e->dy_late; return C2V_OK; }
   if (!strcmp(key, "fuse_target_adam")) { *value = e->fuse_tgt; return C2V_OK; }
@@ -1376,8 +1405,12 @@ int c2v_target_backward(c2v_engine* e, const float* code_all, int32_t Bt, const 
   {
     PhaseTimer pt(e, PH_XENT, st);
     const int chunks = (int)((e->ws.ldS / 4 + 256 * 8 - 1) / (256 * 8));
-    C2V_LAUNCH(e, (softmax_grad_kernel<<<dim3(chunks, Bt), 256, 0, st>>>(S, e->ws.ldS, e->dims.target_vocab, lse, target, inv_batch, row_offset,
-                                                                       (is_tc(e) && is_3x(e)) ? wsp<float>(e, e->ws.S_lo) : nullptr)));
+    if (is_3x(e))
+      C2V_LAUNCH(e, (softmax_grad_kernel<true><<<dim3(chunks, Bt), 256, 0, st>>>(S, e->ws.ldS, e->dims.target_vocab, lse, target, inv_batch,
+                                                                               row_offset, wsp<float>(e, e->ws.S_lo))));
+    else
+      C2V_LAUNCH(e, (softmax_grad_kernel<false><<<dim3(chunks, Bt), 256, 0, st>>>(S, e->ws.ldS, e->dims.target_vocab, lse, target, inv_batch,
+                                                                                row_offset, nullptr)));
   }
   return target_grad_gemms(e, st, code_all, Bt, dv_partial);
 }

@@ -129,11 +129,11 @@ attn_fwd_kernel(const float* __restrict__ H, const float* __restrict__ a, const 
 // Attention backward:  dalpha_c = h_c.dv ; dz = alpha (dalpha - sum alpha dalpha) ;
 // dh = alpha dv + dz a ; du = dh (1 - h^2) written over H ; da partial per example.
 // ---------------------------------------------------------------------------------------------
-template <int NV>
+template <int NV, bool SPLIT>
 __global__ void __launch_bounds__(kAttnThreads)
 attn_bwd_kernel(float* __restrict__ H, const float* __restrict__ alpha, const float* __restrict__ dv,
                 const float* __restrict__ a, int C, int D, float* __restrict__ da_part, float* __restrict__ H_lo) {
-  // H_lo != nullptr (3xTF32): dU is written as its tf32 split, high parts over H and residuals into H_lo
+  // SPLIT (3xTF32): dU is written as its tf32 split, high parts over H and residuals into H_lo
   extern __shared__ float sm[];
   float* dal = sm;                      // [C]
   float* red = dal + ((C + 3) & ~3);    // [32]
@@ -181,7 +181,7 @@ attn_bwd_kernel(float* __restrict__ H, const float* __restrict__ alpha, const fl
         const int j = i * 128 + lane * 4;
         if (j < D) {
           *reinterpret_cast<float4*>(h + j) = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (H_lo) *reinterpret_cast<float4*>(H_lo + ((size_t)b * C + c) * D + j) = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (SPLIT) *reinterpret_cast<float4*>(H_lo + ((size_t)b * C + c) * D + j) = make_float4(0.f, 0.f, 0.f, 0.f);
         }
       }
       continue;
@@ -197,7 +197,7 @@ attn_bwd_kernel(float* __restrict__ H, const float* __restrict__ alpha, const fl
         du.y = (al * gv[i].y + dz * av[i].y) * (1.f - hv.y * hv.y);
         du.z = (al * gv[i].z + dz * av[i].z) * (1.f - hv.z * hv.z);
         du.w = (al * gv[i].w + dz * av[i].w) * (1.f - hv.w * hv.w);
-        if (H_lo) {
+        if (SPLIT) {
           float4 hi, lo;
           split_tf32(du, hi, lo);
           *reinterpret_cast<float4*>(h + j) = hi;
@@ -303,10 +303,11 @@ xent_combine_kernel(const float2* __restrict__ partial, int n_tiles, const float
 }
 
 // S <- (softmax(S) - onehot(target)) * inv_batch in place, padding columns zeroed.  grid (chunks, B).
+template <bool SPLIT>
 __global__ void __launch_bounds__(256)
 softmax_grad_kernel(float* __restrict__ S, size_t ldS, int Y, const float* __restrict__ lse, const int32_t* __restrict__ target,
-                    float inv_batch, int row0 = 0, float* __restrict__ S_lo = nullptr) {
-  // S_lo != nullptr (3xTF32): the gradient is written as its tf32 split (high parts over S, residuals into S_lo)
+                    float inv_batch, int row0, float* __restrict__ S_lo) {
+  // SPLIT (3xTF32): the gradient is written as its tf32 split (high parts over S, residuals into S_lo)
   const int b = blockIdx.y;
   float* row = S + (size_t)b * ldS;
   const float l = lse[b];
@@ -323,7 +324,7 @@ softmax_grad_kernel(float* __restrict__ S, size_t ldS, int Y, const float* __res
       if (y == j) x.x -= inv_batch; else if (y == j + 1) x.y -= inv_batch;
       else if (y == j + 2) x.z -= inv_batch; else x.w -= inv_batch;
     }
-    if (S_lo) {
+    if (SPLIT) {
       float4 hi, lo;
       split_tf32(x, hi, lo);
       *reinterpret_cast<float4*>(row + j) = hi;
@@ -410,8 +411,11 @@ sampled_softmax_fwd_kernel(const float* __restrict__ v, const float* __restrict_
   }
 }
 
-// target-table gradient of the sampled softmax into a zeroed dense [Y, D] buffer:
-// blocks [0, B): true rows  g[y_b] += dl[b,0] v_b ;  blocks [B, B+S): g[sampled_s] += sum_b dl[b,1+s] v_b.
+// target-table gradient of the sampled softmax, added into gradient rows that are zero on entry:
+// grid.x in [0, B): true rows  g[y_b] += dl[b,0] v_b ;
+// grid.x in [B, B + S * chunks): g[sampled_s] += sum_{b in chunk} dl[b,1+s] v_b  (chunks of kSampledChunk examples, so the
+// S sums spread over S * chunks blocks instead of S).
+constexpr int kSampledChunk = 64;
 __global__ void __launch_bounds__(kSampledThreads)
 sampled_softmax_bwd_kernel(const float* __restrict__ v, const float* __restrict__ dl, const int32_t* __restrict__ target,
                            const int32_t* __restrict__ sampled, int B, int S, int D, float* __restrict__ g_tgt) {
@@ -421,11 +425,13 @@ sampled_softmax_bwd_kernel(const float* __restrict__ v, const float* __restrict_
     float* dst = g_tgt + (size_t)target[blk] * D;
     for (int i = threadIdx.x; i < D; i += kSampledThreads) atomicAdd(dst + i, g * v[(size_t)blk * D + i]);
   } else {
-    const int s = blk - B;
+    const int chunks = (B + kSampledChunk - 1) / kSampledChunk;
+    const int s = (blk - B) / chunks, c = (blk - B) % chunks;
+    const int b0 = c * kSampledChunk, b1 = min(B, b0 + kSampledChunk);
     float* dst = g_tgt + (size_t)sampled[s] * D;
     for (int i = threadIdx.x; i < D; i += kSampledThreads) {
       float acc = 0.f;
-      for (int b = 0; b < B; ++b) acc += dl[(size_t)b * (S + 1) + 1 + s] * v[(size_t)b * D + i];
+      for (int b = b0; b < b1; ++b) acc += dl[(size_t)b * (S + 1) + 1 + s] * v[(size_t)b * D + i];
       atomicAdd(dst + i, acc);
     }
   }
@@ -702,10 +708,11 @@ adam_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m,
 // so the three projection GEMMs can be fed by TMA; and its inverse, the scatter-add of dX' rows
 // into the embedding gradient tables.  One warp per context row, 128-bit accesses.
 // ---------------------------------------------------------------------------------------------
+template <bool SPLIT>
 __global__ void __launch_bounds__(256)
 gather_ctx_kernel(const __grid_constant__ ContextSource cs, const __grid_constant__ Dropout dp, float* __restrict__ Xg,
                   float* __restrict__ Xlo) {
-  // Xlo != nullptr (3xTF32): X' is written as its tf32 split
+  // SPLIT (3xTF32): X' is written as its tf32 split (high parts into Xg, residuals into Xlo)
   const int n = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (n >= cs.rows) return;
   const int K3 = 3 * cs.d;
@@ -726,7 +733,7 @@ gather_ctx_kernel(const __grid_constant__ ContextSource cs, const __grid_constan
       if (j < K3) {
         const float4 m = dropout_mult4(dp, n, j >> 2);
         x[u].x *= m.x; x[u].y *= m.y; x[u].z *= m.z; x[u].w *= m.w;
-        if (Xlo) {
+        if (SPLIT) {
           float4 hi, lo;
           split_tf32(x[u], hi, lo);
           *reinterpret_cast<float4*>(dst + j) = hi;
@@ -808,20 +815,86 @@ enum { ADAM_ROWS_CATCHUP = 0, ADAM_ROWS_FLUSH = 2 };
 constexpr int kLrRing = 1 << 16;
 constexpr int kLrRingMask = kLrRing - 1;
 
-// Persistent grid: every warp scans 32 rows at a time (one coalesced read of their stamps and
-// `last` values), then the whole warp walks the rows that need work, one 128-bit access per lane
-// and array.  A row that is behind (last < t_done) replays steps last+1 .. t_done: the first of
-// them with whatever its gradient row holds -- the scatter-add of the step that last touched it,
-// or zeros -- and the rest with a zero gradient; the gradient row is cleared on the way.  So a
-// row the batch references costs one pass (theta, m, v, g in; theta, m, v, 0 out) per step instead
-// of a catch-up pass before the forward and an update pass after the backward.
-// OCC = resident blocks per SM the kernel is compiled for (4: 64 registers, no spills; 5: 48 registers,
-// a few spilled words); the persistent grid is launched as exactly one wave of num_sms * OCC blocks.
+// One row's pending steps last+1 .. t_done, by the whole warp (lane -> 4 consecutive elements of every
+// 128-column slice): the first with whatever the gradient row holds -- the scatter-add of the step that last
+// touched the row, or zeros -- and the rest with a zero gradient, in the dense kernel's operations and order;
+// the gradient row is cleared on the way.
+//
+// "theta rests" exit (rest_ok): in a zero-gradient step m shrinks by b1 (~0.9) while sqrt(v) + eps shrinks by
+// at most sqrt(b2) (~0.9995) and lr_s grows by less than 1.3 % per step (s >= 2), so the update
+// delta_s = lr_s m_s / (sqrt(v_s) + eps) shrinks monotonically in magnitude and keeps its sign.  Rounding is
+// monotone, so once fl(theta - delta_s) == theta for EVERY element of the row it stays so for all later steps:
+// theta is left alone and only m <- fl(m b1), v <- fl(v b2) continue, without the division and square root.
+// Bit-identical to the dense kernel (tests/test_lazy_adam_model.py on the CPU, tests/test_gpu_lazy_adam.py on
+// the GPU); the engine enables it only for 0 < b1 <= 0.95, 0.99 <= b2 < 1.
+__device__ __forceinline__ void replay_row(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+                                           size_t row_off, int d, int32_t from, int32_t t_done, const float* __restrict__ lr_tab,
+                                           float b1, float b2, float eps, float omb1, float omb2, int lane, bool rest_ok) {
+  for (int j0 = 0; j0 < d; j0 += 128) {          // every lane walks every slice: the vote below needs all 32
+    const int j = j0 + lane * 4;
+    const bool act = j < d;
+    const size_t o = row_off + (act ? j : 0);
+    float4 P = make_float4(0.f, 0.f, 0.f, 0.f), M = P, V = P, G = P;
+    if (act) {
+      P = *reinterpret_cast<float4*>(p + o); M = *reinterpret_cast<float4*>(m + o); V = *reinterpret_cast<float4*>(v + o);
+      G = *reinterpret_cast<const float4*>(g + o);
+    }
+    float* pp = reinterpret_cast<float*>(&P);
+    float* mm = reinterpret_cast<float*>(&M);
+    float* vv = reinterpret_cast<float*>(&V);
+    const float* gg = reinterpret_cast<const float*>(&G);
+    {  // step from+1: the deferred gradient step (the dense kernel's exact operations)
+      const float lr_s = lr_tab[(from + 1) & kLrRingMask];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        mm[q] = __fadd_rn(__fmul_rn(mm[q], b1), __fmul_rn(omb1, gg[q]));
+        vv[q] = __fadd_rn(__fmul_rn(vv[q], b2), __fmul_rn(omb2, __fmul_rn(gg[q], gg[q])));
+        pp[q] = __fsub_rn(pp[q], __fdiv_rn(__fmul_rn(lr_s, mm[q]), __fadd_rn(__fsqrt_rn(vv[q]), eps)));
+      }
+    }
+    // the zero-gradient steps after it: m*b1 + (1-b1)*0, v*b2 + (1-b2)*(0*0)
+    int32_t s = from + 2;
+    for (; s <= t_done; ++s) {
+      const float lr_s = lr_tab[s & kLrRingMask];
+      bool moved = false;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        mm[q] = __fadd_rn(__fmul_rn(mm[q], b1), __fmul_rn(omb1, 0.f));
+        vv[q] = __fadd_rn(__fmul_rn(vv[q], b2), __fmul_rn(omb2, 0.f));
+        const float np = __fsub_rn(pp[q], __fdiv_rn(__fmul_rn(lr_s, mm[q]), __fadd_rn(__fsqrt_rn(vv[q]), eps)));
+        moved |= (__float_as_uint(np) != __float_as_uint(pp[q]));
+        pp[q] = np;
+      }
+      if (rest_ok && !__any_sync(0xffffffffu, moved)) { ++s; break; }
+    }
+    for (; s <= t_done; ++s) {                    // theta rests: only the slots still decay
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        mm[q] = __fadd_rn(__fmul_rn(mm[q], b1), __fmul_rn(omb1, 0.f));
+        vv[q] = __fadd_rn(__fmul_rn(vv[q], b2), __fmul_rn(omb2, 0.f));
+      }
+    }
+    if (act) {
+      *reinterpret_cast<float4*>(p + o) = P;
+      *reinterpret_cast<float4*>(m + o) = M;
+      *reinterpret_cast<float4*>(v + o) = V;
+      if ((__float_as_uint(G.x) | __float_as_uint(G.y) | __float_as_uint(G.z) | __float_as_uint(G.w)) != 0u)
+        *reinterpret_cast<float4*>(g + o) = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  }
+}
+
+// Catch-up of the rows a batch references.  Persistent grid: every warp scans 32 rows at a time (one coalesced
+// read of their stamps and `last` values), then the whole warp walks the rows that need work.  So a row the
+// batch references costs one pass (theta, m, v, g in; theta, m, v, 0 out) per step instead of a catch-up pass
+// before the forward and an update pass after the backward.
+// OCC = resident blocks per SM the kernel is compiled for; the persistent grid is launched as exactly one wave
+// of num_sms * OCC blocks.
 template <int MODE, int OCC>
 __global__ void __launch_bounds__(256, OCC)
 adam_rows_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, int rows, int d,
                  const int32_t* __restrict__ stamp, int32_t epoch, int32_t* __restrict__ last, int32_t t_done,
-                 const float* __restrict__ lr_tab, float b1, float b2, float eps) {
+                 const float* __restrict__ lr_tab, float b1, float b2, float eps, int rest_ok) {
   const int lane = threadIdx.x & 31;
   const int warp_global = (blockIdx.x * 256 + threadIdx.x) >> 5;
   const int total_warps = (gridDim.x * 256) >> 5;
@@ -841,43 +914,30 @@ adam_rows_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict
     while (todo) {
       const int b = __ffs(todo) - 1;
       todo &= todo - 1;
-      const int row = base + b;
       const int32_t from = __shfl_sync(0xffffffffu, from_l, b);
-      for (int j = lane * 4; j < d; j += 128) {
-        const size_t o = (size_t)row * d + j;
-        float4 P = *reinterpret_cast<float4*>(p + o), M = *reinterpret_cast<float4*>(m + o), V = *reinterpret_cast<float4*>(v + o);
-        const float4 G = *reinterpret_cast<const float4*>(g + o);
-        float* pp = reinterpret_cast<float*>(&P);
-        float* mm = reinterpret_cast<float*>(&M);
-        float* vv = reinterpret_cast<float*>(&V);
-        const float* gg = reinterpret_cast<const float*>(&G);
-        {  // step from+1: the deferred gradient step (the dense kernel's exact operations)
-          const float lr_s = lr_tab[(from + 1) & kLrRingMask];
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            mm[q] = __fadd_rn(__fmul_rn(mm[q], b1), __fmul_rn(omb1, gg[q]));
-            vv[q] = __fadd_rn(__fmul_rn(vv[q], b2), __fmul_rn(omb2, __fmul_rn(gg[q], gg[q])));
-            pp[q] = __fsub_rn(pp[q], __fdiv_rn(__fmul_rn(lr_s, mm[q]), __fadd_rn(__fsqrt_rn(vv[q]), eps)));
-          }
-        }
-        // the zero-gradient steps after it: m*b1 + (1-b1)*0, v*b2 + (1-b2)*(0*0)
-        for (int32_t s = from + 2; s <= t_done; ++s) {
-          const float lr_s = lr_tab[s & kLrRingMask];
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            mm[q] = __fadd_rn(__fmul_rn(mm[q], b1), __fmul_rn(omb1, 0.f));
-            vv[q] = __fadd_rn(__fmul_rn(vv[q], b2), __fmul_rn(omb2, 0.f));
-            pp[q] = __fsub_rn(pp[q], __fdiv_rn(__fmul_rn(lr_s, mm[q]), __fadd_rn(__fsqrt_rn(vv[q]), eps)));
-          }
-        }
-        *reinterpret_cast<float4*>(p + o) = P;
-        *reinterpret_cast<float4*>(m + o) = M;
-        *reinterpret_cast<float4*>(v + o) = V;
-        if ((__float_as_uint(G.x) | __float_as_uint(G.y) | __float_as_uint(G.z) | __float_as_uint(G.w)) != 0u)
-          *reinterpret_cast<float4*>(g + o) = make_float4(0.f, 0.f, 0.f, 0.f);
-      }
+      replay_row(p, g, m, v, (size_t)(base + b) * d, d, from, t_done, lr_tab, b1, b2, eps, omb1, omb2, lane, rest_ok != 0);
     }
     if (hit) last[r] = t_done;
+  }
+}
+
+// Sweep / flush: EVERY row of [0, rows) that is behind is brought up to date, one warp per row (grid-stride), so
+// a slice of a few ten thousand rows still spreads over every resident warp of the GPU.
+template <int OCC>
+__global__ void __launch_bounds__(256, OCC)
+adam_sweep_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, int rows, int d,
+                  int32_t* __restrict__ last, int32_t t_done, const float* __restrict__ lr_tab, float b1, float b2, float eps,
+                  int rest_ok) {
+  const int lane = threadIdx.x & 31;
+  const int warp_global = (blockIdx.x * 256 + threadIdx.x) >> 5;
+  const int total_warps = (gridDim.x * 256) >> 5;
+  const float omb1 = __fsub_rn(1.f, b1), omb2 = __fsub_rn(1.f, b2);
+  for (int row = warp_global; row < rows; row += total_warps) {
+    const int32_t from = last[row];
+    if (from >= t_done) continue;
+    replay_row(p, g, m, v, (size_t)row * d, d, from, t_done, lr_tab, b1, b2, eps, omb1, omb2, lane, rest_ok != 0);
+    __syncwarp();
+    if (lane == 0) last[row] = t_done;
   }
 }
 

@@ -179,15 +179,15 @@ struct EpiStore {
   __device__ __forceinline__ void store4(float* c, size_t off, float4 v, const Pre&) const { *reinterpret_cast<float4*>(c + off) = v; }
   __device__ __forceinline__ void store1(float* c, size_t off, float x) const { c[off] = x; }
 };
-struct EpiTanhStore {
+template <bool PRECISE>      // PRECISE: tanhf (the fp32-faithful 3xTF32 mode); else the ex2.approx form
+struct EpiTanhStoreT {
   using State = EpiNoState;
   float* C;
   size_t ldc;
-  int precise;           // 1: tanhf (the fp32-faithful 3xTF32 mode); 0: the ex2.approx form
   __device__ __forceinline__ void begin(State&) const {}
   __device__ __forceinline__ void end(int, int, int, bool, State&) const {}
   __device__ __forceinline__ void observe(int, int, const uint32_t (&)[32], int, State&) const {}
-  __device__ __forceinline__ float map(float x) const { return precise ? tanhf(x) : fast_tanh(x); }
+  __device__ __forceinline__ float map(float x) const { return PRECISE ? tanhf(x) : fast_tanh(x); }
   __device__ __forceinline__ float* out(int) const { return C; }
   using Pre = EpiNoState;
   static constexpr int kRowBatch = 8;
@@ -200,14 +200,14 @@ struct EpiTanhStore {
 // Logits epilogue: stores the tile of S and folds the row-wise (max, sum exp) of this warp's columns
 // into a per-(row, half tile) partial, so the cross entropy needs no extra pass over S for its
 // log-sum-exp (tensorflow_model.py:227-230).
-struct EpiStoreLse {
+template <bool PRECISE>      // PRECISE: expf (3xTF32 mode); else ex2.approx
+struct EpiStoreLseT {
   struct State { float mx, sum; };
   float* C;
   size_t ldc;
   float2* partial;       // [M, slots]; slot = 2 * n_tile + column half
   int slots;
-  int precise;           // 1: expf (3xTF32 mode); 0: ex2.approx
-  __device__ __forceinline__ float ex(float x) const { return precise ? expf(x) : __expf(x); }
+  __device__ __forceinline__ float ex(float x) const { return PRECISE ? expf(x) : __expf(x); }
   __device__ __forceinline__ void begin(State& st) const { st.mx = -INFINITY; st.sum = 0.f; }
   __device__ __forceinline__ void end(int m, int slot, int, bool row_ok, State& st) const {
     if (row_ok) partial[(size_t)m * slots + slot] = make_float2(st.mx, st.sum);
@@ -237,6 +237,11 @@ struct EpiStoreLse {
     st.sum += (a0 + a1) + (a2 + a3);
   }
 };
+
+using EpiTanhStore = EpiTanhStoreT<false>;
+using EpiTanhStorePrecise = EpiTanhStoreT<true>;
+using EpiStoreLse = EpiStoreLseT<false>;
+using EpiStoreLsePrecise = EpiStoreLseT<true>;
 
 // Target-table gradient epilogue with the optimizer folded in (option "fuse_target_adam"): the
 // accumulator element is dYtab[y, j]; instead of writing it out for adam_kernel to read back, the
@@ -439,32 +444,36 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         decode(item, mt, nt, sp);
         const int kb0 = sp * gs.kblocks_per_split;
         const int kb1 = min(total_kblocks, kb0 + gs.kblocks_per_split);
-        for (int kb = kb0; kb < kb1; ++kb) {
-          for (int t = 0; t < gs.terms; ++t) {
-            // 3xTF32 term order: the two small cross terms first, then hi.hi
-            const CUtensorMap* mA = (gs.terms == 3 && t == 0) ? &tmAlo : &tmA;
-            const CUtensorMap* mB = (gs.terms == 3 && t == 1) ? &tmBlo : &tmB;
-            mbar_wait(&empty_bar[stage], phase ^ 1);
-            uint8_t* sa = smem + stage * L::kStageBytes;
-            uint8_t* sb = sa + L::kABytes;
-            mbar_expect_tx(&full_bar[stage], L::kStageBytes);
-            if (A_MN) {
-              // global A^T is [K rows, M contiguous]: boxes of {32 m, BK k-rows} (4 KB each)
+        // 3xTF32: the two small cross terms (A_lo.B_hi, A_hi.B_lo) over the whole K range first, then A_hi.B_hi.
+        // The tensor core adds into the fp32 accumulator with truncation, ~half an ulp of the accumulator per
+        // MMA; while only the 2^-11-sized cross terms have been added that loss is negligible, so the
+        // accumulation error is that of ONE pass over K instead of three.
+        auto load_stage = [&](const CUtensorMap* mA, const CUtensorMap* mB, int kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * L::kStageBytes;
+          uint8_t* sb = sa + L::kABytes;
+          mbar_expect_tx(&full_bar[stage], L::kStageBytes);
+          if (A_MN) {
+            // global A^T is [K rows, M contiguous]: boxes of {32 m, BK k-rows} (4 KB each)
 #pragma unroll
-              for (int c = 0; c < BM / 32; ++c) tma_load_2d(sa + c * (BK * 128), mA, &full_bar[stage], mt * BM + c * 32, kb * BK);
-            } else {
-              // global A is [M rows, K contiguous]: one box {BK k, BM rows}
-              tma_load_2d(sa, mA, &full_bar[stage], kb * BK, mt * BM);
-            }
-            if (B_MN) {
-#pragma unroll
-              for (int c = 0; c < BN / 32; ++c) tma_load_2d(sb + c * (BK * 128), mB, &full_bar[stage], nt * BN + c * 32, kb * BK);
-            } else {
-              tma_load_2d(sb, mB, &full_bar[stage], kb * BK, nt * BN);
-            }
-            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            for (int c = 0; c < BM / 32; ++c) tma_load_2d(sa + c * (BK * 128), mA, &full_bar[stage], mt * BM + c * 32, kb * BK);
+          } else {
+            // global A is [M rows, K contiguous]: one box {BK k, BM rows}
+            tma_load_2d(sa, mA, &full_bar[stage], kb * BK, mt * BM);
           }
+          if (B_MN) {
+#pragma unroll
+            for (int c = 0; c < BN / 32; ++c) tma_load_2d(sb + c * (BK * 128), mB, &full_bar[stage], nt * BN + c * 32, kb * BK);
+          } else {
+            tma_load_2d(sb, mB, &full_bar[stage], kb * BK, nt * BN);
+          }
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        };
+        if (gs.terms == 3) {
+          for (int kb = kb0; kb < kb1; ++kb) load_stage(&tmAlo, &tmB, kb);
+          for (int kb = kb0; kb < kb1; ++kb) load_stage(&tmA, &tmBlo, kb);
         }
+        for (int kb = kb0; kb < kb1; ++kb) load_stage(&tmA, &tmB, kb);
       }
     }
   } else if (warp == 1) {
@@ -492,22 +501,21 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1);          // epilogue has drained this accumulator
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + acc * BN;
-        for (int kb = kb0; kb < kb1; ++kb) {
-          for (int t = 0; t < gs.terms; ++t) {
-            mbar_wait(&full_bar[stage], phase);
-            tc_fence_after();
-            const uint32_t sa = smem_u32(smem + stage * L::kStageBytes);
-            const uint32_t sb = sa + L::kABytes;
-            const uint64_t adesc = make_smem_desc(sa, a_lbo, a_sbo, a_lt);
-            const uint64_t bdesc = make_smem_desc(sb, b_lbo, b_sbo, b_lt);
+        const int n_steps = (kb1 - kb0) * gs.terms;          // 3xTF32: three passes over the K range (see the producer)
+        for (int it = 0; it < n_steps; ++it) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * L::kStageBytes);
+          const uint32_t sb = sa + L::kABytes;
+          const uint64_t adesc = make_smem_desc(sa, a_lbo, a_sbo, a_lt);
+          const uint64_t bdesc = make_smem_desc(sb, b_lbo, b_sbo, b_lt);
 #pragma unroll
-            for (int k = 0; k < BK / UMMA_K; ++k) {
-              mma_tf32(tmem_d, adesc + (uint64_t)((k * a_kstep) >> 4), bdesc + (uint64_t)((k * b_kstep) >> 4), idesc,
-                       (kb > kb0 || t > 0 || k > 0) ? 1u : 0u);
-            }
-            tc_commit(&empty_bar[stage]);                       // frees the smem stage when the MMAs retire
-            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          for (int k = 0; k < BK / UMMA_K; ++k) {
+            mma_tf32(tmem_d, adesc + (uint64_t)((k * a_kstep) >> 4), bdesc + (uint64_t)((k * b_kstep) >> 4), idesc,
+                     (it > 0 || k > 0) ? 1u : 0u);
           }
+          tc_commit(&empty_bar[stage]);                       // frees the smem stage when the MMAs retire
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
         tc_commit(&tfull_bar[acc]);                           // accumulator complete -> epilogue
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }

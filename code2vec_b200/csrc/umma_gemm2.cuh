@@ -132,31 +132,32 @@ umma_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         const int kb1 = min(total_kblocks, kb0 + gs.kblocks_per_split);
         const int m0 = mt * (2 * BM) + (int)cta * BM;             // this CTA's rows of A
         const int n0 = nt * BN + (int)cta * (BN / 2);             // this CTA's columns of B
-        for (int kb = kb0; kb < kb1; ++kb) {
-          for (int t = 0; t < gs.terms; ++t) {
-            const CUtensorMap* mA = (gs.terms == 3 && t == 0) ? &tmAlo : &tmA;     // 3xTF32: lo.hi, hi.lo, hi.hi
-            const CUtensorMap* mB = (gs.terms == 3 && t == 1) ? &tmBlo : &tmB;
-            mbar_wait(&empty_bar[stage], phase ^ 1);
-            uint8_t* sa = smem + stage * L::kStageBytes;
-            uint8_t* sb = sa + L::kABytes;
-            const uint32_t leader_full = mapa_u32(smem_u32(&full_bar[stage]), 0);
-            if (A_MN) {
+        auto load_stage = [&](const CUtensorMap* mA, const CUtensorMap* mB, int kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * L::kStageBytes;
+          uint8_t* sb = sa + L::kABytes;
+          const uint32_t leader_full = mapa_u32(smem_u32(&full_bar[stage]), 0);
+          if (A_MN) {
 #pragma unroll
-              for (int c = 0; c < BM / 32; ++c) tma_load_2d_pair(sa + c * (BK * 128), mA, leader_full, m0 + c * 32, kb * BK);
-            } else {
-              tma_load_2d_pair(sa, mA, leader_full, kb * BK, m0);
-            }
-            if (B_MN) {
-#pragma unroll
-              for (int c = 0; c < BN / 64; ++c) tma_load_2d_pair(sb + c * (BK * 128), mB, leader_full, n0 + c * 32, kb * BK);
-            } else {
-              tma_load_2d_pair(sb, mB, leader_full, kb * BK, n0);
-            }
-            if (cta == 0) mbar_expect_tx(&full_bar[stage], 2 * L::kStageBytes);     // bytes of both CTAs land on this barrier
-            else mbar_arrive_cluster(leader_full);
-            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            for (int c = 0; c < BM / 32; ++c) tma_load_2d_pair(sa + c * (BK * 128), mA, leader_full, m0 + c * 32, kb * BK);
+          } else {
+            tma_load_2d_pair(sa, mA, leader_full, kb * BK, m0);
           }
+          if (B_MN) {
+#pragma unroll
+            for (int c = 0; c < BN / 64; ++c) tma_load_2d_pair(sb + c * (BK * 128), mB, leader_full, n0 + c * 32, kb * BK);
+          } else {
+            tma_load_2d_pair(sb, mB, leader_full, kb * BK, n0);
+          }
+          if (cta == 0) mbar_expect_tx(&full_bar[stage], 2 * L::kStageBytes);     // bytes of both CTAs land on this barrier
+          else mbar_arrive_cluster(leader_full);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        };
+        if (gs.terms == 3) {                                                     // 3xTF32: cross terms first (umma_gemm.cuh)
+          for (int kb = kb0; kb < kb1; ++kb) load_stage(&tmAlo, &tmB, kb);
+          for (int kb = kb0; kb < kb1; ++kb) load_stage(&tmA, &tmBlo, kb);
         }
+        for (int kb = kb0; kb < kb1; ++kb) load_stage(&tmA, &tmB, kb);
       }
     }
   } else if (warp == 1) {
@@ -179,22 +180,21 @@ umma_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1);          // both CTAs' epilogues have drained this accumulator
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + acc * BN;
-        for (int kb = kb0; kb < kb1; ++kb) {
-          for (int t = 0; t < gs.terms; ++t) {
-            mbar_wait(&full_bar[stage], phase);
-            tc_fence_after();
-            const uint32_t sa = smem_u32(smem + stage * L::kStageBytes);
-            const uint32_t sb = sa + L::kABytes;
-            const uint64_t adesc = make_smem_desc(sa, a_lbo, a_sbo, a_lt);
-            const uint64_t bdesc = make_smem_desc(sb, b_lbo, b_sbo, b_lt);
+        const int n_steps = (kb1 - kb0) * gs.terms;
+        for (int it = 0; it < n_steps; ++it) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * L::kStageBytes);
+          const uint32_t sb = sa + L::kABytes;
+          const uint64_t adesc = make_smem_desc(sa, a_lbo, a_sbo, a_lt);
+          const uint64_t bdesc = make_smem_desc(sb, b_lbo, b_sbo, b_lt);
 #pragma unroll
-            for (int k = 0; k < BK / UMMA_K; ++k) {
-              mma_tf32_pair(tmem_d, adesc + (uint64_t)((k * a_kstep) >> 4), bdesc + (uint64_t)((k * b_kstep) >> 4), idesc,
-                            (kb > kb0 || t > 0 || k > 0) ? 1u : 0u);
-            }
-            tc_commit_pair(&empty_bar[stage]);                  // frees this stage in both CTAs
-            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          for (int k = 0; k < BK / UMMA_K; ++k) {
+            mma_tf32_pair(tmem_d, adesc + (uint64_t)((k * a_kstep) >> 4), bdesc + (uint64_t)((k * b_kstep) >> 4), idesc,
+                          (it > 0 || k > 0) ? 1u : 0u);
           }
+          tc_commit_pair(&empty_bar[stage]);                  // frees this stage in both CTAs
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
         tc_commit_pair(&tfull_bar[acc]);                      // accumulator complete in both CTAs
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }

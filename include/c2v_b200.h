@@ -130,7 +130,11 @@ int c2v_bind_adam_state(c2v_engine* e, const c2v_tensors* m, const c2v_tensors* 
  * [rows*(t mod R)/R, rows*(t mod R + 1)/R) of each lazily updated table up to date, so that no row is
  * ever more than R steps behind -- this bounds the replay a rarely referenced row costs when a batch
  * finally reads it, and the cost of c2v_sync_tables, whatever the index distribution; results are
- * unchanged, the deferred steps are only applied earlier). */
+ * unchanged, the deferred steps are only applied earlier), "adam_rest_shortcut" (0/1, default 1: a row's
+ * zero-gradient replay stops dividing / taking square roots once an update no longer changes any element of
+ * the row -- updates shrink monotonically from there, so the parameters provably stay put and only the
+ * slots keep decaying; bit-identical to the full replay for 0 < beta1 <= 0.95 and 0.99 <= beta2 < 1, and
+ * not applied outside that range). */
 int c2v_set_option(c2v_engine* e, const char* key, int64_t value);
 int c2v_get_option(const c2v_engine* e, const char* key, int64_t* value);
 

@@ -189,3 +189,45 @@ def test_sampled_softmax_updates_target_rows_lazily_and_exactly():
         assert np.abs(a[k] - b[k]).max() < 2e-6, k
     assert torch.allclose(lazy.adam_m["tgt"], dense.adam_m["tgt"], atol=1e-7)
     assert torch.allclose(lazy.adam_v["tgt"], dense.adam_v["tgt"], atol=1e-9)
+
+
+@pytest.mark.parametrize("period", [0, 32])
+@pytest.mark.parametrize("embed_dim", [32, 128, 256])
+def test_long_idle_rows_replay_exactly(embed_dim, period):
+    """Rows touched once and then left alone for 300 steps (the "theta rests" exit of replay_row fires after ~150 idle
+    steps; with the sweep they are replayed in slices of <= 32 steps, without it in one go at the flush), and rows
+    never touched at all, against the dense engine: bit for bit.  embed_dim 32 / 256 cover rows narrower and wider
+    than one 128-column slice of the warp."""
+    import torch
+    dims = O.Dims(token_vocab=1501, path_vocab=701, target_vocab=101, embed_dim=embed_dim, code_dim=64, max_contexts=6)
+    steps = 300
+    first = O.synthetic_batch(dims, B, seed=900)
+    later = O.synthetic_batch(dims, B, seed=901)
+    later = tuple(np.where(a > 0, 1 + (a % 40), a).astype(a.dtype) if i < 3 else a for i, a in enumerate(later))   # rows 1..40 only
+    lazy, params0 = make_engine(dims, max_batch=B)
+    dense, _ = make_engine(dims, max_batch=B, params=params0)
+    lazy.set_option("lazy_adam", 1)
+    lazy.set_option("adam_sweep_period", period)
+    for s in range(steps):
+        src, pth, tgt, mask, target = first if s == 0 else later
+        for eng in (lazy, dense):
+            eng.train_step(*dev_batch(eng, src, pth, tgt, mask, target), keep=1.0)
+            eng.adam_step()
+    a, b = lazy.export_params(), dense.export_params()
+    for name, cols in (("tok", (0, 2)), ("path", (1,))):
+        counts = np.zeros(a[name].shape[0], dtype=np.int64)
+        for c in cols:
+            np.add.at(counts, first[c][first[3] > 0], 1)
+        idle = counts == 1
+        idle[:41] = False                                   # rows the later batches keep using
+        assert idle.sum() > 20
+        assert np.array_equal(a[name][idle].view(np.uint32), b[name][idle].view(np.uint32)), name
+        assert np.abs(a[name][idle] - params0[name][idle]).max() > 1e-4          # they did move, then rested
+        never = counts == 0
+        never[:41] = False
+        assert np.array_equal(a[name][never], params0[name][never])
+        sel = torch.from_numpy(idle | never).to(lazy.dev)          # rows free of atomic-order effects: slots agree bit for bit too
+        assert torch.equal(lazy.adam_m[name][sel], dense.adam_m[name][sel])
+        assert torch.equal(lazy.adam_v[name][sel], dense.adam_v[name][sel])
+    # the exit can be switched off; the result is the same
+    assert lazy.get_option("adam_rest_shortcut") == 1
