@@ -429,7 +429,20 @@ def run_ours(args):
     roofline = roofline_of(dominant, dom_ms) if dominant else None
     # north_star's own yardstick, whatever the dominant kernel is: the embedding gather against the HBM roofline on
     # SURVEY 8d's bytes (table rows + indices + mask; the X' it writes is not counted as useful work)
-    gather_roofline = roofline_of("gather", phase_out["gather"]["ms"]) if ("gather" in phase_out and "gather" in work) else None
+    gather_roofline = None
+    if "gather" in phase_out and "gather" in work:
+        gather_roofline = roofline_of("gather", phase_out["gather"]["ms"])
+    elif "ctx_fwd" in phase_out and "gather" in work:
+        # fused gather -> projection kernel: the gather has no launch of its own.  Its bytes over the WHOLE fused kernel's
+        # time (which also runs the projection GEMM and writes H) is a lower bound of the gather's bandwidth; "kernel_total"
+        # counts everything the fused kernel moves (rows in; H out; X' out when training) against the same time.
+        gather_roofline = roofline_of("gather", phase_out["ctx_fwd"]["ms"])
+        if gather_roofline["bound"] == "hbm":
+            N, D, d3 = B * C, w["code_dim"], 3 * w["embed_dim"]
+            total = work["gather"][1] + 4.0 * N * D + (4.0 * N * d3 if mode != "fwd_loss" else 0.0)
+            ach = total / (phase_out["ctx_fwd"]["ms"] * 1e-3) / 1e9
+            gather_roofline.update({"kernel": "ctx_fused (gather + projection + tanh)", "lower_bound": True,
+                                    "kernel_total": {"bytes": total, "achieved": round(ach, 1), "frac": round(ach / peaks["hbm"], 4)}})
 
     cpu = None
     if world == 1 and not args.no_cpu_baseline:

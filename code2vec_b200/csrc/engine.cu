@@ -17,6 +17,7 @@
 #include "sgemm.cuh"
 #include "umma_gemm.cuh"
 #include "umma_gemm2.cuh"
+#include "ctx_fused.cuh"
 
 using namespace c2v;
 
@@ -157,6 +158,7 @@ struct c2v_engine {
   bool has_theta, has_grad, has_adam;
   bool emb_grads_clean;      // token/path gradient tables are known to be all-zero
   int math_mode;
+  int fuse_gather = 1;       // option "fuse_gather": gather -> projection -> tanh as one kernel on the tf32 path (ctx_fused.cuh)
   int cta_pair = 2;          // tcgen05 GEMMs as CTA pairs (cta_group::2, UMMA 256 x BN): 0 never, 1 always, 2 auto
   int num_sms;
   cudaEvent_t ev_tgt_ready = nullptr;   // recorded after dY (caller-owned)
@@ -492,9 +494,19 @@ int split_small(c2v_engine* e, cudaStream_t st, const float* x, size_t n, size_t
 }
 
 // H = tanh(X' . W)   (tensorflow_model.py:238-252)
-int run_ctx_fwd(c2v_engine* e, cudaStream_t st, const ContextSource& cs, const Dropout& dp, float* H) {
+int run_ctx_fwd(c2v_engine* e, cudaStream_t st, const ContextSource& cs, const Dropout& dp, float* H, bool keep_x) {
   const int D = e->dims.code_dim, K = 3 * e->dims.embed_dim;
   { int rc0 = prepare_rows(e, st, cs); if (rc0) return rc0; }
+  if (is_tc(e) && !is_3x(e) && e->fuse_gather && e->dims.embed_dim % 32 == 0 && cs.rows % 4 == 0 &&
+      (((uintptr_t)cs.src | (uintptr_t)cs.pth | (uintptr_t)cs.tgt) % 16) == 0) {
+    // gather -> dropout -> projection -> tanh in one kernel (ctx_fused.cuh); X' is written out only when a backward
+    // pass will need it (dW = X'^T . dU)
+    PhaseTimer pt(e, PH_CTX_FWD, st);
+    umma::EpiTanhStore ep{H, (size_t)D};
+    C2V_LAUNCH(e, C2V_CUDA(e, (umma::launch_ctx_fused<192, 4>(st, cs.rows, D, e->theta.W, (size_t)D, cs, dp,
+                                                              keep_x ? wsp<float>(e, e->ws.Xg) : nullptr, ep, e->num_sms))));
+    return C2V_OK;
+  }
   if (is_tc(e)) {
     float* Xg = wsp<float>(e, e->ws.Xg);
     const bool x3 = is_3x(e);
@@ -563,10 +575,10 @@ int run_logits(c2v_engine* e, cudaStream_t st, const float* v, int B, float* S, 
 }
 
 int forward_impl(c2v_engine* e, cudaStream_t st, const int32_t* src, const int32_t* pth, const int32_t* tgt,
-                 const float* mask, int B, const Dropout& dp, float* code_vec, float* attn) {
+                 const float* mask, int B, const Dropout& dp, float* code_vec, float* attn, bool keep_x = false) {
   ContextSource cs = make_source(e, src, pth, tgt, B);
   float* H = wsp<float>(e, e->ws.H);
-  int rc = run_ctx_fwd(e, st, cs, dp, H);
+  int rc = run_ctx_fwd(e, st, cs, dp, H, keep_x);
   if (rc) return rc;
   return launch_attn_fwd(e, st, H, mask, B, attn, code_vec);
 }
@@ -808,7 +820,7 @@ int train_step_impl(c2v_engine* e, cudaStream_t st, const int32_t* src, const in
   float* loss_b = wsp<float>(e, e->ws.loss_b);
   float* lse = wsp<float>(e, e->ws.lse);
   int rc;
-  if ((rc = run_ctx_fwd(e, st, cs, dp, H))) return rc;
+  if ((rc = run_ctx_fwd(e, st, cs, dp, H, true))) return rc;
   if ((rc = launch_attn_fwd(e, st, H, mask, B, alpha, v))) return rc;
   const bool fused_lse = (is_tc(e));
   if ((rc = run_logits(e, st, v, B, S, fused_lse))) return rc;
@@ -850,7 +862,7 @@ int sampled_train_step_impl(c2v_engine* e, cudaStream_t st, const int32_t* src, 
   float* loss_b = wsp<float>(e, e->ws.loss_b);
   float* dl = wsp<float>(e, e->ws.dl);
   int rc;
-  if ((rc = run_ctx_fwd(e, st, cs, dp, H))) return rc;
+  if ((rc = run_ctx_fwd(e, st, cs, dp, H, true))) return rc;
   if ((rc = launch_attn_fwd(e, st, H, mask, B, alpha, v))) return rc;
   const float invB = 1.0f / (float)B;
   if (e->lazy && e->has_adam && e->table_world == 1) {
@@ -1087,6 +1099,7 @@ int c2v_set_option(c2v_engine* e, const char* key, int64_t value) {
     return C2V_OK;
   }
   if (!strcmp(key, "fuse_target_adam")) { e->fuse_tgt = value ? 1 : 0; return C2V_OK; }
+  if (!strcmp(key, "fuse_gather")) { e->fuse_gather = value ? 1 : 0; return C2V_OK; }
   if (!strcmp(key, "adam_rest_shortcut")) { e->rest_shortcut = value ? 1 : 0; return C2V_OK; }
   if (!strcmp(key, "adam_sweep_period")) {
     if (value < 0 || value > kLrRing / 2) return fail(e, C2V_ERR_INVALID, "adam_sweep_period must be in [0, 32768]");
@@ -1175,6 +1188,7 @@ int c2v_get_option(const c2v_engine* e, const char* key, int64_t* value) {
   if (!strcmp(key, "cta_pair")) { *value = e->cta_pair; return C2V_OK; }
   if (!strcmp(key, "dy_late")) { *value = e->dy_late; return C2V_OK; }
   if (!strcmp(key, "fuse_target_adam")) { *value = e->fuse_tgt; return C2V_OK; }
+  if (!strcmp(key, "fuse_gather")) { *value = e->fuse_gather; return C2V_OK; }
   if (!strcmp(key, "adam_step_count")) { *value = e->adam_t_done; return C2V_OK; }
   if (!strcmp(key, "target_adam_fused_step")) { *value = e->tgt_fused_t; return C2V_OK; }
   if (!strcmp(key, "early_catchup_count")) { *value = e->early_count; return C2V_OK; }
@@ -1360,7 +1374,7 @@ int c2v_context_forward(c2v_engine* e, const int32_t* src, const int32_t* path, 
   if (!(keep_prob > 0.f) || keep_prob > 1.f) return fail(e, C2V_ERR_INVALID, "keep_prob must be in (0, 1]");
   C2V_CUDA(e, cudaSetDevice(e->device));
   const Dropout dp = make_dropout(e->dims, keep_prob, seed, step, dropout_mask);
-  return forward_impl(e, (cudaStream_t)stream, src, path, tgt, mask, B, dp, code_vec, wsp<float>(e, e->ws.alpha));
+  return forward_impl(e, (cudaStream_t)stream, src, path, tgt, mask, B, dp, code_vec, wsp<float>(e, e->ws.alpha), true);
 }
 
 int c2v_target_forward(c2v_engine* e, const float* code_all, int32_t Bt, const int32_t* target, int32_t row_offset,

@@ -68,3 +68,31 @@ def test_tf32_train_step(dims, B, cta_pair):
         # updates are +-lr whatever the gradient's size, so a tf32-level difference in a near-zero gradient
         # element moves that parameter by a full step; at D = 768 the loss drifts by ~1e-4 after two of them.
         assert abs(l - lr) < (1e-4 if t == 1 or dims.code_dim <= 384 else 3e-4), (t, l, lr)
+
+
+@pytest.mark.parametrize("dims,B,keep", [(TINY, 64, 1.0), (TINY, 64, 0.75), (MID, 48, 0.75), (LARGE, 12, 0.75), (MID, 3, 1.0)])
+def test_fused_gather_projection_is_bit_identical_to_the_unfused_path(dims, B, keep):
+    """ctx_fused.cuh (gather -> dropout -> tcgen05 projection -> tanh in one kernel) feeds the tensor core the same
+    operand image TMA would have loaded from a materialised X', so everything downstream of it must carry the same
+    bits as with option fuse_gather = 0: code vectors, attention, loss, and the gradients that do not go through
+    float atomics (dW reads the X' the fused kernel wrote out)."""
+    import torch
+    src, pth, tgt, mask, target = O.synthetic_batch(dims, B, seed=41)
+    out = {}
+    for fuse in (1, 0):
+        eng, _ = make_engine(dims, max_batch=B)
+        eng.set_option("math_mode", 1)
+        eng.set_option("fuse_gather", fuse)
+        assert eng.get_option("fuse_gather") == fuse
+        d = dev_batch(eng, src, pth, tgt, mask, target)
+        code, attn = eng.forward(*d[:4])
+        loss = eng.train_step(*d, keep=keep, seed=11, step=3)
+        torch.cuda.synchronize()
+        out[fuse] = (code.cpu().numpy(), attn.cpu().numpy(), float(loss.cpu()[0]), eng.export_grads())
+        eng.close()
+    assert np.array_equal(out[1][0], out[0][0]) and np.array_equal(out[1][1], out[0][1])
+    assert out[1][2] == out[0][2]
+    for k in ("W", "a", "tgt"):
+        assert np.array_equal(out[1][3][k], out[0][3][k]), k
+    for k in ("tok", "path"):
+        assert rel_err(out[1][3][k], out[0][3][k]) < 1e-5, k
