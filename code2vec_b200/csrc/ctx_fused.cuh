@@ -2,18 +2,18 @@
 // (tensorflow_model.py:238-252) in ONE kernel -- the embedding gather feeds the tensor core directly, the
 // gathered context matrix X' is never read back from HBM.
 //
-// Persistent, warp-specialised, one CTA per SM (448 threads):
+// Persistent, warp-specialised, one CTA per SM (576 threads):
 //   warp 0        : TMA producer of the B operand (W tiles, cp.async.bulk.tensor, 128-byte swizzle, MN-major);
 //                   also stages each tile's index triples (src, path, tgt) into shared memory with 1-D TMA
 //                   bulk copies (cp.async.bulk.shared.global) one tile ahead
 //   warp 1        : MMA issuer -- tcgen05.mma.cta_group::1.kind::tf32 (UMMA 128 x BN x 8), TMEM allocation
 //   warps 2..9    : epilogue -- tcgen05.ld of their TMEM lane quadrant, tanh, coalesced stores of H
-//   warps 10..13  : GATHER producers of the A operand.  A stage is 128 contexts x 32 floats (one 128-byte swizzle
-//                   row per context): 8 lanes read the 128 contiguous bytes of one table row segment with 128-bit
-//                   loads (4 rows per warp instruction), apply the Philox dropout multipliers in registers and
-//                   store 16-byte chunks at the SWIZZLE_128B position (chunk ^ (row & 7)) the tensor core expects --
-//                   exactly the image TMA would have written from a materialised X'.  The loads of k-block i+1 are
-//                   issued before k-block i is stored, so every producer thread keeps 8-16 row segments in flight.
+//   warps 10..17  : GATHER producers of the A operand, one PAIR of warps per shared-memory stage.  A stage is 128
+//                   contexts x 32 floats (one 128-byte swizzle row per context): 8 lanes read the 128 contiguous bytes of
+//                   one table row segment with 128-bit loads (4 rows per warp instruction, 16 per thread), apply the
+//                   Philox dropout multipliers in registers and store 16-byte chunks at the SWIZZLE_128B position
+//                   (chunk ^ (row & 7)) the tensor core expects -- exactly the image TMA would have written from a
+//                   materialised X'.  The four pairs work a quarter period apart: 64 KB of rows in flight per SM.
 //                   When training, the dropped-out rows are also written out once (X', for the dW = X'^T.dU GEMM
 //                   of the backward pass): a write the unfused path made too, without its read-back.
 // Barriers: full[s] collects the TMA transaction of the W tile plus one arrival per gather warp (after a
@@ -25,10 +25,10 @@
 namespace c2v {
 namespace umma {
 
-constexpr int kGatherWarps = 4;
+constexpr int kGatherWarps = 8;
 constexpr int kGatherWarp0 = kEpiWarp0 + kEpiWarps;              // 10
-constexpr int kFusedThreads = 32 * (kGatherWarp0 + kGatherWarps);   // 448
-constexpr int kGatherRowsPerThread = BM * 8 / (32 * kGatherWarps);  // 8 chunks of 16 B per thread per stage
+constexpr int kFusedThreads = 32 * (kGatherWarp0 + kGatherWarps);   // 576
+constexpr int kGatherRowsPerThread = BM * 8 / (32 * kGatherWarps);  // 4 chunks of 16 B per thread per stage
 constexpr int kIdxBufs = 3;          // index triples are staged two tiles ahead of the gather warps
 
 __device__ __forceinline__ void bulk_copy_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
@@ -50,6 +50,7 @@ struct FusedSmem {
 };
 
 template <int BN, int STAGES, class Epi>
+// 576 threads: the register file is handed out to a CTA in units of 4 warps, so 20 x 32 x 96 registers is the most that fits
 __global__ void __launch_bounds__(kFusedThreads, 1)
 ctx_fused_kernel(const __grid_constant__ CUtensorMap tmB, GemmShape gs, const __grid_constant__ ContextSource cs,
                  const __grid_constant__ Dropout dp, float* __restrict__ Xout, Epi epi) {
@@ -72,7 +73,8 @@ ctx_fused_kernel(const __grid_constant__ CUtensorMap tmB, GemmShape gs, const __
   const int kps = cs.d / BK;                     // k-blocks per segment (source token | path | target token)
 
   if (warp == 0 && lane == 0) {
-    for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1 + kGatherWarps); mbar_init(&empty_bar[s], 1); }
+    // full: the TMA transaction of the W tile + the stage's pair of gather warps
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1 + 2); mbar_init(&empty_bar[s], 1); }
     for (int a = 0; a < 2; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], kEpiWarps); }
     for (int a = 0; a < kIdxBufs; ++a) { mbar_init(&ifull_bar[a], 1); mbar_init(&iempty_bar[a], kGatherWarps); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -186,62 +188,71 @@ ctx_fused_kernel(const __grid_constant__ CUtensorMap tmB, GemmShape gs, const __
     }
   } else {
     // ===================== gather producers of the A operand =====================
-    const int gl = (warp - kGatherWarp0) * 32 + lane;        // 0 .. 127
-    const int c = gl & 7;                                    // 16-byte chunk of the 128-byte row segment
-    const int rg = gl >> 3;                                  // rows rg, rg + 16, ..., rg + 112
-    constexpr int R = kGatherRowsPerThread;                  // 8
-    int stage = 0;
-    uint32_t phase = 0;
-    int ib = 0;
-    uint32_t iphase = 0;
-    for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
-      int mt, nt;
-      decode(item, mt, nt);
-      const int m0 = mt * BM;
-      mbar_wait(&ifull_bar[ib], iphase);
-      const int32_t* my_idx = sidx + ib * 3 * BM;
-      float4 cur[R], nxt[R];
-      auto issue = [&](int kb, float4 (&x)[R]) {
-        const int seg = kb / kps;
-        const int col = (kb - seg * kps) * BK + c * 4;
-        const int32_t* ids = my_idx + seg * BM;
-#pragma unroll
-        for (int i = 0; i < R; ++i) {
-          const int r = rg + 16 * i;
-          if (m0 + r < gs.M) {
-            const float* rowp = (seg == 1) ? table_row(cs.path, ids[r], cs.d) : table_row(cs.tok, ids[r], cs.d);
-            x[i] = __ldg(reinterpret_cast<const float4*>(rowp + col));
-          } else {
-            x[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-          }
-        }
-      };
-      issue(0, cur);
-      for (int kb = 0; kb < total_kblocks; ++kb) {
-        if (kb + 1 < total_kblocks) issue(kb + 1, nxt);              // next k-block's rows are in flight while this one is stored
-        mbar_wait(&empty_bar[stage], phase ^ 1);
-        uint8_t* sa = smem + stage * L::kStageBytes;
-#pragma unroll
-        for (int i = 0; i < R; ++i) {
-          const int r = rg + 16 * i;
-          float4 x = cur[i];
-          const float4 mlt = dropout_mult4(dp, m0 + r, (kb * BK + c * 4) >> 2);
-          x.x *= mlt.x; x.y *= mlt.y; x.z *= mlt.z; x.w *= mlt.w;
-          *reinterpret_cast<float4*>(sa + r * 128 + ((c ^ (r & 7)) << 4)) = x;
-          if (Xout != nullptr && nt == 0 && m0 + r < gs.M)
-            *reinterpret_cast<float4*>(Xout + (size_t)(m0 + r) * gs.K + kb * BK + c * 4) = x;
-        }
-        fence_proxy_async_smem();                                    // generic-proxy stores -> visible to the tensor core
+    // The (tile, k-block) steps of this CTA form one stream g = 0, 1, 2, ...; step g lands in smem stage g % STAGES.
+    // A PAIR of warps owns every STAGES-th step (pair p <-> stage p): its 64 threads issue the 16 row-segment loads
+    // (16 B each) of their step, wait for the stage to be free, apply dropout, store the swizzled chunks, fence and
+    // arrive.  The four pairs run a quarter period apart, so four stages' worth of rows (64 KB per SM) are in flight
+    // while no thread ever executes its proxy fence with loads of a LATER step outstanding (the fence would wait
+    // for them and serialise the stream).
+    static_assert(kGatherWarps == 2 * STAGES, "one pair of gather warps per shared-memory stage");
+    const int gw = warp - kGatherWarp0;
+    const int pair = gw >> 1;                                // == the smem stage this pair fills
+    const int t64 = (gw & 1) * 32 + lane;                    // 0 .. 63 within the pair
+    const int c = t64 & 7;                                   // 16-byte chunk of the 128-byte row segment
+    const int rg = t64 >> 3;                                 // rows rg, rg + 8, ..., rg + 120
+    constexpr int R = BM / 8;                                // 16 rows per thread
+    const uint32_t soff = (uint32_t)(rg * 128 + ((c ^ rg) << 4));     // (r & 7) == rg for every row of this thread
+    const bool drop = dp.enabled != 0;
+    const int items_here = (total_items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+    const int total_steps = items_here * total_kblocks;
+    uint8_t* sa = smem + pair * L::kStageBytes + soff;
+    int released = 0;                                        // tiles whose index buffers this warp has released
+    auto release_to = [&](int k_end) {                       // this warp will not read the indices of tiles < k_end again
+      for (; released < k_end; ++released) {
         __syncwarp();
-        if (lane == 0) mbar_arrive(&full_bar[stage]);
-        if (++stage == STAGES) { stage = 0; phase ^= 1; }
-#pragma unroll
-        for (int i = 0; i < R; ++i) cur[i] = nxt[i];
+        if (lane == 0) mbar_arrive(&iempty_bar[released % kIdxBufs]);
       }
+    };
+    uint32_t visit = 0;
+    for (int g = pair; g < total_steps; g += STAGES, ++visit) {
+      const int k = g / total_kblocks, kb = g - k * total_kblocks;
+      const int item = blockIdx.x + k * gridDim.x;
+      const int nt = item % gs.n_tiles;
+      const int m0 = (item / gs.n_tiles) * BM;
+      release_to(k);
+      mbar_wait(&ifull_bar[k % kIdxBufs], (uint32_t)(k / kIdxBufs) & 1u);       // the tile's index triples have landed
+      const int seg = kb / kps;
+      const int col = (kb - seg * kps) * BK + c * 4;
+      const int32_t* ids = sidx + (k % kIdxBufs) * 3 * BM + seg * BM;
+      float4 x[R];
+#pragma unroll
+      for (int i = 0; i < R; ++i) {
+        const int r = rg + 8 * i;
+        if (m0 + r < gs.M) {
+          const float* rowp = (seg == 1) ? table_row(cs.path, ids[r], cs.d) : table_row(cs.tok, ids[r], cs.d);
+          x[i] = __ldg(reinterpret_cast<const float4*>(rowp + col));
+        } else {
+          x[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      }
+      mbar_wait(&empty_bar[pair], (visit & 1u) ^ 1u);        // the MMAs that read this stage last time have retired
+      const bool wx = (Xout != nullptr) && nt == 0;
+      float* xo = Xout + (size_t)(m0 + rg) * gs.K + kb * BK + c * 4;
+#pragma unroll
+      for (int i = 0; i < R; ++i) {
+        float4 v = x[i];
+        if (drop) {
+          const float4 mlt = dropout_mult4(dp, m0 + rg + 8 * i, kb * (BK / 4) + c);
+          v.x *= mlt.x; v.y *= mlt.y; v.z *= mlt.z; v.w *= mlt.w;
+        }
+        *reinterpret_cast<float4*>(sa + i * (8 * 128)) = v;
+        if (wx && m0 + rg + 8 * i < gs.M) *reinterpret_cast<float4*>(xo + (size_t)i * 8 * gs.K) = v;
+      }
+      fence_proxy_async_smem();                              // generic-proxy stores -> visible to the tensor core
       __syncwarp();
-      if (lane == 0) mbar_arrive(&iempty_bar[ib]);                   // this warp is done with the tile's indices
-      if (++ib == kIdxBufs) { ib = 0; iphase ^= 1; }
+      if (lane == 0) mbar_arrive(&full_bar[pair]);
     }
+    release_to(items_here);
   }
   tc_fence_before();
   __syncthreads();
