@@ -126,8 +126,14 @@ class Code2VecModel(Code2VecModelBase):
         # steps, the reference's own fp32 FMA class for evaluate()/predict() so that top-k is decided on
         # fp32 logits.  C2V_MATH=fp32|tf32 forces one mode for both.
         forced = os.environ.get("C2V_MATH", "").lower()
-        self._math_train = {"fp32": 0, "tf32": 1}.get(forced, 1)
-        self._math_eval = {"fp32": 0, "tf32": 1}.get(forced, 0)
+        modes = {"fp32": 0, "tf32": 1, "3xtf32": 2}
+        self._math_train = modes.get(forced, 1)
+        # evaluate()/predict(): the tensor cores at fp32-equivalent accuracy (3xTF32), so top-k is decided on fp32-class
+        # logits at tensor-core speed; both choices are logged, nothing switches silently
+        self._math_eval = modes.get(forced, 2)
+        self.log("b200 backend arithmetic: train = %s, evaluate/predict = %s (C2V_MATH=fp32|tf32|3xtf32 forces one for both)" % (
+            {0: "fp32 FFMA", 1: "tf32 tensor cores", 2: "3xTF32 tensor cores (fp32-equivalent)"}[self._math_train],
+            {0: "fp32 FFMA", 1: "tf32 tensor cores", 2: "3xTF32 tensor cores (fp32-equivalent)"}[self._math_eval]))
         # C2V_HINT_NEXT=1: pass each next batch to the engine (c2v_hint_next_batch); no measured gain on one GPU
         self._hint_next = os.environ.get("C2V_HINT_NEXT", "0") == "1"
         if self.config.is_training:
@@ -226,7 +232,20 @@ class Code2VecModel(Code2VecModelBase):
                                          config=cfg, estimator_action=EstimatorAction.Train)
         self.log("Started reader...")
         former = _TrainInputFormer()
-        for batch, following in _with_next(_prefetch(train_reader.get_dataset())):
+        # pinned-host batch ring + copy stream (batch_ring.py): the reader thread draws every batch straight into a
+        # page-locked slot, its upload overlaps the previous step, and the loop never waits for the GPU except to read
+        # the losses at each progress line.  C2V_BATCH_RING=0 (or a reader without the native tensoriser) keeps the
+        # synchronous c2v_train_batch_host path.
+        ring = None
+        if os.environ.get("C2V_BATCH_RING", "1") != "0" and not self._hint_next and train_reader._native_ready():
+            import torch
+            from .batch_ring import PinnedBatchRing
+            ring = PinnedBatchRing(torch, self.engine.dev, cfg.TRAIN_BATCH_SIZE, cfg.MAX_CONTEXTS)
+            train_reader.batch_ring = ring
+            loss_hist = torch.zeros(max(int(cfg.NUM_BATCHES_TO_LOG_PROGRESS), 1), dtype=torch.float32).pin_memory()
+            n_hist = 0
+        self.h2d_bytes = 0
+        for batch, following in _with_next(_prefetch(train_reader.get_dataset(), depth=4 if ring else 8)):
             t = former.from_model_input_form(batch)
             nxt = None
             if self._hint_next and following is not None:
@@ -234,8 +253,24 @@ class Code2VecModel(Code2VecModelBase):
                 nxt = (n.path_source_token_indices, n.path_indices, n.path_target_token_indices)
             batch_num += 1
             self.engine.set_option("math_mode", self._math_train)
-            batch_loss = self.trainer.step_host(t.path_source_token_indices, t.path_indices, t.path_target_token_indices,
-                                                t.context_valid_mask, t.target_index, next_batch=nxt)
+            if ring is not None:
+                rows = int(t.target_index.shape[0])
+                d, buf = ring.upload_next(rows)
+                loss_dev = self.trainer.step_device(d["src"], d["path"], d["tgt"], d["mask"], d["target"])
+                ring.mark_compute_done(buf)
+                loss_hist[n_hist:n_hist + 1].copy_(loss_dev, non_blocking=True)
+                n_hist += 1
+                self.h2d_bytes += rows * (4 * cfg.MAX_CONTEXTS + 1) * 4
+                flush = (batch_num % cfg.NUM_BATCHES_TO_LOG_PROGRESS == 0) or (batch_num % num_batches_to_save_and_eval == 0) \
+                    or n_hist == loss_hist.numel()
+                batch_loss = 0.0
+                if flush:                          # the losses of the steps since the last progress line reach the host here
+                    torch.cuda.current_stream(self.engine.dev).synchronize()
+                    batch_loss = float(loss_hist[:n_hist].sum())
+                    n_hist = 0
+            else:
+                batch_loss = self.trainer.step_host(t.path_source_token_indices, t.path_indices, t.path_target_token_indices,
+                                                    t.context_valid_mask, t.target_index, next_batch=nxt)
             sum_loss += batch_loss
             if batch_num % cfg.NUM_BATCHES_TO_LOG_PROGRESS == 0:
                 self._trace_training(sum_loss, batch_num, multi_batch_start_time)
@@ -251,6 +286,13 @@ class Code2VecModel(Code2VecModelBase):
                     results = self.evaluate()
                     text = str(results).replace("topk", "top{}".format(cfg.TOP_K_WORDS_CONSIDERED_DURING_PREDICTION))
                     self.log("After {nr_epochs} epochs -- {evaluation_results}".format(nr_epochs=epoch_num, evaluation_results=text))
+        if ring is not None:
+            import torch
+            torch.cuda.current_stream(self.engine.dev).synchronize()
+            if n_hist:
+                sum_loss += float(loss_hist[:n_hist].sum())
+            ring.close()
+            train_reader.batch_ring = None
         self.log("Done training")
         if cfg.MODEL_SAVE_PATH:
             self.save(cfg.MODEL_SAVE_PATH)

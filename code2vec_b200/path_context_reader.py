@@ -413,12 +413,18 @@ class PathContextReader:
         # replacement from the pool (tf.data's shuffle(buffer) draws the same way, one row at a time)
         S = max(int(self.config.SHUFFLE_BUFFER_SIZE), 1)
         pool = _RowPool()
+        ring = getattr(self, "batch_ring", None)          # PinnedBatchRing: batches are drawn straight into pinned slots
+
+        def draw(b):
+            if ring is None:
+                return pool.take(b, self._rng)
+            return pool.take(b, self._rng, out=ring.acquire().arrays())
         for chunk in self._native_chunks():
             self._native_parse_into(chunk, pool)
             while pool.n >= S + B:
-                yield emit(pool.take(B, self._rng), None)
+                yield emit(draw(B), None)
         while pool.n > 0:
-            yield emit(pool.take(min(B, pool.n), self._rng), None)
+            yield emit(draw(min(B, pool.n)), None)
 
     def _iterate_batches(self, input_data_rows):
         action = self.estimator_action
@@ -501,10 +507,17 @@ class _RowPool:
                     a[holes] = a[movers]
         self.n += kept
 
-    def take(self, b: int, rng) -> tuple:
+    def take(self, b: int, rng, out=None) -> tuple:
+        """b rows drawn uniformly without replacement.  out: five arrays with at least b rows (e.g. a page-locked batch
+        slot) the rows are gathered into; the views of their first b rows are returned."""
         n = self.n
         pick = rng.choice(n, size=b, replace=False) if b < n else rng.permutation(n)
-        out = tuple(a[pick] for a in self.arrays)
+        if out is None:
+            out = tuple(a[pick] for a in self.arrays)
+        else:
+            for a, o in zip(self.arrays, out):
+                np.take(a, pick, axis=0, out=o[:b])
+            out = tuple(o[:b] for o in out)
         # fill the holes left below the new end with the surviving rows of the tail
         new_n = n - b
         chosen = np.zeros(n, dtype=bool)

@@ -17,7 +17,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 
-def main(n_lines=65536, C=200, n_tok=200000, n_path=150000, n_tgt=30000, threads=16):
+def main(n_lines=131072, C=200, n_tok=200000, n_path=150000, n_tgt=30000, threads=16):
     from code2vec_b200.b200_model import Code2VecModel
     from code2vec_b200.config import Config
     tmp = tempfile.mkdtemp()
@@ -51,14 +51,18 @@ def main(n_lines=65536, C=200, n_tok=200000, n_path=150000, n_tgt=30000, threads
     model = Code2VecModel(cfg)
     import torch
     stamps = []
-    inner = model.trainer.step_host
+    # the training loop uploads batches through the pinned ring and launches steps asynchronously (step_device); with
+    # C2V_BATCH_RING=0 it calls the synchronous step_host instead.  Either way the host time at which step k was issued is
+    # recorded: the ring bounds how far the host can run ahead of the GPU (10 slots), so over hundreds of steps the issue
+    # rate is the execution rate.
+    for name in ("step_host", "step_device"):
+        inner = getattr(model.trainer, name)
 
-    def stamped(*a, **k):
-        out = inner(*a, **k)           # returns after the step's loss has reached the host
-        stamps.append(time.time())
-        return out
-
-    model.trainer.step_host = stamped
+        def stamped(*a, _inner=inner, **k):
+            out = _inner(*a, **k)
+            stamps.append(time.time())
+            return out
+        setattr(model.trainer, name, stamped)
     torch.cuda.synchronize()
     t0 = time.time()
     model.train()
@@ -72,6 +76,8 @@ def main(n_lines=65536, C=200, n_tok=200000, n_path=150000, n_tgt=30000, threads
                       "path_contexts_per_s": round(n_lines * C / dt, 1),
                       "steady_state_path_contexts_per_s": round(steady, 1), "batches": len(stamps), "file_MB": round(size_mb, 1),
                       "text_MB_per_s": round(size_mb / dt, 1), "reader_threads": threads, "host_cores": os.cpu_count(),
+                      "batch_ring": os.environ.get("C2V_BATCH_RING", "1") != "0",
+                      "h2d_bytes_total": int(getattr(model, "h2d_bytes", 0)),
                       "dataset_generation_s": round(gen_s, 1)}))
     model.close_session()
 
