@@ -17,7 +17,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 
-def main(n_lines=131072, C=200, n_tok=200000, n_path=150000, n_tgt=30000, threads=16):
+def main(n_lines=131072, C=200, n_tok=200000, n_path=150000, n_tgt=30000, threads=16, epochs=4):
     from code2vec_b200.b200_model import Code2VecModel
     from code2vec_b200.config import Config
     tmp = tempfile.mkdtemp()
@@ -43,7 +43,7 @@ def main(n_lines=131072, C=200, n_tok=200000, n_path=150000, n_tgt=30000, thread
     cfg.VERBOSE_MODE = 0
     cfg.DL_FRAMEWORK = "b200"
     cfg.TRAIN_DATA_PATH_PREFIX = prefix
-    cfg.NUM_TRAIN_EPOCHS = 1
+    cfg.NUM_TRAIN_EPOCHS = epochs
     cfg.SAVE_EVERY_EPOCHS = 1000
     cfg.READER_NUM_PARALLEL_BATCHES = threads
     cfg.SHUFFLE_BUFFER_SIZE = 4096
@@ -71,11 +71,11 @@ def main(n_lines=131072, C=200, n_tok=200000, n_path=150000, n_tgt=30000, thread
     skip = max(len(stamps) // 4, 1)    # steady state: after the reader threads and the prefetch queue have filled
     steady = (len(stamps) - 1 - skip) * cfg.TRAIN_BATCH_SIZE * C / max(stamps[-1] - stamps[skip], 1e-9)
     size_mb = os.path.getsize(prefix + ".train.c2v") / 1e6
-    print(json.dumps({"what": "Code2VecModel.train() end to end (file -> native reader -> engine)", "examples": n_lines,
-                      "contexts_per_example": C, "seconds": round(dt, 3), "examples_per_s": round(n_lines / dt, 1),
-                      "path_contexts_per_s": round(n_lines * C / dt, 1),
+    print(json.dumps({"what": "Code2VecModel.train() end to end (file -> native reader -> engine)", "examples": n_lines * epochs, "epochs": epochs,
+                      "contexts_per_example": C, "seconds": round(dt, 3), "examples_per_s": round(n_lines * epochs / dt, 1),
+                      "path_contexts_per_s": round(n_lines * epochs * C / dt, 1),
                       "steady_state_path_contexts_per_s": round(steady, 1), "batches": len(stamps), "file_MB": round(size_mb, 1),
-                      "text_MB_per_s": round(size_mb / dt, 1), "reader_threads": threads, "host_cores": os.cpu_count(),
+                      "text_MB_per_s": round(size_mb * epochs / dt, 1), "reader_threads": threads, "host_cores": os.cpu_count(),
                       "batch_ring": os.environ.get("C2V_BATCH_RING", "1") != "0",
                       "h2d_bytes_total": int(getattr(model, "h2d_bytes", 0)),
                       "dataset_generation_s": round(gen_s, 1)}))
