@@ -243,10 +243,14 @@ def run_ours(args):
     eng.init_params(seed=4321)                       # replicated: same seed on every rank
     eng.set_option("math_mode", MATH_MODES[args.math])
     eng.set_option("cta_pair", args.cta_pair)
+    if args.no_sort_peer:
+        eng.set_option("sort_peer_access", 0)
+    if args.fuse_gather:
+        eng.set_option("fuse_gather", 1)
     trainer = None
     if mode != "fwd_loss":
         trainer = Trainer(eng, keep_prob=KEEP_PROB, seed=99, schedule=args.dp_schedule, fuse_target_adam=not args.no_fuse_adam,
-                          lazy_adam=not args.no_lazy_adam)
+                          lazy_adam=not args.no_lazy_adam, push_grads=not args.no_push_grads)
         if args.dy_late >= 0:
             eng.set_option("dy_late", args.dy_late)
         if args.adam_rows_occ:
@@ -629,6 +633,10 @@ def main():
                     help="train = BASELINE configs[1] (default); fwd_loss = configs[2] forward + full-softmax loss; "
                          "sampled = configs[3] train step with sampled softmax")
     ap.add_argument("--no-fp32-equivalent", action="store_true", help="skip the extra 3xTF32 measurement of the default run")
+    ap.add_argument("--no-push-grads", action="store_true",
+                    help="row-sharded tables: remote red.global.add instead of the inbox-based gradient push")
+    ap.add_argument("--no-sort-peer", action="store_true", help="row-sharded tables: plain (unsorted) peer gather / scatter-add")
+    ap.add_argument("--fuse-gather", action="store_true", help="engine option fuse_gather (ctx_fused.cuh)")
     ap.add_argument("--no-lazy-adam", action="store_true", help="dense Adam over the embedding tables every step")
     ap.add_argument("--sweep-period", type=int, default=-1, help="engine option adam_sweep_period (-1 = default 32, 0 = off)")
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -39,6 +39,7 @@ struct Workspace {
   size_t nx_src, nx_pth, nx_tgt;                                  // indices of the hinted NEXT batch (host entry point)
   size_t stamp_tok, stamp_path, last_tok, last_path, lr_tab;     // lazy Adam bookkeeping
   size_t stamp_tgt, last_tgt;                                    // ... of the target table (sampled softmax)
+  size_t perm, bkt_count, bkt_cursor, bkt_starts;                            // locality-sorted peer gather / scatter (sharded tables)
   size_t total;
   size_t ldS;
 };
@@ -95,6 +96,10 @@ Workspace carve(const c2v_dims& d) {
   w.last_tok = take((size_t)d.token_vocab * 4);
   w.last_path = take((size_t)d.path_vocab * 4);
   w.lr_tab = take((size_t)kLrRing * 4);
+  w.perm = take(3 * N * 4);
+  w.bkt_count = take((size_t)kMaxBuckets * 4);
+  w.bkt_cursor = take((size_t)kMaxBuckets * 4);
+  w.bkt_starts = take((size_t)(kMaxBuckets + 1) * 4);
   w.stamp_tgt = take((size_t)d.target_vocab * 4);
   w.last_tgt = take((size_t)d.target_vocab * 4);
   // 3xTF32 (C2V_MATH_3XTF32): low parts of the GEMM operands that are produced inside a step, and the
@@ -158,6 +163,9 @@ struct c2v_engine {
   bool has_theta, has_grad, has_adam;
   bool emb_grads_clean;      // token/path gradient tables are known to be all-zero
   int math_mode;
+  InboxSet inbox{};          // push-based gradient exchange (c2v_bind_scatter_inbox); world == 0: not bound
+  int sort_peer = 1;         // option "sort_peer_access": sharded tables are gathered / scattered in (owner, 2 MB page) order
+  bool bkt_zeroed = false;   // the bucket counters have been cleared once (bucket_scan_kernel leaves them cleared)
   int fuse_gather = 0;       // option "fuse_gather": gather -> projection -> tanh as one kernel on the tf32 path (ctx_fused.cuh);
                              // bit-identical to the two-kernel path, but measured slower on B200 so far (0.31 vs 0.27 ms forward) -> off
   int cta_pair = 2;          // tcgen05 GEMMs as CTA pairs (cta_group::2, UMMA 256 x BN): 0 never, 1 always, 2 auto
@@ -494,6 +502,42 @@ int split_small(c2v_engine* e, cudaStream_t st, const float* x, size_t n, size_t
   return C2V_OK;
 }
 
+// Sharded tables: bucket the batch's 3 B C context entries by (owner rank, 2 MB page of the owner's shard) into ws.perm.
+// Returns false when the plan does not apply (tables not sharded, option off, too many buckets).
+bool plan_buckets(c2v_engine* e, BucketPlan* bp, bool force = false) {
+  if (e->table_world <= 1) return false;
+  const c2v_dims& d = e->dims;
+  // sort_peer_access: 0 never, 1 (default) when the tables are large enough for random peer accesses to thrash the TLB
+  // (measured: a loss at 1.1 GB of tables, 1.8-3.4x faster at 5 GB), 2 always; the inbox exchange always needs the order
+  const double table_bytes = ((double)d.token_vocab + d.path_vocab) * d.embed_dim * 4.0;
+  if (!force && (e->sort_peer == 0 || (e->sort_peer == 1 && table_bytes < 2.0e9))) return false;
+  const int W = e->table_world;
+  int rows_per_page = (int)((2u << 20) / ((size_t)d.embed_dim * 4));
+  int ps = 0;
+  while ((2 << ps) <= rows_per_page) ++ps;
+  bp->shift = e->th_tok.shift; bp->mask = e->th_tok.mask; bp->page_shift = ps;
+  const int rows_tok = (d.token_vocab + W - 1) / W, rows_path = (d.path_vocab + W - 1) / W;
+  bp->pages_tok = (rows_tok >> ps) + 1;
+  bp->pages_path = (rows_path >> ps) + 1;
+  bp->n_buckets = W * (bp->pages_tok + bp->pages_path);
+  return bp->n_buckets <= kMaxBuckets;
+}
+int sort_entries(c2v_engine* e, cudaStream_t st, const ContextSource& cs, const BucketPlan& bp) {
+  int32_t* counts = wsp<int32_t>(e, e->ws.bkt_count);
+  int32_t* cursor = wsp<int32_t>(e, e->ws.bkt_cursor);
+  if (!e->bkt_zeroed) {
+    C2V_CUDA(e, cudaMemsetAsync(counts, 0, (size_t)kMaxBuckets * 4, st));
+    e->bkt_zeroed = true;
+  }
+  const int total = 3 * cs.rows;
+  int blocks = (total + 255) / 256;
+  if (blocks > e->num_sms * 8) blocks = e->num_sms * 8;
+  C2V_LAUNCH(e, (bucket_count_kernel<<<blocks, 256, (size_t)bp.n_buckets * 4, st>>>(cs, bp, counts)));
+  C2V_LAUNCH(e, (bucket_scan_kernel<<<1, 1024, 0, st>>>(counts, cursor, wsp<int32_t>(e, e->ws.bkt_starts), bp.n_buckets)));
+  C2V_LAUNCH(e, (bucket_fill_kernel<<<blocks, 256, 0, st>>>(cs, bp, cursor, wsp<int32_t>(e, e->ws.perm))));
+  return C2V_OK;
+}
+
 // H = tanh(X' . W)   (tensorflow_model.py:238-252)
 int run_ctx_fwd(c2v_engine* e, cudaStream_t st, const ContextSource& cs, const Dropout& dp, float* H, bool keep_x) {
   const int D = e->dims.code_dim, K = 3 * e->dims.embed_dim;
@@ -513,7 +557,14 @@ int run_ctx_fwd(c2v_engine* e, cudaStream_t st, const ContextSource& cs, const D
     const bool x3 = is_3x(e);
     {
       PhaseTimer pt(e, PH_GATHER, st);
-      if (x3) C2V_LAUNCH(e, (gather_ctx_kernel<true><<<(cs.rows + 7) / 8, 256, 0, st>>>(cs, dp, Xg, wsp<float>(e, e->ws.Xg_lo))));
+      BucketPlan bp;
+      if (plan_buckets(e, &bp)) {           // peer shards: walk the entries page by page
+        int rcs = sort_entries(e, st, cs, bp);
+        if (rcs) return rcs;
+        const int32_t* perm = wsp<int32_t>(e, e->ws.perm);
+        if (x3) C2V_LAUNCH(e, (gather_sorted_kernel<true><<<(3 * cs.rows + 7) / 8, 256, 0, st>>>(cs, dp, perm, Xg, wsp<float>(e, e->ws.Xg_lo))));
+        else C2V_LAUNCH(e, (gather_sorted_kernel<false><<<(3 * cs.rows + 7) / 8, 256, 0, st>>>(cs, dp, perm, Xg, nullptr)));
+      } else if (x3) C2V_LAUNCH(e, (gather_ctx_kernel<true><<<(cs.rows + 7) / 8, 256, 0, st>>>(cs, dp, Xg, wsp<float>(e, e->ws.Xg_lo))));
       else C2V_LAUNCH(e, (gather_ctx_kernel<false><<<(cs.rows + 7) / 8, 256, 0, st>>>(cs, dp, Xg, nullptr)));
     }
     if (x3) { int rcs = split_small(e, st, e->theta.W, (size_t)K * D, e->ws.W_hi, e->ws.W_lo); if (rcs) return rcs; }
@@ -648,7 +699,22 @@ int context_backward(c2v_engine* e, cudaStream_t st, const ContextSource& cs, co
     C2V_CUDA(e, cudaStreamWaitEvent(e->side, e->ev_fork, 0));
     {
       PhaseTimer pt(e, PH_DX_SCATTER, e->side);
-      C2V_LAUNCH(e, (scatter_dx_kernel<<<(N + 7) / 8, 256, 0, e->side>>>(cs, dp, mask, dXg, e->gr_tok, e->gr_path, e->grad_scale)));
+      BucketPlan bp;
+      if (e->inbox.world > 1 && plan_buckets(e, &bp, true)) {
+        // push: every owner's rows go densely into this rank's region of the owner's inbox (plain coalesced stores over
+        // NVLink); the owners fold them in with local atomics after the caller's barrier (c2v_apply_scatter_inbox)
+        if ((rc = sort_entries(e, e->side, cs, bp))) return rc;
+        const int32_t* starts = wsp<int32_t>(e, e->ws.bkt_starts);
+        C2V_LAUNCH(e, (inbox_counts_kernel<<<1, 32, 0, e->side>>>(e->inbox, bp, starts)));
+        C2V_LAUNCH(e, (scatter_inbox_kernel<<<(3 * N + 7) / 8, 256, 0, e->side>>>(cs, dp, mask, wsp<int32_t>(e, e->ws.perm), starts, bp, dXg,
+                                                                              e->inbox, e->grad_scale)));
+      } else if (plan_buckets(e, &bp)) {    // peer shards: the red.adds walk the owners' pages in order
+        if ((rc = sort_entries(e, e->side, cs, bp))) return rc;
+        C2V_LAUNCH(e, (scatter_sorted_kernel<<<(3 * N + 7) / 8, 256, 0, e->side>>>(cs, dp, mask, wsp<int32_t>(e, e->ws.perm), dXg, e->gr_tok,
+                                                                               e->gr_path, e->grad_scale)));
+      } else {
+        C2V_LAUNCH(e, (scatter_dx_kernel<<<(N + 7) / 8, 256, 0, e->side>>>(cs, dp, mask, dXg, e->gr_tok, e->gr_path, e->grad_scale)));
+      }
     }
     if ((rc = early_catchup(e, e->side))) return rc;
     C2V_CUDA(e, cudaEventRecord(e->ev_join, e->side));
@@ -1049,6 +1115,7 @@ int c2v_bind_workspace(c2v_engine* e, void* dev_ptr, size_t bytes) {
   if (bytes < e->ws.total) return fail(e, C2V_ERR_INVALID, "workspace smaller than c2v_workspace_bytes()");
   e->wbase = (char*)dev_ptr;
   e->wbytes = bytes;
+  e->bkt_zeroed = false;
   return C2V_OK;
 }
 
@@ -1101,6 +1168,11 @@ int c2v_set_option(c2v_engine* e, const char* key, int64_t value) {
   }
   if (!strcmp(key, "fuse_target_adam")) { e->fuse_tgt = value ? 1 : 0; return C2V_OK; }
   if (!strcmp(key, "fuse_gather")) { e->fuse_gather = value ? 1 : 0; return C2V_OK; }
+  if (!strcmp(key, "sort_peer_access")) {
+    if (value < 0 || value > 2) return fail(e, C2V_ERR_INVALID, "sort_peer_access must be 0 (never), 1 (auto) or 2 (always)");
+    e->sort_peer = (int)value;
+    return C2V_OK;
+  }
   if (!strcmp(key, "adam_rest_shortcut")) { e->rest_shortcut = value ? 1 : 0; return C2V_OK; }
   if (!strcmp(key, "adam_sweep_period")) {
     if (value < 0 || value > kLrRing / 2) return fail(e, C2V_ERR_INVALID, "adam_sweep_period must be in [0, 32768]");
@@ -1190,6 +1262,7 @@ int c2v_get_option(const c2v_engine* e, const char* key, int64_t* value) {
   if (!strcmp(key, "dy_late")) { *value = e->dy_late; return C2V_OK; }
   if (!strcmp(key, "fuse_target_adam")) { *value = e->fuse_tgt; return C2V_OK; }
   if (!strcmp(key, "fuse_gather")) { *value = e->fuse_gather; return C2V_OK; }
+  if (!strcmp(key, "sort_peer_access")) { *value = e->sort_peer; return C2V_OK; }
   if (!strcmp(key, "adam_step_count")) { *value = e->adam_t_done; return C2V_OK; }
   if (!strcmp(key, "target_adam_fused_step")) { *value = e->tgt_fused_t; return C2V_OK; }
   if (!strcmp(key, "early_catchup_count")) { *value = e->early_count; return C2V_OK; }
@@ -1329,6 +1402,40 @@ int c2v_bind_table_shards(c2v_engine* e, const c2v_table_shards* params, const c
   }
   e->table_world = w;
   e->grad_scale = grad_scale;
+  return C2V_OK;
+}
+
+size_t c2v_scatter_inbox_bytes(const c2v_dims* dims, int32_t world) {
+  std::string why;
+  if (!dims_ok(dims, &why) || world < 1 || world > kMaxShards) { g_create_error = why.empty() ? "bad world" : why; return 0; }
+  const size_t cap = (size_t)3 * dims->max_batch * dims->max_contexts;
+  return inbox_val_offset(world, cap) + (size_t)world * cap * dims->embed_dim * 4;
+}
+
+int c2v_bind_scatter_inbox(c2v_engine* e, void* const* inbox, int32_t world, int32_t rank) {
+  if (!e) return C2V_ERR_INVALID;
+  if (!inbox) { e->inbox = InboxSet{}; return C2V_OK; }           // unbind: back to remote red.add
+  if (world != e->table_world || world < 2) return fail(e, C2V_ERR_STATE, "bind the table shards first (same world)");
+  if (rank < 0 || rank >= world) return fail(e, C2V_ERR_INVALID, "rank out of range");
+  InboxSet s{};
+  for (int i = 0; i < world; ++i) {
+    if (!inbox[i]) return fail(e, C2V_ERR_INVALID, "NULL inbox pointer");
+    s.base[i] = (char*)inbox[i];
+  }
+  s.cap = (size_t)3 * e->dims.max_batch * e->dims.max_contexts;
+  s.world = world; s.rank = rank;
+  e->inbox = s;
+  return C2V_OK;
+}
+
+int c2v_apply_scatter_inbox(c2v_engine* e, void* stream) {
+  if (!e) return C2V_ERR_INVALID;
+  if (e->inbox.world < 2) return fail(e, C2V_ERR_STATE, "no scatter inbox bound (c2v_bind_scatter_inbox)");
+  C2V_CUDA(e, cudaSetDevice(e->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  PhaseTimer pt(e, PH_DX_SCATTER, st);
+  C2V_LAUNCH(e, (inbox_apply_kernel<<<e->num_sms * 8, 256, 0, st>>>(e->inbox, e->dims.embed_dim, e->gr_tok.base[e->inbox.rank],
+                                                                    e->gr_path.base[e->inbox.rank])));
   return C2V_OK;
 }
 

@@ -769,6 +769,228 @@ scatter_dx_kernel(const __grid_constant__ ContextSource cs, const __grid_constan
 }
 
 // ---------------------------------------------------------------------------------------------
+// Row-sharded tables (peer memory over NVLink): locality-sorted gather / scatter-add.
+//
+// With the tables of BASELINE configs[4] (3M x 256 and 2M x 256 floats: 5 GB of parameters and 5 GB of gradient
+// shards mapped from the peers) random row accesses to peer memory ran at 70-90 GB/s against ~600 GB/s for the
+// java14m tables: every access touches a different 2 MB page of a mapping far larger than the GPU's TLB reach.
+// The context entries (n, segment) of a batch are therefore bucketed by (owner rank, 2 MB page of the owner's shard)
+// with a counting sort -- bucket_count / bucket_scan / bucket_fill -- and the gather and the scatter-add walk the
+// entries in bucket order: each remote page is visited once, by neighbouring warps, instead of once per access.
+// The order inside a bucket is whatever the atomics give; it only changes the order of accesses, not any result
+// (the scatter-add's float atomics are order-free up to rounding, as before).
+// ---------------------------------------------------------------------------------------------
+constexpr int kMaxBuckets = 8192;
+
+struct BucketPlan {
+  int shift, mask;          // as ShardedTable: owner = idx & mask, local row = idx >> shift
+  int page_shift;           // rows per 2 MB page = 1 << page_shift
+  int pages_tok, pages_path;   // pages per shard
+  int n_buckets;            // (mask + 1) * (pages_tok + pages_path)
+};
+__device__ __forceinline__ int bucket_of(const BucketPlan& bp, int seg, int idx) {
+  const int owner = idx & bp.mask, page = (idx >> bp.shift) >> bp.page_shift;
+  return (seg == 1) ? (bp.mask + 1) * bp.pages_tok + owner * bp.pages_path + page : owner * bp.pages_tok + page;
+}
+__device__ __forceinline__ int entry_index(const ContextSource& cs, int e) {      // e = 3 n + seg
+  const int n = e / 3, seg = e - 3 * n;
+  return seg == 0 ? cs.src[n] : (seg == 1 ? cs.pth[n] : cs.tgt[n]);
+}
+
+__global__ void __launch_bounds__(256)
+bucket_count_kernel(const __grid_constant__ ContextSource cs, const __grid_constant__ BucketPlan bp, int32_t* __restrict__ counts) {
+  extern __shared__ int32_t hist[];
+  for (int i = threadIdx.x; i < bp.n_buckets; i += 256) hist[i] = 0;
+  __syncthreads();
+  const int total = 3 * cs.rows;
+  for (int e = blockIdx.x * 256 + threadIdx.x; e < total; e += gridDim.x * 256) {
+    const int n = e / 3, seg = e - 3 * n;
+    atomicAdd(&hist[bucket_of(bp, seg, entry_index(cs, e))], 1);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < bp.n_buckets; i += 256)
+    if (hist[i]) atomicAdd(&counts[i], hist[i]);
+}
+
+// exclusive scan of counts[0, n) into cursor[0, n) and starts[0, n] (one block); counts are cleared for the next batch
+__global__ void __launch_bounds__(1024)
+bucket_scan_kernel(int32_t* __restrict__ counts, int32_t* __restrict__ cursor, int32_t* __restrict__ starts, int n) {
+  __shared__ int32_t part[1024];
+  const int per = (n + 1023) / 1024;
+  const int lo = threadIdx.x * per, hi = min(n, lo + per);
+  int s = 0;
+  for (int i = lo; i < hi; ++i) s += counts[i];
+  part[threadIdx.x] = s;
+  __syncthreads();
+  for (int o = 1; o < 1024; o <<= 1) {
+    const int v = (threadIdx.x >= o) ? part[threadIdx.x - o] : 0;
+    __syncthreads();
+    part[threadIdx.x] += v;
+    __syncthreads();
+  }
+  int run = part[threadIdx.x] - s;
+  for (int i = lo; i < hi; ++i) {
+    const int c = counts[i];
+    cursor[i] = run;
+    starts[i] = run;
+    run += c;
+    counts[i] = 0;
+  }
+  if (threadIdx.x == 1023) starts[n] = part[1023];      // total number of entries
+}
+
+__global__ void __launch_bounds__(256)
+bucket_fill_kernel(const __grid_constant__ ContextSource cs, const __grid_constant__ BucketPlan bp, int32_t* __restrict__ cursor,
+                   int32_t* __restrict__ perm) {
+  const int total = 3 * cs.rows;
+  for (int e = blockIdx.x * 256 + threadIdx.x; e < total; e += gridDim.x * 256) {
+    const int n = e / 3, seg = e - 3 * n;
+    perm[atomicAdd(&cursor[bucket_of(bp, seg, entry_index(cs, e))], 1)] = e;
+  }
+}
+
+// X'[n, seg*d : (seg+1)*d] = dropout(table row) for the entries in bucket order; one warp per entry.
+template <bool SPLIT>
+__global__ void __launch_bounds__(256)
+gather_sorted_kernel(const __grid_constant__ ContextSource cs, const __grid_constant__ Dropout dp, const int32_t* __restrict__ perm,
+                     float* __restrict__ Xg, float* __restrict__ Xlo) {
+  const int w = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (w >= 3 * cs.rows) return;
+  const int e = perm[w];
+  const int n = e / 3, seg = e - 3 * n;
+  const int idx = seg == 0 ? cs.src[n] : (seg == 1 ? cs.pth[n] : cs.tgt[n]);
+  const float* row = (seg == 1) ? table_row(cs.path, idx, cs.d) : table_row(cs.tok, idx, cs.d);
+  const size_t o = (size_t)n * (3 * cs.d) + (size_t)seg * cs.d;
+  constexpr int kU = 2;                          // d <= 256 in one batch of loads
+  for (int j0 = lane * 4; j0 < cs.d; j0 += 128 * kU) {
+    float4 x[kU];
+#pragma unroll
+    for (int u = 0; u < kU; ++u)
+      if (j0 + u * 128 < cs.d) x[u] = __ldg(reinterpret_cast<const float4*>(row + j0 + u * 128));
+#pragma unroll
+    for (int u = 0; u < kU; ++u) {
+      const int j = j0 + u * 128;
+      if (j < cs.d) {
+        const float4 m = dropout_mult4(dp, n, (seg * cs.d + j) >> 2);
+        x[u].x *= m.x; x[u].y *= m.y; x[u].z *= m.z; x[u].w *= m.w;
+        if (SPLIT) {
+          float4 hi, lo;
+          split_tf32(x[u], hi, lo);
+          *reinterpret_cast<float4*>(Xg + o + j) = hi;
+          *reinterpret_cast<float4*>(Xlo + o + j) = lo;
+        } else {
+          *reinterpret_cast<float4*>(Xg + o + j) = x[u];
+        }
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256)
+scatter_sorted_kernel(const __grid_constant__ ContextSource cs, const __grid_constant__ Dropout dp, const float* __restrict__ mask,
+                      const int32_t* __restrict__ perm, const float* __restrict__ dXg, const __grid_constant__ ShardedTable g_tok,
+                      const __grid_constant__ ShardedTable g_path, float grad_scale) {
+  const int w = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (w >= 3 * cs.rows) return;
+  const int e = perm[w];
+  const int n = e / 3, seg = e - 3 * n;
+  if (mask[n] == 0.f) return;                 // masked contexts carry exact zeros
+  const int idx = seg == 0 ? cs.src[n] : (seg == 1 ? cs.pth[n] : cs.tgt[n]);
+  float* row = (seg == 1) ? table_row(g_path, idx, cs.d) : table_row(g_tok, idx, cs.d);
+  const float* src = dXg + (size_t)n * (3 * cs.d) + (size_t)seg * cs.d;
+  for (int j = lane * 4; j < cs.d; j += 128) {
+    float4 g = *reinterpret_cast<const float4*>(src + j);
+    const float4 m = dropout_mult4(dp, n, (seg * cs.d + j) >> 2);
+    g.x *= m.x * grad_scale; g.y *= m.y * grad_scale; g.z *= m.z * grad_scale; g.w *= m.w * grad_scale;
+    atomicAdd(reinterpret_cast<float4*>(row + j), g);
+  }
+}
+
+// ---- push-based gradient exchange (c2v_bind_scatter_inbox) -------------------------------------------------------
+// Inbox of one rank: [counts: 2 ints per sender, padded to 256 B][row ids: world x cap ints][values: world x cap x d floats]
+// with cap = 3 * max_batch * max_contexts (a sender can never have more entries).  Sender s owns slots [s*cap, (s+1)*cap):
+// its token-table rows first (count[2s]), then its path-table rows (count[2s+1]).
+struct InboxView {
+  int32_t* cnt;
+  int32_t* ids;
+  float* val;
+};
+__host__ __device__ inline size_t inbox_ids_offset(int world) { return ((size_t)world * 2 * 4 + 255) / 256 * 256; }
+__host__ __device__ inline size_t inbox_val_offset(int world, size_t cap) {
+  return (inbox_ids_offset(world) + (size_t)world * cap * 4 + 255) / 256 * 256;
+}
+struct InboxSet {
+  char* base[kMaxShards];    // every rank's inbox as mapped here
+  size_t cap;
+  int world, rank;
+};
+__device__ __forceinline__ InboxView inbox_of(const InboxSet& s, int owner) {
+  InboxView v;
+  v.cnt = reinterpret_cast<int32_t*>(s.base[owner]);
+  v.ids = reinterpret_cast<int32_t*>(s.base[owner] + inbox_ids_offset(s.world));
+  v.val = reinterpret_cast<float*>(s.base[owner] + inbox_val_offset(s.world, s.cap));
+  return v;
+}
+
+// starts[b] = first sorted position of bucket b (bucket_scan_kernel); the buckets of owner o are contiguous per table.
+__global__ void inbox_counts_kernel(const __grid_constant__ InboxSet inbox, const __grid_constant__ BucketPlan bp,
+                                    const int32_t* __restrict__ starts) {
+  const int o = threadIdx.x;
+  if (o > bp.mask) return;
+  const int W = bp.mask + 1, t0 = o * bp.pages_tok, p0 = W * bp.pages_tok + o * bp.pages_path;
+  InboxView v = inbox_of(inbox, o);
+  v.cnt[2 * inbox.rank] = starts[t0 + bp.pages_tok] - starts[t0];
+  v.cnt[2 * inbox.rank + 1] = starts[p0 + bp.pages_path] - starts[p0];
+}
+
+// one warp per sorted entry: the (dropout-scaled) gradient row goes into the owner's inbox, densely
+__global__ void __launch_bounds__(256)
+scatter_inbox_kernel(const __grid_constant__ ContextSource cs, const __grid_constant__ Dropout dp, const float* __restrict__ mask,
+                     const int32_t* __restrict__ perm, const int32_t* __restrict__ starts, const __grid_constant__ BucketPlan bp,
+                     const float* __restrict__ dXg, const __grid_constant__ InboxSet inbox, float grad_scale) {
+  const int w = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (w >= 3 * cs.rows) return;
+  const int e = perm[w];
+  const int n = e / 3, seg = e - 3 * n;
+  const int idx = seg == 0 ? cs.src[n] : (seg == 1 ? cs.pth[n] : cs.tgt[n]);
+  const int o = idx & bp.mask, W = bp.mask + 1;
+  const int t0 = o * bp.pages_tok, p0 = W * bp.pages_tok + o * bp.pages_path;
+  const int k = (seg == 1) ? (starts[t0 + bp.pages_tok] - starts[t0]) + (w - starts[p0]) : (w - starts[t0]);
+  InboxView v = inbox_of(inbox, o);
+  const size_t slot = (size_t)inbox.rank * inbox.cap + k;
+  const bool live = mask[n] != 0.f;           // masked contexts carry exact zeros: the owner skips the slot
+  if (lane == 0) v.ids[slot] = live ? (idx >> bp.shift) : -1;
+  if (!live) return;
+  const float* src = dXg + (size_t)n * (3 * cs.d) + (size_t)seg * cs.d;
+  float* dst = v.val + slot * cs.d;
+  for (int j = lane * 4; j < cs.d; j += 128) {
+    float4 g = *reinterpret_cast<const float4*>(src + j);
+    const float4 m = dropout_mult4(dp, n, (seg * cs.d + j) >> 2);
+    g.x *= m.x * grad_scale; g.y *= m.y * grad_scale; g.z *= m.z * grad_scale; g.w *= m.w * grad_scale;
+    *reinterpret_cast<float4*>(dst + j) = g;
+  }
+}
+
+// the owner folds its inbox into its own gradient shards (local atomics); persistent grid, one warp per slot
+__global__ void __launch_bounds__(256)
+inbox_apply_kernel(const __grid_constant__ InboxSet inbox, int d, float* __restrict__ g_tok, float* __restrict__ g_path) {
+  const int lane = threadIdx.x & 31;
+  const int warp_global = (blockIdx.x * 256 + threadIdx.x) >> 5, total_warps = (gridDim.x * 256) >> 5;
+  InboxView v = inbox_of(inbox, inbox.rank);
+  for (int s = 0; s < inbox.world; ++s) {
+    const int n_tok = v.cnt[2 * s], n_all = n_tok + v.cnt[2 * s + 1];
+    for (int k = warp_global; k < n_all; k += total_warps) {
+      const size_t slot = (size_t)s * inbox.cap + k;
+      const int row = v.ids[slot];
+      if (row < 0) continue;
+      float* dst = (k < n_tok ? g_tok : g_path) + (size_t)row * d;
+      const float* src = v.val + slot * d;
+      for (int j = lane * 4; j < d; j += 128) atomicAdd(reinterpret_cast<float4*>(dst + j), *reinterpret_cast<const float4*>(src + j));
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // Lazy-but-exact dense Adam for the two embedding tables (single GPU).
 //
 // TF1's Adam is dense: every row decays m, v and moves theta on every step, gradient or not

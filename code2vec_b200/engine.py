@@ -72,6 +72,9 @@ _SIGNATURES = {
     "c2v_adam_step_range": (C.c_int, [_P, _P, _P, _P, _P, C.c_size_t, C.c_float, C.c_float, C.c_float, C.c_float,
                                       C.c_int64, _I32, _P]),
     "c2v_bind_table_shards": (C.c_int, [_P, C.POINTER(c2v_table_shards), C.POINTER(c2v_table_shards), C.c_float]),
+    "c2v_scatter_inbox_bytes": (C.c_size_t, [C.POINTER(c2v_dims), _I32]),
+    "c2v_bind_scatter_inbox": (C.c_int, [_P, C.POINTER(_P), _I32, _I32]),
+    "c2v_apply_scatter_inbox": (C.c_int, [_P, _P]),
     "c2v_ipc_alloc": (C.c_int, [C.c_int, C.c_size_t, C.POINTER(_P), C.c_char_p]),
     "c2v_ipc_open": (C.c_int, [C.c_int, C.c_char_p, C.POINTER(_P)]),
     "c2v_ipc_close": (C.c_int, [C.c_int, _P]),
@@ -473,7 +476,12 @@ class PathAttentionEngine:
                                                   dv.data_ptr(), self._stream()))
 
     # ---- row-sharded embedding tables over peer memory (data-parallel runs) ----------------------
-    def enable_table_sharding(self, group=None):
+    def apply_scatter_inbox(self):
+        """Owner side of the push-based gradient exchange: fold this rank's inbox into its gradient shards (call after
+        the cross-rank barrier that follows every rank's backward pass)."""
+        self._check(self.lib.c2v_apply_scatter_inbox(self.h, self._stream()))
+
+    def enable_table_sharding(self, group=None, push_grads: bool = True):
         """Re-homes WORDS_VOCAB / PATHS_VOCAB (+ gradients, Adam slots) as row-interleaved shards: global
         row r -> rank r % world, local row r // world.  Parameter and gradient shards live in
         cudaMalloc'ed memory whose CUDA-IPC handles are exchanged once, so every rank's kernels can
@@ -489,6 +497,16 @@ class PathAttentionEngine:
         d = self.dims.embed_dim
         rows = {"tok": (self.dims.token_vocab + world - 1) // world, "path": (self.dims.path_vocab + world - 1) // world}
         own, handles = {}, {}
+        self.push_grads = bool(push_grads) and self.training and world > 1
+        if self.push_grads:          # one inbox per rank for the embedding-gradient rows its peers push (c2v_bind_scatter_inbox)
+            cd = self.dims.to_c()
+            nbytes = self.lib.c2v_scatter_inbox_bytes(C.byref(cd), world)
+            ptr, hbuf = _P(), C.create_string_buffer(64)
+            rc = self.lib.c2v_ipc_alloc(self.device, nbytes, C.byref(ptr), hbuf)
+            if rc != 0:
+                raise EngineError(rc, self.lib.c2v_last_error(None).decode())
+            own[("inbox", "all")] = ptr.value
+            handles[("inbox", "all")] = hbuf.raw
         for role in ("params", "grads"):
             for name in ("tok", "path"):
                 ptr, hbuf = _P(), C.create_string_buffer(64)
@@ -524,6 +542,9 @@ class PathAttentionEngine:
 
         sp, sg = shards("params"), shards("grads")
         self._check(self.lib.c2v_bind_table_shards(self.h, C.byref(sp), C.byref(sg) if self.training else None, 1.0 / world))
+        if self.push_grads:
+            arr = (_P * world)(*[ptrs[(r, "inbox", "all")] for r in range(world)])
+            self._check(self.lib.c2v_bind_scatter_inbox(self.h, arr, world, rank))
         view = lambda key, name: torch.as_tensor(_DeviceArray(own[key], (rows[name], d)), device=self.dev)
         self.table_world, self.table_rank = world, rank
         self.shard_params = {n: view(("params", n), n) for n in ("tok", "path")}

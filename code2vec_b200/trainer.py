@@ -132,7 +132,7 @@ def shard_bounds(n: int, rank: int, world: int):
 class Trainer:
     def __init__(self, engine: PathAttentionEngine, keep_prob: float = 0.75, seed: int = 0, group=None,
                  adam: Optional[dict] = None, schedule: str = "table_sharded", lazy_adam: bool = True,
-                 fuse_target_adam: bool = True):
+                 fuse_target_adam: bool = True, push_grads: bool = True):
         self.e = engine
         self.keep = float(keep_prob)
         self.seed = int(seed)
@@ -149,7 +149,7 @@ class Trainer:
             if not hasattr(engine, "target_row0"):
                 raise ValueError("the fully_sharded schedule needs an engine from make_fully_sharded_engine()")
             with torch.cuda.device(engine.dev):
-                engine.enable_table_sharding(group)
+                engine.enable_table_sharding(group, push_grads=push_grads)
             engine.set_option("grad_scale_inverse", 1)     # dv already carries the 1/global-batch factor
             Bl, Bt, D = engine.local_batch, engine.local_batch * self.world, engine.dims.code_dim
             f32, i32, dev = torch.float32, torch.int32, engine.dev
@@ -171,7 +171,7 @@ class Trainer:
                              target=torch.empty((B,), dtype=i32, device=engine.dev))
         if self.schedule == "table_sharded":
             with torch.cuda.device(engine.dev):
-                engine.enable_table_sharding(group)
+                engine.enable_table_sharding(group, push_grads=push_grads)
             (a0, a1), _ = engine.bucket_bounds()
             layout, total = engine.flat_layout()
             small0 = [off for k, off, n in layout if k == "W"][0]         # W, a: the tail of the flat buffer
@@ -273,6 +273,8 @@ class Trainer:
         s0, s1 = self._small
         # sum (not mean): dv already carries 1/global batch.  Completion == every rank's scatter-add has landed.
         dist.all_reduce(e.flat_grads[s0:s1], op=dist.ReduceOp.SUM, group=self.group)
+        if getattr(e, "push_grads", False):
+            e.apply_scatter_inbox()          # every peer's rows have landed in this rank's inbox: fold them into the shards
         for name in ("tok", "path"):
             e.adam_step_range(e.shard_params[name], e.shard_grads[name], e.shard_m[name], e.shard_v[name], t,
                               zero_grad=True, **self.adam)
@@ -298,6 +300,8 @@ class Trainer:
         # its completion also tells this rank that every peer's red.adds into its shards have landed
         ws = dist.all_reduce(e.flat_grads[s0:s1], op=dist.ReduceOp.AVG, group=self.group, async_op=True)
         ws.wait()
+        if getattr(e, "push_grads", False):
+            e.apply_scatter_inbox()
         for name in ("tok", "path"):
             e.adam_step_range(e.shard_params[name], e.shard_grads[name], e.shard_m[name], e.shard_v[name], t,
                               zero_grad=True, **self.adam)

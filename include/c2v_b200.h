@@ -278,6 +278,17 @@ typedef struct c2v_table_shards {
 int c2v_bind_table_shards(c2v_engine* e, const c2v_table_shards* params, const c2v_table_shards* grads,
                           float grad_scale);
 
+/* Push-based embedding-gradient exchange for row-sharded tables.  Every rank owns an INBOX in peer-visible memory
+ * (c2v_ipc_alloc, c2v_scatter_inbox_bytes(dims, world) bytes) with one region per sending rank.  With inboxes bound,
+ * the backward pass no longer issues 16-byte red.global.add over NVLink: it sorts its 3 B C gradient rows by owning
+ * rank and writes each owner's rows -- (local row id, d floats) -- DENSELY into its region of that owner's inbox with
+ * plain coalesced stores; after the caller's cross-rank barrier (the same one that ordered the remote red.adds before)
+ * each owner folds its inbox into its own gradient shards with local atomics (c2v_apply_scatter_inbox).
+ * inbox[r] = rank r's inbox as mapped into this process (r == rank: the local allocation). */
+size_t c2v_scatter_inbox_bytes(const c2v_dims* dims, int32_t world);
+int c2v_bind_scatter_inbox(c2v_engine* e, void* const* inbox, int32_t world, int32_t rank);
+int c2v_apply_scatter_inbox(c2v_engine* e, void* stream);
+
 /* cudaMalloc'ed, zero-filled, IPC-shareable device memory for the shards (not tied to an engine;
  * errors are reported through c2v_last_error(NULL)).  handle64 is a 64-byte cudaIpcMemHandle_t. */
 int c2v_ipc_alloc(int device, size_t bytes, void** dev_ptr, unsigned char* handle64);
