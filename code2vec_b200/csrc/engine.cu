@@ -122,10 +122,11 @@ Workspace carve(const c2v_dims& d) {
 // Phases of a pass, for per-kernel timing (option "profile"): CUDA events bracket each phase on
 // the launching stream; c2v_phase_stats() resolves them.
 enum Phase { PH_CTX_FWD = 0, PH_ATTN_FWD, PH_LOGITS, PH_XENT, PH_DV, PH_DY, PH_ATTN_BWD, PH_DW, PH_DX_SCATTER,
-             PH_ADAM, PH_TOPK, PH_SAMPLED, PH_GATHER, PH_DX_GEMM, PH_ADAM_CATCHUP, PH_SPLIT, PH_ADAM_SWEEP, PH_COUNT };
+             PH_ADAM, PH_TOPK, PH_SAMPLED, PH_GATHER, PH_DX_GEMM, PH_ADAM_CATCHUP, PH_SPLIT, PH_ADAM_SWEEP, PH_PEER_SORT, PH_INBOX_APPLY,
+             PH_COUNT };
 const char* const kPhaseNames[PH_COUNT] = {"ctx_fwd", "attn_fwd", "logits", "xent", "dv", "dY", "attn_bwd", "dW",
                                            "dx_scatter", "adam", "topk", "sampled_softmax", "gather", "dx_gemm",
-                                           "adam_catchup", "split", "adam_sweep"};
+                                           "adam_catchup", "split", "adam_sweep", "peer_sort", "inbox_apply"};
 struct PhaseLog {
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pending;
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> free_list;
@@ -163,6 +164,8 @@ struct c2v_engine {
   bool has_theta, has_grad, has_adam;
   bool emb_grads_clean;      // token/path gradient tables are known to be all-zero
   int math_mode;
+  const int32_t* sorted_src = nullptr;   // ws.perm / ws.bkt_starts hold the bucket order of THIS batch (set by the forward pass)
+  int sorted_rows = 0;
   InboxSet inbox{};          // push-based gradient exchange (c2v_bind_scatter_inbox); world == 0: not bound
   int sort_peer = 1;         // option "sort_peer_access": sharded tables are gathered / scattered in (owner, 2 MB page) order
   bool bkt_zeroed = false;   // the bucket counters have been cleared once (bucket_scan_kernel leaves them cleared)
@@ -523,6 +526,7 @@ bool plan_buckets(c2v_engine* e, BucketPlan* bp, bool force = false) {
   return bp->n_buckets <= kMaxBuckets;
 }
 int sort_entries(c2v_engine* e, cudaStream_t st, const ContextSource& cs, const BucketPlan& bp) {
+  PhaseTimer pt(e, PH_PEER_SORT, st);
   int32_t* counts = wsp<int32_t>(e, e->ws.bkt_count);
   int32_t* cursor = wsp<int32_t>(e, e->ws.bkt_cursor);
   if (!e->bkt_zeroed) {
@@ -558,9 +562,18 @@ int run_ctx_fwd(c2v_engine* e, cudaStream_t st, const ContextSource& cs, const D
     {
       PhaseTimer pt(e, PH_GATHER, st);
       BucketPlan bp;
+      e->sorted_src = nullptr;
+      if (e->inbox.world > 1 && plan_buckets(e, &bp, true) && !plan_buckets(e, &bp)) {
+        // the backward pass will push gradient rows owner by owner: bucket the batch now, while the SMs are free (in
+        // the backward pass the same three small kernels would queue behind the persistent dW GEMM)
+        int rcs = sort_entries(e, st, cs, bp);
+        if (rcs) return rcs;
+        e->sorted_src = cs.src; e->sorted_rows = cs.rows;
+      }
       if (plan_buckets(e, &bp)) {           // peer shards: walk the entries page by page
         int rcs = sort_entries(e, st, cs, bp);
         if (rcs) return rcs;
+        e->sorted_src = cs.src; e->sorted_rows = cs.rows;
         const int32_t* perm = wsp<int32_t>(e, e->ws.perm);
         if (x3) C2V_LAUNCH(e, (gather_sorted_kernel<true><<<(3 * cs.rows + 7) / 8, 256, 0, st>>>(cs, dp, perm, Xg, wsp<float>(e, e->ws.Xg_lo))));
         else C2V_LAUNCH(e, (gather_sorted_kernel<false><<<(3 * cs.rows + 7) / 8, 256, 0, st>>>(cs, dp, perm, Xg, nullptr)));
@@ -703,7 +716,10 @@ int context_backward(c2v_engine* e, cudaStream_t st, const ContextSource& cs, co
       if (e->inbox.world > 1 && plan_buckets(e, &bp, true)) {
         // push: every owner's rows go densely into this rank's region of the owner's inbox (plain coalesced stores over
         // NVLink); the owners fold them in with local atomics after the caller's barrier (c2v_apply_scatter_inbox)
-        if ((rc = sort_entries(e, e->side, cs, bp))) return rc;
+        if (e->sorted_src != cs.src || e->sorted_rows != cs.rows) {     // not bucketed by this step's forward pass
+          if ((rc = sort_entries(e, e->side, cs, bp))) return rc;
+        }
+        e->sorted_src = nullptr;
         const int32_t* starts = wsp<int32_t>(e, e->ws.bkt_starts);
         C2V_LAUNCH(e, (inbox_counts_kernel<<<1, 32, 0, e->side>>>(e->inbox, bp, starts)));
         C2V_LAUNCH(e, (scatter_inbox_kernel<<<(3 * N + 7) / 8, 256, 0, e->side>>>(cs, dp, mask, wsp<int32_t>(e, e->ws.perm), starts, bp, dXg,
@@ -1433,7 +1449,7 @@ int c2v_apply_scatter_inbox(c2v_engine* e, void* stream) {
   if (e->inbox.world < 2) return fail(e, C2V_ERR_STATE, "no scatter inbox bound (c2v_bind_scatter_inbox)");
   C2V_CUDA(e, cudaSetDevice(e->device));
   cudaStream_t st = (cudaStream_t)stream;
-  PhaseTimer pt(e, PH_DX_SCATTER, st);
+  PhaseTimer pt(e, PH_INBOX_APPLY, st);
   C2V_LAUNCH(e, (inbox_apply_kernel<<<e->num_sms * 8, 256, 0, st>>>(e->inbox, e->dims.embed_dim, e->gr_tok.base[e->inbox.rank],
                                                                     e->gr_path.base[e->inbox.rank])));
   return C2V_OK;

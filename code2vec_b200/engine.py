@@ -481,7 +481,7 @@ class PathAttentionEngine:
         the cross-rank barrier that follows every rank's backward pass)."""
         self._check(self.lib.c2v_apply_scatter_inbox(self.h, self._stream()))
 
-    def enable_table_sharding(self, group=None, push_grads: bool = True):
+    def enable_table_sharding(self, group=None, push_grads: bool = False):
         """Re-homes WORDS_VOCAB / PATHS_VOCAB (+ gradients, Adam slots) as row-interleaved shards: global
         row r -> rank r % world, local row r // world.  Parameter and gradient shards live in
         cudaMalloc'ed memory whose CUDA-IPC handles are exchanged once, so every rank's kernels can

@@ -132,7 +132,7 @@ def shard_bounds(n: int, rank: int, world: int):
 class Trainer:
     def __init__(self, engine: PathAttentionEngine, keep_prob: float = 0.75, seed: int = 0, group=None,
                  adam: Optional[dict] = None, schedule: str = "table_sharded", lazy_adam: bool = True,
-                 fuse_target_adam: bool = True, push_grads: bool = True):
+                 fuse_target_adam: bool = True, push_grads: bool = False):
         self.e = engine
         self.keep = float(keep_prob)
         self.seed = int(seed)
