@@ -169,6 +169,9 @@ struct c2v_engine {
   InboxSet inbox{};          // push-based gradient exchange (c2v_bind_scatter_inbox); world == 0: not bound
   int sort_peer = 1;         // option "sort_peer_access": sharded tables are gathered / scattered in (owner, 2 MB page) order
   bool bkt_zeroed = false;   // the bucket counters have been cleared once (bucket_scan_kernel leaves them cleared)
+  int fuse_sg = 1;           // option "fuse_softmax_grad": dv / dY compute dL/dlogits from the logits slab on the fly (tf32 mode)
+  bool sg_live = false;      // ws.S holds LOGITS and sg describes how dv / dY turn them into dL/dlogits
+  umma::SoftmaxGradArgs sg{};
   int fuse_gather = 0;       // option "fuse_gather": gather -> projection -> tanh as one kernel on the tf32 path (ctx_fused.cuh);
                              // bit-identical to the two-kernel path, but measured slower on B200 so far (0.31 vs 0.27 ms forward) -> off
   int cta_pair = 2;          // tcgen05 GEMMs as CTA pairs (cta_group::2, UMMA 256 x BN): 0 never, 1 always, 2 auto
@@ -810,7 +813,13 @@ int run_dv(c2v_engine* e, cudaStream_t st, int B, float* dv) {
     if (want > kSplitDv) want = kSplitDv;
     const int ks = umma::effective_splits(Y, want);
     umma::EpiStore ep{part, (size_t)D, (size_t)B * D};
-    C2V_LAUNCH(e, C2V_CUDA(e, (C2V_UMMA_192(st, B, D, Y, want, opA, opB, ep, e->num_sms))));
+    if (e->sg_live) {       // A = the logits slab, rewritten to dL/dlogits tile by tile in shared memory
+      umma::AXSoftmaxGradK<4> ax{e->sg};
+      C2V_LAUNCH(e, C2V_CUDA(e, (umma::launch_cfg<192, 4, false, true, umma::EpiStore, umma::AXSoftmaxGradK<4>>(st, B, D, Y, want, opA, opB, ep,
+                                                                                                            e->num_sms, ax))));
+    } else {
+      C2V_LAUNCH(e, C2V_CUDA(e, (C2V_UMMA_192(st, B, D, Y, want, opA, opB, ep, e->num_sms))));
+    }
     return launch_colsum(e, st, part, (size_t)B * D, ks, B * D, dv);
   }
   simt::RowsK al{S, e->ws.ldS};
@@ -844,13 +853,25 @@ int run_dy(c2v_engine* e, cudaStream_t st, const float* v, int B) {
                             (1.0 - pow((double)e->tgt_b1, (double)e->tgt_t));
         umma::EpiAdam ep{e->theta.tgt, e->am.tgt, e->av.tgt, (size_t)D, (float)lr_t, e->tgt_b1, e->tgt_b2, e->tgt_eps,
                          1.f - e->tgt_b1, 1.f - e->tgt_b2};
-        C2V_LAUNCH(e, C2V_CUDA(e, (C2V_UMMA_FIXED(192, true, true, false, umma::EpiAdam, st, Y, D, B, 1, opA, opB, ep, e->num_sms))));
+        if (e->sg_live) {
+          umma::AXSoftmaxGradMN<2> ax{e->sg};
+          C2V_LAUNCH(e, C2V_CUDA(e, (umma::launch_cfg<192, 4, true, true, umma::EpiAdam, umma::AXSoftmaxGradMN<2>>(st, Y, D, B, 1, opA, opB, ep,
+                                                                                                               e->num_sms, ax))));
+        } else {
+          C2V_LAUNCH(e, C2V_CUDA(e, (C2V_UMMA_FIXED(192, true, true, false, umma::EpiAdam, st, Y, D, B, 1, opA, opB, ep, e->num_sms))));
+        }
         e->tgt_armed = false;
         e->tgt_fused_t = e->tgt_t;
         e->tgt_split_valid = false;
       } else {
         umma::EpiStore ep{e->grad.tgt, (size_t)D, 0};
-        C2V_LAUNCH(e, C2V_CUDA(e, (C2V_UMMA_192_SINGLE(st, Y, D, B, 1, opA, opB, ep, e->num_sms))));
+        if (e->sg_live) {
+          umma::AXSoftmaxGradMN<2> ax{e->sg};
+          C2V_LAUNCH(e, C2V_CUDA(e, (umma::launch_cfg<192, 4, true, true, umma::EpiStore, umma::AXSoftmaxGradMN<2>>(st, Y, D, B, 1, opA, opB, ep,
+                                                                                                                e->num_sms, ax))));
+        } else {
+          C2V_LAUNCH(e, C2V_CUDA(e, (C2V_UMMA_192_SINGLE(st, Y, D, B, 1, opA, opB, ep, e->num_sms))));
+        }
       }
     } else {
       simt::ColsX al{S, e->ws.ldS};
@@ -915,9 +936,14 @@ int train_step_impl(c2v_engine* e, cudaStream_t st, const int32_t* src, const in
       C2V_LAUNCH(e, (xent_combine_kernel<<<B, 256, 0, st>>>(wsp<float2>(e, e->ws.lse_part), n_tiles, S, e->ws.ldS, target,
                                                             loss_b, lse)));
       const int chunks = (int)((e->ws.ldS / 4 + 256 * 8 - 1) / (256 * 8));
+      e->sg_live = false;
       if (is_3x(e))
         C2V_LAUNCH(e, (softmax_grad_kernel<true><<<dim3(chunks, B), 256, 0, st>>>(S, e->ws.ldS, Y, lse, target, invB, 0, wsp<float>(e, e->ws.S_lo))));
-      else
+      else if (e->fuse_sg) {
+        // no pass over the slab: the dv and dY GEMMs turn logits into (softmax - onehot) / B as their A tiles land
+        e->sg = umma::SoftmaxGradArgs{lse, target, 0, invB};
+        e->sg_live = true;
+      } else
         C2V_LAUNCH(e, (softmax_grad_kernel<false><<<dim3(chunks, B), 256, 0, st>>>(S, e->ws.ldS, Y, lse, target, invB, 0, nullptr)));
     } else {
       C2V_LAUNCH(e, (xent_kernel<<<B, kXentThreads, 0, st>>>(S, e->ws.ldS, target, Y, invB, loss_b, lse, 1)));
@@ -1184,6 +1210,7 @@ int c2v_set_option(c2v_engine* e, const char* key, int64_t value) {
   }
   if (!strcmp(key, "fuse_target_adam")) { e->fuse_tgt = value ? 1 : 0; return C2V_OK; }
   if (!strcmp(key, "fuse_gather")) { e->fuse_gather = value ? 1 : 0; return C2V_OK; }
+  if (!strcmp(key, "fuse_softmax_grad")) { e->fuse_sg = value ? 1 : 0; return C2V_OK; }
   if (!strcmp(key, "sort_peer_access")) {
     if (value < 0 || value > 2) return fail(e, C2V_ERR_INVALID, "sort_peer_access must be 0 (never), 1 (auto) or 2 (always)");
     e->sort_peer = (int)value;
@@ -1278,6 +1305,7 @@ int c2v_get_option(const c2v_engine* e, const char* key, int64_t* value) {
   if (!strcmp(key, "dy_late")) { *value = e->dy_late; return C2V_OK; }
   if (!strcmp(key, "fuse_target_adam")) { *value = e->fuse_tgt; return C2V_OK; }
   if (!strcmp(key, "fuse_gather")) { *value = e->fuse_gather; return C2V_OK; }
+  if (!strcmp(key, "fuse_softmax_grad")) { *value = e->fuse_sg; return C2V_OK; }
   if (!strcmp(key, "sort_peer_access")) { *value = e->sort_peer; return C2V_OK; }
   if (!strcmp(key, "adam_step_count")) { *value = e->adam_t_done; return C2V_OK; }
   if (!strcmp(key, "target_adam_fused_step")) { *value = e->tgt_fused_t; return C2V_OK; }
@@ -1543,10 +1571,14 @@ int c2v_target_backward(c2v_engine* e, const float* code_all, int32_t Bt, const 
   {
     PhaseTimer pt(e, PH_XENT, st);
     const int chunks = (int)((e->ws.ldS / 4 + 256 * 8 - 1) / (256 * 8));
+    e->sg_live = false;
     if (is_3x(e))
       C2V_LAUNCH(e, (softmax_grad_kernel<true><<<dim3(chunks, Bt), 256, 0, st>>>(S, e->ws.ldS, e->dims.target_vocab, lse, target, inv_batch,
                                                                                row_offset, wsp<float>(e, e->ws.S_lo))));
-    else
+    else if (is_tc(e) && e->fuse_sg) {
+      e->sg = umma::SoftmaxGradArgs{lse, target, row_offset, inv_batch};
+      e->sg_live = true;
+    } else
       C2V_LAUNCH(e, (softmax_grad_kernel<false><<<dim3(chunks, Bt), 256, 0, st>>>(S, e->ws.ldS, e->dims.target_vocab, lse, target, inv_batch,
                                                                                 row_offset, nullptr)));
   }

@@ -370,6 +370,81 @@ __device__ __forceinline__ void drain_accumulator(const Epi& epi, typename Epi::
   }
 }
 
+// ---- A-operand transforms ---------------------------------------------------------------------------------
+// Optional warps between TMA and the tensor core: they wait for a stage to land, rewrite the A tile IN PLACE in
+// shared memory (element-wise, so the swizzled layout is untouched), fence the generic-proxy writes for the async
+// proxy and only then release the stage to the MMA issuer.  Used to feed the two target-side gradient GEMMs with
+// dL/dlogits = (softmax(S) - onehot) / B computed on the fly from the LOGITS slab S and the per-row log-sum-exp, so
+// that the separate pass that rewrote the 1.07 GB slab (read + write) disappears:
+//   dv = P . Ytab     A = S, K-major   (rows = examples, K = classes)      -> AXSoftmaxGradK
+//   dY = P^T . v      A = S^T, MN-major (rows = classes, K = examples)     -> AXSoftmaxGradMN
+struct AXNone {
+  static constexpr int kWarps = 0;
+  __device__ __forceinline__ void apply(uint8_t*, int, int, int, int, int) const {}
+};
+
+struct SoftmaxGradArgs {
+  const float* lse;          // [examples] log-sum-exp of each row of S (all classes, all ranks)
+  const int32_t* target;     // [examples] true class (global id)
+  int row0;                  // first class held in S (row-sharded target table), 0 otherwise
+  float inv_batch;
+};
+__device__ __forceinline__ float4 softmax_grad4(float4 x, float l, float invb, int y0, int ymax, int tgt) {
+  float4 p;
+  p.x = (y0 + 0 < ymax) ? __expf(x.x - l) * invb : 0.f;
+  p.y = (y0 + 1 < ymax) ? __expf(x.y - l) * invb : 0.f;
+  p.z = (y0 + 2 < ymax) ? __expf(x.z - l) * invb : 0.f;
+  p.w = (y0 + 3 < ymax) ? __expf(x.w - l) * invb : 0.f;
+  const int t = tgt - y0;
+  if (t == 0) p.x -= invb; else if (t == 1) p.y -= invb; else if (t == 2) p.z -= invb; else if (t == 3) p.w -= invb;
+  return p;
+}
+// A tile = BM example rows x BK classes, K-major SWIZZLE_128B: row r at r*128, 16-byte chunk c at (c ^ (r & 7)) * 16.
+template <int NW>
+struct AXSoftmaxGradK {
+  static constexpr int kWarps = NW;
+  SoftmaxGradArgs a;
+  __device__ __forceinline__ void apply(uint8_t* sa, int t, int m0, int k0, int M, int K) const {
+    for (int r = t; r < BM; r += 32 * NW) {
+      const int b = m0 + r;
+      if (b >= M) continue;                                  // rows past the batch: TMA zero fill, results are discarded
+      const float l = a.lse[b];
+      const int tgt = a.target[b] - a.row0;
+      uint8_t* row = sa + r * 128;
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        float4* q = reinterpret_cast<float4*>(row + ((c ^ (r & 7)) << 4));
+        *q = softmax_grad4(*q, l, a.inv_batch, k0 + c * 4, K, tgt);
+      }
+    }
+  }
+};
+// A tile = BM classes x BK examples, MN-major SWIZZLE_128B_BASE32B: BM/32 blocks of [BK example rows x 128 B]; in a row the
+// 32-byte unit u (8 classes) sits at (u ^ (row & 3)) * 32.
+template <int NW>
+struct AXSoftmaxGradMN {
+  static constexpr int kWarps = NW;
+  SoftmaxGradArgs a;
+  __device__ __forceinline__ void apply(uint8_t* sa, int t, int m0, int k0, int M, int K) const {
+    for (int i = t; i < (BM / 32) * BK; i += 32 * NW) {
+      const int ch = i / BK, kr = i - ch * BK;
+      const int b = k0 + kr;
+      uint8_t* row = sa + ch * (BK * 128) + kr * 128;
+      if (b >= K) continue;                                  // examples past the batch: zero fill stays zero
+      const float l = a.lse[b];
+      const int tgt = a.target[b] - a.row0;
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          float4* q = reinterpret_cast<float4*>(row + ((u ^ (kr & 3)) << 5) + (h << 4));
+          *q = softmax_grad4(*q, l, a.inv_batch, m0 + ch * 32 + u * 8 + h * 4, M, tgt);
+        }
+      }
+    }
+  }
+};
+
 // ---- kernel -------------------------------------------------------------------------------------------
 struct GemmShape {
   int M, N, K;
@@ -390,10 +465,11 @@ struct SmemLayout {
   static_assert(kTotal <= 232448, "exceeds the 227 KB of shared memory a CTA can opt into");
 };
 
-template <int BN, int STAGES, bool A_MN, bool B_MN, class Epi>
-__global__ void __launch_bounds__(kThreads, 1)
+template <int BN, int STAGES, bool A_MN, bool B_MN, class Epi, class AX = AXNone>
+__global__ void __launch_bounds__(kThreads + 32 * AX::kWarps, 1)
 umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                 const __grid_constant__ CUtensorMap tmAlo, const __grid_constant__ CUtensorMap tmBlo, GemmShape gs, Epi epi) {
+                 const __grid_constant__ CUtensorMap tmAlo, const __grid_constant__ CUtensorMap tmBlo, GemmShape gs, Epi epi,
+                 AX ax = AX{}) {
   using L = SmemLayout<BN, STAGES>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -401,15 +477,20 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tfull_bar = empty_bar + STAGES;      // [2]
   uint64_t* tempty_bar = tfull_bar + 2;          // [2]
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  uint64_t* xf_bar = tempty_bar + 2;             // [STAGES] A tile transformed (only with an A transform)
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(xf_bar + STAGES);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   constexpr uint32_t kTmemCols = (2 * BN <= 256) ? 256 : 512;
+  constexpr bool kXform = AX::kWarps > 0;
   const int total_items = gs.m_tiles * gs.n_tiles * gs.splits;
   const int total_kblocks = (gs.K + BK - 1) / BK;
 
   if (warp == 0 && lane == 0) {
-    for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1);
+      if (kXform) mbar_init(&xf_bar[s], AX::kWarps);
+    }
     for (int a = 0; a < 2; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], kEpiWarps); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -503,7 +584,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const uint32_t tmem_d = tmem_base + acc * BN;
         const int n_steps = (kb1 - kb0) * gs.terms;          // 3xTF32: three passes over the K range (see the producer)
         for (int it = 0; it < n_steps; ++it) {
-          mbar_wait(&full_bar[stage], phase);
+          mbar_wait(kXform ? &xf_bar[stage] : &full_bar[stage], phase);    // with a transform: once the A tile has been rewritten
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + stage * L::kStageBytes);
           const uint32_t sb = sa + L::kABytes;
@@ -519,6 +600,25 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
         tc_commit(&tfull_bar[acc]);                           // accumulator complete -> epilogue
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else if (kXform && warp >= kEpiWarp0 + kEpiWarps) {
+    // ===================== A-transform warps =====================
+    const int t = (warp - kEpiWarp0 - kEpiWarps) * 32 + lane;
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
+      int mt, nt, sp;
+      decode(item, mt, nt, sp);
+      const int kb0 = sp * gs.kblocks_per_split;
+      const int kb1 = min(total_kblocks, kb0 + gs.kblocks_per_split);
+      for (int kb = kb0; kb < kb1; ++kb) {
+        mbar_wait(&full_bar[stage], phase);                   // the TMA tiles of this stage have landed
+        ax.apply(smem + stage * L::kStageBytes, t, mt * BM, kb * BK, gs.M, gs.K);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&xf_bar[stage]);
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
     }
   } else {
@@ -619,9 +719,9 @@ struct Operand {
   const float* lo = nullptr;
 };
 
-template <int BN, int STAGES, bool A_MN, bool B_MN, class Epi>
+template <int BN, int STAGES, bool A_MN, bool B_MN, class Epi, class AX = AXNone>
 inline cudaError_t launch_cfg(cudaStream_t st, int M, int N, int K, int splits, const Operand& A, const Operand& B, const Epi& epi,
-                              int num_sms) {
+                              int num_sms, const AX& ax = AX{}) {
   using L = SmemLayout<BN, STAGES>;
   CUtensorMap tmA, tmB, tmAlo, tmBlo;
   const bool three = A.lo != nullptr && B.lo != nullptr;
@@ -649,12 +749,13 @@ inline cudaError_t launch_cfg(cudaStream_t st, int M, int N, int K, int splits, 
   gs.splits = (total_kblocks + gs.kblocks_per_split - 1) / gs.kblocks_per_split;
   // few, wide n-tiles under many m-tiles: walk n fastest so the (large) A tile is fetched from HBM once
   gs.n_fastest = (gs.n_tiles < gs.m_tiles) ? 1 : 0;
-  auto kern = umma_gemm_kernel<BN, STAGES, A_MN, B_MN, Epi>;
+  if (AX::kWarps > 0 && three) return cudaErrorInvalidValue;      // the transforms rewrite a single fp32 tile
+  auto kern = umma_gemm_kernel<BN, STAGES, A_MN, B_MN, Epi, AX>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal);
   if (e != cudaSuccess) return e;
   int grid = gs.m_tiles * gs.n_tiles * gs.splits;
   if (grid > num_sms) grid = num_sms;
-  kern<<<grid, kThreads, L::kTotal, st>>>(tmA, tmB, tmAlo, tmBlo, gs, epi);
+  kern<<<grid, kThreads + 32 * AX::kWarps, L::kTotal, st>>>(tmA, tmB, tmAlo, tmBlo, gs, epi, ax);
   return cudaGetLastError();
 }
 

@@ -49,14 +49,19 @@ def _worker(rank, world, port, schedule, math_mode, out_dir):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("schedule", ["allreduce", "sharded", "table_sharded", "fully_sharded"])
-def test_two_rank_data_parallel_matches_single_engine(tmp_path, schedule):
+@pytest.mark.parametrize("schedule,math_mode", [("allreduce", 0), ("sharded", 0), ("table_sharded", 0), ("fully_sharded", 0),
+                                                 ("fully_sharded", 1), ("fully_sharded", 2)])
+def test_two_rank_data_parallel_matches_single_engine(tmp_path, schedule, math_mode):
+    """math_mode 1 / 2: the tensor-core paths of the fully sharded schedule (row-sharded target table: the gradient GEMMs
+    build dL/dlogits from the local logits slab with the target's row offset; 3xTF32 splits), at their tolerances."""
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     import torch.multiprocessing as mp
     world, port = 2, 29500 + (os.getpid() % 1000)
-    mp.spawn(_worker, args=(world, port, schedule, 0, str(tmp_path)), nprocs=world, join=True)
+    # tf32: an element whose tiny gradient changes sign moves the other way by a full Adam step (1e-3) in each of the 3 steps
+    tol = {0: 5e-5, 1: 8e-3, 2: 2e-4}[math_mode]
+    mp.spawn(_worker, args=(world, port, schedule, math_mode, str(tmp_path)), nprocs=world, join=True)
     r0 = np.load(str(tmp_path / "rank0.npz"))
     r1 = np.load(str(tmp_path / "rank1.npz"))
     replicated = {"table_sharded": ("tgt", "W", "a"), "fully_sharded": ("W", "a")}.get(schedule, O.PARAM_NAMES)
@@ -70,16 +75,16 @@ def test_two_rank_data_parallel_matches_single_engine(tmp_path, schedule):
         eng.train_batch_host(src, pth, tgt, mask, target, keep=1.0)
     ref = eng.export_params()
     for k in replicated:
-        assert np.abs(r0[k] - ref[k]).max() < 5e-5, k
+        assert np.abs(r0[k] - ref[k]).max() < tol, k
     if schedule == "fully_sharded":
         from code2vec_b200.trainer import target_row_block
         for r, res in ((0, r0), (1, r1)):
             lo, hi = target_row_block(DIMS.target_vocab, r, 2)
-            assert np.abs(res["tgt"][:hi - lo] - ref["tgt"][lo:hi]).max() < 5e-5, r
+            assert np.abs(res["tgt"][:hi - lo] - ref["tgt"][lo:hi]).max() < tol, r
         assert abs(float(r0["losses"][0]) - float(r1["losses"][0])) < 1e-6      # the loss is global here
     if schedule in ("table_sharded", "fully_sharded"):
         # row r of the global table lives on rank r % 2 at local row r // 2
         for r, res in ((0, r0), (1, r1)):
             for name, shard in (("tok", res["tok_shard"]), ("path", res["path_shard"])):
                 want = ref[name][r::2]
-                assert np.abs(shard[:want.shape[0]] - want).max() < 5e-5, (name, r)
+                assert np.abs(shard[:want.shape[0]] - want).max() < tol, (name, r)

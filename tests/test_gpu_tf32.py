@@ -96,3 +96,26 @@ def test_fused_gather_projection_is_bit_identical_to_the_unfused_path(dims, B, k
         assert np.array_equal(out[1][3][k], out[0][3][k]), k
     for k in ("tok", "path"):
         assert rel_err(out[1][3][k], out[0][3][k]) < 1e-5, k
+
+
+@pytest.mark.parametrize("dims,B", [(TINY, 64), (ODD, 37), (MID, 48), (LARGE, 12)])
+def test_softmax_gradient_computed_inside_the_gradient_gemms(dims, B):
+    """Option fuse_softmax_grad (default): the dv = P.Ytab and dY = P^T.v GEMMs read the LOGITS slab and turn each A tile
+    into (softmax - onehot)/B in shared memory (umma_gemm.cuh, AXSoftmaxGradK / AXSoftmaxGradMN) instead of reading a slab
+    that a separate pass rewrote.  Same gradients as with the separate pass, to the rounding of one exp (ex2.approx vs expf
+    on values that are then cut to tf32 anyway), and as the oracle's at the tf32 tolerance."""
+    src, pth, tgt, mask, target = O.synthetic_batch(dims, B, seed=51)
+    out = {}
+    for fuse in (1, 0):
+        eng, params = make_engine(dims, max_batch=B)
+        eng.set_option("math_mode", 1)
+        eng.set_option("fuse_softmax_grad", fuse)
+        assert eng.get_option("fuse_softmax_grad") == fuse
+        loss = float(eng.train_step(*dev_batch(eng, src, pth, tgt, mask, target), keep=1.0).cpu()[0])
+        out[fuse] = (loss, eng.export_grads())
+        eng.close()
+    assert out[1][0] == out[0][0]                       # the loss does not depend on it
+    _, g_ref, _ = O.train_loss_and_grads(params, src, pth, tgt, mask, target)
+    for k in O.PARAM_NAMES:
+        assert rel_err(out[1][1][k], out[0][1][k]) < 2e-3, k
+        assert rel_err(out[1][1][k], g_ref[k]) < 1e-2, k
