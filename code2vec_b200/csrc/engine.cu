@@ -169,7 +169,10 @@ struct c2v_engine {
   InboxSet inbox{};          // push-based gradient exchange (c2v_bind_scatter_inbox); world == 0: not bound
   int sort_peer = 1;         // option "sort_peer_access": sharded tables are gathered / scattered in (owner, 2 MB page) order
   bool bkt_zeroed = false;   // the bucket counters have been cleared once (bucket_scan_kernel leaves them cleared)
-  int fuse_sg = 1;           // option "fuse_softmax_grad": dv / dY compute dL/dlogits from the logits slab on the fly (tf32 mode)
+  int fuse_sg = 0;           // option "fuse_softmax_grad": dv / dY compute dL/dlogits from the logits slab on the fly (tf32 mode).
+                             // Correct, and it removes the 2.1 GB softmax-gradient pass (0.36 -> 0.02 ms), but with 32-bit operands the two
+                             // GEMMs are already shared-memory-bandwidth bound and the in-place rewrite of the A stage costs more than
+                             // it saves on B200 (dv 0.34 -> 0.63 ms, dY 0.69 -> 1.02 ms): off by default
   bool sg_live = false;      // ws.S holds LOGITS and sg describes how dv / dY turn them into dL/dlogits
   umma::SoftmaxGradArgs sg{};
   int fuse_gather = 0;       // option "fuse_gather": gather -> projection -> tanh as one kernel on the tf32 path (ctx_fused.cuh);

@@ -380,7 +380,9 @@ __device__ __forceinline__ void drain_accumulator(const Epi& epi, typename Epi::
 //   dY = P^T . v      A = S^T, MN-major (rows = classes, K = examples)     -> AXSoftmaxGradMN
 struct AXNone {
   static constexpr int kWarps = 0;
-  __device__ __forceinline__ void apply(uint8_t*, int, int, int, int, int) const {}
+  struct Pre {};
+  __device__ __forceinline__ void load(int, int, int, int, int, Pre&) const {}
+  __device__ __forceinline__ void apply(uint8_t*, int, int, int, int, int, const Pre&) const {}
 };
 
 struct SoftmaxGradArgs {
@@ -389,58 +391,103 @@ struct SoftmaxGradArgs {
   int row0;                  // first class held in S (row-sharded target table), 0 otherwise
   float inv_batch;
 };
-__device__ __forceinline__ float4 softmax_grad4(float4 x, float l, float invb, int y0, int ymax, int tgt) {
-  float4 p;
-  p.x = (y0 + 0 < ymax) ? __expf(x.x - l) * invb : 0.f;
-  p.y = (y0 + 1 < ymax) ? __expf(x.y - l) * invb : 0.f;
-  p.z = (y0 + 2 < ymax) ? __expf(x.z - l) * invb : 0.f;
-  p.w = (y0 + 3 < ymax) ? __expf(x.w - l) * invb : 0.f;
-  const int t = tgt - y0;
-  if (t == 0) p.x -= invb; else if (t == 1) p.y -= invb; else if (t == 2) p.z -= invb; else if (t == 3) p.w -= invb;
+// p = exp(x - lse) / B as ONE fused multiply-add and one ex2: 2^(x log2(e) + c), c = -lse log2(e) + log2(1/B).  No branches, so
+// the 32 values of a row are independent instruction streams (a single warp transforms a whole stage: it needs the ILP).
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+constexpr float kLog2e = 1.4426950408889634f;
+__device__ __forceinline__ float4 softmax_grad4(float4 x, float c) {
+  return make_float4(ex2_approx(fmaf(x.x, kLog2e, c)), ex2_approx(fmaf(x.y, kLog2e, c)), ex2_approx(fmaf(x.z, kLog2e, c)),
+                     ex2_approx(fmaf(x.w, kLog2e, c)));
+}
+__device__ __forceinline__ float4 softmax_grad4_tail(float4 x, float c, int y0, int ymax) {     // classes >= ymax are zero fill: keep 0
+  float4 p = softmax_grad4(x, c);
+  p.x = (y0 + 0 < ymax) ? p.x : 0.f; p.y = (y0 + 1 < ymax) ? p.y : 0.f;
+  p.z = (y0 + 2 < ymax) ? p.z : 0.f; p.w = (y0 + 3 < ymax) ? p.w : 0.f;
   return p;
 }
+// ONE warp rewrites a whole stage (warp w owns every kWarps-th step of the CTA's k-block stream), so kWarps stages are
+// being transformed at any time.  load() runs BEFORE the wait for the stage: the per-example exponent offset and target are in
+// registers by the time the tile has landed.  The "- onehot / B" term touches at most one element per example row and is
+// applied to that element after the row has been rewritten.
+//
 // A tile = BM example rows x BK classes, K-major SWIZZLE_128B: row r at r*128, 16-byte chunk c at (c ^ (r & 7)) * 16.
+// Lane l rewrites rows l, l + 32, l + 64, l + 96.
 template <int NW>
 struct AXSoftmaxGradK {
   static constexpr int kWarps = NW;
   SoftmaxGradArgs a;
-  __device__ __forceinline__ void apply(uint8_t* sa, int t, int m0, int k0, int M, int K) const {
-    for (int r = t; r < BM; r += 32 * NW) {
-      const int b = m0 + r;
-      if (b >= M) continue;                                  // rows past the batch: TMA zero fill, results are discarded
-      const float l = a.lse[b];
-      const int tgt = a.target[b] - a.row0;
-      uint8_t* row = sa + r * 128;
+  struct Pre { float c[BM / 32]; int tgt[BM / 32]; };
+  __device__ __forceinline__ void load(int lane, int m0, int, int M, int, Pre& p) const {
+    const float lb = log2f(a.inv_batch);
 #pragma unroll
-      for (int c = 0; c < 8; ++c) {
-        float4* q = reinterpret_cast<float4*>(row + ((c ^ (r & 7)) << 4));
-        *q = softmax_grad4(*q, l, a.inv_batch, k0 + c * 4, K, tgt);
+    for (int j = 0; j < BM / 32; ++j) {
+      const int b = m0 + lane + 32 * j;
+      p.c[j] = (b < M) ? fmaf(-a.lse[b], kLog2e, lb) : 0.f;
+      p.tgt[j] = (b < M) ? a.target[b] - a.row0 : -1;
+    }
+  }
+  __device__ __forceinline__ void apply(uint8_t* sa, int lane, int m0, int k0, int M, int K, const Pre& p) const {
+    const bool full = k0 + BK <= K;
+#pragma unroll
+    for (int j = 0; j < BM / 32; ++j) {
+      const int r = lane + 32 * j;
+      if (m0 + r >= M) continue;                             // rows past the batch: TMA zero fill, results are discarded
+      uint8_t* row = sa + r * 128;
+      float4 v[8];
+#pragma unroll
+      for (int c = 0; c < 8; ++c) v[c] = *reinterpret_cast<const float4*>(row + ((c ^ (r & 7)) << 4));
+      if (full) {
+#pragma unroll
+        for (int c = 0; c < 8; ++c) v[c] = softmax_grad4(v[c], p.c[j]);
+      } else {
+#pragma unroll
+        for (int c = 0; c < 8; ++c) v[c] = softmax_grad4_tail(v[c], p.c[j], k0 + c * 4, K);
       }
+#pragma unroll
+      for (int c = 0; c < 8; ++c) *reinterpret_cast<float4*>(row + ((c ^ (r & 7)) << 4)) = v[c];
+      const int e = p.tgt[j] - k0;                           // the example's own class, if it is in this tile: - 1/B
+      if (e >= 0 && e < BK) *(reinterpret_cast<float*>(row + (((e >> 2) ^ (r & 7)) << 4)) + (e & 3)) -= a.inv_batch;
     }
   }
 };
 // A tile = BM classes x BK examples, MN-major SWIZZLE_128B_BASE32B: BM/32 blocks of [BK example rows x 128 B]; in a row the
-// 32-byte unit u (8 classes) sits at (u ^ (row & 3)) * 32.
+// 32-byte unit u (8 classes) sits at (u ^ (row & 3)) * 32.  Lane l rewrites example row l of every block.
 template <int NW>
 struct AXSoftmaxGradMN {
   static constexpr int kWarps = NW;
   SoftmaxGradArgs a;
-  __device__ __forceinline__ void apply(uint8_t* sa, int t, int m0, int k0, int M, int K) const {
-    for (int i = t; i < (BM / 32) * BK; i += 32 * NW) {
-      const int ch = i / BK, kr = i - ch * BK;
-      const int b = k0 + kr;
-      uint8_t* row = sa + ch * (BK * 128) + kr * 128;
-      if (b >= K) continue;                                  // examples past the batch: zero fill stays zero
-      const float l = a.lse[b];
-      const int tgt = a.target[b] - a.row0;
+  struct Pre { float c; int tgt; };
+  __device__ __forceinline__ void load(int lane, int, int k0, int, int K, Pre& p) const {
+    const int b = k0 + lane;
+    p.c = (b < K) ? fmaf(-a.lse[b], kLog2e, log2f(a.inv_batch)) : 0.f;
+    p.tgt = (b < K) ? a.target[b] - a.row0 : -1;
+  }
+  __device__ __forceinline__ void apply(uint8_t* sa, int lane, int m0, int k0, int M, int K, const Pre& p) const {
+    static_assert(BK == 32, "one example row per lane");
+    if (k0 + lane >= K) return;                              // examples past the batch: zero fill stays zero
+    const bool full = m0 + BM <= M;
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
+    for (int ch = 0; ch < BM / 32; ++ch) {
+      uint8_t* row = sa + ch * (BK * 128) + lane * 128;
+      float4 v[8];                                           // v[2u + h] = classes m0 + 32 ch + 8 u + 4 h ..+3
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          float4* q = reinterpret_cast<float4*>(row + ((u ^ (kr & 3)) << 5) + (h << 4));
-          *q = softmax_grad4(*q, l, a.inv_batch, m0 + ch * 32 + u * 8 + h * 4, M, tgt);
-        }
+      for (int q = 0; q < 8; ++q) v[q] = *reinterpret_cast<const float4*>(row + (((q >> 1) ^ (lane & 3)) << 5) + ((q & 1) << 4));
+      if (full) {
+#pragma unroll
+        for (int q = 0; q < 8; ++q) v[q] = softmax_grad4(v[q], p.c);
+      } else {
+#pragma unroll
+        for (int q = 0; q < 8; ++q) v[q] = softmax_grad4_tail(v[q], p.c, m0 + ch * 32 + q * 4, M);
       }
+#pragma unroll
+      for (int q = 0; q < 8; ++q) *reinterpret_cast<float4*>(row + (((q >> 1) ^ (lane & 3)) << 5) + ((q & 1) << 4)) = v[q];
+      const int e = p.tgt - (m0 + ch * 32);
+      if (e >= 0 && e < 32)
+        *(reinterpret_cast<float*>(row + (((e >> 3) ^ (lane & 3)) << 5) + (((e >> 2) & 1) << 4)) + (e & 3)) -= a.inv_batch;
     }
   }
 };
@@ -489,7 +536,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1);
-      if (kXform) mbar_init(&xf_bar[s], AX::kWarps);
+      if (kXform) mbar_init(&xf_bar[s], 1);
     }
     for (int a = 0; a < 2; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], kEpiWarps); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -604,21 +651,27 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
   } else if (kXform && warp >= kEpiWarp0 + kEpiWarps) {
     // ===================== A-transform warps =====================
-    const int t = (warp - kEpiWarp0 - kEpiWarps) * 32 + lane;
-    int stage = 0;
-    uint32_t phase = 0;
+    // warp w takes every kWarps-th step of this CTA's (item, k-block) stream; step g lives in stage g % STAGES
+    constexpr int kXW = kXform ? AX::kWarps : 1;
+    static_assert(STAGES % kXW == 0, "a transform warp must always meet the same stages");
+    const int xw = warp - kEpiWarp0 - kEpiWarps;
+    int g = 0;
     for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
       int mt, nt, sp;
       decode(item, mt, nt, sp);
       const int kb0 = sp * gs.kblocks_per_split;
       const int kb1 = min(total_kblocks, kb0 + gs.kblocks_per_split);
-      for (int kb = kb0; kb < kb1; ++kb) {
+      for (int kb = kb0; kb < kb1; ++kb, ++g) {
+        if (g % kXW != xw) continue;
+        const int stage = g % STAGES;
+        const uint32_t phase = (uint32_t)(g / STAGES) & 1u;
+        typename AX::Pre pre;
+        ax.load(lane, mt * BM, kb * BK, gs.M, gs.K, pre);     // per-example scalars: in flight while the tile lands
         mbar_wait(&full_bar[stage], phase);                   // the TMA tiles of this stage have landed
-        ax.apply(smem + stage * L::kStageBytes, t, mt * BM, kb * BK, gs.M, gs.K);
+        ax.apply(smem + stage * L::kStageBytes, lane, mt * BM, kb * BK, gs.M, gs.K, pre);
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncwarp();
         if (lane == 0) mbar_arrive(&xf_bar[stage]);
-        if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
     }
   } else {

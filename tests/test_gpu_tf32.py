@@ -100,7 +100,7 @@ def test_fused_gather_projection_is_bit_identical_to_the_unfused_path(dims, B, k
 
 @pytest.mark.parametrize("dims,B", [(TINY, 64), (ODD, 37), (MID, 48), (LARGE, 12)])
 def test_softmax_gradient_computed_inside_the_gradient_gemms(dims, B):
-    """Option fuse_softmax_grad (default): the dv = P.Ytab and dY = P^T.v GEMMs read the LOGITS slab and turn each A tile
+    """Option fuse_softmax_grad (off by default: measured slower on B200): the dv = P.Ytab and dY = P^T.v GEMMs read the LOGITS slab and turn each A tile
     into (softmax - onehot)/B in shared memory (umma_gemm.cuh, AXSoftmaxGradK / AXSoftmaxGradMN) instead of reading a slab
     that a separate pass rewrote.  Same gradients as with the separate pass, to the rounding of one exp (ex2.approx vs expf
     on values that are then cut to tf32 anyway), and as the oracle's at the tf32 tolerance."""
