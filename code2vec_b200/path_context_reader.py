@@ -516,7 +516,7 @@ class _RowPool:
             out = tuple(a[pick] for a in self.arrays)
         else:
             for a, o in zip(self.arrays, out):
-                np.take(a, pick, axis=0, out=o[:b])
+                np.take(a, pick, axis=0, out=o[:b], mode="clip")     # indices are in range; "raise" would buffer the output
             out = tuple(o[:b] for o in out)
         # fill the holes left below the new end with the surviving rows of the tail
         new_n = n - b
