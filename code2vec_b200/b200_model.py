@@ -255,10 +255,7 @@ class Code2VecModel(Code2VecModelBase):
             self.engine.set_option("math_mode", self._math_train)
             if ring is not None:
                 rows = int(t.target_index.shape[0])
-                d, buf = ring.upload_next(rows)
-                loss_dev = self.trainer.step_device(d["src"], d["path"], d["tgt"], d["mask"], d["target"])
-                ring.mark_compute_done(buf)
-                loss_hist[n_hist:n_hist + 1].copy_(loss_dev, non_blocking=True)
+                self.trainer.step_ring(ring, rows, loss_hist[n_hist:n_hist + 1])      # upload + step queued; nothing waited for
                 n_hist += 1
                 self.h2d_bytes += rows * (4 * cfg.MAX_CONTEXTS + 1) * 4
                 flush = (batch_num % cfg.NUM_BATCHES_TO_LOG_PROGRESS == 0) or (batch_num % num_batches_to_save_and_eval == 0) \

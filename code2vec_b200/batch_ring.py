@@ -84,6 +84,18 @@ class PinnedBatchRing:
         torch.cuda.current_stream(self.device).wait_event(ev)
         return {k: v[:rows] for k, v in d.items()}, i
 
+    def submit_next(self, engine, rows: int, loss_out, **step_args):
+        """The whole step of the next filled slot as ONE C-ABI call (c2v_train_batch_async): upload on the engine's copy
+        stream, the step queued behind it, nothing waited for.  The Python side of a step is then a single call that
+        releases the GIL -- the reader thread, which is what bounds a text-fed run, keeps the interpreter."""
+        s = self.slots[self._use % len(self.slots)]
+        self._use += 1
+        ev = self.torch.cuda.Event()
+        t = s.t
+        engine.train_batch_async(t["src"], t["path"], t["tgt"], t["mask"], t["target"], rows, loss_out, upload_done=ev, **step_args)
+        s.h2d_done = ev
+        s.free.set()
+
     def mark_compute_done(self, i: int):
         ev = self.torch.cuda.Event()
         ev.record(self.torch.cuda.current_stream(self.device))

@@ -37,6 +37,7 @@ struct Workspace {
   size_t Xg_lo, H_lo, S_lo, tgt_hi, tgt_lo, W_hi, W_lo, v_hi, v_lo;     // 3xTF32 operand splits
   size_t st_src, st_pth, st_tgt, st_mask, st_target, st_topk_idx, st_topk_val, st_code, st_attn;
   size_t nx_src, nx_pth, nx_tgt;                                  // indices of the hinted NEXT batch (host entry point)
+  size_t sb_src, sb_pth, sb_tgt, sb_mask, sb_target;              // second staging set (c2v_train_batch_async double buffer)
   size_t stamp_tok, stamp_path, last_tok, last_path, lr_tab;     // lazy Adam bookkeeping
   size_t stamp_tgt, last_tgt;                                    // ... of the target table (sampled softmax)
   size_t perm, bkt_count, bkt_cursor, bkt_starts;                            // locality-sorted peer gather / scatter (sharded tables)
@@ -87,6 +88,11 @@ Workspace carve(const c2v_dims& d) {
   w.nx_pth = take(N * 4);
   w.nx_tgt = take(N * 4);
   w.st_target = take(B * 4);
+  w.sb_src = take(N * 4);
+  w.sb_pth = take(N * 4);
+  w.sb_tgt = take(N * 4);
+  w.sb_mask = take(N * 4);
+  w.sb_target = take(B * 4);
   w.st_topk_idx = take(B * (size_t)d.top_k * 4);
   w.st_topk_val = take(B * (size_t)d.top_k * 4);
   w.st_code = take(B * D * 4);
@@ -185,6 +191,10 @@ struct c2v_engine {
   int pending_dy_B = 0;
   cudaStream_t side = nullptr;          // engine-owned: the embedding scatter-add runs here, next to the dY / dW GEMMs
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  cudaStream_t copy = nullptr;          // engine-owned: host -> device copies of c2v_train_batch_async
+  cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_used[2] = {nullptr, nullptr};
+  bool used_valid[2] = {false, false};
+  uint64_t async_n = 0;
   cudaStream_t side2 = nullptr;         // engine-owned: the dY (+ target Adam) GEMM with dy_late == 2
   cudaEvent_t ev_fork2 = nullptr, ev_join2 = nullptr;
   bool dy_in_flight = false;            // a dY launched on side2 has not been joined yet
@@ -1127,7 +1137,12 @@ int c2v_create(const c2v_dims* dims, int device, c2v_engine** out) {
       cudaEventCreateWithFlags(&e->ev_join, cudaEventDisableTiming) != cudaSuccess ||
       cudaStreamCreateWithFlags(&e->side2, cudaStreamNonBlocking) != cudaSuccess ||
       cudaEventCreateWithFlags(&e->ev_fork2, cudaEventDisableTiming) != cudaSuccess ||
-      cudaEventCreateWithFlags(&e->ev_join2, cudaEventDisableTiming) != cudaSuccess) {
+      cudaEventCreateWithFlags(&e->ev_join2, cudaEventDisableTiming) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&e->copy, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaEventCreateWithFlags(&e->ev_h2d[0], cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&e->ev_h2d[1], cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&e->ev_used[0], cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&e->ev_used[1], cudaEventDisableTiming) != cudaSuccess) {
     delete e;
     return fail(nullptr, C2V_ERR_CUDA, "could not create the engine's side stream / events");
   }
@@ -1146,6 +1161,11 @@ void c2v_destroy(c2v_engine* e) {
   if (e->ev_fork2) cudaEventDestroy(e->ev_fork2);
   if (e->ev_join2) cudaEventDestroy(e->ev_join2);
   if (e->side2) cudaStreamDestroy(e->side2);
+  for (int i = 0; i < 2; ++i) {
+    if (e->ev_h2d[i]) cudaEventDestroy(e->ev_h2d[i]);
+    if (e->ev_used[i]) cudaEventDestroy(e->ev_used[i]);
+  }
+  if (e->copy) cudaStreamDestroy(e->copy);
   for (auto& L : e->phase) {
     for (auto& ev : L.pending) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
     for (auto& ev : L.free_list) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
@@ -1659,6 +1679,41 @@ int c2v_train_batch_host(c2v_engine* e, const int32_t* h_src, const int32_t* h_p
   if ((rc = adam_impl(e, st, lr, beta1, beta2, eps, t))) return rc;
   C2V_CUDA(e, cudaMemcpyAsync(h_loss, loss, 4, cudaMemcpyDeviceToHost, st));
   C2V_CUDA(e, cudaStreamSynchronize(st));
+  return C2V_OK;
+}
+
+int c2v_train_batch_async(c2v_engine* e, const int32_t* h_src, const int32_t* h_path, const int32_t* h_tgt, const float* h_mask,
+                          const int32_t* h_target, int32_t B, float keep_prob, uint64_t seed, int64_t t, float lr, float beta1,
+                          float beta2, float eps, float* h_loss, void* upload_done_event, void* stream) {
+  int rc = check_batch(e, B);
+  if (rc) return rc;
+  if (!h_src || !h_path || !h_tgt || !h_mask || !h_target || !h_loss) return fail(e, C2V_ERR_INVALID, "NULL argument");
+  C2V_CUDA(e, cudaSetDevice(e->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  const int i = (int)(e->async_n++ & 1);
+  const size_t nb = (size_t)B * e->dims.max_contexts * 4;
+  int32_t* src = wsp<int32_t>(e, i ? e->ws.sb_src : e->ws.st_src);
+  int32_t* pth = wsp<int32_t>(e, i ? e->ws.sb_pth : e->ws.st_pth);
+  int32_t* tgt = wsp<int32_t>(e, i ? e->ws.sb_tgt : e->ws.st_tgt);
+  float* mask = wsp<float>(e, i ? e->ws.sb_mask : e->ws.st_mask);
+  int32_t* target = wsp<int32_t>(e, i ? e->ws.sb_target : e->ws.st_target);
+  float* loss = wsp<float>(e, e->ws.loss) + 1 + i;          // one device slot per buffer: the previous step's read-back may be in flight
+  // upload on the copy stream, behind the step that last read this staging set; the step waits for the upload only
+  if (e->used_valid[i]) C2V_CUDA(e, cudaStreamWaitEvent(e->copy, e->ev_used[i], 0));
+  C2V_CUDA(e, cudaMemcpyAsync(src, h_src, nb, cudaMemcpyHostToDevice, e->copy));
+  C2V_CUDA(e, cudaMemcpyAsync(pth, h_path, nb, cudaMemcpyHostToDevice, e->copy));
+  C2V_CUDA(e, cudaMemcpyAsync(tgt, h_tgt, nb, cudaMemcpyHostToDevice, e->copy));
+  C2V_CUDA(e, cudaMemcpyAsync(mask, h_mask, nb, cudaMemcpyHostToDevice, e->copy));
+  C2V_CUDA(e, cudaMemcpyAsync(target, h_target, (size_t)B * 4, cudaMemcpyHostToDevice, e->copy));
+  C2V_CUDA(e, cudaEventRecord(e->ev_h2d[i], e->copy));
+  if (upload_done_event) C2V_CUDA(e, cudaEventRecord((cudaEvent_t)upload_done_event, e->copy));
+  C2V_CUDA(e, cudaStreamWaitEvent(st, e->ev_h2d[i], 0));
+  if (e->fuse_tgt && (rc = c2v_arm_target_adam(e, lr, beta1, beta2, eps, t))) return rc;
+  if ((rc = train_step_impl(e, st, src, pth, tgt, mask, target, B, keep_prob, seed, (uint64_t)t, nullptr, loss))) return rc;
+  if ((rc = adam_impl(e, st, lr, beta1, beta2, eps, t))) return rc;
+  C2V_CUDA(e, cudaMemcpyAsync(h_loss, loss, 4, cudaMemcpyDeviceToHost, st));
+  C2V_CUDA(e, cudaEventRecord(e->ev_used[i], st));
+  e->used_valid[i] = true;
   return C2V_OK;
 }
 

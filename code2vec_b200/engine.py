@@ -81,6 +81,8 @@ _SIGNATURES = {
     "c2v_ipc_free": (C.c_int, [C.c_int, _P]),
     "c2v_train_batch_host": (C.c_int, [_P, _P, _P, _P, _P, _P, _I32, C.c_float, C.c_uint64, C.c_int64,
                                        C.c_float, C.c_float, C.c_float, C.c_float, _P, _P]),
+    "c2v_train_batch_async": (C.c_int, [_P, _P, _P, _P, _P, _P, _I32, C.c_float, C.c_uint64, C.c_int64,
+                                        C.c_float, C.c_float, C.c_float, C.c_float, _P, _P, _P]),
     "c2v_predict_batch_host": (C.c_int, [_P, _P, _P, _P, _P, _I32, _I32, _P, _P, _P, _P, _P]),
     "c2v_selftest_gemm": (C.c_int, [_P, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _P, C.c_size_t, _P, C.c_size_t,
                                     _P, C.c_size_t, _P]),
@@ -581,6 +583,23 @@ class PathAttentionEngine:
             float(keep), int(seed), int(self.adam_t + 1), lr, beta1, beta2, eps, loss.ctypes.data, self._stream()))
         self.adam_t += 1          # only once the step went through: a failed call leaves host and engine counters in step
         return float(loss[0])
+
+    def train_batch_async(self, src, path, tgt, mask, target, rows: int, loss_out, upload_done=None, keep: float = 1.0,
+                          seed: int = 0, lr=1e-3, beta1=0.9, beta2=0.999, eps=1e-8):
+        """c2v_train_batch_async on PINNED torch tensors (first `rows` rows): the upload runs on the engine's copy stream,
+        the step is queued behind it, nothing is waited for.  loss_out: pinned float32 tensor of one element; upload_done:
+        torch.cuda.Event recorded when the inputs have left the host buffers."""
+        for x in (src, path, tgt, mask, target, loss_out):
+            if not x.is_pinned():
+                raise ValueError("c2v_train_batch_async needs page-locked host tensors")
+        ev = None
+        if upload_done is not None:
+            upload_done.record(self.torch.cuda.current_stream(self.dev))      # forces creation of the cudaEvent_t; re-recorded by the engine
+            ev = upload_done.cuda_event
+        self._check(self.lib.c2v_train_batch_async(
+            self.h, src.data_ptr(), path.data_ptr(), tgt.data_ptr(), mask.data_ptr(), target.data_ptr(), int(rows),
+            float(keep), int(seed), int(self.adam_t + 1), lr, beta1, beta2, eps, loss_out.data_ptr(), ev, self._stream()))
+        self.adam_t += 1
 
     def predict_batch_host(self, src, path, tgt, mask, normalize: bool = False, want_code: bool = True,
                            want_attention: bool = True):

@@ -358,7 +358,7 @@ class PathContextReader:
         """Complete-line byte chunks of the data file, one pass per epoch like _raw_lines."""
         action = self.estimator_action
         path = self.config.data_path(is_evaluating=action.is_evaluate)
-        chunk_bytes = 8 << 20
+        chunk_bytes = 16 << 20
         passes = 1
         if action.is_train and not self.repeat_endlessly and self.config.NUM_TRAIN_EPOCHS > 1:
             passes = self.config.NUM_TRAIN_EPOCHS
@@ -387,6 +387,41 @@ class PathContextReader:
                         break
                     f.seek(start + cut + 1)          # re-read the partial last line with the next chunk
                     yield buf[:cut + 1]
+
+    def _native_chunks_ahead(self, depth: int = 2):
+        """_native_chunks read `depth` chunks ahead by a helper thread (file reads and the slicing of complete lines release
+        the GIL), so the disk/page-cache read of chunk k+1 overlaps the tensorisation of chunk k."""
+        import queue
+        import threading
+        q: "queue.Queue" = queue.Queue(maxsize=depth)
+        done, stop = object(), threading.Event()
+
+        def run():
+            try:
+                for chunk in self._native_chunks():
+                    while not stop.is_set():
+                        try:
+                            q.put(chunk, timeout=0.1)
+                            break
+                        except queue.Full:
+                            continue
+                    if stop.is_set():
+                        return
+                q.put(done)
+            except BaseException as exc:
+                q.put(exc)
+
+        threading.Thread(target=run, daemon=True).start()
+        try:
+            while True:
+                item = q.get()
+                if item is done:
+                    return
+                if isinstance(item, BaseException):
+                    raise item
+                yield item
+        finally:
+            stop.set()
 
     def _iterate_batches_native(self):
         action = self.estimator_action
@@ -419,7 +454,7 @@ class PathContextReader:
             if ring is None:
                 return pool.take(b, self._rng)
             return pool.take(b, self._rng, out=ring.acquire().arrays())
-        for chunk in self._native_chunks():
+        for chunk in self._native_chunks_ahead():
             self._native_parse_into(chunk, pool)
             while pool.n >= S + B:
                 yield emit(draw(B), None)

@@ -238,6 +238,12 @@ class Trainer:
             self._sharded_update(t)
         return loss
 
+    def step_ring(self, ring, rows: int, loss_out):
+        """One training step on the next filled slot of a PinnedBatchRing, fully asynchronous (single GPU)."""
+        if self.schedule != "single":
+            raise RuntimeError("step_ring is single-GPU")
+        ring.submit_next(self.e, rows, loss_out, keep=self.keep, seed=self.seed, **self.adam)
+
     def step_device_sampled(self, src, path, tgt, mask, target, sampled, logq_true, logq_sampled):
         """BASELINE config 3: one training step with the sampled softmax (c2v_sampled_train_step) + Adam.  Single
         GPU.  With lazy Adam the target table's rows are updated lazily too (only the B + S rows the step reads)."""

@@ -312,6 +312,17 @@ int c2v_train_batch_host(c2v_engine* e, const int32_t* h_src, const int32_t* h_p
                          int32_t B, float keep_prob, uint64_t seed, int64_t t, float lr,
                          float beta1, float beta2, float eps, float* h_loss, void* stream);
 
+/* The same step WITHOUT waiting for it: the asynchronous half of the batcher that replaces tf.data's prefetch
+ * (path_context_reader.py:150).  The five h_* arrays must be page-locked host memory that stays untouched until
+ * `upload_done_event` (a cudaEvent_t, may be NULL) has completed: the copies run on an engine-owned copy stream, behind the
+ * step that last used the same one of two device staging sets, so the upload of batch t+1 overlaps the kernels of batch t.
+ * The step itself (arm target Adam if "fuse_target_adam", train step, Adam step t) is queued on `stream` behind the upload;
+ * the loss is copied to h_loss (page-locked, 4 bytes) on `stream` and is valid once `stream` has been synchronised. */
+int c2v_train_batch_async(c2v_engine* e, const int32_t* h_src, const int32_t* h_path, const int32_t* h_tgt,
+                          const float* h_mask, const int32_t* h_target, int32_t B, float keep_prob,
+                          uint64_t seed, int64_t t, float lr, float beta1, float beta2, float eps,
+                          float* h_loss, void* upload_done_event, void* stream);
+
 /* One `sess.run([top_words, top_values, ..., code_vectors])` of the test graph
  * (tensorflow_model.py:157-161,331-335).  Outputs are HOST pointers; h_code_vec [B, D] and
  * h_attn [B, C] may be NULL. */

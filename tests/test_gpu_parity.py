@@ -273,3 +273,29 @@ def test_sampled_softmax_train_step(dims, B, S, math):
     np.add.at(g_tok, src.reshape(-1), dx[:, :dd]); np.add.at(g_path, pth.reshape(-1), dx[:, dd:2 * dd])
     np.add.at(g_tok, tgt.reshape(-1), dx[:, 2 * dd:])
     assert rel_err(g["tok"], g_tok) < 5e-5 and rel_err(g["path"], g_path) < 5e-5
+
+
+def test_async_pinned_entry_point_matches_the_synchronous_one():
+    """c2v_train_batch_async (uploads on the engine's copy stream, double-buffered staging, nothing waited for) against
+    c2v_train_batch_host step by step: same losses, same model, and the upload-done events release the pinned buffers."""
+    import torch
+    dims, B = TINY, 64
+    a, params = make_engine(dims, max_batch=B)
+    b, _ = make_engine(dims, max_batch=B, params=params)
+    steps = 6
+    batches = [O.synthetic_batch(dims, B, seed=300 + s) for s in range(steps)]
+    pinned = [[torch.from_numpy(np.ascontiguousarray(x)).pin_memory() for x in bt] for bt in batches]
+    losses = torch.zeros(steps, dtype=torch.float32).pin_memory()
+    events = []
+    for s in range(steps):
+        ev = torch.cuda.Event()
+        a.train_batch_async(*pinned[s], rows=B, loss_out=losses[s:s + 1], upload_done=ev, keep=0.75, seed=7)
+        events.append(ev)
+    for ev in events:
+        ev.synchronize()
+    torch.cuda.synchronize()
+    ref = [b.train_batch_host(*batches[s], keep=0.75, seed=7) for s in range(steps)]
+    assert np.allclose(losses.numpy(), np.array(ref, dtype=np.float32), rtol=0, atol=1e-6)
+    pa, pb = a.export_params(), b.export_params()
+    for k in O.PARAM_NAMES:
+        assert np.abs(pa[k] - pb[k]).max() < 2e-6, k

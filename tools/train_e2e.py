@@ -51,11 +51,11 @@ def main(n_lines=131072, C=200, n_tok=200000, n_path=150000, n_tgt=30000, thread
     model = Code2VecModel(cfg)
     import torch
     stamps = []
-    # the training loop uploads batches through the pinned ring and launches steps asynchronously (step_device); with
+    # the training loop uploads batches through the pinned ring and launches steps asynchronously (step_ring); with
     # C2V_BATCH_RING=0 it calls the synchronous step_host instead.  Either way the host time at which step k was issued is
     # recorded: the ring bounds how far the host can run ahead of the GPU (10 slots), so over hundreds of steps the issue
     # rate is the execution rate.
-    for name in ("step_host", "step_device"):
+    for name in ("step_host", "step_ring"):
         inner = getattr(model.trainer, name)
 
         def stamped(*a, _inner=inner, **k):
