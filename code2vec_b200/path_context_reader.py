@@ -63,6 +63,14 @@ def load_native_tensoriser():
 _INT64_MIN = -(1 << 63)
 
 
+class _Chunk:
+    """A file buffer and the number of leading bytes that are complete lines (what the tensoriser is given)."""
+    __slots__ = ("buf", "n")
+
+    def __init__(self, buf: bytes, n: int):
+        self.buf, self.n = buf, n
+
+
 def _raise_parse_error(n: int, kind: int, max_contexts: int):
     """c2v_parse_chunk's negative return values as the reader's ValueErrors."""
     if n == _INT64_MIN:
@@ -303,11 +311,12 @@ class PathContextReader:
                                 _NativeVocab(lib, self.vocabs.target_vocab))
         return bool(self._native)
 
-    def _native_parse(self, data: bytes):
+    def _native_parse(self, chunk):
         """bytes of complete lines -> (ReaderInputTensors of all rows, keep mask, target strings or None)."""
         lib, tok, pth, tgt = self._native
         Cn = self.config.MAX_CONTEXTS
-        cap = len(data) // (Cn + 1) + 1              # a line is at least MAX_CONTEXTS spaces + a newline long
+        data, nbytes = (chunk.buf, chunk.n) if isinstance(chunk, _Chunk) else (chunk, len(chunk))
+        cap = nbytes // (Cn + 1) + 1              # a line is at least MAX_CONTEXTS spaces + a newline long
         bufs = getattr(self, "_parse_bufs", None)
         if bufs is None or bufs[0].shape[0] < cap:   # scratch reused across chunks (no page faults per chunk)
             bufs = (np.empty((cap, Cn), dtype=np.int32), np.empty((cap, Cn), dtype=np.int32),
@@ -320,7 +329,7 @@ class PathContextReader:
         err = C.c_int32(0)
         mode = 0 if self.estimator_action.is_train else 1
         threads = max(1, int(self.config.READER_NUM_PARALLEL_BATCHES or 1))
-        n = lib.c2v_parse_chunk(data, len(data), Cn, tok.h, pth.h, tgt.h, mode, threads, cap, src.ctypes.data,
+        n = lib.c2v_parse_chunk(data, nbytes, Cn, tok.h, pth.h, tgt.h, mode, threads, cap, src.ctypes.data,
                                 path.ctypes.data, dst.ctypes.data, mask.ctypes.data, target.ctypes.data, keep.ctypes.data,
                                 toff.ctypes.data, tlen.ctypes.data, C.byref(err))
         if n < 0:
@@ -332,12 +341,13 @@ class PathContextReader:
             strings = [data[o:o + l].decode("utf-8") if l else oov for o, l, k in zip(toff[:n], tlen[:n], sel) if k]
         return (src[:n][sel], path[:n][sel], dst[:n][sel], mask[:n][sel], target[:n][sel]), strings
 
-    def _native_parse_into(self, data: bytes, pool: "_RowPool"):
+    def _native_parse_into(self, chunk, pool: "_RowPool"):
         """Train path: rows are parsed straight into the tail of the shuffle pool (no scratch copy, no
         selection copy); rows the filter drops are then overwritten by kept rows from the end."""
         lib, tok, pth, tgt = self._native
         Cn = self.config.MAX_CONTEXTS
-        cap = len(data) // (Cn + 1) + 1              # a line is at least MAX_CONTEXTS spaces + a newline long; the
+        data, nbytes = (chunk.buf, chunk.n) if isinstance(chunk, _Chunk) else (chunk, len(chunk))
+        cap = nbytes // (Cn + 1) + 1                 # a line is at least MAX_CONTEXTS spaces + a newline long; the
         #                                              reserve is address space only -- pages are touched as rows land
         pool.reserve(cap, Cn)
         small = getattr(self, "_parse_small", None)
@@ -348,7 +358,7 @@ class PathContextReader:
         src, path, dst, mask, target = pool.tail_pointers()
         err = C.c_int32(0)
         threads = max(1, int(self.config.READER_NUM_PARALLEL_BATCHES or 1))
-        n = lib.c2v_parse_chunk(data, len(data), Cn, tok.h, pth.h, tgt.h, 0, threads, cap, src, path, dst, mask, target,
+        n = lib.c2v_parse_chunk(data, nbytes, Cn, tok.h, pth.h, tgt.h, 0, threads, cap, src, path, dst, mask, target,
                                 keep.ctypes.data, toff.ctypes.data, tlen.ctypes.data, C.byref(err))
         if n < 0:
             _raise_parse_error(n, err.value, Cn)
@@ -377,16 +387,16 @@ class PathContextReader:
                     if cut < 0:
                         if at_eof:
                             if buf.strip(b"\r\n"):
-                                yield buf
+                                yield _Chunk(buf, len(buf))
                             break
                         f.seek(start)                # a line longer than the chunk: retry with a bigger one
                         size *= 2
                         continue
                     if at_eof:
-                        yield buf                    # includes a last line without a trailing newline
+                        yield _Chunk(buf, len(buf))  # includes a last line without a trailing newline
                         break
                     f.seek(start + cut + 1)          # re-read the partial last line with the next chunk
-                    yield buf[:cut + 1]
+                    yield _Chunk(buf, cut + 1)           # no slice copy: the parser is told where the complete lines end
 
     def _native_chunks_ahead(self, depth: int = 2):
         """_native_chunks read `depth` chunks ahead by a helper thread (file reads and the slicing of complete lines release
