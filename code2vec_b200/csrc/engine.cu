@@ -35,6 +35,7 @@ constexpr int kSplitDw = 48;   // split-K slices for dW = X'^T . dU  (K = B*C)
 struct Workspace {
   size_t H, Xg, dXg, alpha, v, dv, S, loss_b, lse, loss, part, da_part, lse_part, dl;
   size_t Xg_lo, H_lo, S_lo, tgt_hi, tgt_lo, W_hi, W_lo, v_hi, v_lo;     // 3xTF32 operand splits
+  size_t true_logit;
   size_t st_src, st_pth, st_tgt, st_mask, st_target, st_topk_idx, st_topk_val, st_code, st_attn;
   size_t nx_src, nx_pth, nx_tgt;                                  // indices of the hinted NEXT batch (host entry point)
   size_t sb_src, sb_pth, sb_tgt, sb_mask, sb_target;              // second staging set (c2v_train_batch_async double buffer)
@@ -73,6 +74,7 @@ Workspace carve(const c2v_dims& d) {
   w.S = take(B * w.ldS * 4);
   w.loss_b = take(B * 4);
   w.lse = take(B * 4);
+  w.true_logit = take(B * 4);
   w.loss = take(64);
   size_t part = (size_t)kSplitDv * B * D;
   if ((size_t)kSplitDw * X * D > part) part = (size_t)kSplitDw * X * D;
@@ -175,6 +177,8 @@ struct c2v_engine {
   InboxSet inbox{};          // push-based gradient exchange (c2v_bind_scatter_inbox); world == 0: not bound
   int sort_peer = 1;         // option "sort_peer_access": sharded tables are gathered / scattered in (owner, 2 MB page) order
   bool bkt_zeroed = false;   // the bucket counters have been cleared once (bucket_scan_kernel leaves them cleared)
+  int recompute = 1;         // option "recompute_logits" (tensor-core modes): the train step runs the logits GEMM twice -- once for the
+                             // log-sum-exp only, once writing dL/dlogits from its epilogue -- instead of writing logits and rewriting them
   int fuse_sg = 0;           // option "fuse_softmax_grad": dv / dY compute dL/dlogits from the logits slab on the fly (tf32 mode).
                              // Correct, and it removes the 2.1 GB softmax-gradient pass (0.36 -> 0.02 ms), but with 32-bit operands the two
                              // GEMMs are already shared-memory-bandwidth bound and the in-place rewrite of the A stage costs more than
@@ -619,7 +623,10 @@ int run_ctx_fwd(c2v_engine* e, cudaStream_t st, const ContextSource& cs, const D
 
 // S[B, Y] = v . Ytab^T   (tensorflow_model.py:226,297)
 // with_lse (tf32 path only): also emit per-(row, 256-column tile) log-sum-exp partials into ws.lse_part.
-int run_logits(c2v_engine* e, cudaStream_t st, const float* v, int B, float* S, bool with_lse = false) {
+// grad != nullptr: the pass writes dL/dlogits (EpiSoftmaxGrad); lse_only: nothing but the log-sum-exp partials.
+struct LogitsGrad { const float* lse; const int32_t* target; int row0; float inv_batch; };
+int run_logits(c2v_engine* e, cudaStream_t st, const float* v, int B, float* S, bool with_lse = false, bool lse_only = false,
+               const LogitsGrad* grad = nullptr) {
   const int D = e->dims.code_dim, Y = e->dims.target_vocab;
   { int rcl = end_target_lazy(e, st); if (rcl) return rcl; }      // a pass over the whole table needs every row current
   if (is_tc(e) && (reinterpret_cast<uintptr_t>(v) % 16 == 0)) {
@@ -635,7 +642,20 @@ int run_logits(c2v_engine* e, cudaStream_t st, const float* v, int B, float* S, 
       opB.base = wsp<float>(e, e->ws.tgt_hi); opB.lo = wsp<float>(e, e->ws.tgt_lo);
     }
     PhaseTimer pt(e, PH_LOGITS, st);
-    if (with_lse && x3) {
+    const int slots = 2 * ((Y + 255) / 256);
+    if (grad && x3) {
+      umma::EpiSoftmaxGradT<true, true> ep{S, wsp<float>(e, e->ws.S_lo), e->ws.ldS, grad->lse, grad->target, grad->row0, grad->inv_batch, B};
+      C2V_LAUNCH(e, C2V_CUDA(e, (C2V_UMMA_FIXED(256, false, false, true, decltype(ep), st, B, Y, D, 1, opA, opB, ep, e->num_sms))));
+    } else if (grad) {
+      umma::EpiSoftmaxGradT<false, false> ep{S, nullptr, e->ws.ldS, grad->lse, grad->target, grad->row0, grad->inv_batch, B};
+      C2V_LAUNCH(e, C2V_CUDA(e, (C2V_UMMA_FIXED(256, false, false, true, decltype(ep), st, B, Y, D, 1, opA, opB, ep, e->num_sms))));
+    } else if (lse_only && x3) {
+      umma::EpiLseOnlyT<true> ep{{S, e->ws.ldS, wsp<float2>(e, e->ws.lse_part), slots}};
+      C2V_LAUNCH(e, C2V_CUDA(e, (C2V_UMMA_FIXED(256, false, false, true, decltype(ep), st, B, Y, D, 1, opA, opB, ep, e->num_sms))));
+    } else if (lse_only) {
+      umma::EpiLseOnlyT<false> ep{{S, e->ws.ldS, wsp<float2>(e, e->ws.lse_part), slots}};
+      C2V_LAUNCH(e, C2V_CUDA(e, (C2V_UMMA_FIXED(256, false, false, true, decltype(ep), st, B, Y, D, 1, opA, opB, ep, e->num_sms))));
+    } else if (with_lse && x3) {
       umma::EpiStoreLsePrecise ep{S, e->ws.ldS, wsp<float2>(e, e->ws.lse_part), 2 * ((Y + 255) / 256)};
       C2V_LAUNCH(e, C2V_CUDA(e, (C2V_UMMA_FIXED(256, false, false, true, umma::EpiStoreLsePrecise, st, B, Y, D, 1, opA, opB, ep, e->num_sms))));
     } else if (with_lse) {
@@ -940,8 +960,26 @@ int train_step_impl(c2v_engine* e, cudaStream_t st, const int32_t* src, const in
   if ((rc = run_ctx_fwd(e, st, cs, dp, H, true))) return rc;
   if ((rc = launch_attn_fwd(e, st, H, mask, B, alpha, v))) return rc;
   const bool fused_lse = (is_tc(e));
-  if ((rc = run_logits(e, st, v, B, S, fused_lse))) return rc;
   const float invB = 1.0f / (float)B;
+  if (fused_lse && e->recompute && !e->fuse_sg) {
+    // the slab is written ONCE, as dL/dlogits: pass 1 of the logits GEMM leaves only log-sum-exp partials, the true-class
+    // logit comes from a B-row dot product, pass 2 repeats the product and its epilogue writes (softmax - onehot) / B
+    if ((rc = run_logits(e, st, v, B, S, false, true))) return rc;
+    float* tl = wsp<float>(e, e->ws.true_logit);
+    {
+      PhaseTimer pt(e, PH_XENT, st);
+      C2V_LAUNCH(e, (true_logit_kernel<<<(B + 7) / 8, 256, 0, st>>>(v, e->theta.tgt, target, 0, Y, e->dims.code_dim, B, tl)));
+      C2V_LAUNCH(e, (xent_combine_kernel<<<B, 256, 0, st>>>(wsp<float2>(e, e->ws.lse_part), 2 * ((Y + 255) / 256), S, e->ws.ldS, target,
+                                                            loss_b, lse, tl)));
+      C2V_LAUNCH(e, (loss_reduce_kernel<<<1, 256, 0, st>>>(loss_b, B, invB, loss_out)));
+    }
+    e->sg_live = false;
+    const LogitsGrad lg{lse, target, 0, invB};
+    if ((rc = run_logits(e, st, v, B, S, false, false, &lg))) return rc;
+    if ((rc = target_grad_gemms(e, st, v, B, dv))) return rc;
+    return context_backward(e, st, cs, mask, B, dp, dv);
+  }
+  if ((rc = run_logits(e, st, v, B, S, fused_lse))) return rc;
   {
     PhaseTimer pt(e, PH_XENT, st);
     if (fused_lse) {
@@ -1234,6 +1272,7 @@ int c2v_set_option(c2v_engine* e, const char* key, int64_t value) {
   if (!strcmp(key, "fuse_target_adam")) { e->fuse_tgt = value ? 1 : 0; return C2V_OK; }
   if (!strcmp(key, "fuse_gather")) { e->fuse_gather = value ? 1 : 0; return C2V_OK; }
   if (!strcmp(key, "fuse_softmax_grad")) { e->fuse_sg = value ? 1 : 0; return C2V_OK; }
+  if (!strcmp(key, "recompute_logits")) { e->recompute = value ? 1 : 0; return C2V_OK; }
   if (!strcmp(key, "sort_peer_access")) {
     if (value < 0 || value > 2) return fail(e, C2V_ERR_INVALID, "sort_peer_access must be 0 (never), 1 (auto) or 2 (always)");
     e->sort_peer = (int)value;
@@ -1329,6 +1368,7 @@ int c2v_get_option(const c2v_engine* e, const char* key, int64_t* value) {
   if (!strcmp(key, "fuse_target_adam")) { *value = e->fuse_tgt; return C2V_OK; }
   if (!strcmp(key, "fuse_gather")) { *value = e->fuse_gather; return C2V_OK; }
   if (!strcmp(key, "fuse_softmax_grad")) { *value = e->fuse_sg; return C2V_OK; }
+  if (!strcmp(key, "recompute_logits")) { *value = e->recompute; return C2V_OK; }
   if (!strcmp(key, "sort_peer_access")) { *value = e->sort_peer; return C2V_OK; }
   if (!strcmp(key, "adam_step_count")) { *value = e->adam_t_done; return C2V_OK; }
   if (!strcmp(key, "target_adam_fused_step")) { *value = e->tgt_fused_t; return C2V_OK; }

@@ -282,7 +282,8 @@ xent_kernel(float* __restrict__ S, size_t ldS, const int32_t* __restrict__ targe
 // xent_combine_kernel: lse_b from the partials, loss_b = lse_b - S[b, y_b].   One CTA per row.
 __global__ void __launch_bounds__(256)
 xent_combine_kernel(const float2* __restrict__ partial, int n_tiles, const float* __restrict__ S, size_t ldS,
-                    const int32_t* __restrict__ target, float* __restrict__ loss_b, float* __restrict__ lse_out) {
+                    const int32_t* __restrict__ target, float* __restrict__ loss_b, float* __restrict__ lse_out,
+                    const float* __restrict__ true_logit = nullptr) {
   __shared__ float red[32];
   const int b = blockIdx.x;
   const float2* p = partial + (size_t)b * n_tiles;
@@ -298,8 +299,29 @@ xent_combine_kernel(const float2* __restrict__ partial, int n_tiles, const float
   if (threadIdx.x == 0) {
     const float lse = M + logf(s);
     lse_out[b] = lse;
-    loss_b[b] = lse - S[(size_t)b * ldS + target[b]];
+    loss_b[b] = lse - (true_logit ? true_logit[b] : S[(size_t)b * ldS + target[b]]);     // true_logit: the slab holds no logits
   }
+}
+
+// tl[b] = v_b . Ytab[target_b - row0]  (fp32), or 0 when the example's class is not one of this rank's Y rows: the true-class
+// logit of the loss when the logits themselves are never written out (recompute_logits).  One warp per example.
+__global__ void __launch_bounds__(256)
+true_logit_kernel(const float* __restrict__ v, const float* __restrict__ Ytab, const int32_t* __restrict__ target, int row0, int Y,
+                  int D, int B, float* __restrict__ tl) {
+  const int b = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (b >= B) return;
+  const int t = target[b] - row0;
+  float acc = 0.f;
+  if (t >= 0 && t < Y) {
+    const float* y = Ytab + (size_t)t * D;
+    const float* x = v + (size_t)b * D;
+    for (int j = lane * 4; j < D; j += 128) {
+      const float4 a = *reinterpret_cast<const float4*>(x + j), c = *reinterpret_cast<const float4*>(y + j);
+      acc += a.x * c.x + a.y * c.y + a.z * c.z + a.w * c.w;
+    }
+    acc = warp_sum(acc);
+  }
+  if (lane == 0) tl[b] = acc;
 }
 
 // S <- (softmax(S) - onehot(target)) * inv_batch in place, padding columns zeroed.  grid (chunks, B).
@@ -445,7 +467,8 @@ sampled_softmax_bwd_kernel(const float* __restrict__ v, const float* __restrict_
 __global__ void __launch_bounds__(256)
 row_maxsum_kernel(const float2* __restrict__ partial, int slots, const float* __restrict__ S, size_t ldS, int Y,
                   const int32_t* __restrict__ target, int row0, float* __restrict__ row_max, float* __restrict__ row_sum,
-                  float* __restrict__ true_logit) {
+                  float* __restrict__ true_logit, int have_true_logit = 0) {
+  // have_true_logit: true_logit[] was already filled by true_logit_kernel (the slab holds no logits)
   __shared__ float red[32];
   const int b = blockIdx.x;
   const float* row = S + (size_t)b * ldS;
@@ -468,7 +491,7 @@ row_maxsum_kernel(const float2* __restrict__ partial, int slots, const float* __
     row_max[b] = m;
     row_sum[b] = s;
     const int t = target[b] - row0;                  // local row of the example's target, if it lives here
-    true_logit[b] = (t >= 0 && t < Y) ? row[t] : 0.f;
+    if (!have_true_logit) true_logit[b] = (t >= 0 && t < Y) ? row[t] : 0.f;
   }
 }
 

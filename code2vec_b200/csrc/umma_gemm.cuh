@@ -238,6 +238,64 @@ struct EpiStoreLseT {
   }
 };
 
+// Logits pass 1 of the recomputing schedule: ONLY the per-(row, half tile) (max, sum exp) partials -- nothing is stored, so the
+// epilogue neither transposes through shared memory nor writes the 1.07 GB slab (tensorflow_model.py:227-230).
+template <bool PRECISE>
+struct EpiLseOnlyT : EpiStoreLseT<PRECISE> {
+  static constexpr bool kStores = false;
+};
+// Logits pass 2: the same product again, and the epilogue writes dL/dlogits = (softmax - onehot) / B straight from the
+// accumulator, given each row's log-sum-exp from pass 1: the slab is written once, as the gradient, and never read back
+// by a softmax pass.  SPLIT (3xTF32): written as its tf32 split (high parts to C, residuals to C_lo).
+template <bool PRECISE, bool SPLIT>
+struct EpiSoftmaxGradT {
+  struct State { float l; int tgt; };
+  float* C;
+  float* C_lo;
+  size_t ldc;
+  const float* lse;        // [M]
+  const int32_t* target;   // [M] global class ids
+  int row0;                // first class of this slab (row-sharded target table)
+  float inv_batch;
+  int M;
+  __device__ __forceinline__ void begin(State& st) const { st.l = 0.f; st.tgt = -1; }
+  __device__ __forceinline__ void end(int, int, int, bool, State&) const {}
+  // called with this thread's row before any of its elements is mapped
+  __device__ __forceinline__ void observe(int m, int, const uint32_t (&)[32], int, State& st) const {
+    st.l = lse[m];
+    st.tgt = target[m] - row0;
+  }
+  __device__ __forceinline__ float map(float x) const { return x; }
+  __device__ __forceinline__ float map_at(float x, int col, const State& st) const {
+    const float p = (PRECISE ? expf(x - st.l) : __expf(x - st.l)) * inv_batch;
+    return col == st.tgt ? p - inv_batch : p;
+  }
+  __device__ __forceinline__ float* out(int) const { return C; }
+  using Pre = EpiNoState;
+  static constexpr int kRowBatch = 8;
+  static constexpr bool kWideDrain = true;
+  __device__ __forceinline__ void prefetch(const float*, size_t, Pre&) const {}
+  __device__ __forceinline__ void store4(float* c, size_t off, float4 v, const Pre&) const {
+    if (SPLIT) {
+      float4 hi, lo;
+      split_tf32(v, hi, lo);
+      *reinterpret_cast<float4*>(c + off) = hi;
+      *reinterpret_cast<float4*>(C_lo + off) = lo;
+    } else {
+      *reinterpret_cast<float4*>(c + off) = v;
+    }
+  }
+  __device__ __forceinline__ void store1(float* c, size_t off, float x) const {
+    if (SPLIT) {
+      float hi, lo;
+      split_tf32(x, hi, lo);
+      c[off] = hi; C_lo[off] = lo;
+    } else {
+      c[off] = x;
+    }
+  }
+};
+
 using EpiTanhStore = EpiTanhStoreT<false>;
 using EpiTanhStorePrecise = EpiTanhStoreT<true>;
 using EpiStoreLse = EpiStoreLseT<false>;
@@ -290,15 +348,30 @@ struct EpiAdam {
 constexpr int kEpiStageBytes = 32 * 32 * 4;      // one 32 x 32 fp32 block per epilogue warp
 
 // One 32-column chunk: registers (thread = row) -> swizzled smem -> coalesced global stores.
+// element-wise transform on the way out: functors with a (row, column)-dependent transform define map_at(x, column, state)
 template <class Epi>
-__device__ __forceinline__ void store_chunk(const Epi& epi, const uint32_t (&r)[32], float* stage, int lane, int m_base, int n,
-                                            int M, int N, float* cbase, size_t ldc) {
+__device__ __forceinline__ auto epi_map(const Epi& epi, float x, int col, const typename Epi::State& st, int)
+    -> decltype(epi.map_at(x, col, st)) {
+  return epi.map_at(x, col, st);
+}
+template <class Epi>
+__device__ __forceinline__ float epi_map(const Epi& epi, float x, int, const typename Epi::State&, long) {
+  return epi.map(x);
+}
+template <class Epi>
+constexpr bool epi_stores(...) { return true; }
+template <class Epi, bool V = Epi::kStores>
+constexpr bool epi_stores(int) { return V; }
+
+template <class Epi>
+__device__ __forceinline__ void store_chunk(const Epi& epi, const typename Epi::State& est, const uint32_t (&r)[32], float* stage, int lane,
+                                            int m_base, int n, int M, int N, float* cbase, size_t ldc) {
 #pragma unroll
   for (int j4 = 0; j4 < 8; ++j4) {
     const int pos = j4 ^ (lane & 7);
     *reinterpret_cast<float4*>(stage + lane * 32 + pos * 4) =
-        make_float4(epi.map(__uint_as_float(r[4 * j4])), epi.map(__uint_as_float(r[4 * j4 + 1])),
-                    epi.map(__uint_as_float(r[4 * j4 + 2])), epi.map(__uint_as_float(r[4 * j4 + 3])));
+        make_float4(epi_map(epi, __uint_as_float(r[4 * j4]), n + 4 * j4, est, 0), epi_map(epi, __uint_as_float(r[4 * j4 + 1]), n + 4 * j4 + 1, est, 0),
+                    epi_map(epi, __uint_as_float(r[4 * j4 + 2]), n + 4 * j4 + 2, est, 0), epi_map(epi, __uint_as_float(r[4 * j4 + 3]), n + 4 * j4 + 3, est, 0));
   }
   __syncwarp();
   const int col4 = lane & 7;
@@ -350,11 +423,11 @@ __device__ __forceinline__ void drain_accumulator(const Epi& epi, typename Epi::
     const int n = n_tile0 + c;
     if (n < N) {
       if (m < M) epi.observe(m, n, r0, N - n, est);
-      store_chunk(epi, r0, stage, lane, m_base, n, M, N, cbase, epi.ldc);
+      if (epi_stores<Epi>(0)) store_chunk(epi, est, r0, stage, lane, m_base, n, M, N, cbase, epi.ldc);
     }
     if (n + 32 < N) {
       if (m < M) epi.observe(m, n + 32, r1, N - n - 32, est);
-      store_chunk(epi, r1, stage, lane, m_base, n + 32, M, N, cbase, epi.ldc);
+      if (epi_stores<Epi>(0)) store_chunk(epi, est, r1, stage, lane, m_base, n + 32, M, N, cbase, epi.ldc);
     }
   }
 #pragma unroll 1
@@ -365,7 +438,7 @@ __device__ __forceinline__ void drain_accumulator(const Epi& epi, typename Epi::
     const int n = n_tile0 + c;
     if (n < N) {
       if (m < M) epi.observe(m, n, r, N - n, est);
-      store_chunk(epi, r, stage, lane, m_base, n, M, N, cbase, epi.ldc);
+      if (epi_stores<Epi>(0)) store_chunk(epi, est, r, stage, lane, m_base, n, M, N, cbase, epi.ldc);
     }
   }
 }

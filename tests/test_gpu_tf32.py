@@ -119,3 +119,28 @@ def test_softmax_gradient_computed_inside_the_gradient_gemms(dims, B):
     for k in O.PARAM_NAMES:
         assert rel_err(out[1][1][k], out[0][1][k]) < 2e-3, k
         assert rel_err(out[1][1][k], g_ref[k]) < 1e-2, k
+
+
+@pytest.mark.parametrize("math", [1, 2])
+@pytest.mark.parametrize("dims,B", [(TINY, 64), (ODD, 37), (MID, 48)])
+def test_recomputed_logits_schedule_matches_the_stored_one(dims, B, math):
+    """Option recompute_logits (default in the tensor-core modes): the logits GEMM runs twice -- once leaving only the
+    log-sum-exp partials, once writing (softmax - onehot)/B from its epilogue -- so the [B, Y] slab is written once and never
+    rewritten.  The gradients must be those of the schedule that stores logits and rewrites them (same products, same exp),
+    the loss may differ by the fp32-vs-tensor-core rounding of the one true-class logit per example."""
+    src, pth, tgt, mask, target = O.synthetic_batch(dims, B, seed=61)
+    out = {}
+    for rec in (1, 0):
+        eng, params = make_engine(dims, max_batch=B)
+        eng.set_option("math_mode", math)
+        eng.set_option("recompute_logits", rec)
+        assert eng.get_option("recompute_logits") == rec
+        loss = float(eng.train_step(*dev_batch(eng, src, pth, tgt, mask, target), keep=1.0).cpu()[0])
+        out[rec] = (loss, eng.export_grads())
+        eng.close()
+    assert abs(out[1][0] - out[0][0]) < (2e-4 if math == 1 else 2e-6)
+    loss_ref, g_ref, _ = O.train_loss_and_grads(params, src, pth, tgt, mask, target)
+    assert abs(out[1][0] - loss_ref) < 1e-4
+    for k in O.PARAM_NAMES:
+        assert rel_err(out[1][1][k], out[0][1][k]) < (1e-4 if math == 1 else 2e-6), k
+        assert rel_err(out[1][1][k], g_ref[k]) < (1e-2 if math == 1 else 5e-5), k
