@@ -177,8 +177,10 @@ struct c2v_engine {
   InboxSet inbox{};          // push-based gradient exchange (c2v_bind_scatter_inbox); world == 0: not bound
   int sort_peer = 1;         // option "sort_peer_access": sharded tables are gathered / scattered in (owner, 2 MB page) order
   bool bkt_zeroed = false;   // the bucket counters have been cleared once (bucket_scan_kernel leaves them cleared)
-  int recompute = 1;         // option "recompute_logits" (tensor-core modes): the train step runs the logits GEMM twice -- once for the
-                             // log-sum-exp only, once writing dL/dlogits from its epilogue -- instead of writing logits and rewriting them
+  int recompute = 0;         // option "recompute_logits" (tensor-core modes, single-GPU step): the logits GEMM runs twice -- once for the
+                             // log-sum-exp only, once writing dL/dlogits from its epilogue -- instead of writing logits and rewriting them.
+                             // Measured: logits 0.42 + xent 0.36 -> 0.69 + 0.02 ms in tf32 (the LSE-only pass is epilogue-bound too), but
+                             // 6.3 -> 7.1 ms in 3xTF32 (a third 3x GEMM and a second table split): off by default
   int fuse_sg = 0;           // option "fuse_softmax_grad": dv / dY compute dL/dlogits from the logits slab on the fly (tf32 mode).
                              // Correct, and it removes the 2.1 GB softmax-gradient pass (0.36 -> 0.02 ms), but with 32-bit operands the two
                              // GEMMs are already shared-memory-bandwidth bound and the in-place rewrite of the A stage costs more than

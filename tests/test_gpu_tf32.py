@@ -124,7 +124,7 @@ def test_softmax_gradient_computed_inside_the_gradient_gemms(dims, B):
 @pytest.mark.parametrize("math", [1, 2])
 @pytest.mark.parametrize("dims,B", [(TINY, 64), (ODD, 37), (MID, 48)])
 def test_recomputed_logits_schedule_matches_the_stored_one(dims, B, math):
-    """Option recompute_logits (default in the tensor-core modes): the logits GEMM runs twice -- once leaving only the
+    """Option recompute_logits (off by default: a 0.06 ms gain in tf32, a loss in 3xTF32): the logits GEMM runs twice -- once leaving only the
     log-sum-exp partials, once writing (softmax - onehot)/B from its epilogue -- so the [B, Y] slab is written once and never
     rewritten.  The gradients must be those of the schedule that stores logits and rewrites them (same products, same exp),
     the loss may differ by the fp32-vs-tensor-core rounding of the one true-class logit per example."""
