@@ -33,7 +33,12 @@ constexpr int kEpiWarp0 = 2;
 
 // fast transcendental forms for the tensor-core path (operands are already tf32-rounded):
 // exp via ex2.approx (rel. error 2^-22), tanh(x) = 1 - 2 / (exp(2x) + 1) (abs. error ~1e-7).
-__device__ __forceinline__ float fast_tanh(float x) { return 1.f - __fdividef(2.f, __expf(2.f * x) + 1.f); }
+__device__ __forceinline__ float fast_tanh(float x) {
+  float e, r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * 2.885390081777927f));      // exp(2x) = 2^(2 log2(e) x); +-inf / 0 at the ends are fine
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(e + 1.f));
+  return fmaf(-2.f, r, 1.f);
+}
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -222,17 +227,36 @@ struct EpiStoreLseT {
   __device__ __forceinline__ void store1(float* c, size_t off, float x) const { c[off] = x; }
   __device__ __forceinline__ void observe(int, int, const uint32_t (&r)[32], int nvalid, State& st) const {
     float cm = -INFINITY;
+    if (nvalid >= 32) {              // a full chunk (all but the last tile of a row): no per-element bounds
 #pragma unroll
-    for (int j = 0; j < 32; ++j)
-      if (j < nvalid) cm = fmaxf(cm, __uint_as_float(r[j]));
+      for (int j = 0; j < 32; ++j) cm = fmaxf(cm, __uint_as_float(r[j]));
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (j < nvalid) cm = fmaxf(cm, __uint_as_float(r[j]));
+    }
     if (cm > st.mx) { st.sum *= ex(st.mx - cm); st.mx = cm; }
     float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    if (!PRECISE && nvalid >= 32) {
+      // exp(x - mx) as one FFMA + one ex2.approx: 2^(x log2e - mx log2e)   (same 2^-22 relative accuracy as __expf)
+      constexpr float L2E = 1.4426950408889634f;
+      const float c = -st.mx * L2E;
+      auto e2 = [](float t) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(t)); return y; };
 #pragma unroll
-    for (int j = 0; j < 32; j += 4) {
-      if (j + 0 < nvalid) a0 += ex(__uint_as_float(r[j + 0]) - st.mx);
-      if (j + 1 < nvalid) a1 += ex(__uint_as_float(r[j + 1]) - st.mx);
-      if (j + 2 < nvalid) a2 += ex(__uint_as_float(r[j + 2]) - st.mx);
-      if (j + 3 < nvalid) a3 += ex(__uint_as_float(r[j + 3]) - st.mx);
+      for (int j = 0; j < 32; j += 4) {
+        a0 += e2(fmaf(__uint_as_float(r[j + 0]), L2E, c));
+        a1 += e2(fmaf(__uint_as_float(r[j + 1]), L2E, c));
+        a2 += e2(fmaf(__uint_as_float(r[j + 2]), L2E, c));
+        a3 += e2(fmaf(__uint_as_float(r[j + 3]), L2E, c));
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) {
+        if (j + 0 < nvalid) a0 += ex(__uint_as_float(r[j + 0]) - st.mx);
+        if (j + 1 < nvalid) a1 += ex(__uint_as_float(r[j + 1]) - st.mx);
+        if (j + 2 < nvalid) a2 += ex(__uint_as_float(r[j + 2]) - st.mx);
+        if (j + 3 < nvalid) a3 += ex(__uint_as_float(r[j + 3]) - st.mx);
+      }
     }
     st.sum += (a0 + a1) + (a2 + a3);
   }
