@@ -249,6 +249,8 @@ def run_ours(args):
         eng.set_option("fuse_gather", 1)
     if args.fuse_softmax_grad:
         eng.set_option("fuse_softmax_grad", 1)
+    if args.recompute_logits >= 0:
+        eng.set_option("recompute_logits", args.recompute_logits)
     trainer = None
     if mode != "fwd_loss":
         trainer = Trainer(eng, keep_prob=KEEP_PROB, seed=99, schedule=args.dp_schedule, fuse_target_adam=not args.no_fuse_adam,
@@ -640,6 +642,7 @@ def main():
                          "measured slower at 8 GPUs (4.62 vs 4.29 ms), off by default")
     ap.add_argument("--no-sort-peer", action="store_true", help="row-sharded tables: plain (unsorted) peer gather / scatter-add")
     ap.add_argument("--fuse-gather", action="store_true", help="engine option fuse_gather (ctx_fused.cuh)")
+    ap.add_argument("--recompute-logits", type=int, default=-1, choices=[-1, 0, 1], help="engine option recompute_logits (-1 = default)")
     ap.add_argument("--fuse-softmax-grad", action="store_true", help="engine option fuse_softmax_grad (A-operand transform warps)")
     ap.add_argument("--no-lazy-adam", action="store_true", help="dense Adam over the embedding tables every step")
     ap.add_argument("--sweep-period", type=int, default=-1, help="engine option adam_sweep_period (-1 = default 32, 0 = off)")

@@ -273,7 +273,7 @@ struct EpiLseOnlyT : EpiStoreLseT<PRECISE> {
 // by a softmax pass.  SPLIT (3xTF32): written as its tf32 split (high parts to C, residuals to C_lo).
 template <bool PRECISE, bool SPLIT>
 struct EpiSoftmaxGradT {
-  struct State { float l; int tgt; };
+  struct State { float l; int tgt; };      // l: the row's log-sum-exp (PRECISE) or its exponent offset -lse log2e + log2(1/B)
   float* C;
   float* C_lo;
   size_t ldc;
@@ -286,12 +286,17 @@ struct EpiSoftmaxGradT {
   __device__ __forceinline__ void end(int, int, int, bool, State&) const {}
   // called with this thread's row before any of its elements is mapped
   __device__ __forceinline__ void observe(int m, int, const uint32_t (&)[32], int, State& st) const {
-    st.l = lse[m];
+    st.l = PRECISE ? lse[m] : fmaf(-lse[m], 1.4426950408889634f, log2f(inv_batch));
     st.tgt = target[m] - row0;
   }
   __device__ __forceinline__ float map(float x) const { return x; }
   __device__ __forceinline__ float map_at(float x, int col, const State& st) const {
-    const float p = (PRECISE ? expf(x - st.l) : __expf(x - st.l)) * inv_batch;
+    float p;
+    if (PRECISE) {
+      p = expf(x - st.l) * inv_batch;
+    } else {          // exp(x - lse) / B as one FFMA + one ex2.approx
+      asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(p) : "f"(fmaf(x, 1.4426950408889634f, st.l)));
+    }
     return col == st.tgt ? p - inv_batch : p;
   }
   __device__ __forceinline__ float* out(int) const { return C; }
