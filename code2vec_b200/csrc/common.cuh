@@ -20,6 +20,26 @@ __device__ __forceinline__ float warp_max(float v) {
 }
 
 // ---------------------------------------------------------------------------------------------
+// theta <- theta - (lr_t m) / (sqrt(v) + eps): the parameter move of TF1 Adam in correctly rounded fp32 operations, shared by
+// every kernel that applies it (adam_kernel, the lazy row replay, the dY epilogue) so that they stay bit-identical.
+// A ZERO numerator -- an element whose gradient has been exactly zero so far (dropout masks a quarter of every row; rows
+// no batch has touched), or lr_t m underflowing -- makes the correctly rounded quotient a zero of the numerator's sign
+// (the denominator is positive), so theta - num is the same bits as theta - num / den.  Dividing anyway sends div.rn.f32
+// through its out-of-line slow path (zero / denormal operands), which a profile of the row replay showed on 46 % of the
+// divisions of a 25-step run; the branch keeps it for genuinely denormal numerators only.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float adam_move(float theta, float lr_t, float m, float v, float eps) {
+  const float num = __fmul_rn(lr_t, m);
+  if (num == 0.f) return __fsub_rn(theta, num);
+  return __fsub_rn(theta, __fdiv_rn(num, __fadd_rn(__fsqrt_rn(v), eps)));
+}
+// The same move without the test, for dense gradients (the target table's update in the dY epilogue, adam_kernel): zero
+// numerators are rare there and the branch costs more than the occasional slow path.  Identical bits by the argument above.
+__device__ __forceinline__ float adam_move_dense(float theta, float lr_t, float m, float v, float eps) {
+  return __fsub_rn(theta, __fdiv_rn(__fmul_rn(lr_t, m), __fadd_rn(__fsqrt_rn(v), eps)));
+}
+
+// ---------------------------------------------------------------------------------------------
 // 3xTF32 operand split (C2V_MATH_3XTF32): x = hi + lo + O(2^-22 |x|) with hi, lo representable in tf32
 // (10 explicit mantissa bits), both rounded to nearest so the tensor core's own handling of the low
 // 13 bits of a 32-bit operand never matters.  A fp32 product a.b is then issued as

@@ -709,7 +709,7 @@ adam_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m,
   auto upd = [&](float& pp, float gg, float& mm, float& vv) {
     mm = __fadd_rn(__fmul_rn(mm, b1), __fmul_rn(omb1, gg));
     vv = __fadd_rn(__fmul_rn(vv, b2), __fmul_rn(omb2, __fmul_rn(gg, gg)));
-    pp = __fsub_rn(pp, __fdiv_rn(__fmul_rn(lr_t, mm), __fadd_rn(__fsqrt_rn(vv), eps)));
+    pp = adam_move_dense(pp, lr_t, mm, vv, eps);
   };
   const size_t stride = (size_t)gridDim.x * blockDim.x;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
@@ -1094,7 +1094,7 @@ __device__ __forceinline__ void replay_row(float* __restrict__ p, float* __restr
       for (int q = 0; q < 4; ++q) {
         mm[q] = __fadd_rn(__fmul_rn(mm[q], b1), __fmul_rn(omb1, gg[q]));
         vv[q] = __fadd_rn(__fmul_rn(vv[q], b2), __fmul_rn(omb2, __fmul_rn(gg[q], gg[q])));
-        pp[q] = __fsub_rn(pp[q], __fdiv_rn(__fmul_rn(lr_s, mm[q]), __fadd_rn(__fsqrt_rn(vv[q]), eps)));
+        pp[q] = adam_move(pp[q], lr_s, mm[q], vv[q], eps);
       }
     }
     // the zero-gradient steps after it: m*b1 + (1-b1)*0, v*b2 + (1-b2)*(0*0)
@@ -1106,7 +1106,7 @@ __device__ __forceinline__ void replay_row(float* __restrict__ p, float* __restr
       for (int q = 0; q < 4; ++q) {
         mm[q] = __fadd_rn(__fmul_rn(mm[q], b1), __fmul_rn(omb1, 0.f));
         vv[q] = __fadd_rn(__fmul_rn(vv[q], b2), __fmul_rn(omb2, 0.f));
-        const float np = __fsub_rn(pp[q], __fdiv_rn(__fmul_rn(lr_s, mm[q]), __fadd_rn(__fsqrt_rn(vv[q]), eps)));
+        const float np = adam_move(pp[q], lr_s, mm[q], vv[q], eps);
         moved |= (__float_as_uint(np) != __float_as_uint(pp[q]));
         pp[q] = np;
       }
@@ -1156,9 +1156,20 @@ adam_rows_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict
       }
     }
     unsigned todo = __ballot_sync(0xffffffffu, hit);
+    auto prefetch_row = [&](int row) {           // the four 512-byte pieces of a row towards L2 while the previous row is replayed
+      const size_t o = (size_t)row * d + lane * 4;
+      if (lane * 4 < d) {
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(p + o));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(m + o));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(v + o));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(g + o));
+      }
+    };
+    if (todo) prefetch_row(base + __ffs(todo) - 1);
     while (todo) {
       const int b = __ffs(todo) - 1;
       todo &= todo - 1;
+      if (todo) prefetch_row(base + __ffs(todo) - 1);
       const int32_t from = __shfl_sync(0xffffffffu, from_l, b);
       replay_row(p, g, m, v, (size_t)(base + b) * d, d, from, t_done, lr_tab, b1, b2, eps, omb1, omb2, lane, rest_ok != 0);
     }
