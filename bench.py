@@ -282,13 +282,21 @@ def run_ours(args):
         return eng.loss(code, b[4])
 
     loss_pin = torch.zeros(1, dtype=torch.float32).pin_memory()
+    loss_hist = torch.zeros(max(args.steps, 16) + 8, dtype=torch.float32).pin_memory()
 
     def step_e2e(i):
         """The user-facing call with HOST buffers: pinned host -> device copies of this step's inputs, the step, and
         the loss read back -- all inside the timed region."""
         b = pinned[i % n_batches]
+        if mode == "train" and world == 1 and not args.sync_e2e:
+            # what Code2VecModel.train() calls per batch: c2v_train_batch_async -- this step's host -> device copies (engine copy
+            # stream), the step, and the loss copied back into pinned host memory; the host does not wait per step (the timed
+            # region ends with a synchronize, after which all K losses are on the host)
+            eng.train_batch_async(*b[:5], rows=B, loss_out=loss_hist[i % loss_hist.numel():i % loss_hist.numel() + 1], keep=KEEP_PROB,
+                                  seed=trainer.seed, **trainer.adam)
+            return None
         if mode == "train":
-            return trainer.step_host(*b, next_batch=nxt(pinned, i))     # c2v_train_batch_host (copies inside the C call)
+            return trainer.step_host(*b, next_batch=nxt(pinned, i))     # c2v_train_batch_host (copies inside the C call, waits for the loss)
         for dst, src_t in zip(stage, b):
             dst.copy_(src_t, non_blocking=True)
         if mode == "sampled":
@@ -481,7 +489,10 @@ def run_ours(args):
                        args.bags, "zipf(1.2)" if args.zipf else "uniform", C),
                    "valid_context_fraction": round(float(np.mean([b[3].mean() for b in host])), 4)},
         "e2e": {"value": round(e2e_value, 1), "unit": "path-contexts/s", "h2d_bytes_per_step": h2d,
-                "d2h_bytes_per_step": 4, "ms_per_step": round(ms_e2e / K, 4)},
+                "d2h_bytes_per_step": 4, "ms_per_step": round(ms_e2e / K, 4),
+                "api": ("c2v_train_batch_async (pinned host buffers; copies on the engine's copy stream; loss to pinned memory every step)"
+                        if (mode == "train" and world == 1 and not args.sync_e2e) else
+                        "c2v_train_batch_host" if mode == "train" else "torch H2D + device entry points + loss read-back")},
         "gpu_launches": int(launches),
         "clocks": clk,
         "roofline": roofline,
@@ -636,6 +647,8 @@ def main():
     ap.add_argument("--mode", default="train", choices=["train", "fwd_loss", "sampled"],
                     help="train = BASELINE configs[1] (default); fwd_loss = configs[2] forward + full-softmax loss; "
                          "sampled = configs[3] train step with sampled softmax")
+    ap.add_argument("--sync-e2e", action="store_true",
+                    help="e2e through c2v_train_batch_host (waits for every step's loss) instead of c2v_train_batch_async")
     ap.add_argument("--no-fp32-equivalent", action="store_true", help="skip the extra 3xTF32 measurement of the default run")
     ap.add_argument("--push-grads", action="store_true",
                     help="row-sharded tables: inbox-based gradient push (c2v_bind_scatter_inbox) instead of remote red.global.add; "
