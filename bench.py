@@ -251,6 +251,10 @@ def run_ours(args):
         eng.set_option("fuse_softmax_grad", 1)
     if args.recompute_logits >= 0:
         eng.set_option("recompute_logits", args.recompute_logits)
+    if args.no_exp_slab:
+        eng.set_option("exp_slab", 0)
+    if args.adam_prefetch:
+        eng.set_option("adam_epilogue_prefetch", 1)
     trainer = None
     if mode != "fwd_loss":
         trainer = Trainer(eng, keep_prob=KEEP_PROB, seed=99, schedule=args.dp_schedule, fuse_target_adam=not args.no_fuse_adam,
@@ -398,6 +402,10 @@ def run_ours(args):
                             terms=3 if args.math == "3xtf32" else 1,
                             remote_frac=(world - 1.0) / world if sharded_tables else 0.0,
                             sweep_period=int(eng.get_option("adam_sweep_period")) if lazy_on else 0)
+    if world == 1 and mode == "train" and tc and eng.get_option("exp_slab") and not args.fuse_softmax_grad and args.recompute_logits <= 0:
+        # deferred normalisation: no pass over the slab -- the phase is B true-class rows, the per-tile partials and B patches
+        n_part = 2 * ((w["target_vocab"] + 255) // 256)
+        work["xent"] = ("hbm", 4.0 * B * (w["code_dim"] * 3 + 2 * n_part + 8))
     if schedule == "fully_sharded":
         # each rank runs the context side on its own B bags and the target side on its 1/world of the classes for all world*B
         w_local = dict(w, target_vocab=(w["target_vocab"] + world - 1) // world)
@@ -484,6 +492,8 @@ def run_ours(args):
                    "l2": "no flush: >9 GB of parameter/optimizer traffic per step and %d rotating input batches exceed the 126 MB L2" % n_batches,
                    "math_mode": args.math, "fused_target_adam": fused, "lazy_adam": lazy_on,
                    "adam_sweep_period": int(eng.get_option("adam_sweep_period")) if lazy_on else None,
+                   "exp_slab": bool(eng.get_option("exp_slab")) and world == 1 and mode == "train" and args.math != "fp32",
+                   "exp_slab_fallbacks": int(eng.get_option("exp_slab_fallbacks")),
                    "next_batch_hint": bool(world == 1 and args.hint and fused), "last_loss": round(last_loss, 5),
                    "inputs": "%s bags, %s indices; all %d slots per example are counted in the metric" % (
                        args.bags, "zipf(1.2)" if args.zipf else "uniform", C),
@@ -656,6 +666,8 @@ def main():
     ap.add_argument("--no-sort-peer", action="store_true", help="row-sharded tables: plain (unsorted) peer gather / scatter-add")
     ap.add_argument("--fuse-gather", action="store_true", help="engine option fuse_gather (ctx_fused.cuh)")
     ap.add_argument("--recompute-logits", type=int, default=-1, choices=[-1, 0, 1], help="engine option recompute_logits (-1 = default)")
+    ap.add_argument("--adam-prefetch", action="store_true", help="engine option adam_epilogue_prefetch = 1 (measured slower)")
+    ap.add_argument("--no-exp-slab", action="store_true", help="engine option exp_slab = 0: the two-pass softmax schedule (logits stored, then rewritten)")
     ap.add_argument("--fuse-softmax-grad", action="store_true", help="engine option fuse_softmax_grad (A-operand transform warps)")
     ap.add_argument("--no-lazy-adam", action="store_true", help="dense Adam over the embedding tables every step")
     ap.add_argument("--sweep-period", type=int, default=-1, help="engine option adam_sweep_period (-1 = default 32, 0 = off)")

@@ -33,6 +33,11 @@ __device__ __forceinline__ float adam_move(float theta, float lr_t, float m, flo
   if (num == 0.f) return __fsub_rn(theta, num);
   return __fsub_rn(theta, __fdiv_rn(num, __fadd_rn(__fsqrt_rn(v), eps)));
 }
+// exp_slab schedule (umma::EpiExpSumT, expsum_combine_kernel): a row's largest U = exp(logit - c_row) must stay inside this
+// window for the deferred normalisation to be used; fp32 then still resolves elements e^-27 below the row's maximum and
+// a sum of 2^18 such terms cannot overflow.
+constexpr float kExpSlabMin = 1e-26f, kExpSlabMax = 1e30f;
+
 // The same move without the test, for dense gradients (the target table's update in the dY epilogue, adam_kernel): zero
 // numerators are rare there and the branch costs more than the occasional slow path.  Identical bits by the argument above.
 __device__ __forceinline__ float adam_move_dense(float theta, float lr_t, float m, float v, float eps) {

@@ -35,7 +35,7 @@ constexpr int kSplitDw = 48;   // split-K slices for dW = X'^T . dU  (K = B*C)
 struct Workspace {
   size_t H, Xg, dXg, alpha, v, dv, S, loss_b, lse, loss, part, da_part, lse_part, dl;
   size_t Xg_lo, H_lo, S_lo, tgt_hi, tgt_lo, W_hi, W_lo, v_hi, v_lo;     // 3xTF32 operand splits
-  size_t true_logit;
+  size_t true_logit, rscale, v_scaled, slab_flag;                  // exp_slab schedule: row factors, scaled code vectors, {range flag, fallback count}
   size_t st_src, st_pth, st_tgt, st_mask, st_target, st_topk_idx, st_topk_val, st_code, st_attn;
   size_t nx_src, nx_pth, nx_tgt;                                  // indices of the hinted NEXT batch (host entry point)
   size_t sb_src, sb_pth, sb_tgt, sb_mask, sb_target;              // second staging set (c2v_train_batch_async double buffer)
@@ -75,6 +75,9 @@ Workspace carve(const c2v_dims& d) {
   w.loss_b = take(B * 4);
   w.lse = take(B * 4);
   w.true_logit = take(B * 4);
+  w.rscale = take(B * 4);
+  w.v_scaled = take(B * D * 4);
+  w.slab_flag = take(64);
   w.loss = take(64);
   size_t part = (size_t)kSplitDv * B * D;
   if ((size_t)kSplitDw * X * D > part) part = (size_t)kSplitDw * X * D;
@@ -181,6 +184,15 @@ struct c2v_engine {
                              // log-sum-exp only, once writing dL/dlogits from its epilogue -- instead of writing logits and rewriting them.
                              // Measured: logits 0.42 + xent 0.36 -> 0.69 + 0.02 ms in tf32 (the LSE-only pass is epilogue-bound too), but
                              // 6.3 -> 7.1 ms in 3xTF32 (a third 3x GEMM and a second table split): off by default
+  int exp_slab = 1;          // option "exp_slab" (tensor-core modes, single-GPU full-softmax step; default on): the logits epilogue writes
+                             // U = exp(s - true logit) and the softmax's normalisation is deferred into per-row factors applied by the
+                             // dv / dY GEMMs, so no pass re-reads the slab to turn logits into dL/dlogits.  Rows
+                             // outside the fp32 window make that step fall back, on the device, to the two-pass schedule.
+  bool slab_flag_zeroed = false;
+  int gather_occ[2] = {0, 0};         // resident CTAs per SM of gather_ctx_kernel<false / true>, queried once
+  int adam_epi_prefetch = 0; // option "adam_epilogue_prefetch" (measured slower, off): the dY epilogue's Adam update prefetches its (theta, m, v)
+                             // lines into L2 one tile ahead
+  const float* row_scale = nullptr;   // while the step's dv GEMM runs: the per-example factor its split-K reduction applies
   int fuse_sg = 0;           // option "fuse_softmax_grad": dv / dY compute dL/dlogits from the logits slab on the fly (tf32 mode).
                              // Correct, and it removes the 2.1 GB softmax-gradient pass (0.36 -> 0.02 ms), but with 32-bit operands the two
                              // GEMMs are already shared-memory-bandwidth bound and the in-place rewrite of the A stage costs more than
@@ -341,10 +353,11 @@ int launch_attn_fwd(c2v_engine* e, cudaStream_t st, const float* H, const float*
   return C2V_OK;
 }
 
-int launch_attn_bwd(c2v_engine* e, cudaStream_t st, float* H, const float* alpha, const float* dv, int B, float* da_part,
-                    float* H_lo) {
+// v: the code vectors the forward pass produced for these examples (ws.v)
+int launch_attn_bwd(c2v_engine* e, cudaStream_t st, float* H, const float* alpha, const float* dv, const float* v, int B,
+                    float* da_part, float* H_lo) {
   const int C = e->dims.max_contexts, D = e->dims.code_dim;
-  const size_t smem = ((size_t)((C + 3) & ~3) + 32 + (size_t)kAttnWarps * D) * sizeof(float);
+  const size_t smem = (size_t)kAttnWarps * D * sizeof(float);
   const float* a = e->theta.a;
   PhaseTimer pt(e, PH_ATTN_BWD, st);
 #define C2V_AB(NV)                                                                                        \
@@ -352,11 +365,11 @@ int launch_attn_bwd(c2v_engine* e, cudaStream_t st, float* H, const float* alpha
     if (H_lo) {                                                                                           \
       if (smem > 48 * 1024)                                                                               \
         C2V_CUDA(e, cudaFuncSetAttribute(attn_bwd_kernel<NV, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-      C2V_LAUNCH(e, (attn_bwd_kernel<NV, true><<<B, kAttnThreads, smem, st>>>(H, alpha, dv, a, C, D, da_part, H_lo))); \
+      C2V_LAUNCH(e, (attn_bwd_kernel<NV, true><<<B, kAttnThreads, smem, st>>>(H, alpha, dv, v, a, C, D, da_part, H_lo))); \
     } else {                                                                                              \
       if (smem > 48 * 1024)                                                                               \
         C2V_CUDA(e, cudaFuncSetAttribute(attn_bwd_kernel<NV, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-      C2V_LAUNCH(e, (attn_bwd_kernel<NV, false><<<B, kAttnThreads, smem, st>>>(H, alpha, dv, a, C, D, da_part, nullptr))); \
+      C2V_LAUNCH(e, (attn_bwd_kernel<NV, false><<<B, kAttnThreads, smem, st>>>(H, alpha, dv, v, a, C, D, da_part, nullptr))); \
     }                                                                                                     \
   } while (0)
   switch ((D + 127) / 128) {
@@ -371,14 +384,17 @@ int launch_attn_bwd(c2v_engine* e, cudaStream_t st, float* H, const float* alpha
   return C2V_OK;
 }
 
-int launch_colsum(c2v_engine* e, cudaStream_t st, const float* in, size_t stride, int R, int n, float* out) {
-  if (R <= 64 && n % 4 == 0 && stride % 4 == 0) {          // split-K slices: few rows, many columns
+// row_scale (optional): the n results are rows of length row_len; row i is multiplied by row_scale[i]
+int launch_colsum(c2v_engine* e, cudaStream_t st, const float* in, size_t stride, int R, int n, float* out,
+                  const float* row_scale = nullptr, int row_len = 0) {
+  if (R <= 64 && n % 4 == 0 && stride % 4 == 0 && (!row_scale || row_len % 4 == 0)) {          // split-K slices: few rows, many columns
     size_t blocks = ((size_t)n / 4 + 255) / 256;
     if (blocks > (size_t)e->num_sms * 16) blocks = (size_t)e->num_sms * 16;
-    C2V_LAUNCH(e, (slice_sum_kernel<<<(unsigned)blocks, 256, 0, st>>>(in, stride, R, (size_t)n / 4, out)));
+    C2V_LAUNCH(e, (slice_sum_kernel<<<(unsigned)blocks, 256, 0, st>>>(in, stride, R, (size_t)n / 4, out, row_scale, row_scale ? row_len / 4 : 1)));
     return C2V_OK;
   }
   C2V_LAUNCH(e, (colsum_kernel<<<(n + 31) / 32, dim3(32, 32), 0, st>>>(in, stride, R, n, out)));
+  if (row_scale) C2V_LAUNCH(e, (scale_rows_kernel<<<(unsigned)(((size_t)n + 255) / 256), 256, 0, st>>>(out, row_scale, out, row_len, (size_t)n)));
   return C2V_OK;
 }
 
@@ -564,6 +580,19 @@ int sort_entries(c2v_engine* e, cudaStream_t st, const ContextSource& cs, const 
   return C2V_OK;
 }
 
+// Grid of the gather: one wave of resident CTAs (8 warps each; a warp strides over the rows), never more CTAs than rows / 8.
+unsigned gather_blocks(c2v_engine* e, int rows, bool split) {
+  int& occ = e->gather_occ[split ? 1 : 0];
+  if (occ == 0) {
+    int n = 0;
+    cudaError_t rc = split ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, gather_ctx_kernel<true>, 256, 0)
+                           : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, gather_ctx_kernel<false>, 256, 0);
+    occ = (rc == cudaSuccess && n > 0) ? n : 4;
+  }
+  const long want = (rows + 7) / 8, wave = (long)e->num_sms * occ;
+  return (unsigned)(want < wave ? want : wave);
+}
+
 // H = tanh(X' . W)   (tensorflow_model.py:238-252)
 int run_ctx_fwd(c2v_engine* e, cudaStream_t st, const ContextSource& cs, const Dropout& dp, float* H, bool keep_x) {
   const int D = e->dims.code_dim, K = 3 * e->dims.embed_dim;
@@ -599,8 +628,8 @@ int run_ctx_fwd(c2v_engine* e, cudaStream_t st, const ContextSource& cs, const D
         const int32_t* perm = wsp<int32_t>(e, e->ws.perm);
         if (x3) C2V_LAUNCH(e, (gather_sorted_kernel<true><<<(3 * cs.rows + 7) / 8, 256, 0, st>>>(cs, dp, perm, Xg, wsp<float>(e, e->ws.Xg_lo))));
         else C2V_LAUNCH(e, (gather_sorted_kernel<false><<<(3 * cs.rows + 7) / 8, 256, 0, st>>>(cs, dp, perm, Xg, nullptr)));
-      } else if (x3) C2V_LAUNCH(e, (gather_ctx_kernel<true><<<(cs.rows + 7) / 8, 256, 0, st>>>(cs, dp, Xg, wsp<float>(e, e->ws.Xg_lo))));
-      else C2V_LAUNCH(e, (gather_ctx_kernel<false><<<(cs.rows + 7) / 8, 256, 0, st>>>(cs, dp, Xg, nullptr)));
+      } else if (x3) C2V_LAUNCH(e, (gather_ctx_kernel<true><<<gather_blocks(e, cs.rows, true), 256, 0, st>>>(cs, dp, Xg, wsp<float>(e, e->ws.Xg_lo))));
+      else C2V_LAUNCH(e, (gather_ctx_kernel<false><<<gather_blocks(e, cs.rows, false), 256, 0, st>>>(cs, dp, Xg, nullptr)));
     }
     if (x3) { int rcs = split_small(e, st, e->theta.W, (size_t)K * D, e->ws.W_hi, e->ws.W_lo); if (rcs) return rcs; }
     PhaseTimer pt(e, PH_CTX_FWD, st);
@@ -627,8 +656,11 @@ int run_ctx_fwd(c2v_engine* e, cudaStream_t st, const ContextSource& cs, const D
 // with_lse (tf32 path only): also emit per-(row, 256-column tile) log-sum-exp partials into ws.lse_part.
 // grad != nullptr: the pass writes dL/dlogits (EpiSoftmaxGrad); lse_only: nothing but the log-sum-exp partials.
 struct LogitsGrad { const float* lse; const int32_t* target; int row0; float inv_batch; };
+// exp_offset != nullptr: the pass writes U = exp(logit - exp_offset[row]) and (max U, sum U) partials (EpiExpSum).
+// gate != nullptr (with_lse): the launch is the exp_slab schedule's fallback, a no-op while *gate == 0; it reuses the operand
+// splits the step's first pass made.
 int run_logits(c2v_engine* e, cudaStream_t st, const float* v, int B, float* S, bool with_lse = false, bool lse_only = false,
-               const LogitsGrad* grad = nullptr) {
+               const LogitsGrad* grad = nullptr, const float* exp_offset = nullptr, const int* gate = nullptr) {
   const int D = e->dims.code_dim, Y = e->dims.target_vocab;
   { int rcl = end_target_lazy(e, st); if (rcl) return rcl; }      // a pass over the whole table needs every row current
   if (is_tc(e) && (reinterpret_cast<uintptr_t>(v) % 16 == 0)) {
@@ -637,15 +669,29 @@ int run_logits(c2v_engine* e, cudaStream_t st, const float* v, int B, float* S, 
     umma::Operand opB{e->theta.tgt, (size_t)D, false};
     if (x3) {      // fp32-faithful: both operands as tf32 (hi, lo) pairs; the table is re-split on every pass over it
       int rcs;
-      if ((rcs = split_small(e, st, v, (size_t)B * D, e->ws.v_hi, e->ws.v_lo))) return rcs;
-      if ((rcs = split_small(e, st, e->theta.tgt, (size_t)Y * D, e->ws.tgt_hi, e->ws.tgt_lo))) return rcs;
+      if (!gate) {
+        if ((rcs = split_small(e, st, v, (size_t)B * D, e->ws.v_hi, e->ws.v_lo))) return rcs;
+        if ((rcs = split_small(e, st, e->theta.tgt, (size_t)Y * D, e->ws.tgt_hi, e->ws.tgt_lo))) return rcs;
+      }
       e->tgt_split_valid = true;
       opA.base = wsp<float>(e, e->ws.v_hi); opA.lo = wsp<float>(e, e->ws.v_lo);
       opB.base = wsp<float>(e, e->ws.tgt_hi); opB.lo = wsp<float>(e, e->ws.tgt_lo);
     }
     PhaseTimer pt(e, PH_LOGITS, st);
     const int slots = 2 * ((Y + 255) / 256);
-    if (grad && x3) {
+    if (exp_offset && x3) {
+      umma::EpiExpSumT<true, true> ep{S, wsp<float>(e, e->ws.S_lo), e->ws.ldS, exp_offset, wsp<float2>(e, e->ws.lse_part), slots};
+      C2V_LAUNCH(e, C2V_CUDA(e, (C2V_UMMA_FIXED(256, false, false, true, decltype(ep), st, B, Y, D, 1, opA, opB, ep, e->num_sms))));
+    } else if (exp_offset) {
+      umma::EpiExpSumT<false, false> ep{S, nullptr, e->ws.ldS, exp_offset, wsp<float2>(e, e->ws.lse_part), slots};
+      C2V_LAUNCH(e, C2V_CUDA(e, (C2V_UMMA_FIXED(256, false, false, true, decltype(ep), st, B, Y, D, 1, opA, opB, ep, e->num_sms))));
+    } else if (gate && x3) {
+      umma::EpiStoreLseGatedT<true> ep{{S, e->ws.ldS, wsp<float2>(e, e->ws.lse_part), slots}, gate};
+      C2V_LAUNCH(e, C2V_CUDA(e, (C2V_UMMA_FIXED(256, false, false, true, decltype(ep), st, B, Y, D, 1, opA, opB, ep, e->num_sms))));
+    } else if (gate) {
+      umma::EpiStoreLseGatedT<false> ep{{S, e->ws.ldS, wsp<float2>(e, e->ws.lse_part), slots}, gate};
+      C2V_LAUNCH(e, C2V_CUDA(e, (C2V_UMMA_FIXED(256, false, false, true, decltype(ep), st, B, Y, D, 1, opA, opB, ep, e->num_sms))));
+    } else if (grad && x3) {
       umma::EpiSoftmaxGradT<true, true> ep{S, wsp<float>(e, e->ws.S_lo), e->ws.ldS, grad->lse, grad->target, grad->row0, grad->inv_batch, B};
       C2V_LAUNCH(e, C2V_CUDA(e, (C2V_UMMA_FIXED(256, false, false, true, decltype(ep), st, B, Y, D, 1, opA, opB, ep, e->num_sms))));
     } else if (grad) {
@@ -683,7 +729,10 @@ int forward_impl(c2v_engine* e, cudaStream_t st, const int32_t* src, const int32
   float* H = wsp<float>(e, e->ws.H);
   int rc = run_ctx_fwd(e, st, cs, dp, H, keep_x);
   if (rc) return rc;
-  return launch_attn_fwd(e, st, H, mask, B, attn, code_vec);
+  if ((rc = launch_attn_fwd(e, st, H, mask, B, attn, code_vec))) return rc;
+  if (keep_x && code_vec != wsp<float>(e, e->ws.v))      // a backward pass follows (phase-split API): it needs the code vectors
+    C2V_CUDA(e, cudaMemcpyAsync(wsp<float>(e, e->ws.v), code_vec, (size_t)B * e->dims.code_dim * 4, cudaMemcpyDeviceToDevice, st));
+  return C2V_OK;
 }
 
 int topk_impl(c2v_engine* e, cudaStream_t st, const float* code_vec, int B, int32_t* idx, float* val, int normalize) {
@@ -721,7 +770,7 @@ int context_backward(c2v_engine* e, cudaStream_t st, const ContextSource& cs, co
   }
   const bool x3 = is_tc(e) && is_3x(e);
   float* H_lo = x3 ? wsp<float>(e, e->ws.H_lo) : nullptr;
-  rc = launch_attn_bwd(e, st, H, alpha, dv, B, da_part, H_lo);    // H now holds dU (3xTF32: its high parts, H_lo the rest)
+  rc = launch_attn_bwd(e, st, H, alpha, dv, wsp<float>(e, e->ws.v), B, da_part, H_lo);    // H now holds dU (3xTF32: its high parts, H_lo the rest)
   if (rc) return rc;
   rc = launch_colsum(e, st, da_part, (size_t)D, B, D, e->grad.a);
   if (rc) return rc;
@@ -855,7 +904,7 @@ int run_dv(c2v_engine* e, cudaStream_t st, int B, float* dv) {
     } else {
       C2V_LAUNCH(e, C2V_CUDA(e, (C2V_UMMA_192(st, B, D, Y, want, opA, opB, ep, e->num_sms))));
     }
-    return launch_colsum(e, st, part, (size_t)B * D, ks, B * D, dv);
+    return launch_colsum(e, st, part, (size_t)B * D, ks, B * D, dv, e->row_scale, D);
   }
   simt::RowsK al{S, e->ws.ldS};
   simt::ColsX bl{e->theta.tgt, (size_t)D};
@@ -887,7 +936,7 @@ int run_dy(c2v_engine* e, cudaStream_t st, const float* v, int B) {
         const double lr_t = (double)e->tgt_lr * sqrt(1.0 - pow((double)e->tgt_b2, (double)e->tgt_t)) /
                             (1.0 - pow((double)e->tgt_b1, (double)e->tgt_t));
         umma::EpiAdam ep{e->theta.tgt, e->am.tgt, e->av.tgt, (size_t)D, (float)lr_t, e->tgt_b1, e->tgt_b2, e->tgt_eps,
-                         1.f - e->tgt_b1, 1.f - e->tgt_b2};
+                         1.f - e->tgt_b1, 1.f - e->tgt_b2, e->adam_epi_prefetch};
         if (e->sg_live) {
           umma::AXSoftmaxGradMN<2> ax{e->sg};
           C2V_LAUNCH(e, C2V_CUDA(e, (umma::launch_cfg<192, 4, true, true, umma::EpiAdam, umma::AXSoftmaxGradMN<2>>(st, Y, D, B, 1, opA, opB, ep,
@@ -979,6 +1028,48 @@ int train_step_impl(c2v_engine* e, cudaStream_t st, const int32_t* src, const in
     const LogitsGrad lg{lse, target, 0, invB};
     if ((rc = run_logits(e, st, v, B, S, false, false, &lg))) return rc;
     if ((rc = target_grad_gemms(e, st, v, B, dv))) return rc;
+    return context_backward(e, st, cs, mask, B, dp, dv);
+  }
+  if (fused_lse && e->exp_slab && !e->fuse_sg) {
+    // deferred normalisation: U = exp(s - true logit) from the logits epilogue, one patched element and one factor per row;
+    // the gated kernels after the combine are the two-pass schedule, run by the device only when a row left the fp32 window
+    const int D = e->dims.code_dim;
+    const int n_tiles = 2 * ((Y + 255) / 256);
+    float* tl = wsp<float>(e, e->ws.true_logit);
+    float* rscale = wsp<float>(e, e->ws.rscale);
+    float* vs = wsp<float>(e, e->ws.v_scaled);
+    int* flag = wsp<int>(e, e->ws.slab_flag);
+    float* S_lo = is_3x(e) ? wsp<float>(e, e->ws.S_lo) : nullptr;
+    if (!e->slab_flag_zeroed) {
+      C2V_CUDA(e, cudaMemsetAsync(flag, 0, 64, st));
+      e->slab_flag_zeroed = true;
+    }
+    {
+      PhaseTimer pt(e, PH_XENT, st);
+      C2V_LAUNCH(e, (true_logit_kernel<<<(B + 7) / 8, 256, 0, st>>>(v, e->theta.tgt, target, 0, Y, D, B, tl, flag)));
+    }
+    if ((rc = run_logits(e, st, v, B, S, false, false, nullptr, tl))) return rc;
+    {
+      PhaseTimer pt(e, PH_XENT, st);
+      C2V_LAUNCH(e, (expsum_combine_kernel<<<B, 256, 0, st>>>(wsp<float2>(e, e->ws.lse_part), n_tiles, S, S_lo, e->ws.ldS, Y, target, tl, tl, invB,
+                                                              loss_b, lse, rscale, flag)));
+    }
+    if ((rc = run_logits(e, st, v, B, S, true, false, nullptr, nullptr, flag))) return rc;
+    {
+      PhaseTimer pt(e, PH_XENT, st);
+      C2V_LAUNCH(e, (xent_combine_kernel<<<B, 256, 0, st>>>(wsp<float2>(e, e->ws.lse_part), n_tiles, S, e->ws.ldS, target, loss_b, lse, nullptr, flag,
+                                                            rscale, reinterpret_cast<unsigned*>(flag) + 1)));
+      const int chunks = 2;        // the fallback only has to be correct; a small grid keeps the closed gate cheap
+      if (S_lo) C2V_LAUNCH(e, (softmax_grad_kernel<true><<<dim3(chunks, B), 256, 0, st>>>(S, e->ws.ldS, Y, lse, target, invB, 0, S_lo, flag)));
+      else C2V_LAUNCH(e, (softmax_grad_kernel<false><<<dim3(chunks, B), 256, 0, st>>>(S, e->ws.ldS, Y, lse, target, invB, 0, nullptr, flag)));
+      C2V_LAUNCH(e, (scale_rows_kernel<<<(unsigned)(((size_t)B * D + 255) / 256), 256, 0, st>>>(v, rscale, vs, D, (size_t)B * D)));
+      C2V_LAUNCH(e, (loss_reduce_kernel<<<1, 256, 0, st>>>(loss_b, B, invB, loss_out)));
+    }
+    e->sg_live = false;
+    e->row_scale = rscale;
+    rc = target_grad_gemms(e, st, vs, B, dv);
+    e->row_scale = nullptr;
+    if (rc) return rc;
     return context_backward(e, st, cs, mask, B, dp, dv);
   }
   if ((rc = run_logits(e, st, v, B, S, fused_lse))) return rc;
@@ -1221,6 +1312,7 @@ int c2v_bind_workspace(c2v_engine* e, void* dev_ptr, size_t bytes) {
   e->wbase = (char*)dev_ptr;
   e->wbytes = bytes;
   e->bkt_zeroed = false;
+  e->slab_flag_zeroed = false;
   return C2V_OK;
 }
 
@@ -1274,6 +1366,8 @@ int c2v_set_option(c2v_engine* e, const char* key, int64_t value) {
   if (!strcmp(key, "fuse_target_adam")) { e->fuse_tgt = value ? 1 : 0; return C2V_OK; }
   if (!strcmp(key, "fuse_gather")) { e->fuse_gather = value ? 1 : 0; return C2V_OK; }
   if (!strcmp(key, "fuse_softmax_grad")) { e->fuse_sg = value ? 1 : 0; return C2V_OK; }
+  if (!strcmp(key, "exp_slab")) { e->exp_slab = value ? 1 : 0; return C2V_OK; }
+  if (!strcmp(key, "adam_epilogue_prefetch")) { e->adam_epi_prefetch = value ? 1 : 0; return C2V_OK; }
   if (!strcmp(key, "recompute_logits")) { e->recompute = value ? 1 : 0; return C2V_OK; }
   if (!strcmp(key, "sort_peer_access")) {
     if (value < 0 || value > 2) return fail(e, C2V_ERR_INVALID, "sort_peer_access must be 0 (never), 1 (auto) or 2 (always)");
@@ -1370,6 +1464,19 @@ int c2v_get_option(const c2v_engine* e, const char* key, int64_t* value) {
   if (!strcmp(key, "fuse_target_adam")) { *value = e->fuse_tgt; return C2V_OK; }
   if (!strcmp(key, "fuse_gather")) { *value = e->fuse_gather; return C2V_OK; }
   if (!strcmp(key, "fuse_softmax_grad")) { *value = e->fuse_sg; return C2V_OK; }
+  if (!strcmp(key, "exp_slab")) { *value = e->exp_slab; return C2V_OK; }
+  if (!strcmp(key, "adam_epilogue_prefetch")) { *value = e->adam_epi_prefetch; return C2V_OK; }
+  if (!strcmp(key, "exp_slab_fallbacks")) {       // steps so far that left the fp32 window and ran the two-pass schedule (synchronises)
+    *value = 0;
+    if (e->wbase && e->slab_flag_zeroed) {
+      unsigned n = 0;
+      if (cudaDeviceSynchronize() != cudaSuccess ||
+          cudaMemcpy(&n, e->wbase + e->ws.slab_flag + 4, 4, cudaMemcpyDeviceToHost) != cudaSuccess)
+        return C2V_ERR_CUDA;
+      *value = n;
+    }
+    return C2V_OK;
+  }
   if (!strcmp(key, "recompute_logits")) { *value = e->recompute; return C2V_OK; }
   if (!strcmp(key, "sort_peer_access")) { *value = e->sort_peer; return C2V_OK; }
   if (!strcmp(key, "adam_step_count")) { *value = e->adam_t_done; return C2V_OK; }

@@ -7,7 +7,9 @@
 
 namespace c2v {
 
-constexpr int kAttnThreads = 256;
+// one CTA per example: 128 threads and <= 64 registers make 8 CTAs resident per SM, so a 1024-example batch is ONE wave on
+// 148 SMs (1184 slots) -- with 256 threads it was 1.7 waves, the second one 73 % full
+constexpr int kAttnThreads = 128;
 constexpr int kAttnWarps = kAttnThreads / 32;
 
 // Deterministic block-wide sum (fixed tree); `red` is shared scratch of >= 32 floats.
@@ -50,7 +52,7 @@ __device__ __forceinline__ float block_max(float v, float* red) {
 // so H is read once.  A bag with no valid context gives NaN (tf.nn.softmax of all -inf).
 // ---------------------------------------------------------------------------------------------
 template <int NV>
-__global__ void __launch_bounds__(kAttnThreads)
+__global__ void __launch_bounds__(kAttnThreads, NV <= 3 ? 8 : 4)
 attn_fwd_kernel(const float* __restrict__ H, const float* __restrict__ a, const float* __restrict__ mask,
                 int C, int D, float* __restrict__ alpha, float* __restrict__ v) {
   extern __shared__ float sm[];
@@ -126,52 +128,34 @@ attn_fwd_kernel(const float* __restrict__ H, const float* __restrict__ a, const 
 }
 
 // ---------------------------------------------------------------------------------------------
-// Attention backward:  dalpha_c = h_c.dv ; dz = alpha (dalpha - sum alpha dalpha) ;
+// Attention backward:  dalpha_c = h_c . dv ; dz_c = alpha_c (dalpha_c - t), t = sum_c alpha_c dalpha_c ;
 // dh = alpha dv + dz a ; du = dh (1 - h^2) written over H ; da partial per example.
+// t needs no pass of its own: sum_c alpha_c (h_c . dv) = (sum_c alpha_c h_c) . dv = v . dv with the code vector v the
+// forward pass already produced -- so H is read ONCE and overwritten in the same pass (a warp per context: the dot
+// product, dz and du all come from the row the warp holds in registers).
 // ---------------------------------------------------------------------------------------------
 template <int NV, bool SPLIT>
-__global__ void __launch_bounds__(kAttnThreads)
+__global__ void __launch_bounds__(kAttnThreads, NV <= 3 ? 7 : 4)      // 7 x 148 SMs still holds a 1024-example batch in one wave
 attn_bwd_kernel(float* __restrict__ H, const float* __restrict__ alpha, const float* __restrict__ dv,
-                const float* __restrict__ a, int C, int D, float* __restrict__ da_part, float* __restrict__ H_lo) {
+                const float* __restrict__ v, const float* __restrict__ a, int C, int D, float* __restrict__ da_part,
+                float* __restrict__ H_lo) {
   // SPLIT (3xTF32): dU is written as its tf32 split, high parts over H and residuals into H_lo
   extern __shared__ float sm[];
-  float* dal = sm;                      // [C]
-  float* red = dal + ((C + 3) & ~3);    // [32]
-  float* dabuf = red + 32;              // [kAttnWarps][D]
+  float* dabuf = sm;                    // [kAttnWarps][D]
   const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   float4 av[NV], gv[NV], dacc[NV];
+  float tp = 0.f;
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
     const int j = i * 128 + lane * 4;
     const bool ok = j < D;
     av[i] = ok ? *reinterpret_cast<const float4*>(a + j) : make_float4(0.f, 0.f, 0.f, 0.f);
     gv[i] = ok ? *reinterpret_cast<const float4*>(dv + (size_t)b * D + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+    const float4 vv = ok ? *reinterpret_cast<const float4*>(v + (size_t)b * D + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+    tp += vv.x * gv[i].x + vv.y * gv[i].y + vv.z * gv[i].z + vv.w * gv[i].w;
     dacc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
   }
-  for (int c = warp; c < C; c += kAttnWarps) {
-    const float al = alpha[(size_t)b * C + c];
-    float part = 0.f;
-    if (al != 0.f) {
-      const float* h = H + ((size_t)b * C + c) * D;
-#pragma unroll
-      for (int i = 0; i < NV; ++i) {
-        const int j = i * 128 + lane * 4;
-        if (j < D) {
-          const float4 hv = *reinterpret_cast<const float4*>(h + j);
-          part += hv.x * gv[i].x + hv.y * gv[i].y + hv.z * gv[i].z + hv.w * gv[i].w;
-        }
-      }
-      part = warp_sum(part);
-    }
-    if (lane == 0) dal[c] = part;
-  }
-  __syncthreads();
-  float t = 0.f;
-  for (int c = tid; c < C; c += kAttnThreads) {
-    const float al = alpha[(size_t)b * C + c];
-    if (al != 0.f) t += al * dal[c];
-  }
-  t = block_sum(t, red);
+  const float t = warp_sum(tp);         // the same value, bit for bit, in every warp of the CTA
   for (int c = warp; c < C; c += kAttnWarps) {
     const float al = alpha[(size_t)b * C + c];
     float* h = H + ((size_t)b * C + c) * D;
@@ -186,17 +170,24 @@ attn_bwd_kernel(float* __restrict__ H, const float* __restrict__ alpha, const fl
       }
       continue;
     }
-    const float dz = al * (dal[c] - t);
+    float4 hv[NV];
+    float part = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int j = i * 128 + lane * 4;
+      hv[i] = (j < D) ? *reinterpret_cast<const float4*>(h + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+      part += hv[i].x * gv[i].x + hv[i].y * gv[i].y + hv[i].z * gv[i].z + hv[i].w * gv[i].w;
+    }
+    const float dz = al * (warp_sum(part) - t);
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
       const int j = i * 128 + lane * 4;
       if (j < D) {
-        const float4 hv = *reinterpret_cast<const float4*>(h + j);
         float4 du;
-        du.x = (al * gv[i].x + dz * av[i].x) * (1.f - hv.x * hv.x);
-        du.y = (al * gv[i].y + dz * av[i].y) * (1.f - hv.y * hv.y);
-        du.z = (al * gv[i].z + dz * av[i].z) * (1.f - hv.z * hv.z);
-        du.w = (al * gv[i].w + dz * av[i].w) * (1.f - hv.w * hv.w);
+        du.x = (al * gv[i].x + dz * av[i].x) * (1.f - hv[i].x * hv[i].x);
+        du.y = (al * gv[i].y + dz * av[i].y) * (1.f - hv[i].y * hv[i].y);
+        du.z = (al * gv[i].z + dz * av[i].z) * (1.f - hv[i].z * hv[i].z);
+        du.w = (al * gv[i].w + dz * av[i].w) * (1.f - hv[i].w * hv[i].w);
         if (SPLIT) {
           float4 hi, lo;
           split_tf32(du, hi, lo);
@@ -205,7 +196,7 @@ attn_bwd_kernel(float* __restrict__ H, const float* __restrict__ alpha, const fl
         } else {
           *reinterpret_cast<float4*>(h + j) = du;
         }
-        dacc[i].x += dz * hv.x; dacc[i].y += dz * hv.y; dacc[i].z += dz * hv.z; dacc[i].w += dz * hv.w;
+        dacc[i].x += dz * hv[i].x; dacc[i].y += dz * hv[i].y; dacc[i].z += dz * hv[i].z; dacc[i].w += dz * hv[i].w;
       }
     }
   }
@@ -283,9 +274,15 @@ xent_kernel(float* __restrict__ S, size_t ldS, const int32_t* __restrict__ targe
 __global__ void __launch_bounds__(256)
 xent_combine_kernel(const float2* __restrict__ partial, int n_tiles, const float* __restrict__ S, size_t ldS,
                     const int32_t* __restrict__ target, float* __restrict__ loss_b, float* __restrict__ lse_out,
-                    const float* __restrict__ true_logit = nullptr) {
+                    const float* __restrict__ true_logit = nullptr, const int* __restrict__ gate = nullptr,
+                    float* __restrict__ rscale_one = nullptr, unsigned* __restrict__ gate_count = nullptr) {
+  // gate: this launch is the fallback of the exp_slab schedule and does nothing while *gate == 0; when it runs, the rows'
+  // deferred factors become 1 (the slab will hold the finished gradient) and the fallback counter moves
+  if (gate && *gate == 0) return;
   __shared__ float red[32];
   const int b = blockIdx.x;
+  if (rscale_one && threadIdx.x == 0) rscale_one[b] = 1.f;
+  if (gate_count && b == 0 && threadIdx.x == 0) *gate_count += 1u;
   const float2* p = partial + (size_t)b * n_tiles;
   float m = -INFINITY;
   for (int i = threadIdx.x; i < n_tiles; i += 256) m = fmaxf(m, p[i].x);
@@ -307,7 +304,8 @@ xent_combine_kernel(const float2* __restrict__ partial, int n_tiles, const float
 // logit of the loss when the logits themselves are never written out (recompute_logits).  One warp per example.
 __global__ void __launch_bounds__(256)
 true_logit_kernel(const float* __restrict__ v, const float* __restrict__ Ytab, const int32_t* __restrict__ target, int row0, int Y,
-                  int D, int B, float* __restrict__ tl) {
+                  int D, int B, float* __restrict__ tl, int* __restrict__ clear_flag = nullptr) {
+  if (clear_flag && blockIdx.x == 0 && threadIdx.x == 0) *clear_flag = 0;      // the exp_slab range flag of the step that starts here
   const int b = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (b >= B) return;
   const int t = target[b] - row0;
@@ -324,12 +322,62 @@ true_logit_kernel(const float* __restrict__ v, const float* __restrict__ Ytab, c
   if (lane == 0) tl[b] = acc;
 }
 
+// exp_slab schedule: the logits epilogue (umma::EpiExpSumT) left U = exp(s - c_b) in the slab and (max U, sum U) partials.
+// Per example b, with Z = sum_j U[b, j]:  log-sum-exp = c_b + log Z,  loss_b = (c_b - true logit) + log Z,
+// softmax - onehot = (U - Z [j == y_b]) / Z  -- so ONE element of the row is patched (U[b, y_b] -= Z) and the row's factor
+// 1 / (B Z) (rscale) is handed to the two gradient GEMMs: it scales dv's rows in the split-K reduction and the code vectors
+// that are dY's small operand (scale_rows_kernel).  A row whose largest U is outside [kExpSlabMin, kExpSlabMax] (or not a
+// number) raises *bad: the gated two-pass kernels that follow then redo the step's softmax the classic way.  One CTA per row.
+__global__ void __launch_bounds__(256)
+expsum_combine_kernel(const float2* __restrict__ partial, int n_tiles, float* __restrict__ U, float* __restrict__ U_lo, size_t ldS, int Y,
+                      const int32_t* __restrict__ target, const float* __restrict__ offset, const float* __restrict__ true_logit,
+                      float inv_batch, float* __restrict__ loss_b, float* __restrict__ lse_out, float* __restrict__ rscale,
+                      int* __restrict__ bad) {
+  __shared__ float red[32];
+  const int b = blockIdx.x;
+  const float2* p = partial + (size_t)b * n_tiles;
+  float m = 0.f, s = 0.f;
+  for (int i = threadIdx.x; i < n_tiles; i += 256) {
+    const float2 q = p[i];
+    m = fmaxf(m, q.x);
+    s += q.y;
+  }
+  const float M = block_max(m, red);
+  s = block_sum(s, red);
+  if (threadIdx.x == 0) {
+    if (!(M >= kExpSlabMin && M <= kExpSlabMax && s <= 3.0e38f)) *bad = 1;      // NaN fails every comparison
+    const float lz = logf(s);
+    lse_out[b] = offset[b] + lz;
+    loss_b[b] = (offset[b] - true_logit[b]) + lz;
+    rscale[b] = inv_batch / s;
+    const int y = target[b];
+    if (y >= 0 && y < Y) {
+      const size_t at = (size_t)b * ldS + y;
+      if (U_lo) {
+        float hi, lo;
+        split_tf32((U[at] + U_lo[at]) - s, hi, lo);
+        U[at] = hi; U_lo[at] = lo;
+      } else {
+        U[at] -= s;
+      }
+    }
+  }
+}
+
+// out[b, :] = x[b, :] * f[b]   (rows of length D; out may be x)
+__global__ void __launch_bounds__(256)
+scale_rows_kernel(const float* x, const float* __restrict__ f, float* out, int D, size_t n) {
+  const size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;
+  if (i < n) out[i] = x[i] * f[i / D];
+}
+
 // S <- (softmax(S) - onehot(target)) * inv_batch in place, padding columns zeroed.  grid (chunks, B).
 template <bool SPLIT>
 __global__ void __launch_bounds__(256)
 softmax_grad_kernel(float* __restrict__ S, size_t ldS, int Y, const float* __restrict__ lse, const int32_t* __restrict__ target,
-                    float inv_batch, int row0, float* __restrict__ S_lo) {
+                    float inv_batch, int row0, float* __restrict__ S_lo, const int* __restrict__ gate = nullptr) {
   // SPLIT (3xTF32): the gradient is written as its tf32 split (high parts over S, residuals into S_lo)
+  if (gate && *gate == 0) return;        // fallback pass of the exp_slab schedule: not needed this step
   const int b = blockIdx.y;
   float* row = S + (size_t)b * ldS;
   const float l = lse[b];
@@ -544,13 +592,19 @@ __global__ void __launch_bounds__(1024) colsum_kernel(const float* __restrict__ 
 // out[i] = sum_{r<R} in[r*stride + i] for the few, long slices a split-K GEMM leaves behind
 // (R <= ~64, n up to millions): one float4 column per thread, slices added in fixed order.
 __global__ void __launch_bounds__(256)
-slice_sum_kernel(const float* __restrict__ in, size_t stride, int R, size_t n4, float* __restrict__ out) {
+slice_sum_kernel(const float* __restrict__ in, size_t stride, int R, size_t n4, float* __restrict__ out,
+                 const float* __restrict__ row_scale = nullptr, int row_len4 = 1) {
+  // row_scale: the result is a [rows, 4 * row_len4] matrix whose row i is multiplied by row_scale[i] on the way out
   const size_t step = (size_t)gridDim.x * 256;
   for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < n4; i += step) {
     float4 acc = reinterpret_cast<const float4*>(in)[i];
     for (int r = 1; r < R; ++r) {
       const float4 x = *reinterpret_cast<const float4*>(in + (size_t)r * stride + 4 * i);
       acc.x += x.x; acc.y += x.y; acc.z += x.z; acc.w += x.w;
+    }
+    if (row_scale) {
+      const float f = row_scale[i / (size_t)row_len4];
+      acc.x *= f; acc.y *= f; acc.z *= f; acc.w *= f;
     }
     reinterpret_cast<float4*>(out)[i] = acc;
   }
@@ -736,36 +790,55 @@ __global__ void __launch_bounds__(256)
 gather_ctx_kernel(const __grid_constant__ ContextSource cs, const __grid_constant__ Dropout dp, float* __restrict__ Xg,
                   float* __restrict__ Xlo) {
   // SPLIT (3xTF32): X' is written as its tf32 split (high parts into Xg, residuals into Xlo)
-  const int n = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  // Launched as one resident wave (gather_blocks()): a warp walks rows n, n + stride, ... and loads the three indices of
+  // its NEXT row before it touches the current one, so a row costs one dependent memory round trip (the table rows),
+  // not two (index, then rows).
+  const int lane = threadIdx.x & 31;
+  const int stride = gridDim.x * 8;
+  int n = blockIdx.x * 8 + (threadIdx.x >> 5);
   if (n >= cs.rows) return;
   const int K3 = 3 * cs.d;
-  float* dst = Xg + (size_t)n * K3;
-  // all loads of the row are issued before any is consumed: with peer (NVLink) shards each load is a
-  // multi-microsecond round trip, so memory-level parallelism per warp is what sets the bandwidth
-  constexpr int kU = 3;                          // covers 3d <= 384 (d = 128) in one batch
-  for (int j0 = lane * 4; j0 < K3; j0 += 128 * kU) {
-    float4 x[kU];
+  int i0 = __ldg(cs.src + n), i1 = __ldg(cs.pth + n), i2 = __ldg(cs.tgt + n);
+  for (; n < cs.rows; n += stride) {
+    const int nn = n + stride;
+    int p0 = 0, p1 = 0, p2 = 0;
+    if (nn < cs.rows) { p0 = __ldg(cs.src + nn); p1 = __ldg(cs.pth + nn); p2 = __ldg(cs.tgt + nn); }
+    const float* r0 = table_row(cs.tok, i0, cs.d);
+    const float* r1 = table_row(cs.path, i1, cs.d);
+    const float* r2 = table_row(cs.tok, i2, cs.d);
+    float* dst = Xg + (size_t)n * K3;
+    // all loads of the row are issued before any is consumed: with peer (NVLink) shards each load is a
+    // multi-microsecond round trip, so memory-level parallelism per warp is what sets the bandwidth
+    constexpr int kU = 3;                          // covers 3d <= 384 (d = 128) in one batch
+    for (int j0 = lane * 4; j0 < K3; j0 += 128 * kU) {
+      float4 x[kU];
 #pragma unroll
-    for (int u = 0; u < kU; ++u) {
-      const int j = j0 + u * 128;
-      if (j < K3) x[u] = __ldg(reinterpret_cast<const float4*>(ctx_ptr(cs, n, j)));
-    }
+      for (int u = 0; u < kU; ++u) {
+        const int j = j0 + u * 128;
+        if (j < K3) {
+          const int seg = j / cs.d, off = j - seg * cs.d;
+          const float* r = seg == 0 ? r0 : (seg == 1 ? r1 : r2);
+          x[u] = __ldg(reinterpret_cast<const float4*>(r + off));
+        }
+      }
 #pragma unroll
-    for (int u = 0; u < kU; ++u) {
-      const int j = j0 + u * 128;
-      if (j < K3) {
-        const float4 m = dropout_mult4(dp, n, j >> 2);
-        x[u].x *= m.x; x[u].y *= m.y; x[u].z *= m.z; x[u].w *= m.w;
-        if (SPLIT) {
-          float4 hi, lo;
-          split_tf32(x[u], hi, lo);
-          *reinterpret_cast<float4*>(dst + j) = hi;
-          *reinterpret_cast<float4*>(Xlo + (size_t)n * K3 + j) = lo;
-        } else {
-          *reinterpret_cast<float4*>(dst + j) = x[u];
+      for (int u = 0; u < kU; ++u) {
+        const int j = j0 + u * 128;
+        if (j < K3) {
+          const float4 m = dropout_mult4(dp, n, j >> 2);
+          x[u].x *= m.x; x[u].y *= m.y; x[u].z *= m.z; x[u].w *= m.w;
+          if (SPLIT) {
+            float4 hi, lo;
+            split_tf32(x[u], hi, lo);
+            *reinterpret_cast<float4*>(dst + j) = hi;
+            *reinterpret_cast<float4*>(Xlo + (size_t)n * K3 + j) = lo;
+          } else {
+            *reinterpret_cast<float4*>(dst + j) = x[u];
+          }
         }
       }
     }
+    i0 = p0; i1 = p1; i2 = p2;
   }
 }
 

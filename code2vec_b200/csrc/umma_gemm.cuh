@@ -325,6 +325,89 @@ struct EpiSoftmaxGradT {
   }
 };
 
+// Logits epilogue of the deferred-normalisation schedule (option "exp_slab"): the slab receives U = exp(s - c_row) instead
+// of the logits, c_row a per-example constant known before the product (the example's true-class logit), and the per-(row,
+// half tile) partial holds (max U, sum U).  softmax - onehot is then U with one patched element per row times a per-row
+// factor 1 / sum U, which the two gradient GEMMs apply to their small operand / result: no pass ever reads the slab back
+// to normalise it (tensorflow_model.py:227-230).  max U is the range guard: the caller falls back to the two-pass
+// schedule when some row's largest U leaves [kExpSlabMin, kExpSlabMax] (common.cuh).  SPLIT (3xTF32): U is written as its tf32 split.
+template <bool PRECISE, bool SPLIT>
+struct EpiExpSumT {
+  struct State { float mx, sum; };
+  float* C;
+  float* C_lo;
+  size_t ldc;
+  const float* offset;   // [M] c_row
+  float2* partial;       // [M, slots]; slot = 2 * n_tile + column half
+  int slots;
+  __device__ __forceinline__ void begin(State& st) const { st.mx = 0.f; st.sum = 0.f; }
+  __device__ __forceinline__ void end(int m, int slot, int, bool row_ok, State& st) const {
+    if (row_ok) partial[(size_t)m * slots + slot] = make_float2(st.mx, st.sum);
+  }
+  __device__ __forceinline__ float map(float x) const { return x; }
+  __device__ __forceinline__ float* out(int) const { return C; }
+  using Pre = EpiNoState;
+  static constexpr int kRowBatch = 8;
+  static constexpr bool kWideDrain = true;
+  __device__ __forceinline__ void prefetch(const float*, size_t, Pre&) const {}
+  __device__ __forceinline__ void store4(float* c, size_t off, float4 v, const Pre&) const {
+    if (SPLIT) {
+      float4 hi, lo;
+      split_tf32(v, hi, lo);
+      *reinterpret_cast<float4*>(c + off) = hi;
+      *reinterpret_cast<float4*>(C_lo + off) = lo;
+    } else {
+      *reinterpret_cast<float4*>(c + off) = v;
+    }
+  }
+  __device__ __forceinline__ void store1(float* c, size_t off, float x) const {
+    if (SPLIT) {
+      float hi, lo;
+      split_tf32(x, hi, lo);
+      c[off] = hi; C_lo[off] = lo;
+    } else {
+      c[off] = x;
+    }
+  }
+  // rewrites the chunk's accumulators IN PLACE (the store that follows maps with the identity)
+  __device__ __forceinline__ void observe(int m, int, uint32_t (&r)[32], int nvalid, State& st) const {
+    const float c = offset[m];
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f, x0 = 0.f, x1 = 0.f, x2 = 0.f, x3 = 0.f;
+    if (!PRECISE && nvalid >= 32) {
+      constexpr float L2E = 1.4426950408889634f;
+      const float c2 = -c * L2E;           // exp(x - c) as one FFMA + one ex2.approx
+      auto e2 = [](float t) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(t)); return y; };
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) {
+        const float u0 = e2(fmaf(__uint_as_float(r[j + 0]), L2E, c2)), u1 = e2(fmaf(__uint_as_float(r[j + 1]), L2E, c2));
+        const float u2 = e2(fmaf(__uint_as_float(r[j + 2]), L2E, c2)), u3 = e2(fmaf(__uint_as_float(r[j + 3]), L2E, c2));
+        r[j + 0] = __float_as_uint(u0); r[j + 1] = __float_as_uint(u1); r[j + 2] = __float_as_uint(u2); r[j + 3] = __float_as_uint(u3);
+        a0 += u0; a1 += u1; a2 += u2; a3 += u3;
+        x0 = fmaxf(x0, u0); x1 = fmaxf(x1, u1); x2 = fmaxf(x2, u2); x3 = fmaxf(x3, u3);
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        float u = 0.f;
+        if (j < nvalid) u = PRECISE ? expf(__uint_as_float(r[j]) - c) : __expf(__uint_as_float(r[j]) - c);
+        r[j] = __float_as_uint(u);
+        if ((j & 3) == 0) { a0 += u; x0 = fmaxf(x0, u); }
+        else if ((j & 3) == 1) { a1 += u; x1 = fmaxf(x1, u); }
+        else if ((j & 3) == 2) { a2 += u; x2 = fmaxf(x2, u); }
+        else { a3 += u; x3 = fmaxf(x3, u); }
+      }
+    }
+    st.sum += (a0 + a1) + (a2 + a3);
+    st.mx = fmaxf(st.mx, fmaxf(fmaxf(x0, x1), fmaxf(x2, x3)));
+  }
+};
+// The two-pass fallback of that schedule is launched every step behind a device-side gate: a logits epilogue that carries
+// `gate` makes the whole kernel return at once while *gate == 0.
+template <bool PRECISE>
+struct EpiStoreLseGatedT : EpiStoreLseT<PRECISE> {
+  const int* gate;
+};
+
 using EpiTanhStore = EpiTanhStoreT<false>;
 using EpiTanhStorePrecise = EpiTanhStoreT<true>;
 using EpiStoreLse = EpiStoreLseT<false>;
@@ -342,6 +425,7 @@ struct EpiAdam {
   float* Vo;
   size_t ldc;
   float lr_t, b1, b2, eps, omb1, omb2;
+  int l2_prefetch;   // engine option "adam_epilogue_prefetch"
   __device__ __forceinline__ void begin(State&) const {}
   __device__ __forceinline__ void end(int, int, int, bool, State&) const {}
   __device__ __forceinline__ void observe(int, int, const uint32_t (&)[32], int, State&) const {}
@@ -351,6 +435,18 @@ struct EpiAdam {
     mm = __fadd_rn(__fmul_rn(mm, b1), __fmul_rn(omb1, gg));
     vv = __fadd_rn(__fmul_rn(vv, b2), __fmul_rn(omb2, __fmul_rn(gg, gg)));
     pp = adam_move_dense(pp, lr_t, mm, vv, eps);
+  }
+  // Called by an epilogue warp one tile AHEAD of the tile it is about to drain (row m, columns [n0, n0 + ncols)): pulls the
+  // (theta, m, v) lines of that region into L2, so that the update's loads -- only kRowBatch rows of them in flight per
+  // thread -- see L2 latency rather than DRAM latency.
+  __device__ __forceinline__ void prefetch_tile(int m, int n0, int ncols, int M, int N) const {
+    if (m >= M || !l2_prefetch) return;
+    const size_t row = (size_t)m * ldc;
+    for (int n = n0; n < n0 + ncols && n < N; n += 32) {
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(P + row + n));
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(Mo + row + n));
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(Vo + row + n));
+    }
   }
   struct Pre { float4 p, m, v; };
   static constexpr int kRowBatch = 4;            // 8 rows in flight spill and measured slower (dY 0.77 vs 0.68 ms)
@@ -387,6 +483,17 @@ template <class Epi>
 __device__ __forceinline__ float epi_map(const Epi& epi, float x, int, const typename Epi::State&, long) {
   return epi.map(x);
 }
+template <class Epi>
+__device__ __forceinline__ auto epi_gate_closed(const Epi& epi, int) -> decltype(*epi.gate == 0) { return *epi.gate == 0; }
+template <class Epi>
+__device__ __forceinline__ bool epi_gate_closed(const Epi&, long) { return false; }
+template <class Epi>
+__device__ __forceinline__ auto epi_prefetch_tile(const Epi& epi, int m, int n0, int ncols, int M, int N, int)
+    -> decltype(epi.prefetch_tile(m, n0, ncols, M, N)) {
+  epi.prefetch_tile(m, n0, ncols, M, N);
+}
+template <class Epi>
+__device__ __forceinline__ void epi_prefetch_tile(const Epi&, int, int, int, int, int, long) {}
 template <class Epi>
 constexpr bool epi_stores(...) { return true; }
 template <class Epi, bool V = Epi::kStores>
@@ -619,6 +726,7 @@ __global__ void __launch_bounds__(kThreads + 32 * AX::kWarps, 1)
 umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ CUtensorMap tmAlo, const __grid_constant__ CUtensorMap tmBlo, GemmShape gs, Epi epi,
                  AX ax = AX{}) {
+  if (epi_gate_closed(epi, 0)) return;      // gated fallback pass: nothing to do (uniform over the grid)
   using L = SmemLayout<BN, STAGES>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -783,9 +891,17 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     constexpr int kChunksPerHalf = BN / 64;
     int acc = 0;
     uint32_t acc_phase = 0;
+    auto prefetch_item = [&](int it) {            // read-modify-write epilogues: warm L2 with the tile's destination lines
+      if (it >= total_items) return;
+      int mt2, nt2, sp2;
+      decode(it, mt2, nt2, sp2);
+      epi_prefetch_tile(epi, mt2 * BM + q * 32 + lane, nt2 * BN + half * kChunksPerHalf * 32, kChunksPerHalf * 32, gs.M, gs.N, 0);
+    };
+    prefetch_item(blockIdx.x);
     for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
       int mt, nt, sp;
       decode(item, mt, nt, sp);
+      prefetch_item(item + gridDim.x);
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
       const int m = mt * BM + q * 32 + lane;

@@ -77,6 +77,7 @@ template <int BN, int STAGES, bool A_MN, bool B_MN, class Epi>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 umma_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                   const __grid_constant__ CUtensorMap tmAlo, const __grid_constant__ CUtensorMap tmBlo, GemmShape gs, Epi epi) {
+  if (epi_gate_closed(epi, 0)) return;      // gated fallback pass: both CTAs of every pair leave together
   using L = SmemLayout2<BN, STAGES>;
   static_assert(BN % 64 == 0, "each CTA stages BN/2 columns of B in 32-element chunks");
   extern __shared__ uint8_t smem_raw[];

@@ -134,7 +134,19 @@ int c2v_bind_adam_state(c2v_engine* e, const c2v_tensors* m, const c2v_tensors* 
  * zero-gradient replay stops dividing / taking square roots once an update no longer changes any element of
  * the row -- updates shrink monotonically from there, so the parameters provably stay put and only the
  * slots keep decaying; bit-identical to the full replay for 0 < beta1 <= 0.95 and 0.99 <= beta2 < 1, and
- * not applied outside that range). */
+ * not applied outside that range), "exp_slab" (0/1, default 1; tensor-core math modes, single-GPU full-softmax
+ * train step): the logits GEMM's epilogue writes U = exp(logit - true-class logit) instead of the logits, one element
+ * per row is patched and the softmax's 1 / sum is applied as a per-example factor by the two target-side gradient
+ * GEMMs, so no pass re-reads the [B, Y] slab to normalise it; a step in which some row's largest U leaves the fp32
+ * window [1e-26, 1e30] is redone on the device as the two-pass schedule (logits stored, then rewritten) -- read-only
+ * "exp_slab_fallbacks" counts those steps (the read synchronises the device), "sort_peer_access" (row-sharded
+ * tables over peer memory: 0 never, 1 = default: when a table exceeds 2 GB, 2 always -- the step's row indices are
+ * counting-sorted by (owner, 2 MB page) before the peer gather / scatter-add).
+ * Experimental schedules, all correct, all measured slower on B200 and therefore 0 by default (DESIGN.md sections
+ * 4.6 - 4.8): "fuse_gather" (the gather feeds the context GEMM's shared-memory stages directly), "fuse_softmax_grad"
+ * (dv / dY turn logits into dL/dlogits as their A tiles land; tf32 mode), "recompute_logits" (the logits GEMM runs
+ * twice instead of storing logits), "adam_epilogue_prefetch" (the dY GEMM's Adam epilogue prefetches the (theta, m, v)
+ * lines of its next tile into L2: dY 0.77 ms instead of 0.69). */
 int c2v_set_option(c2v_engine* e, const char* key, int64_t value);
 int c2v_get_option(const c2v_engine* e, const char* key, int64_t* value);
 

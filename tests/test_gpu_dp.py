@@ -57,13 +57,26 @@ def test_two_rank_data_parallel_matches_single_engine(tmp_path, schedule, math_m
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
+    _run_and_compare(tmp_path, schedule, math_mode, world=2)
+
+
+@pytest.mark.parametrize("schedule,math_mode", [("fully_sharded", 0), ("fully_sharded", 1), ("fully_sharded", 2)])
+def test_sharded_schedules_on_a_single_rank_match_the_fused_step(tmp_path, schedule, math_mode):
+    """The same schedules with a process group of ONE rank, so a one-GPU box exercises the multi-GPU code path end to end:
+    tables re-homed into CUDA-IPC memory, the phase-split entry points (c2v_context_forward / c2v_target_forward /
+    c2v_lse_combine / c2v_target_backward / c2v_context_backward), the collectives (trivial here) and the per-shard
+    Adam -- against c2v_train_batch_host's fused step on the same batch."""
+    _run_and_compare(tmp_path, schedule, math_mode, world=1)
+
+
+def _run_and_compare(tmp_path, schedule, math_mode, world):
     import torch.multiprocessing as mp
-    world, port = 2, 29500 + (os.getpid() % 1000)
+    port = 29500 + (os.getpid() % 1000)
     # tf32: an element whose tiny gradient changes sign moves the other way by a full Adam step (1e-3) in each of the 3 steps
     tol = {0: 5e-5, 1: 8e-3, 2: 2e-4}[math_mode]
     mp.spawn(_worker, args=(world, port, schedule, math_mode, str(tmp_path)), nprocs=world, join=True)
     r0 = np.load(str(tmp_path / "rank0.npz"))
-    r1 = np.load(str(tmp_path / "rank1.npz"))
+    r1 = np.load(str(tmp_path / "rank1.npz")) if world > 1 else r0
     replicated = {"table_sharded": ("tgt", "W", "a"), "fully_sharded": ("W", "a")}.get(schedule, O.PARAM_NAMES)
     for k in replicated:
         assert np.array_equal(r0[k], r1[k]), "replicas diverged on %s" % k
@@ -79,12 +92,16 @@ def test_two_rank_data_parallel_matches_single_engine(tmp_path, schedule, math_m
     if schedule == "fully_sharded":
         from code2vec_b200.trainer import target_row_block
         for r, res in ((0, r0), (1, r1)):
-            lo, hi = target_row_block(DIMS.target_vocab, r, 2)
+            if r >= world:
+                continue
+            lo, hi = target_row_block(DIMS.target_vocab, r, world)
             assert np.abs(res["tgt"][:hi - lo] - ref["tgt"][lo:hi]).max() < tol, r
         assert abs(float(r0["losses"][0]) - float(r1["losses"][0])) < 1e-6      # the loss is global here
     if schedule in ("table_sharded", "fully_sharded"):
-        # row r of the global table lives on rank r % 2 at local row r // 2
+        # row r of the global table lives on rank r % world at local row r // world
         for r, res in ((0, r0), (1, r1)):
+            if r >= world:
+                continue
             for name, shard in (("tok", res["tok_shard"]), ("path", res["path_shard"])):
-                want = ref[name][r::2]
+                want = ref[name][r::world]
                 assert np.abs(shard[:want.shape[0]] - want).max() < tol, (name, r)

@@ -109,6 +109,7 @@ def test_softmax_gradient_computed_inside_the_gradient_gemms(dims, B):
     for fuse in (1, 0):
         eng, params = make_engine(dims, max_batch=B)
         eng.set_option("math_mode", 1)
+        eng.set_option("exp_slab", 0)                # compare against the two-pass schedule that stores logits
         eng.set_option("fuse_softmax_grad", fuse)
         assert eng.get_option("fuse_softmax_grad") == fuse
         loss = float(eng.train_step(*dev_batch(eng, src, pth, tgt, mask, target), keep=1.0).cpu()[0])
@@ -133,6 +134,7 @@ def test_recomputed_logits_schedule_matches_the_stored_one(dims, B, math):
     for rec in (1, 0):
         eng, params = make_engine(dims, max_batch=B)
         eng.set_option("math_mode", math)
+        eng.set_option("exp_slab", 0)                # "the stored one" = the two-pass schedule
         eng.set_option("recompute_logits", rec)
         assert eng.get_option("recompute_logits") == rec
         loss = float(eng.train_step(*dev_batch(eng, src, pth, tgt, mask, target), keep=1.0).cpu()[0])
@@ -144,3 +146,70 @@ def test_recomputed_logits_schedule_matches_the_stored_one(dims, B, math):
     for k in O.PARAM_NAMES:
         assert rel_err(out[1][1][k], out[0][1][k]) < (1e-4 if math == 1 else 2e-6), k
         assert rel_err(out[1][1][k], g_ref[k]) < (1e-2 if math == 1 else 5e-5), k
+
+
+@pytest.mark.parametrize("math", [1, 2])
+@pytest.mark.parametrize("dims,B", [(TINY, 64), (ODD, 37), (MID, 48), (LARGE, 12)])
+def test_deferred_softmax_normalisation_matches_the_two_pass_schedule(dims, B, math):
+    """Option exp_slab (default on in the tensor-core modes): the logits epilogue writes U = exp(s - true logit), the combine
+    kernel patches one element per row and leaves a per-row factor 1/(B sum U) that the dv reduction and dY's small operand
+    apply -- no pass rewrites the slab.  Same gradients as the two-pass schedule (logits stored, then rewritten to
+    (softmax - onehot)/B) up to the rounding of one multiply per element; the loss uses the fp32 true-class logit instead of
+    the tensor-core one, as recompute_logits does.  No step may have needed the device-side fallback."""
+    src, pth, tgt, mask, target = O.synthetic_batch(dims, B, seed=71)
+    out = {}
+    for slab in (1, 0):
+        eng, params = make_engine(dims, max_batch=B)
+        eng.set_option("math_mode", math)
+        eng.set_option("exp_slab", slab)
+        assert eng.get_option("exp_slab") == slab
+        loss = float(eng.train_step(*dev_batch(eng, src, pth, tgt, mask, target), keep=1.0).cpu()[0])
+        out[slab] = (loss, eng.export_grads())
+        assert eng.get_option("exp_slab_fallbacks") == 0
+        eng.close()
+    assert abs(out[1][0] - out[0][0]) < (2e-4 if math == 1 else 2e-6)
+    loss_ref, g_ref, _ = O.train_loss_and_grads(params, src, pth, tgt, mask, target)
+    assert abs(out[1][0] - loss_ref) < (1e-4 if math == 1 else 5e-6)
+    for k in O.PARAM_NAMES:
+        assert rel_err(out[1][1][k], out[0][1][k]) < (2e-3 if math == 1 else 2e-5), k
+        assert rel_err(out[1][1][k], g_ref[k]) < (1e-2 if math == 1 else 5e-5), k
+
+
+@pytest.mark.parametrize("math", [1, 2])
+def test_exp_slab_falls_back_on_the_device_when_a_row_leaves_the_fp32_window(math):
+    """Logits hundreds of units apart: exp(s - true logit) overflows fp32 for some rows, the combine kernel raises the range
+    flag and the gated kernels behind it redo the step's softmax as the two-pass schedule -- so the step's loss and
+    gradients are exactly those of an engine with exp_slab off.  The flag is per step: the next step, on ordinary
+    parameters, runs the deferred schedule again (the fallback counter stays at 1)."""
+    dims, B = ODD, 37
+    src, pth, tgt, mask, target = O.synthetic_batch(dims, B, seed=81)
+    wild = O.init_params(dims, seed=9)
+    v, _, _ = O.forward(wild, src, pth, tgt, mask)
+    spread = np.abs(O.logits_of(wild, v)).max()
+    wild["tgt"] = (wild["tgt"] * np.float32(400.0 / spread)).astype(np.float32)       # logits up to +-400
+    lg = O.logits_of(wild, v)
+    assert (lg.max(axis=1) - lg[np.arange(B), target]).max() > 100
+    calm = O.init_params(dims, seed=10)
+    out = {}
+    for slab in (1, 0):
+        eng, _ = make_engine(dims, max_batch=B, params=wild)
+        eng.set_option("math_mode", math)
+        eng.set_option("exp_slab", slab)
+        batch = dev_batch(eng, src, pth, tgt, mask, target)
+        loss = float(eng.train_step(*batch, keep=1.0).cpu()[0])
+        g = eng.export_grads()
+        assert eng.get_option("exp_slab_fallbacks") == slab
+        eng.load_params(calm)
+        loss2 = float(eng.train_step(*batch, keep=1.0).cpu()[0])
+        g2 = eng.export_grads()
+        assert eng.get_option("exp_slab_fallbacks") == slab
+        out[slab] = (loss, g, loss2, g2)
+        eng.close()
+    assert np.isfinite(out[1][0]) and out[1][0] == out[0][0]
+    for k in ("tgt", "W", "a"):
+        assert np.array_equal(out[1][1][k], out[0][1][k]), k
+    for k in ("tok", "path"):                    # float atomics: the same addends in whatever order
+        assert rel_err(out[1][1][k], out[0][1][k]) < 1e-5, k
+    assert abs(out[1][2] - out[0][2]) < (2e-4 if math == 1 else 2e-6)
+    for k in O.PARAM_NAMES:
+        assert rel_err(out[1][3][k], out[0][3][k]) < (2e-3 if math == 1 else 2e-5), k
