@@ -132,7 +132,7 @@ def shard_bounds(n: int, rank: int, world: int):
 class Trainer:
     def __init__(self, engine: PathAttentionEngine, keep_prob: float = 0.75, seed: int = 0, group=None,
                  adam: Optional[dict] = None, schedule: str = "table_sharded", lazy_adam: bool = True,
-                 fuse_target_adam: bool = True, push_grads: bool = False):
+                 fuse_target_adam: bool = True, push_grads: bool = False, allow_single_rank: bool = False):
         self.e = engine
         self.keep = float(keep_prob)
         self.seed = int(seed)
@@ -140,10 +140,14 @@ class Trainer:
         self.adam = dict(ADAM_DEFAULTS, **(adam or {}))
         torch = engine.torch
         dist = _dist()
-        self.world = dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
+        grouped = dist.is_available() and dist.is_initialized()
+        self.world = dist.get_world_size(group) if grouped else 1
         self.rank = dist.get_rank(group) if self.world > 1 else 0
-        self.schedule = schedule if self.world > 1 else "single"
-        if self.schedule in ("table_sharded", "fully_sharded") and self.world not in (2, 4, 8):
+        # allow_single_rank: keep the fully sharded schedule (IPC-homed tables, phase-split entry points, collectives) in a
+        # process group of ONE rank -- no use in production, but it lets a one-GPU box run that whole code path
+        self.multi = self.world > 1 or (allow_single_rank and grouped and schedule == "fully_sharded")
+        self.schedule = schedule if self.multi else "single"
+        if self.schedule in ("table_sharded", "fully_sharded") and self.world not in (1, 2, 4, 8):
             self.schedule = "sharded"
         if self.schedule == "fully_sharded":
             if not hasattr(engine, "target_row0"):
@@ -162,7 +166,7 @@ class Trainer:
             self._small = (small0, total)
         B, C = engine.dims.max_batch, engine.dims.max_contexts
         self._dev = None
-        if self.world > 1:
+        if self.multi:
             i32, f32 = torch.int32, torch.float32
             self._dev = dict(src=torch.empty((B, C), dtype=i32, device=engine.dev),
                              path=torch.empty((B, C), dtype=i32, device=engine.dev),
@@ -347,7 +351,7 @@ class Trainer:
         """One training step on HOST buffers (numpy / pinned tensors); returns the loss (synchronises).
         next_batch: optional host (src, path, tgt) of the following batch (see step_device)."""
         e = self.e
-        if self.world == 1:
+        if not self.multi:
             if next_batch is not None and self.fuse_tgt:
                 e.hint_next_batch_host(*next_batch[:3])
             return e.train_batch_host(src, path, tgt, mask, target, keep=self.keep, seed=self.seed, **self.adam)

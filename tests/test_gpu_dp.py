@@ -35,7 +35,8 @@ def _worker(rank, world, port, schedule, math_mode, out_dir):
         eng = PathAttentionEngine(gdims, device=rank, training=True)
         eng.load_params(full)
     eng.set_option("math_mode", math_mode)
-    tr = Trainer(eng, keep_prob=1.0, seed=0, schedule=schedule)
+    tr = Trainer(eng, keep_prob=1.0, seed=0, schedule=schedule, allow_single_rank=True)
+    assert tr.schedule == schedule
     src, pth, tgt, mask, target = O.synthetic_batch(DIMS, B_LOCAL * world, seed=77)
     lo, hi = rank * B_LOCAL, (rank + 1) * B_LOCAL
     losses = []
