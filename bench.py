@@ -402,10 +402,6 @@ def run_ours(args):
                             terms=3 if args.math == "3xtf32" else 1,
                             remote_frac=(world - 1.0) / world if sharded_tables else 0.0,
                             sweep_period=int(eng.get_option("adam_sweep_period")) if lazy_on else 0)
-    if world == 1 and mode == "train" and tc and eng.get_option("exp_slab") and not args.fuse_softmax_grad and args.recompute_logits <= 0:
-        # deferred normalisation: no pass over the slab -- the phase is B true-class rows, the per-tile partials and B patches
-        n_part = 2 * ((w["target_vocab"] + 255) // 256)
-        work["xent"] = ("hbm", 4.0 * B * (w["code_dim"] * 3 + 2 * n_part + 8))
     if schedule == "fully_sharded":
         # each rank runs the context side on its own B bags and the target side on its 1/world of the classes for all world*B
         w_local = dict(w, target_vocab=(w["target_vocab"] + world - 1) // world)
@@ -414,6 +410,13 @@ def run_ours(args):
         ctx_side = algorithmic_work(w, B, world=world, remote_frac=(world - 1.0) / world)
         work = dict(ctx_side, **{k: tgt_side[k] for k in ("logits", "dv", "dY", "xent", "split")})
         work["adam"] = ("hbm", 24.0 * ((w["token_vocab"] + w["path_vocab"]) * w["embed_dim"]) / world)
+    slab_on = (mode == "train" and tc and bool(eng.get_option("exp_slab")) and not args.fuse_softmax_grad and
+               (schedule == "fully_sharded" or (world == 1 and args.recompute_logits <= 0)))
+    if slab_on:
+        # deferred normalisation: no pass over the slab -- the phase is the true-class rows, the per-tile partials and the patches
+        rows = B * (world if schedule == "fully_sharded" else 1)
+        y_loc = (w["target_vocab"] + world - 1) // world if schedule == "fully_sharded" else w["target_vocab"]
+        work["xent"] = ("hbm", 4.0 * rows * (w["code_dim"] * 3 + 2 * 2 * ((y_loc + 255) // 256) + 8))
     traffic = ncu_traffic()
     phase_out = {}
     dominant, dom_ms = None, -1.0
@@ -492,7 +495,7 @@ def run_ours(args):
                    "l2": "no flush: >9 GB of parameter/optimizer traffic per step and %d rotating input batches exceed the 126 MB L2" % n_batches,
                    "math_mode": args.math, "fused_target_adam": fused, "lazy_adam": lazy_on,
                    "adam_sweep_period": int(eng.get_option("adam_sweep_period")) if lazy_on else None,
-                   "exp_slab": bool(eng.get_option("exp_slab")) and world == 1 and mode == "train" and args.math != "fp32",
+                   "exp_slab": slab_on,
                    "exp_slab_fallbacks": int(eng.get_option("exp_slab_fallbacks")),
                    "next_batch_hint": bool(world == 1 and args.hint and fused), "last_loss": round(last_loss, 5),
                    "inputs": "%s bags, %s indices; all %d slots per example are counted in the metric" % (

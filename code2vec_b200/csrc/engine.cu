@@ -189,6 +189,7 @@ struct c2v_engine {
                              // dv / dY GEMMs, so no pass re-reads the slab to turn logits into dL/dlogits.  Rows
                              // outside the fp32 window make that step fall back, on the device, to the two-pass schedule.
   bool slab_flag_zeroed = false;
+  bool slab_exp_live = false;         // c2v_target_forward left U (not logits) in the slab: c2v_target_backward finishes that schedule
   int gather_occ[2] = {0, 0};         // resident CTAs per SM of gather_ctx_kernel<false / true>, queried once
   int adam_epi_prefetch = 0; // option "adam_epilogue_prefetch" (measured slower, off): the dY epilogue's Adam update prefetches its (theta, m, v)
                              // lines into L2 one tile ahead
@@ -1711,11 +1712,40 @@ int c2v_target_forward(c2v_engine* e, const float* code_all, int32_t Bt, const i
   float* S = wsp<float>(e, e->ws.S);
   const int Y = e->dims.target_vocab;
   const bool fused = (is_tc(e)) && (reinterpret_cast<uintptr_t>(code_all) % 16 == 0);
+  const int n_tiles = 2 * ((Y + 255) / 256);
+  e->slab_exp_live = false;
+  if (fused && e->exp_slab && !e->fuse_sg && e->has_grad) {
+    // deferred normalisation over a row-sharded table: (c_b, sum U) stand in for (row max, sum exp) in the cross-rank combine
+    float* tl = wsp<float>(e, e->ws.true_logit);
+    int* flag = wsp<int>(e, e->ws.slab_flag);
+    if (!e->slab_flag_zeroed) {
+      C2V_CUDA(e, cudaMemsetAsync(flag, 0, 64, st));
+      e->slab_flag_zeroed = true;
+    }
+    {
+      PhaseTimer pt(e, PH_XENT, st);
+      C2V_LAUNCH(e, (true_logit_kernel<<<(Bt + 7) / 8, 256, 0, st>>>(code_all, e->theta.tgt, target, row_offset, Y, e->dims.code_dim, Bt, tl, flag)));
+      C2V_CUDA(e, cudaMemcpyAsync(true_logit, tl, (size_t)Bt * 4, cudaMemcpyDeviceToDevice, st));
+    }
+    if ((rc = run_logits(e, st, code_all, Bt, S, false, false, nullptr, tl))) return rc;
+    {
+      PhaseTimer pt(e, PH_XENT, st);
+      C2V_LAUNCH(e, (expsum_rows_kernel<<<Bt, 256, 0, st>>>(wsp<float2>(e, e->ws.lse_part), n_tiles, tl, row_max, row_sum, flag)));
+    }
+    // a row left the fp32 window: the statistics that go to the other ranks are redone the classic way (gated, usually a no-op)
+    if ((rc = run_logits(e, st, code_all, Bt, S, true, false, nullptr, nullptr, flag))) return rc;
+    {
+      PhaseTimer pt(e, PH_XENT, st);
+      C2V_LAUNCH(e, (row_maxsum_kernel<<<Bt, 256, 0, st>>>(wsp<float2>(e, e->ws.lse_part), n_tiles, S, e->ws.ldS, Y, target, row_offset, row_max,
+                                                           row_sum, true_logit, 1, flag)));
+    }
+    e->slab_exp_live = true;
+    return C2V_OK;
+  }
   if ((rc = run_logits(e, st, code_all, Bt, S, fused))) return rc;
   PhaseTimer pt(e, PH_XENT, st);
-  C2V_LAUNCH(e, (row_maxsum_kernel<<<Bt, 256, 0, st>>>(fused ? wsp<float2>(e, e->ws.lse_part) : nullptr,
-                                                       2 * ((Y + 255) / 256), S, e->ws.ldS, Y, target, row_offset, row_max,
-                                                       row_sum, true_logit)));
+  C2V_LAUNCH(e, (row_maxsum_kernel<<<Bt, 256, 0, st>>>(fused ? wsp<float2>(e, e->ws.lse_part) : nullptr, n_tiles, S, e->ws.ldS, Y, target,
+                                                       row_offset, row_max, row_sum, true_logit)));
   return C2V_OK;
 }
 
@@ -1740,6 +1770,35 @@ int c2v_target_backward(c2v_engine* e, const float* code_all, int32_t Bt, const 
   C2V_CUDA(e, cudaSetDevice(e->device));
   cudaStream_t st = (cudaStream_t)stream;
   float* S = wsp<float>(e, e->ws.S);
+  if (e->slab_exp_live) {
+    // the slab holds U = exp(s - c_b): patch the true-class elements, hand the rows' factors to the two GEMMs
+    e->slab_exp_live = false;
+    e->sg_live = false;
+    const int Y = e->dims.target_vocab, D = e->dims.code_dim;
+    float* tl = wsp<float>(e, e->ws.true_logit);
+    float* rscale = wsp<float>(e, e->ws.rscale);
+    float* vs = wsp<float>(e, e->ws.v_scaled);
+    int* flag = wsp<int>(e, e->ws.slab_flag);
+    float* S_lo = is_3x(e) ? wsp<float>(e, e->ws.S_lo) : nullptr;
+    {
+      PhaseTimer pt(e, PH_XENT, st);
+      C2V_LAUNCH(e, (expsum_finish_kernel<<<(Bt + 255) / 256, 256, 0, st>>>(S, S_lo, e->ws.ldS, Y, target, row_offset, tl, lse, inv_batch, Bt, rscale, flag)));
+    }
+    // fallback (gated): logits again, then the classic rewrite with the global log-sum-exp; the rows' factors become 1
+    if ((rc = run_logits(e, st, code_all, Bt, S, true, false, nullptr, nullptr, flag))) return rc;
+    {
+      PhaseTimer pt(e, PH_XENT, st);
+      if (S_lo) C2V_LAUNCH(e, (softmax_grad_kernel<true><<<dim3(2, Bt), 256, 0, st>>>(S, e->ws.ldS, Y, lse, target, inv_batch, row_offset, S_lo, flag, rscale,
+                                                                                    reinterpret_cast<unsigned*>(flag) + 1)));
+      else C2V_LAUNCH(e, (softmax_grad_kernel<false><<<dim3(2, Bt), 256, 0, st>>>(S, e->ws.ldS, Y, lse, target, inv_batch, row_offset, nullptr, flag, rscale,
+                                                                                 reinterpret_cast<unsigned*>(flag) + 1)));
+      C2V_LAUNCH(e, (scale_rows_kernel<<<(unsigned)(((size_t)Bt * D + 255) / 256), 256, 0, st>>>(code_all, rscale, vs, D, (size_t)Bt * D)));
+    }
+    e->row_scale = rscale;
+    rc = target_grad_gemms(e, st, vs, Bt, dv_partial);
+    e->row_scale = nullptr;
+    return rc;
+  }
   {
     PhaseTimer pt(e, PH_XENT, st);
     const int chunks = (int)((e->ws.ldS / 4 + 256 * 8 - 1) / (256 * 8));

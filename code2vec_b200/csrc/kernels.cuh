@@ -371,13 +371,66 @@ scale_rows_kernel(const float* x, const float* __restrict__ f, float* out, int D
   if (i < n) out[i] = x[i] * f[i / D];
 }
 
+// exp_slab with a row-sharded target table (fully sharded schedule): this rank's slab holds U = exp(s - c_b) for its own classes,
+// c_b = the example's true-class logit if that class lives here, else 0.  expsum_rows_kernel hands (c_b, sum U) to the
+// cross-rank log-sum-exp in place of (row max, sum exp) -- the combine is the same formula -- and raises *bad when a row's
+// largest U left the fp32 window.  One CTA per row.
+__global__ void __launch_bounds__(256)
+expsum_rows_kernel(const float2* __restrict__ partial, int n_tiles, const float* __restrict__ offset, float* __restrict__ row_max,
+                   float* __restrict__ row_sum, int* __restrict__ bad) {
+  __shared__ float red[32];
+  const int b = blockIdx.x;
+  const float2* p = partial + (size_t)b * n_tiles;
+  float m = 0.f, s = 0.f;
+  for (int i = threadIdx.x; i < n_tiles; i += 256) {
+    const float2 q = p[i];
+    m = fmaxf(m, q.x);
+    s += q.y;
+  }
+  const float M = block_max(m, red);
+  s = block_sum(s, red);
+  if (threadIdx.x == 0) {
+    if (!(M >= kExpSlabMin && M <= kExpSlabMax && s <= 3.0e38f)) *bad = 1;
+    row_max[b] = offset[b];
+    row_sum[b] = s;
+  }
+}
+// ... and once the global log-sum-exp is known: softmax - onehot = f_b (U - [j == y_b] / f_b) with f_b = exp(c_b - lse_b); the one
+// element is patched here and f_b / B becomes the row's factor for the gradient GEMMs.  A factor outside fp32's comfortable
+// range raises *bad as well (the gated two-pass kernels behind this one then rebuild the slab).  One thread per row.
+__global__ void __launch_bounds__(256)
+expsum_finish_kernel(float* __restrict__ U, float* __restrict__ U_lo, size_t ldS, int Y, const int32_t* __restrict__ target, int row0,
+                     const float* __restrict__ offset, const float* __restrict__ lse, float inv_batch, int Bt,
+                     float* __restrict__ rscale, int* __restrict__ bad) {
+  const int b = blockIdx.x * 256 + threadIdx.x;
+  if (b >= Bt || *bad) return;
+  const float d = offset[b] - lse[b];
+  if (!(d > -80.f && d < 80.f)) { *bad = 1; return; }
+  rscale[b] = inv_batch * expf(d);
+  const int y = target[b] - row0;
+  if (y >= 0 && y < Y) {
+    const size_t at = (size_t)b * ldS + y;
+    const float back = expf(-d);
+    if (U_lo) {
+      float hi, lo;
+      split_tf32((U[at] + U_lo[at]) - back, hi, lo);
+      U[at] = hi; U_lo[at] = lo;
+    } else {
+      U[at] -= back;
+    }
+  }
+}
+
 // S <- (softmax(S) - onehot(target)) * inv_batch in place, padding columns zeroed.  grid (chunks, B).
 template <bool SPLIT>
 __global__ void __launch_bounds__(256)
 softmax_grad_kernel(float* __restrict__ S, size_t ldS, int Y, const float* __restrict__ lse, const int32_t* __restrict__ target,
-                    float inv_batch, int row0, float* __restrict__ S_lo, const int* __restrict__ gate = nullptr) {
+                    float inv_batch, int row0, float* __restrict__ S_lo, const int* __restrict__ gate = nullptr,
+                    float* __restrict__ rscale_one = nullptr, unsigned* __restrict__ gate_count = nullptr) {
   // SPLIT (3xTF32): the gradient is written as its tf32 split (high parts over S, residuals into S_lo)
   if (gate && *gate == 0) return;        // fallback pass of the exp_slab schedule: not needed this step
+  if (rscale_one && blockIdx.x == 0 && threadIdx.x == 0) rscale_one[blockIdx.y] = 1.f;     // the slab will hold the finished gradient
+  if (gate_count && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) *gate_count += 1u;
   const int b = blockIdx.y;
   float* row = S + (size_t)b * ldS;
   const float l = lse[b];
@@ -515,8 +568,10 @@ sampled_softmax_bwd_kernel(const float* __restrict__ v, const float* __restrict_
 __global__ void __launch_bounds__(256)
 row_maxsum_kernel(const float2* __restrict__ partial, int slots, const float* __restrict__ S, size_t ldS, int Y,
                   const int32_t* __restrict__ target, int row0, float* __restrict__ row_max, float* __restrict__ row_sum,
-                  float* __restrict__ true_logit, int have_true_logit = 0) {
+                  float* __restrict__ true_logit, int have_true_logit = 0, const int* __restrict__ gate = nullptr) {
   // have_true_logit: true_logit[] was already filled by true_logit_kernel (the slab holds no logits)
+  // gate: fallback launch of the exp_slab schedule, a no-op while *gate == 0
+  if (gate && *gate == 0) return;
   __shared__ float red[32];
   const int b = blockIdx.x;
   const float* row = S + (size_t)b * ldS;

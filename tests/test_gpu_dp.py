@@ -15,7 +15,18 @@ DIMS = O.Dims(token_vocab=2003, path_vocab=1009, target_vocab=3001, embed_dim=32
 B_LOCAL = 32
 
 
-def _worker(rank, world, port, schedule, math_mode, out_dir):
+def _params(wild):
+    """wild: the target table scaled until logits reach +-400 -- exp(s - true logit) overflows fp32 and every step of the
+    exp_slab schedule must take its device-side fallback."""
+    full = O.init_params(DIMS, seed=4321)
+    if wild:
+        src, pth, tgt, mask, _ = O.synthetic_batch(DIMS, B_LOCAL, seed=77)
+        v, _, _ = O.forward(full, src, pth, tgt, mask)
+        full["tgt"] = (full["tgt"] * np.float32(400.0 / np.abs(O.logits_of(full, v)).max())).astype(np.float32)
+    return full
+
+
+def _worker(rank, world, port, schedule, math_mode, out_dir, wild=False):
     import torch
     import torch.distributed as dist
     os.environ["MASTER_ADDR"] = "127.0.0.1"
@@ -26,7 +37,7 @@ def _worker(rank, world, port, schedule, math_mode, out_dir):
     from code2vec_b200.trainer import Trainer, make_fully_sharded_engine, target_row_block
     gdims = EngineDims(DIMS.token_vocab, DIMS.path_vocab, DIMS.target_vocab, DIMS.embed_dim, DIMS.code_dim,
                        DIMS.max_contexts, B_LOCAL, 10)
-    full = O.init_params(DIMS, seed=4321)
+    full = _params(wild)
     if schedule == "fully_sharded":
         eng = make_fully_sharded_engine(gdims, B_LOCAL, device=rank)
         r0, r1 = target_row_block(DIMS.target_vocab, rank, world)
@@ -43,6 +54,7 @@ def _worker(rank, world, port, schedule, math_mode, out_dir):
     for _ in range(3):
         losses.append(tr.step_host(src[lo:hi], pth[lo:hi], tgt[lo:hi], mask[lo:hi], target[lo:hi]))
     out = eng.export_params()
+    out["fallbacks"] = np.array(eng.get_option("exp_slab_fallbacks"))
     if schedule in ("table_sharded", "fully_sharded"):
         sh = eng.export_table_shards()
         out["tok_shard"], out["path_shard"] = sh["tok"], sh["path"]
@@ -70,12 +82,21 @@ def test_sharded_schedules_on_a_single_rank_match_the_fused_step(tmp_path, sched
     _run_and_compare(tmp_path, schedule, math_mode, world=1)
 
 
-def _run_and_compare(tmp_path, schedule, math_mode, world):
+def test_sharded_exp_slab_fallback_on_a_single_rank(tmp_path):
+    """Logits far outside exp()'s fp32 range: the row-sharded exp_slab schedule must notice on the device (forward: the
+    statistics sent to the other ranks are redone; backward: the slab is rebuilt by the two-pass kernels) in all 3 steps
+    and still match the single engine, which takes its own fallback."""
+    _run_and_compare(tmp_path, "fully_sharded", 2, world=1, wild=True)
+
+
+def _run_and_compare(tmp_path, schedule, math_mode, world, wild=False):
     import torch.multiprocessing as mp
     port = 29500 + (os.getpid() % 1000)
     # tf32: an element whose tiny gradient changes sign moves the other way by a full Adam step (1e-3) in each of the 3 steps
     tol = {0: 5e-5, 1: 8e-3, 2: 2e-4}[math_mode]
-    mp.spawn(_worker, args=(world, port, schedule, math_mode, str(tmp_path)), nprocs=world, join=True)
+    if wild:
+        tol = 7e-3       # near-one-hot softmax: many gradients are rounding noise whose sign Adam amplifies to a full step
+    mp.spawn(_worker, args=(world, port, schedule, math_mode, str(tmp_path), wild), nprocs=world, join=True)
     r0 = np.load(str(tmp_path / "rank0.npz"))
     r1 = np.load(str(tmp_path / "rank1.npz")) if world > 1 else r0
     replicated = {"table_sharded": ("tgt", "W", "a"), "fully_sharded": ("W", "a")}.get(schedule, O.PARAM_NAMES)
@@ -83,10 +104,16 @@ def _run_and_compare(tmp_path, schedule, math_mode, world):
         assert np.array_equal(r0[k], r1[k]), "replicas diverged on %s" % k
     # single engine on the global batch (mean loss over 2*B_LOCAL == average of the two local means)
     from tests.util import make_engine
-    eng, _ = make_engine(DIMS, max_batch=B_LOCAL * world)
+    if schedule == "fully_sharded" and math_mode:
+        assert int(r0["fallbacks"]) == (3 if wild else 0)
+    eng, _ = make_engine(DIMS, max_batch=B_LOCAL * world, params=_params(wild))
+    eng.set_option("math_mode", math_mode)
     src, pth, tgt, mask, target = O.synthetic_batch(DIMS, B_LOCAL * world, seed=77)
-    for _ in range(3):
-        eng.train_batch_host(src, pth, tgt, mask, target, keep=1.0)
+    ref_losses = [eng.train_batch_host(src, pth, tgt, mask, target, keep=1.0) for _ in range(3)]
+    if wild:
+        assert eng.get_option("exp_slab_fallbacks") == 3
+    if schedule == "fully_sharded":          # its loss is the global one
+        assert abs(float(r0["losses"][0]) - ref_losses[0]) < 2e-3 * max(1.0, abs(ref_losses[0]))
     ref = eng.export_params()
     for k in replicated:
         assert np.abs(r0[k] - ref[k]).max() < tol, k
