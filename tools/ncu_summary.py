@@ -13,8 +13,9 @@ import sys
 
 # kernel name fragment -> bench.py phase
 PHASE_OF = [("gather_ctx", "gather"), ("gather_sorted", "gather"), ("ctx_fused", "ctx_fwd"), ("EpiTanhStore", "ctx_fwd"),
-            ("attn_fwd", "attn_fwd"), ("EpiStoreLse", "logits"), ("umma_gemm2_kernel<192, 6, 0, 1, umma::EpiStore>", "dv"),
-            ("umma_gemm2_kernel<192, 6, 0, 0, umma::EpiStore>", "dx_gemm"), ("umma_gemm_kernel<192, 4, 1, 1, umma::EpiStore>", "dW"), ("xent_combine", "xent"), ("softmax_grad", "xent"),
+            ("attn_fwd", "attn_fwd"), ("EpiExpSum", "logits"), ("EpiStoreLse", "logits"), ("expsum_", "xent"), ("true_logit", "xent"),
+            ("scale_rows", "xent"), ("umma_gemm2_kernel<192, 6, 0, 1, umma::EpiStore>", "dv"),
+            ("umma_gemm2_kernel<192, 6, 0, 0, umma::EpiStore>", "dx_gemm"), ("umma_gemm_kernel<192, 4, 1, 1, umma::EpiStore,", "dW"), ("xent_combine", "xent"), ("softmax_grad", "xent"),
             ("EpiAdam", "dY"), ("attn_bwd", "attn_bwd"), ("scatter_dx", "dx_scatter"), ("scatter_sorted", "dx_scatter"),
             ("scatter_inbox", "dx_scatter"), ("inbox_apply", "dx_scatter"), ("adam_rows", "adam_catchup"),
             ("mark_rows", "adam_catchup"), ("adam_sweep", "adam_sweep"), ("split_tf32", "split")]
