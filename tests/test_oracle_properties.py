@@ -110,3 +110,25 @@ def test_repeated_contexts_sum_their_gradients_and_the_token_table_is_shared():
     fd = (loss_tok(eps * direction) - loss_tok(-eps * direction)) / (2 * eps)
     assert abs(fd - g["tok"][5] @ direction) < 1e-8
     assert np.abs(g["tok"][5]).max() > 0 and np.all(g["tok"][11] == 0)   # an unreferenced row gets exactly nothing
+
+
+def test_attention_backward_needs_no_first_pass_over_the_bag():
+    """attn_bwd_kernel (csrc/kernels.cuh) reads H once: the bag-wide term t = sum_c alpha_c (h_c . dv) of the softmax
+    backward equals v . dv with the code vector v = sum_c alpha_c h_c the forward pass already produced.  Checked on the
+    oracle's own forward quantities, ragged bags included, in fp32 -- the two summation orders differ by rounding only."""
+    dims = O.Dims(token_vocab=301, path_vocab=211, target_vocab=97, embed_dim=12, code_dim=36, max_contexts=17)
+    params = O.init_params(dims, seed=11)
+    src, pth, tgt, mask, target = O.synthetic_batch(dims, 29, seed=12)
+    v, alpha, cache = O.forward(params, src, pth, tgt, mask)
+    logits = O.logits_of(params, v)
+    _, dv = O.backward(params, src, pth, tgt, mask, target, cache, v, logits)
+    h = cache.h.reshape(src.shape[0], src.shape[1], -1)
+    t_two_pass = (alpha * np.einsum("bcd,bd->bc", h, dv)).sum(axis=1)
+    t_one_pass = np.einsum("bd,bd->b", v, dv)
+    assert np.abs(t_one_pass - t_two_pass).max() <= 4e-7 * max(np.abs(t_two_pass).max(), 1e-30) + 1e-12
+    # ... and the gradient of the attention vector built from it is the oracle's
+    dalpha = np.einsum("bcd,bd->bc", h, dv)
+    dz = alpha * (dalpha - t_one_pass[:, None])
+    g_a = np.einsum("bc,bcd->d", dz, h)
+    ref, _ = O.backward(params, src, pth, tgt, mask, target, cache, v, logits)
+    assert np.abs(g_a - ref["a"]).max() <= 1e-5 * np.abs(ref["a"]).max() + 1e-12
