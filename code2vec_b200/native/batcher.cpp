@@ -10,8 +10,10 @@
 #include <stdint.h>
 #include <string.h>
 
+#include <algorithm>
 #include <atomic>
 #include <thread>
+#include <functional>
 #include <vector>
 
 namespace {
@@ -263,6 +265,78 @@ int64_t c2v_parse_chunk(const char* text, int64_t len, int32_t max_contexts, con
     return -(lineno[(size_t)J.bad_line.load()] + 1);
   }
   return n;
+}
+
+// Shuffle-pool draw (path_context_reader._RowPool.take) over the five parallel row arrays of the pool -- src / path / dst [cap, C]
+// int32, mask [cap, C] float32, target [cap] int32, of which rows [0, n) are live.  Rows pick[0..b) are copied to the out buffers in
+// pick order; the holes they leave below the new end n - b are then filled with the surviving rows of the tail [n - b, n), both in
+// ascending order -- the numpy statement is  holes = flatnonzero(chosen[:n-b]); movers = n-b + flatnonzero(~chosen[n-b:]);
+// a[holes] = a[movers].  Row copies are spread over n_threads.  Returns 0, or -1 if pick is not b distinct indices in [0, n).
+int32_t c2v_pool_take(int32_t* src, int32_t* path, int32_t* dst, float* mask, int32_t* target, int64_t n, int32_t C,
+                      const int64_t* pick, int32_t b, int32_t* o_src, int32_t* o_path, int32_t* o_dst, float* o_mask,
+                      int32_t* o_target, int32_t n_threads) {
+  if (b < 0 || b > n || C < 1) return -1;
+  std::vector<uint8_t> chosen((size_t)n, 0);
+  for (int32_t i = 0; i < b; ++i) {
+    const int64_t r = pick[i];
+    if (r < 0 || r >= n || chosen[(size_t)r]) return -1;
+    chosen[(size_t)r] = 1;
+  }
+  const int64_t new_n = n - b;
+  std::vector<int64_t> holes, movers;
+  holes.reserve((size_t)b);
+  movers.reserve((size_t)b);
+  for (int64_t r = 0; r < new_n; ++r)
+    if (chosen[(size_t)r]) holes.push_back(r);
+  for (int64_t r = new_n; r < n; ++r)
+    if (!chosen[(size_t)r]) movers.push_back(r);
+  const size_t row = (size_t)C * 4;
+  if (n_threads < 1) n_threads = 1;
+  if (n_threads > 16) n_threads = 16;
+  auto spread = [&](int64_t count, const std::function<void(int64_t, int64_t)>& body) {
+    const int t_n = (int)std::min<int64_t>(n_threads, std::max<int64_t>(count / 64, 1));
+    if (t_n <= 1) { body(0, count); return; }
+    std::vector<std::thread> th;
+    for (int t = 0; t < t_n; ++t) th.emplace_back(body, count * t / t_n, count * (t + 1) / t_n);
+    for (auto& x : th) x.join();
+  };
+  // the copies are random 4 x (C * 4)-byte rows out of tens of MB: latency-bound, so the rows a few iterations ahead are
+  // prefetched (every cache line of them) while the current one is copied
+  auto prefetch_row = [&](size_t r) {
+    for (size_t o = 0; o < row; o += 64) {
+      __builtin_prefetch((const char*)(src + r * C) + o);
+      __builtin_prefetch((const char*)(path + r * C) + o);
+      __builtin_prefetch((const char*)(dst + r * C) + o);
+      __builtin_prefetch((const char*)(mask + r * C) + o);
+    }
+  };
+  constexpr int64_t kAhead = 4;
+  spread(b, [&](int64_t lo, int64_t hi) {
+    for (int64_t i = lo; i < std::min(lo + kAhead, hi); ++i) prefetch_row((size_t)pick[i]);
+    for (int64_t i = lo; i < hi; ++i) {
+      if (i + kAhead < hi) prefetch_row((size_t)pick[i + kAhead]);
+      const size_t r = (size_t)pick[i];
+      memcpy(o_src + (size_t)i * C, src + r * C, row);
+      memcpy(o_path + (size_t)i * C, path + r * C, row);
+      memcpy(o_dst + (size_t)i * C, dst + r * C, row);
+      memcpy(o_mask + (size_t)i * C, mask + r * C, row);
+      o_target[i] = target[r];
+    }
+  });
+  // every picked row has been copied out before any hole is overwritten (spread() joins its threads)
+  spread((int64_t)holes.size(), [&](int64_t lo, int64_t hi) {
+    for (int64_t i = lo; i < std::min(lo + kAhead, hi); ++i) prefetch_row((size_t)movers[(size_t)i]);
+    for (int64_t i = lo; i < hi; ++i) {
+      if (i + kAhead < hi) prefetch_row((size_t)movers[(size_t)(i + kAhead)]);
+      const size_t h = (size_t)holes[(size_t)i], m = (size_t)movers[(size_t)i];
+      memcpy(src + h * C, src + m * C, row);
+      memcpy(path + h * C, path + m * C, row);
+      memcpy(dst + h * C, dst + m * C, row);
+      memcpy(mask + h * C, mask + m * C, row);
+      target[h] = target[m];
+    }
+  });
+  return 0;
 }
 
 }  // extern "C"

@@ -52,6 +52,9 @@ def load_native_tensoriser():
             lib.c2v_vocab_destroy.argtypes = [P]
             lib.c2v_vocab_lookup.restype = I32
             lib.c2v_vocab_lookup.argtypes = [P, C.c_char_p, I64]
+            if hasattr(lib, "c2v_pool_take"):
+                lib.c2v_pool_take.restype = I32
+                lib.c2v_pool_take.argtypes = [P, P, P, P, P, I64, I32, P, I32, P, P, P, P, P, I32]
             lib.c2v_parse_chunk.restype = I64
             lib.c2v_parse_chunk.argtypes = [P, I64, I32, P, P, P, I32, I32, I64, P, P, P, P, P, P, P, P, C.POINTER(I32)]
             _native_lib = lib
@@ -457,7 +460,8 @@ class PathContextReader:
         # train: a pool of at least SHUFFLE_BUFFER_SIZE rows; every batch is a uniform draw without
         # replacement from the pool (tf.data's shuffle(buffer) draws the same way, one row at a time)
         S = max(int(self.config.SHUFFLE_BUFFER_SIZE), 1)
-        pool = _RowPool()
+        # one thread: the draw is ~8 MB of random row copies per batch and thread start-up cost more than it saved when measured
+        pool = _RowPool(native=self._native[0], threads=1)
         ring = getattr(self, "batch_ring", None)          # PinnedBatchRing: batches are drawn straight into pinned slots
 
         def draw(b):
@@ -499,9 +503,11 @@ class _RowPool:
     """Shuffle pool over parallel row arrays: O(rows appended) to add, O(batch) to draw -- drawn rows are
     replaced by rows from the tail, nothing else moves."""
 
-    def __init__(self):
+    def __init__(self, native=None, threads: int = 1):
         self.arrays = None
         self.n = 0
+        self.native = native if (native is not None and hasattr(native, "c2v_pool_take")) else None     # libc2v_batcher.so
+        self.threads = max(1, int(threads))
 
     def append(self, arrs):
         k = arrs[0].shape[0]
@@ -557,6 +563,17 @@ class _RowPool:
         slot) the rows are gathered into; the views of their first b rows are returned."""
         n = self.n
         pick = rng.choice(n, size=b, replace=False) if b < n else rng.permutation(n)
+        if self.native is not None and self._native_layout(out, b):
+            # one native call, row copies spread over the reader's threads: the same gather and the same hole filling as below
+            if out is None:
+                out = tuple(np.empty((b,) + a.shape[1:], dtype=a.dtype) for a in self.arrays)
+            pick = np.ascontiguousarray(pick, dtype=np.int64)
+            rc = self.native.c2v_pool_take(*(a.ctypes.data for a in self.arrays), n, self.arrays[0].shape[1], pick.ctypes.data, b,
+                                           *(o.ctypes.data for o in out), self.threads)
+            if rc != 0:
+                raise RuntimeError("c2v_pool_take rejected the draw (%d rows of %d)" % (b, n))
+            self.n = n - b
+            return tuple(o[:b] for o in out)
         if out is None:
             out = tuple(a[pick] for a in self.arrays)
         else:
@@ -574,6 +591,27 @@ class _RowPool:
                 a[holes] = a[movers]
         self.n = new_n
         return out
+
+
+    def _native_layout(self, out, b: int) -> bool:
+        """The native draw wants the reader's own column layout: three int32 [*, C] matrices, a float32 [*, C] mask, int32 targets,
+        all C-contiguous, and out buffers (if given) of the same kind with at least b rows."""
+        A = self.arrays
+        if A is None or len(A) != 5:
+            return False
+        C = A[0].shape[1] if A[0].ndim == 2 else -1
+        kinds = (np.int32, np.int32, np.int32, np.float32, np.int32)
+        for i, (a, k) in enumerate(zip(A, kinds)):
+            if a.dtype != k or not a.flags.c_contiguous or (a.ndim != (2 if i < 4 else 1)) or (i < 4 and a.shape[1] != C):
+                return False
+        if out is not None:
+            if len(out) != 5:
+                return False
+            for i, (o, k) in enumerate(zip(out, kinds)):
+                if (not isinstance(o, np.ndarray) or o.dtype != k or not o.flags.c_contiguous or o.shape[0] < b or
+                        o.ndim != (2 if i < 4 else 1) or (i < 4 and o.shape[1] != C)):
+                    return False
+        return True
 
 
 class _BatchDataset:

@@ -173,3 +173,51 @@ def test_many_short_lines_raise_a_clear_error(tmp_path):
         r = PathContextReader(vs, cfg, _Former(), EstimatorAction.Evaluate, use_native=native)
         with pytest.raises(ValueError, match="fields"):
             list(r.get_dataset())
+
+
+@pytest.mark.parametrize("b,threads", [(1, 1), (64, 3), (200, 8), (300, 2)])
+def test_native_pool_draw_is_the_numpy_draw(b, threads):
+    """_RowPool.take through c2v_pool_take (one native call, row copies spread over threads) against its numpy statement:
+    with the same random stream both return the same rows in the same order and leave the same pool behind -- draw after
+    draw, into fresh arrays and into caller-provided (ring slot) buffers, down to an empty pool."""
+    from code2vec_b200.path_context_reader import _RowPool
+    lib = load_native_tensoriser()
+    assert hasattr(lib, "c2v_pool_take")
+    C, n = 7, 300
+    rng = np.random.default_rng(5)
+    rows = (rng.integers(0, 1000, size=(n, C), dtype=np.int32), rng.integers(0, 1000, size=(n, C), dtype=np.int32),
+            rng.integers(0, 1000, size=(n, C), dtype=np.int32), rng.integers(0, 2, size=(n, C)).astype(np.float32),
+            rng.integers(0, 1000, size=n, dtype=np.int32))
+    pools = []
+    for native in (None, lib):
+        p = _RowPool(native=native, threads=threads)
+        p.append(rows)
+        assert (p.native is not None) == (native is not None)
+        pools.append(p)
+    r_np, r_nat = np.random.default_rng(9), np.random.default_rng(9)
+    slot = tuple(np.empty((b,) + a.shape[1:], dtype=a.dtype) for a in rows)
+    step = 0
+    while pools[0].n > 0:
+        k = min(b, pools[0].n)
+        into = slot if step % 2 else None
+        got_np = [x.copy() for x in pools[0].take(k, r_np)]
+        got_nat = [x.copy() for x in pools[1].take(k, r_nat, out=into)]
+        for x, y in zip(got_np, got_nat):
+            assert x.dtype == y.dtype and np.array_equal(x, y)
+        assert pools[0].n == pools[1].n
+        for x, y in zip(pools[0].arrays, pools[1].arrays):
+            assert np.array_equal(x[:pools[0].n], y[:pools[1].n])
+        step += 1
+    assert step == -(-n // b)
+
+
+def test_native_pool_draw_rejects_a_bad_pick():
+    lib = load_native_tensoriser()
+    a = np.zeros((4, 3), dtype=np.int32)
+    m = np.zeros((4, 3), dtype=np.float32)
+    t = np.zeros(4, dtype=np.int32)
+    o, om, ot = np.zeros((2, 3), dtype=np.int32), np.zeros((2, 3), dtype=np.float32), np.zeros(2, dtype=np.int32)
+    for pick in ([1, 1], [0, 4], [-1, 2]):
+        pk = np.asarray(pick, dtype=np.int64)
+        assert lib.c2v_pool_take(a.ctypes.data, a.ctypes.data, a.ctypes.data, m.ctypes.data, t.ctypes.data, 4, 3, pk.ctypes.data, 2,
+                                 o.ctypes.data, o.ctypes.data, o.ctypes.data, om.ctypes.data, ot.ctypes.data, 2) == -1
