@@ -1045,6 +1045,7 @@ int train_step_impl(c2v_engine* e, cudaStream_t st, const int32_t* src, const in
       C2V_CUDA(e, cudaMemsetAsync(flag, 0, 64, st));
       e->slab_flag_zeroed = true;
     }
+    if ((rc = end_target_lazy(e, st))) return rc;      // the true-class rows are read below: every target row must be current
     {
       PhaseTimer pt(e, PH_XENT, st);
       C2V_LAUNCH(e, (true_logit_kernel<<<(B + 7) / 8, 256, 0, st>>>(v, e->theta.tgt, target, 0, Y, D, B, tl, flag)));
@@ -1722,6 +1723,7 @@ int c2v_target_forward(c2v_engine* e, const float* code_all, int32_t Bt, const i
       C2V_CUDA(e, cudaMemsetAsync(flag, 0, 64, st));
       e->slab_flag_zeroed = true;
     }
+    if ((rc = end_target_lazy(e, st))) return rc;
     {
       PhaseTimer pt(e, PH_XENT, st);
       C2V_LAUNCH(e, (true_logit_kernel<<<(Bt + 7) / 8, 256, 0, st>>>(code_all, e->theta.tgt, target, row_offset, Y, e->dims.code_dim, Bt, tl, flag)));
