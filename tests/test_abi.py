@@ -52,3 +52,15 @@ def test_engine_refuses_to_run_without_cuda():
         pytest.skip("CUDA present")
     with pytest.raises(RuntimeError):
         E.PathAttentionEngine(E.EngineDims(1001, 501, 1001, 32, 96, 20, 64))
+
+
+def test_every_engine_option_is_documented_in_the_header():
+    """Every key c2v_set_option / c2v_get_option accept (the strcmp chain in engine.cu) is described in include/c2v_b200.h."""
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = open(os.path.join(root, "code2vec_b200", "csrc", "engine.cu")).read()
+    hdr = open(os.path.join(root, "include", "c2v_b200.h")).read()
+    keys = sorted(set(re.findall(r'!strcmp\(key, "([a-z_0-9]+)"\)', src)))
+    assert len(keys) >= 20
+    missing = [k for k in keys if '"%s"' % k not in hdr]
+    assert not missing, missing
