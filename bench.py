@@ -411,7 +411,7 @@ def run_ours(args):
         work = dict(ctx_side, **{k: tgt_side[k] for k in ("logits", "dv", "dY", "xent", "split")})
         work["adam"] = ("hbm", 24.0 * ((w["token_vocab"] + w["path_vocab"]) * w["embed_dim"]) / world)
     slab_on = (mode == "train" and tc and bool(eng.get_option("exp_slab")) and not args.fuse_softmax_grad and
-               (schedule == "fully_sharded" or (world == 1 and args.recompute_logits <= 0)))
+               (schedule == "fully_sharded" or args.recompute_logits <= 0))
     if slab_on:
         # deferred normalisation: no pass over the slab -- the phase is the true-class rows, the per-tile partials and the patches
         rows = B * (world if schedule == "fully_sharded" else 1)
