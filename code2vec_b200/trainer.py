@@ -37,6 +37,12 @@ leaving every replica with bit-identical parameters:
                 (max, sum exp) partials and all-reduce of the true logits [Bt], reduce-scatter of dv
                 [Bt, D].  No logits slab and no table gradient ever crosses NVLink; each rank's Adam
                 covers 1/world of all three tables.
+                In the tensor-core modes the per-row partials are (c, sum exp(s - c)) of the exp_slab
+                schedule (c = the true logit on the rank that owns the class, 0 elsewhere) -- the same
+                combine formula -- and the softmax's normalisation is applied as per-row factors inside
+                the two gradient GEMMs.  Trainer(allow_single_rank=True) keeps
+                this schedule in a process group of ONE rank, so a one-GPU box can run the whole path
+                (tests/test_gpu_dp.py).
 
 torch.distributed (NCCL over NVLink/NVSwitch; gloo in the CPU tests of the host logic) is plumbing;
 all arithmetic stays in the engine's kernels.
